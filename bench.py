@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""Headline benchmark: batched greedy caption decode on the nano configuration (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--dtype bf16|fp32]
+
+One "step" = one `generate()` call: 8 captions (8 synthetic 224x224 images), prompt [[50256]], 64 new tokens, top_k=1,
+KV cache, on-device no-repeat-n-gram ban.  Prints ONE JSON line (see DESIGN.md "measurement").
+  value : tokens/s with the images already resident in HBM and the ids left on the device;
+  e2e   : tokens/s through the public API with HOST buffers: pinned-host images copied to the device and the ids read
+          back every step inside the timed region;
+  roofline: the decode step against the measured HBM peak (MEASURED_PEAKS.json), algorithmic bytes per step stated in
+          DESIGN.md; the dominant kernel (skinny weight-streaming linear) is also timed alone;
+  cpu_baseline: the CPU oracle (port of the reference's cache-less generate loop) timed on this box's host cores on a
+          bounded sample.
+`--impl reference` times that CPU implementation with all host threads (the reference is pure PyTorch; it has no
+compiled artefact to carry to the GPU box, so the port in oracle/ -- pinned to the reference's outputs -- stands in).
+With N > 1 (torchrun) every rank decodes its own 8 captions: independent units, no collective on the data path.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CAPTIONS, NEW_TOKENS, PROMPT = 8, 64, 50256
+
+
+def read_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            d = json.load(fh)
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons with nvidia-smi while the timed region runs."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(int(float(r[0])) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(float(self.rows[0][1])), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def dist_setup(n_gpus):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local
+
+
+def algorithmic_bytes_per_step(spec, batch, dtype_bytes, mean_len):
+    """Bytes one decode step MUST move: every decoder weight once, the self KV cache prefix, the cached
+    cross K/V, the logits row, and the K/V append."""
+    C, L, V, S = spec["n_embd"], spec["n_layer"], spec["vocab_size"], spec["n_cls"]
+    ff = int(spec["ff_mult"] * C)
+    n_cross = sum(1 for d in range(L) if d % 2 == 0 or not spec["skip_alternate_cross_attn"]) if spec["use_cross_attn"] else 0
+    w = L * (3 * C * C + C * C + 2 * C * ff) + n_cross * (2 * C * C) + V * C          # GEMM weights read per step
+    small = L * (3 * C + C + ff + C + 4 * C) * 4 + n_cross * (2 * C + 2 * C) * 4 + 2 * C * 4   # biases + LN params (fp32)
+    kv_read = L * 2 * mean_len * C * batch * dtype_bytes
+    kv_write = L * 2 * C * batch * dtype_bytes
+    xkv = n_cross * 2 * S * C * batch * dtype_bytes
+    logits = batch * V * 4 * 2                                                        # written by the LM head, read by the sampler
+    return w * dtype_bytes + small + kv_read + kv_write + xkv + logits, w * dtype_bytes
+
+
+def run_ours(args):
+    from image2text_b200 import VisionEncoderDecoder, load_training_config
+    from image2text_b200._lib import call, launch_count
+    from image2text_b200.model_spec import synth_state_dict
+    from image2text_b200.synthetic import synth_images
+    from image2text_b200 import ops
+
+    rank, world, local = dist_setup(args.gpus)
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    cd = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    tc = load_training_config(os.path.join(ROOT, "configs", "nano.yaml"))
+    model = VisionEncoderDecoder(tc.model, device=dev, compute_dtype=cd)
+    model.load_state_dict(synth_state_dict(model.spec, seed=0))
+    model.eval()
+    spec = model.spec
+    images_host = synth_images(CAPTIONS, 224, seed=1234 + rank).pin_memory()
+    prompt_host = torch.full((CAPTIONS, 1), PROMPT, dtype=torch.long).pin_memory()
+    images = images_host.to(dev)
+    prompt = prompt_host.to(dev)
+    out_host = torch.empty((CAPTIONS, 1 + NEW_TOKENS), dtype=torch.long).pin_memory()
+
+    def step_resident():
+        return model.generate(images, prompt, max_new_tokens=NEW_TOKENS, temperature=1.0, top_k=1, seed=0)
+
+    def step_e2e():
+        im = images_host.to(dev, non_blocking=True)
+        pr = prompt_host.to(dev, non_blocking=True)
+        ids = model.generate(im, pr, max_new_tokens=NEW_TOKENS, temperature=1.0, top_k=1, seed=0)
+        out_host.copy_(ids, non_blocking=True)
+        return ids
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        barrier()
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    step_e2e()
+    sampler = ClockSampler(local)
+    sampler.start()
+    n0 = launch_count()
+    ms = timed(step_resident, args.steps)
+    eager_launches = launch_count() - n0
+    eng = next(iter(model._decode_engines.values()))
+    # kernels launched through the library directly (encoder, cross-KV prefill) + kernels inside the replayed step graphs
+    launches = eager_launches + args.steps * eng.replays_last * eng.launches_per_step
+    ms_e2e = timed(step_e2e, args.steps)
+    # decode step alone: replay the captured step graph (positions keep advancing inside the cache window)
+    g = next(iter(eng.graphs.values()))
+    eng.pos.fill_(8)
+    reps = 40
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    step_ms = e0.elapsed_time(e1) / reps
+    # dominant kernel alone: the LM-head skinny linear (largest single weight stream), back-to-back launches
+    W = model.weights()
+    wd = ops.F32 if cd == torch.float32 else ops.BF16
+    V, C = spec["vocab_size"], spec["n_embd"]
+    lm_w = W.c("decoder.lm_head.weight")
+    st = ops.stream()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        call("i2t_dec_linear", ops.ptr(eng.x), ops.ptr(W["decoder.transformer.ln_f.weight"]),
+             ops.ptr(W["decoder.transformer.ln_f.bias"]), 1e-5, ops.ptr(lm_w), None, None, ops.ptr(eng.logits), V, CAPTIONS, V, C, 0,
+             wd, 0, None, None, 0, 0, 0, None, st)
+    e1.record()
+    torch.cuda.synchronize()
+    lm_ms = e0.elapsed_time(e1) / reps
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+
+    tokens = CAPTIONS * NEW_TOKENS * world
+    value = tokens * args.steps / (ms / 1e3)
+    e2e = tokens * args.steps / (ms_e2e / 1e3)
+    esz = 2 if cd == torch.bfloat16 else 4
+    step_bytes, weight_bytes = algorithmic_bytes_per_step(spec, CAPTIONS, esz, mean_len=8 + reps / 2)
+    peak, peak_src = read_peaks()
+    achieved = step_bytes / (step_ms / 1e3) / 1e9
+    lm_bytes = V * C * esz + CAPTIONS * V * 4
+    line = {
+        "metric": "decode tok/s (nano.yaml, 8 captions x 64 new tokens, greedy top_k=1, KV cache)",
+        "value": round(value, 1), "unit": "tok/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.dtype, "data": "synthetic (randn 224x224 images, seed 1234+rank; seeded random-init weights)",
+        "config": {"workload": "training_configs/local/nano.yaml decode: 8 captions/step, 64 new tokens, prompt [[50256]], "
+                               "top_k=1, no_repeat_n_grams [2,3,4,5]; one step = ViT-B/16 encode of 8 images + 64 decode steps",
+                   "captions_per_gpu": CAPTIONS, "new_tokens": NEW_TOKENS,
+                   "l2": "decoder weights per step (%.0f MB) exceed the 126 MB L2; no explicit flush" % (weight_bytes / 1e6),
+                   "parallelism": f"replicated model, captions sharded by image over {world} GPU(s), no collective"},
+        "e2e": {"value": round(e2e, 1), "unit": "tok/s", "h2d_bytes_per_step": int(images_host.numel() * 4 + prompt_host.numel() * 8),
+                "d2h_bytes_per_step": int(out_host.numel() * 8), "ms_per_step": round(ms_e2e / args.steps, 3)},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                     "traffic": None, "peak_source": peak_src, "kernel": "decode step (one CUDA-graph replay, %d launches)" % eng.launches_per_step,
+                     "algorithmic_bytes_per_launch": int(step_bytes), "us_per_launch": round(step_ms * 1e3, 2),
+                     "dominant_kernel": {"name": "dec_linear_kernel (LM head 50257x768)", "algorithmic_bytes": int(lm_bytes),
+                                         "us": round(lm_ms * 1e3, 2), "achieved": round(lm_bytes / (lm_ms / 1e3) / 1e9, 1),
+                                         "frac": round(lm_bytes / (lm_ms / 1e3) / 1e9 / peak, 4)}},
+        "clocks": sampler.summary(),
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(sample_tokens=8)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def cpu_generate_tok_s(new_tokens: int, steps: int = 1, warmup: int = 0):
+    """The reference's cache-less generate loop (oracle port) on the host cores: 8 captions x `new_tokens`."""
+    from image2text_b200 import load_training_config
+    from image2text_b200.model_spec import spec_from_config, synth_state_dict
+    from image2text_b200.synthetic import synth_images
+    from oracle import i2t_oracle as O
+    tc = load_training_config(os.path.join(ROOT, "configs", "nano.yaml"))
+    spec = spec_from_config(tc.model)
+    sd = synth_state_dict(spec, seed=0)
+    images = synth_images(CAPTIONS, 224, seed=1234)
+    prompt = torch.full((CAPTIONS, 1), PROMPT, dtype=torch.long)
+    for _ in range(warmup):
+        O.generate(sd, spec, images, prompt, new_tokens, top_k=1)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.generate(sd, spec, images, prompt, new_tokens, top_k=1)
+    dt = time.perf_counter() - t0
+    return CAPTIONS * new_tokens * steps / dt, dt / steps
+
+
+def cpu_baseline(sample_tokens: int):
+    v, sec = cpu_generate_tok_s(sample_tokens)
+    return {"value": round(v, 2), "unit": "tok/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"oracle/i2t_oracle.generate (cache-less loop of the reference), 8 captions x {sample_tokens} new tokens "
+                      f"incl. ViT encode, fp32, {sec:.1f} s; shorter prefixes than the 64-token workload favour the CPU",
+            "host_cpus": os.cpu_count()}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_tokens = 16
+    v, sec = cpu_generate_tok_s(sample_tokens, steps=args.steps, warmup=min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": "decode tok/s (nano.yaml, 8 captions x 64 new tokens, greedy top_k=1, KV cache)",
+        "value": round(v, 2), "unit": "tok/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": round(sec * 1e3, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "fp32", "data": "synthetic (same images / weights as the B200 arm)",
+        "config": {"workload": "training_configs/local/nano.yaml decode: 8 captions/step, prompt [[50256]], top_k=1 "
+                               f"(bounded sample: {sample_tokens} of the 64 new tokens per step)"},
+        "cpu_baseline": {"value": round(v, 2), "unit": "tok/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"8 captions x {sample_tokens} new tokens per step, cache-less reference loop (oracle port), fp32"},
+        "e2e": {"value": round(v, 2), "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dtype", default=os.environ.get("I2T_BENCH_DTYPE", "bf16"), choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

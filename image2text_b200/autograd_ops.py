@@ -1,0 +1,218 @@
+"""torch.autograd.Function wrappers: the forward AND backward of every op is a libi2t kernel; autograd only records the
+graph (it is plumbing -- PyTorch computes nothing here).  Activations flow in the compute dtype (fp32, or bf16 with the
+autocast semantics of SURVEY.md Q9: bf16 linears/attention, fp32 LayerNorm / residual stream / loss / master grads)."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import ops
+from ._lib import call
+from .ops import dt, ptr, stream
+
+
+class LayerNormFn(torch.autograd.Function):
+    """F.layer_norm over the last dim: reference models/layers.py:357-358 (eps 1e-5), torchvision eps 1e-6."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps, out_dtype):
+        x = x.contiguous()
+        need = torch.is_grad_enabled() and (x.requires_grad or gamma.requires_grad)
+        if need:
+            y, mean, rstd = ops.layernorm(x, gamma, beta, eps, out_dtype, want_stats=True)
+            ctx.save_for_backward(x, gamma, mean, rstd)
+            ctx.has_beta = beta is not None
+        else:
+            y = ops.layernorm(x, gamma, beta, eps, out_dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, mean, rstd = ctx.saved_tensors
+        dy = dy.contiguous()
+        want_g = ctx.needs_input_grad[1]
+        dgamma = torch.zeros_like(gamma, dtype=torch.float32) if want_g else None
+        dbeta = torch.zeros_like(gamma, dtype=torch.float32) if (want_g and ctx.has_beta) else None
+        dx = ops.layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, dx_dtype=x.dtype)
+        return dx, dgamma, dbeta, None, None
+
+
+class LinearFn(torch.autograd.Function):
+    """y = act(x W^T + b) + residual with W an nn.Linear weight (N,K): reference models/layers.py:452,469,482,484,
+    models/decoder.py:256, nn.MultiheadAttention projections.  `w_c` is the compute-dtype view of the master weight."""
+
+    @staticmethod
+    def forward(ctx, x2d, w, w_c, bias, residual, act, out_dtype):
+        need = torch.is_grad_enabled() and (x2d.requires_grad or w.requires_grad or
+                                            (residual is not None and residual.requires_grad))
+        if need and act != ops.ACT_NONE:
+            z = ops.gemm(x2d, w_c, bias=bias, out_dtype=x2d.dtype)
+            y = torch.empty(z.shape, device=z.device, dtype=out_dtype)
+            call("i2t_act_fwd", ptr(z), ptr(y), z.numel(), act, dt(z), dt(y), stream())
+            assert residual is None
+        else:
+            z = None
+            y = ops.gemm(x2d, w_c, bias=bias, residual=residual, act=act, out_dtype=out_dtype)
+        if need:
+            ctx.save_for_backward(x2d, w_c, z)
+            ctx.act = act
+            ctx.has_bias = bias is not None
+            ctx.has_res = residual is not None
+            ctx.res_dtype = residual.dtype if residual is not None else None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2d, w_c, z = ctx.saved_tensors
+        dy = dy.contiguous()
+        dres = dy.to(ctx.res_dtype) if (ctx.has_res and ctx.needs_input_grad[4]) else None
+        g = dy
+        if g.dtype != x2d.dtype:
+            g = g.to(x2d.dtype)      # autocast: the linear's grad flows in the activation dtype
+        if z is not None:
+            dz = torch.empty_like(z)
+            call("i2t_act_bwd", ptr(z), ptr(g), ptr(dz), z.numel(), ctx.act, dt(z), dt(g), stream())
+            g = dz
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            # dX[M,K] = dY[M,N] W[N,K]
+            dx = ops.gemm(g, w_c, out_dtype=x2d.dtype, a_kmajor=True, b_kmajor=False)
+        if ctx.needs_input_grad[1]:
+            # dW[N,K] = dY^T[N,M] X[M,K]  (fp32 master gradient)
+            M, N = g.shape
+            K = x2d.shape[1]
+            dw = torch.empty((N, K), device=g.device, dtype=torch.float32)
+            ops.gemm(g, x2d, out=dw, a_kmajor=False, b_kmajor=False, M=N, N=K, K=M, lda=g.stride(0), ldb=x2d.stride(0),
+                     ldc=K)
+        if ctx.has_bias and ctx.needs_input_grad[3]:
+            db = torch.zeros(g.shape[1], device=g.device, dtype=torch.float32)
+            ops.colsum_(g, db)
+        return dx, dw, None, db, dres, None, None
+
+
+def linear(x2d, w, w_c, bias=None, residual=None, act=ops.ACT_NONE, out_dtype=torch.float32):
+    return LinearFn.apply(x2d, w, w_c, bias, residual, act, out_dtype)
+
+
+class AttnFn(torch.autograd.Function):
+    """Self attention on a packed (B*T, 3C) qkv buffer: reference models/layers.py:465 (+ the mask algebra of
+    vision_encoder_decoder.py:75-111 / layers.py:581-595 folded into `mask_mode`), torchvision :113."""
+
+    @staticmethod
+    def forward(ctx, qkv, B, T, H, mask_mode, n_prompt):
+        qkv = qkv.contiguous()
+        if torch.is_grad_enabled() and qkv.requires_grad:
+            out, lse = ops.attention_packed(qkv, B, T, H, mask_mode, n_prompt, want_lse=True)
+            ctx.save_for_backward(qkv, out, lse)
+            ctx.meta = (B, T, H, mask_mode, n_prompt)
+        else:
+            out = ops.attention_packed(qkv, B, T, H, mask_mode, n_prompt)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv, out, lse = ctx.saved_tensors
+        B, T, H, mask_mode, n_prompt = ctx.meta
+        dqkv = ops.attention_packed_bwd(qkv, out, dout.contiguous().to(qkv.dtype), lse, B, T, H, mask_mode, n_prompt)
+        return dqkv, None, None, None, None, None
+
+
+class XAttnFn(torch.autograd.Function):
+    """Cross attention over S <= 64 encoder tokens: reference models/layers.py:537-542,600-605."""
+
+    @staticmethod
+    def forward(ctx, q, kv, B, T, S, H):
+        q, kv = q.contiguous(), kv.contiguous()
+        if torch.is_grad_enabled() and (q.requires_grad or kv.requires_grad):
+            ctx.save_for_backward(q, kv)
+            ctx.meta = (B, T, S, H)
+        return ops.xattn(q, kv, B, T, S, H)
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, kv = ctx.saved_tensors
+        B, T, S, H = ctx.meta
+        dq, dkv = ops.xattn_bwd(q, kv, dout.contiguous().to(q.dtype), B, T, S, H)
+        return dq, dkv.to(kv.dtype), None, None, None, None
+
+
+class EmbedFn(torch.autograd.Function):
+    """cat(prompt, wte[ids])[:T] + wpe[:T]: reference vision_encoder_decoder.py:84-88 + decoder.py:234-243."""
+
+    @staticmethod
+    def forward(ctx, ids, prompt, wte, wpe, T, n_prompt):
+        B, S = ids.shape
+        x = ops.embed(ids, prompt, wte, wpe, B, T, n_prompt, S)
+        ctx.save_for_backward(ids)
+        ctx.meta = (B, T, n_prompt, S, wte.shape, prompt is not None)
+        return x
+
+    @staticmethod
+    def backward(ctx, dx):
+        (ids,) = ctx.saved_tensors
+        B, T, n_prompt, S, wte_shape, has_prompt = ctx.meta
+        dx = dx.contiguous()
+        C = dx.shape[-1]
+        dprompt = dwte = dwpe = None
+        if has_prompt and ctx.needs_input_grad[1]:
+            dprompt = dx[:, :n_prompt].contiguous()
+        if ctx.needs_input_grad[2]:
+            dwte = torch.zeros(wte_shape, device=dx.device, dtype=torch.float32)
+            call("i2t_embed_bwd", ptr(ids), ptr(dx), ptr(dwte), B, T, n_prompt, S, C, stream())
+        if ctx.needs_input_grad[3]:
+            dwpe_t = torch.zeros(T * C, device=dx.device, dtype=torch.float32)
+            ops.colsum_(dx.view(B, T * C), dwpe_t)
+            dwpe = dwpe_t.view(T, C)
+        return None, dprompt, dwte, dwpe, None, None
+
+
+class NormalizeGradientsFn(torch.autograd.Function):
+    """reference models/functions.py:4-27: identity forward; backward g / (||g||_2 + 1e-6) over the whole tensor."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        out = torch.empty_like(g)
+        acc = torch.empty(1, device=g.device, dtype=torch.float64)
+        call("i2t_gradnorm_scale", ptr(g), ptr(out), ptr(acc), g.numel(), dt(g), stream())
+        return out
+
+
+class LmLossFn(torch.autograd.Function):
+    """training/wrapper.py:120-151 (+ get_weights :80-96).  The gradient w.r.t. the logits is produced by the same
+    pass over the vocabulary that computes the loss."""
+
+    @staticmethod
+    def forward(ctx, logits, teacher_logits, labels, temperature, alpha, weight_fn, eos_weight, eos_id, ignore_index):
+        logits = logits.contiguous()
+        B, T_logits, V = logits.shape
+        Tl = min(T_logits, labels.shape[1])
+        labels = labels.contiguous()
+        need = torch.is_grad_enabled() and logits.requires_grad
+        weights = torch.empty(B * Tl, device=logits.device, dtype=torch.float32)
+        rows = torch.empty(B * Tl, device=logits.device, dtype=torch.float32)
+        loss = torch.empty((), device=logits.device, dtype=torch.float32)
+        dlogits = None
+        if need:
+            dlogits = torch.zeros_like(logits) if Tl < T_logits else torch.empty_like(logits)
+        if teacher_logits is not None:
+            teacher_logits = teacher_logits.contiguous().to(logits.dtype)
+        call("i2t_lm_loss", ptr(logits), ptr(teacher_logits), ptr(labels), ptr(weights), ptr(rows), ptr(loss), ptr(dlogits),
+             B, T_logits, Tl, V, labels.shape[1], float(temperature), float(alpha if alpha is not None else 0.0),
+             int(weight_fn == "inverse_sqrt_position"), int(eos_weight is not None),
+             float(eos_weight if eos_weight is not None else 0.0), int(eos_id), int(ignore_index), dt(logits), stream())
+        if need:
+            ctx.save_for_backward(dlogits)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gloss):
+        (dlogits,) = ctx.saved_tensors
+        scale = gloss.reshape(1).to(torch.float32).contiguous()
+        call("i2t_scale_inplace", ptr(dlogits), ptr(scale), dlogits.numel(), dt(dlogits), stream())
+        return dlogits, None, None, None, None, None, None, None, None

@@ -1,0 +1,199 @@
+"""Full-sequence forward of the encoder and the decoder (training and the ``forward()`` API).
+
+Restates WHAT the reference computes (citations per function); HOW is B200-specific: packed QKV buffers consumed in
+place by the fused attention kernels, masks as closed forms, residual adds / bias / GELU folded into GEMM epilogues,
+the LayerNorm output written directly in the GEMM operand dtype.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import ops
+from ._lib import call
+from .autograd_ops import AttnFn, EmbedFn, LayerNormFn, NormalizeGradientsFn, XAttnFn, linear
+from .model_spec import layer_has_cross_attn
+from .ops import ptr, stream
+
+
+def _ln(W, key_w, key_b, x, eps, out_dtype):
+    return LayerNormFn.apply(x, W[key_w], W.get(key_b), eps, out_dtype)
+
+
+def _lin(W, key_w, key_b, x2d, residual=None, act=ops.ACT_NONE, out_dtype=torch.float32, rows: Optional[slice] = None):
+    w = W[key_w]
+    wc = W.c(key_w)
+    b = W.get(key_b) if key_b else None
+    if rows is not None:
+        w, wc = w[rows], wc[rows]
+        b = b[rows] if b is not None else None
+    return linear(x2d, w, wc, b, residual, act, out_dtype)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# encoder: reference models/encoder.py:108-119 over torchvision's VisionTransformer.forward (:268-305)
+# ------------------------------------------------------------------------------------------------------------
+def vit_trunk(W, spec, images: torch.Tensor, cd: torch.dtype, pre: str) -> torch.Tensor:
+    p, d, H = spec["vit_patch"], spec["vit_dim"], spec["vit_heads"]
+    B = images.shape[0]
+    images = images.contiguous().float()
+    patches = ops.patch_im2col(images, p, cd)                                   # (B*np, 3*p*p)
+    conv_w = W[pre + "conv_proj.weight"]
+    po = linear(patches, conv_w.view(d, -1), W.c(pre + "conv_proj.weight").view(d, -1), W[pre + "conv_proj.bias"],
+                None, ops.ACT_NONE, torch.float32)                             # (B*np, d)
+    x = _AssembleFn.apply(po, W[pre + "class_token"], W[pre + "encoder.pos_embedding"], B)   # (B, np+1, d) fp32
+    T = x.shape[1]
+    for i in range(spec["vit_layers"]):
+        lp = f"{pre}encoder.layers.encoder_layer_{i}."
+        y = _ln(W, lp + "ln_1.weight", lp + "ln_1.bias", x, 1e-6, cd)
+        qkv = _lin(W, lp + "self_attention.in_proj_weight", lp + "self_attention.in_proj_bias", y.view(B * T, d),
+                   out_dtype=cd)
+        a = AttnFn.apply(qkv, B, T, H, ops.MASK_NONE, 0)
+        x = _lin(W, lp + "self_attention.out_proj.weight", lp + "self_attention.out_proj.bias", a,
+                 residual=x.view(B * T, d)).view(B, T, d)
+        y = _ln(W, lp + "ln_2.weight", lp + "ln_2.bias", x, 1e-6, cd)
+        h = _lin(W, lp + "mlp.0.weight", lp + "mlp.0.bias", y.view(B * T, d), act=ops.ACT_GELU_ERF, out_dtype=cd)
+        x = _lin(W, lp + "mlp.3.weight", lp + "mlp.3.bias", h, residual=x.view(B * T, d)).view(B, T, d)
+    # final LayerNorm only on token 0 (the reference normalises all tokens and then keeps x[:, 0])
+    cls_tok = x[:, 0, :]
+    if torch.is_grad_enabled() and x.requires_grad:
+        return LayerNormFn.apply(cls_tok.contiguous(), W[pre + "encoder.ln.weight"], W[pre + "encoder.ln.bias"], 1e-6,
+                                 torch.float32)
+    return ops.layernorm(x, W[pre + "encoder.ln.weight"], W[pre + "encoder.ln.bias"], 1e-6, torch.float32, rows=B,
+                         row_stride=T * d)
+
+
+class _AssembleFn(torch.autograd.Function):
+    """prepend class token, add pos_embedding: torchvision vision_transformer.py:294-296,156."""
+
+    @staticmethod
+    def forward(ctx, patch_out, cls, pos, B):
+        return ops.vit_assemble(patch_out, cls, pos, B)
+
+    @staticmethod
+    def backward(ctx, dx):
+        B, T, C = dx.shape
+        dx = dx.contiguous()
+        dpatch = dx[:, 1:, :].reshape(B * (T - 1), C)
+        dcls = dpos = None
+        if ctx.needs_input_grad[2]:
+            acc = torch.zeros(T * C, device=dx.device, dtype=torch.float32)
+            ops.colsum_(dx.view(B, T * C), acc)
+            dpos = acc.view(1, T, C)
+            if ctx.needs_input_grad[1]:
+                dcls = dpos[:, :1, :].clone()
+        return dpatch, dcls, dpos, None
+
+
+class _LshTailFn(torch.autograd.Function):
+    """reference models/layers.py:139-144,211-219 + models/encoder.py:116-117 (forward); the backward is the
+    EmbeddingBag(mean) scatter: d emb[idx[b,s,r,p], :] += d out[b,s,:] / n_proj (the hashing itself has no gradient)."""
+
+    @staticmethod
+    def forward(ctx, feat, tables, num_bins, n_cls, n_proj, E, *emb_weights):
+        B, D = feat.shape
+        n_res = len(num_bins)
+        out = torch.empty((B, n_cls, E), device=feat.device, dtype=torch.float32)
+        need = torch.is_grad_enabled() and any(w.requires_grad for w in emb_weights)
+        idx = torch.empty((B, n_cls, n_res, n_proj), device=feat.device, dtype=torch.int32) if need else None
+        call("i2t_lsh_tail", ptr(feat), ptr(tables["proj"]), ptr(tables["grid"]), ptr(tables["emb"]), ptr(tables["nb"]),
+             ptr(out), ptr(idx), B, D, n_cls, n_res, n_proj, E, stream())
+        if need:
+            ctx.save_for_backward(idx)
+            ctx.meta = (n_cls, n_res, n_proj, E, [w.shape for w in emb_weights])
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (idx,) = ctx.saved_tensors
+        n_cls, n_res, n_proj, E, shapes = ctx.meta
+        dout = dout.contiguous().float()
+        grads = []
+        # tiny tables (<= 672 rows): index_add_ is an accumulation into the gradient buffer, not model arithmetic
+        for s in range(n_cls):
+            for r in range(n_res):
+                g = torch.zeros(shapes[s * n_res + r], device=dout.device, dtype=torch.float32)
+                rows = idx[:, s, r, :].reshape(-1).long()
+                src = (dout[:, s, :] / n_proj).repeat_interleave(n_proj, dim=0)
+                g.index_add_(0, rows, src)
+                grads.append(g)
+        return (None, None, None, None, None, None, *grads)
+
+
+def encoder_forward(W, spec, images: torch.Tensor, cd: torch.dtype, train_trunk: bool = False) -> torch.Tensor:
+    bridged = "encoder.1.weight" in W
+    pre = "encoder.0." if bridged else "encoder."
+    if train_trunk:
+        feat = vit_trunk(W, spec, images, cd, pre + "model.")
+    else:
+        with torch.no_grad():                                   # reference models/encoder.py:109-111
+            feat = vit_trunk(W, spec, images, cd, pre + "model.")
+    if spec["tail"] == "lsh":
+        tables = W.m._lsh_tables(pre)
+        embs = [W[f"{pre}lsh_emb.{s}.emb.{r}.emb.weight"] for s in range(spec["n_cls"])
+                for r in range(len(spec["lsh_num_bins"]))]
+        out = _LshTailFn.apply(feat, tables, spec["lsh_num_bins"], spec["n_cls"], spec["lsh_num_proj"],
+                               spec["n_embd_out_vit"], *embs)
+    else:
+        raise NotImplementedError("per-slot MLP tail (reference models/layers.py:617-638) is not built yet")
+    if bridged:
+        B, n, E = out.shape
+        out = linear(out.view(B * n, E).to(cd), W["encoder.1.weight"], W.c("encoder.1.weight"), None, None, ops.ACT_NONE,
+                     torch.float32).view(B, n, -1)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# decoder: reference models/vision_encoder_decoder.py:84-134 + models/decoder.py:214-256 + models/layers.py:565-614
+# ------------------------------------------------------------------------------------------------------------
+def decoder_forward(W, spec, ids: torch.Tensor, encoder_output: torch.Tensor, cd: torch.dtype, training: bool = False):
+    if spec["decoder"] != "transformer":
+        raise NotImplementedError("HF GPT-2 layout decoder (reference models/decoder.py:285-377) is not built yet")
+    C, H, blk = spec["n_embd"], spec["n_head"], spec["block_size"]
+    B, S = ids.shape
+    n_prompt = spec["n_cls"] if spec["use_soft_prompting"] else 0
+    T = min(n_prompt + S, blk)
+    dp = "decoder.transformer."
+    prompt = encoder_output.contiguous().float() if n_prompt else None
+    x = EmbedFn.apply(ids.contiguous(), prompt, W[dp + "wte.weight"], W[dp + "wpe.weight"], T, n_prompt)
+    if n_prompt:
+        mask_mode = ops.MASK_PROMPT
+    else:
+        mask_mode = ops.MASK_CAUSAL if spec["is_causal"] else ops.MASK_NONE
+    cross = encoder_output if spec["use_cross_attn"] else None
+    S_enc = encoder_output.shape[1]
+    enc_c = None
+    if cross is not None:
+        enc_c = encoder_output.reshape(B * S_enc, C)
+        enc_c = enc_c if enc_c.dtype == cd else enc_c.to(cd)
+    grads = torch.is_grad_enabled()
+    for depth in range(spec["n_layer"]):
+        lp = f"{dp}h.{depth}."
+        y = _ln(W, lp + "ln_1.weight", lp + "ln_1.bias", x, 1e-5, cd)
+        qkv = _lin(W, lp + "attn.c_attn.weight", lp + "attn.c_attn.bias", y.view(B * T, C), out_dtype=cd)
+        a = AttnFn.apply(qkv, B, T, H, mask_mode, n_prompt)
+        x = _lin(W, lp + "attn.c_proj.weight", lp + "attn.c_proj.bias", a, residual=x.view(B * T, C)).view(B, T, C)
+        use_cross = cross is not None and (depth % 2 == 0 if spec["skip_alternate_cross_attn"] else True)
+        if use_cross:
+            if not layer_has_cross_attn(spec, depth):
+                raise ValueError("Model not configured for cross attn inputs!!!")
+            y = _ln(W, lp + "ln_3.weight", lp + "ln_3.bias", x, 1e-5, cd)
+            kw, kb = lp + "cross_attn.in_proj_weight", lp + "cross_attn.in_proj_bias"
+            q = _lin(W, kw, kb, y.view(B * T, C), out_dtype=cd, rows=slice(0, C))
+            kv = _lin(W, kw, kb, enc_c, out_dtype=cd, rows=slice(C, 3 * C))            # raw encoder output, no LN
+            a = XAttnFn.apply(q, kv, B, T, S_enc, H)
+            x = _lin(W, lp + "cross_attn.out_proj.weight", lp + "cross_attn.out_proj.bias", a,
+                     residual=x.view(B * T, C)).view(B, T, C)
+        y = _ln(W, lp + "ln_2.weight", lp + "ln_2.bias", x, 1e-5, cd)
+        h = _lin(W, lp + "mlp.c_fc.weight", lp + "mlp.c_fc.bias", y.view(B * T, C), act=ops.ACT_GELU_TANH, out_dtype=cd)
+        x = _lin(W, lp + "mlp.c_proj.weight", lp + "mlp.c_proj.bias", h, residual=x.view(B * T, C)).view(B, T, C)
+        if grads and x.requires_grad:
+            x = NormalizeGradientsFn.apply(x)                                          # models/layers.py:607-608
+    hidden = _ln(W, dp + "ln_f.weight", dp + "ln_f.bias", x, 1e-5, torch.float32)
+    # logits only for the text rows (the reference computes all rows, then slices [offset:], :132)
+    text = hidden[:, n_prompt:, :].reshape(B * (T - n_prompt), C)
+    text = text if cd == torch.float32 else text.to(cd)
+    logits = linear(text, W["decoder.lm_head.weight"], W.c("decoder.lm_head.weight"), None, None, ops.ACT_NONE,
+                    torch.float32).view(B, T - n_prompt, -1)
+    return logits, hidden

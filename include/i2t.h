@@ -1,0 +1,202 @@
+/*
+ * libi2t -- C ABI of the B200 (sm_100a) encoder-decoder hot path of image2text.
+ *
+ * The reference (iitmdinesh/image2text) is pure Python: it has no FFI / plugin interface, every
+ * hot operation is a PyTorch library call.  Each entry point below therefore names the reference
+ * CALL SITE (file:line, relative to the reference root) whose arithmetic it replaces; the Python
+ * host in image2text_b200/ binds them with ctypes (see INTEGRATION.md for the stub a maintainer of
+ * the reference would add).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every buffer (outputs, workspaces) is allocated by the caller,
+ *     the library never frees or retains a pointer past the call;
+ *   - all pointers are DEVICE pointers unless a parameter says "host";
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on that stream and
+ *     never synchronises;
+ *   - return value: 0 on success, negative I2T_ERR_* otherwise; i2t_last_error() returns a
+ *     thread-local message.  Nothing throws across the ABI;
+ *   - dtype codes: I2T_F32 = 0, I2T_BF16 = 1.  Accumulation is always fp32;
+ *   - row-major tensors, innermost dimension contiguous unless a stride argument says otherwise.
+ */
+#ifndef I2T_H_
+#define I2T_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define I2T_F32 0
+#define I2T_BF16 1
+
+#define I2T_OK 0
+#define I2T_ERR_INVALID (-1)   /* bad argument / unsupported shape */
+#define I2T_ERR_CUDA (-2)      /* a CUDA runtime or driver call failed */
+
+/* activation codes for the GEMM epilogues */
+#define I2T_ACT_NONE 0
+#define I2T_ACT_GELU_TANH 1    /* models/layers.py:477 nn.GELU('tanh'); HF gelu_new */
+#define I2T_ACT_GELU_ERF 2     /* torchvision MLPBlock nn.GELU() */
+
+/* attention mask modes (closed forms of SURVEY.md Appendix C after discrepancy D9) */
+#define I2T_MASK_NONE 0        /* ViT self attention, cross attention */
+#define I2T_MASK_CAUSAL 1      /* key j visible to query i  <=>  j <= i */
+#define I2T_MASK_PROMPT 2      /* i < n_prompt: j <= i ;  i >= n_prompt: n_prompt <= j <= i */
+
+int i2t_version(void);
+const char* i2t_last_error(void);
+/* number of kernel launches issued by this library in the calling process since load */
+int64_t i2t_launch_count(void);
+
+/* ---- LayerNorm: models/layers.py:357-358 (eps 1e-5), torchvision vision_transformer.py:96 (1e-6) --- */
+/* y[r,:] = (x[r,:] - mean) * rstd * gamma + beta.  x rows are x_row_stride elements apart (lets the ViT
+ * final norm read only token 0 of every image).  mean / rstd (fp32, rows) are optional (backward). */
+int i2t_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                      int64_t rows, int64_t cols, int64_t x_row_stride, float eps, int x_dtype, int y_dtype,
+                      void* stream);
+/* dx, and dgamma/dbeta ACCUMULATED (+=) into fp32 buffers (may be NULL).  models/layers.py:357-358 backward. */
+int i2t_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                      void* dx, float* dgamma, float* dbeta, int64_t rows, int64_t cols, int dy_dtype, int x_dtype,
+                      int dx_dtype, void* stream);
+
+/* ---- dense contraction: every nn.Linear / Conv1D / conv_proj on the path
+ *      (models/layers.py:452,469,482,484; models/decoder.py:256; nn.MultiheadAttention in/out proj
+ *      models/layers.py:600-605; torchvision vision_transformer.py:277) -------------------------------- */
+/* C[M,N] = act(op(A) * op(B) + bias[N]) + residual[M,N]
+ *   a_kmajor=1: A is [M][K] (K contiguous, leading dim lda);  0: A is [K][M] (M contiguous)
+ *   b_kmajor=1: B is [N][K] (K contiguous, leading dim ldb) -- nn.Linear weight;  0: B is [K][N] -- HF Conv1D
+ *   accumulate=1: C += result (fp32 C only; used by weight gradients)
+ *   colsum (fp32, N, optional): colsum[n] += sum_m C_new[m,n] is NOT provided here; see i2t_colsum.
+ * fp32 operands run exact fp32 FMA tiles (the parity anchor); bf16 operands run tcgen05 tiles. */
+int i2t_gemm(const void* A, const void* B, const float* bias, const void* residual, void* C, int64_t M, int64_t N,
+             int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int a_kmajor, int b_kmajor, int act, int accumulate,
+             int ab_dtype, int res_dtype, int c_dtype, void* stream);
+/* out[n] += sum_m X[m,n]   (bias gradients) */
+int i2t_colsum(const void* X, float* out, int64_t M, int64_t N, int64_t ldx, int x_dtype, void* stream);
+
+/* ---- fused attention: models/layers.py:465 F.scaled_dot_product_attention, torchvision :113 ---------- */
+/* q,k,v element (b,h,t,e) lives at ptr + b*batch_stride + t*row_stride + h*head_dim + e (so the packed
+ * (B,T,3C) output of c_attn / in_proj is read in place); out is (B,Tq,H*head_dim).
+ * lse (fp32, B*H*Tq, optional) receives the row log-sum-exp for the backward pass. */
+int i2t_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int64_t B, int64_t H,
+                 int64_t Tq, int64_t Tk, int64_t head_dim, int64_t q_batch_stride, int64_t q_row_stride,
+                 int64_t kv_batch_stride, int64_t kv_row_stride, int mask_mode, int64_t n_prompt, int in_dtype,
+                 int out_dtype, void* stream);
+/* Backward of the above (autograd of reference models/layers.py:465).  dq,dk,dv are written with the same strides
+ * as q,k,v; out/dout are (B,Tq,H*head_dim).  workspace: i2t_attn_bwd_workspace_bytes(...) bytes of device memory. */
+int64_t i2t_attn_bwd_workspace_bytes(int64_t B, int64_t H, int64_t Tq, int64_t head_dim);
+int i2t_attn_bwd(const void* q, const void* k, const void* v, const void* out, const void* dout, const float* lse,
+                 void* dq, void* dk, void* dv, void* workspace, int64_t B, int64_t H, int64_t Tq, int64_t Tk,
+                 int64_t head_dim, int64_t q_batch_stride, int64_t q_row_stride, int64_t kv_batch_stride,
+                 int64_t kv_row_stride, int mask_mode, int64_t n_prompt, int dtype, void* stream);
+
+/* ---- ViT patch embedding: torchvision vision_transformer.py:268-296 ---------------------------------- */
+/* images (B,3,H,W) fp32 NCHW -> patches (B*nh*nw, 3*p*p), column = c*p*p + ky*p + kx (conv weight order) */
+int i2t_patch_im2col(const float* images, void* patches, int64_t B, int64_t H, int64_t W, int64_t p, int out_dtype,
+                     void* stream);
+/* x[b,0,:] = cls + pos[0];  x[b,1+i,:] = patch_out[b*np+i,:] + pos[1+i]   (fp32 residual stream) */
+int i2t_vit_assemble(const void* patch_out, const float* cls, const float* pos, float* x, int64_t B, int64_t np,
+                     int64_t C, int patch_dtype, void* stream);
+
+/* ---- LSH tail: models/layers.py:139-144,211-219, models/encoder.py:116-117 ---------------------------- */
+/* feat (B,D) fp32 -> out (B,n_cls,E).  tables: device arrays of n_cls*n_res pointers (slot-major):
+ * proj[i] -> (D,n_proj) fp32, grid[i] -> (num_bins[r]) fp32, emb[i] -> ((num_bins[r]+1)*n_proj, E) fp32.
+ * bucket_out (int32, B*n_cls*n_res*n_proj, optional) receives the EmbeddingBag row indices. */
+int i2t_lsh_tail(const float* feat, const void* const* proj, const void* const* grid, const void* const* emb,
+                 const int32_t* num_bins, float* out, int32_t* bucket_out, int64_t B, int64_t D, int64_t n_cls,
+                 int64_t n_res, int64_t n_proj, int64_t E, void* stream);
+
+/* ---- decoder input: models/vision_encoder_decoder.py:84-88 + models/decoder.py:234-243 ----------------- */
+/* x[b,t,:] = (t < n_prompt ? prompt[b,t,:] : wte[ids[b,t-n_prompt],:]) + wpe[t,:],  t < T */
+int i2t_embed_fwd(const int64_t* ids, const float* prompt, const float* wte, const float* wpe, float* x, int64_t B,
+                  int64_t T, int64_t n_prompt, int64_t S, int64_t C, void* stream);
+
+/* ---- cross attention with a short key/value set: models/layers.py:537-542,600-605 --------------------- */
+/* q (B,T,C) [row stride q_row_stride]; k,v element (b,h,s,e) at ptr + b*kv_batch_stride + s*kv_row_stride
+ * + h*head_dim + e; S <= 64; no mask; out (B,T,C). */
+int i2t_xattn_fwd(const void* q, const void* k, const void* v, void* out, int64_t B, int64_t H, int64_t T, int64_t S,
+                  int64_t head_dim, int64_t q_row_stride, int64_t kv_batch_stride, int64_t kv_row_stride,
+                  int in_dtype, int out_dtype, void* stream);
+
+/* Backward of i2t_xattn_fwd.  dq has q's layout; dk/dv are fp32 buffers the caller zeroed, element (b,h,s,e) at
+ * ptr + b*dkv_batch_stride + s*dkv_row_stride + h*head_dim + e, accumulated with atomicAdd. */
+int i2t_xattn_bwd(const void* q, const void* k, const void* v, const void* dout, void* dq, float* dk, float* dv,
+                  int64_t B, int64_t H, int64_t T, int64_t S, int64_t head_dim, int64_t q_row_stride,
+                  int64_t kv_batch_stride, int64_t kv_row_stride, int64_t dkv_batch_stride, int64_t dkv_row_stride,
+                  int dtype, void* stream);
+
+/* 1 (default): bf16 contractions run on tcgen05 when the shape fits; 0: always the FMA kernel (A/B testing). */
+void i2t_set_tensor_core_gemm(int enabled);
+
+/* ---- KV-cached decode step (no counterpart in the reference, which recomputes the prefix every token:
+ *      models/vision_encoder_decoder.py:144-150).  pos_ptr is a DEVICE int32: the index of the token being processed
+ *      (also its KV-cache slot); every kernel reads it on the device so one CUDA graph replays all steps. ---------- */
+/* x[b,:] = wte[ids[b*ids_ld + pos]] + wpe[n_prompt + pos]            (models/decoder.py:234-243) */
+int i2t_dec_embed(const int64_t* ids, const float* wte, const float* wpe, float* x, const int32_t* pos_ptr, int64_t B,
+                  int64_t C, int64_t ids_ld, int64_t n_prompt, void* stream);
+int i2t_dec_advance(int32_t* pos_ptr, void* stream);
+/* out[b,n] = act(LN?(x)[b,:] . W[n,:] + bias[n]) (+ residual[b,n]);  B <= 16, W is (N,K) fp32 or bf16.
+ * qkv_split=1 (N == 3C): columns [0,C) -> out (B,ldo), [C,2C) -> kcache, [2C,3C) -> vcache at row *pos_ptr of the
+ * (B,Tmax,C) caches (fused KV-cache append).  Replaces c_attn/c_proj/c_fc/lm_head at models/layers.py:452,469,482,484
+ * and models/decoder.py:256 for one new token per sequence. */
+int i2t_dec_linear(const float* x, const float* ln_gamma, const float* ln_beta, float ln_eps, const void* W,
+                   const float* bias, const float* residual, float* out, int64_t ldo, int64_t B, int64_t N, int64_t K,
+                   int act, int w_dtype, int qkv_split, void* kcache, void* vcache, int64_t cache_batch_stride, int64_t C,
+                   int cache_dtype, const int32_t* pos_ptr, void* stream);
+/* one query per (b,h) against a (B,Tmax,C)-layout cache; visible keys = [0, *len_ptr + len_add) (len_ptr may be NULL) */
+int i2t_dec_attn(const float* q, int64_t q_ld, const void* kcache, const void* vcache, int64_t cache_batch_stride,
+                 int64_t cache_row_stride, float* out, int64_t out_ld, const int32_t* len_ptr, int64_t len_add, int64_t B,
+                 int64_t H, int64_t head_dim, int cache_dtype, void* stream);
+
+/* ---- sampler: models/vision_encoder_decoder.py:152-180 + transformers NoRepeatNGramLogitsProcessor ----------------
+ * logits (B,ldl) fp32 are modified in place (/temperature, banned -> -inf).  Tokens ids[b, 0..cur_len) are the history
+ * (cur_len = *pos_ptr + 1 when pos_ptr != NULL, else the cur_len argument); the draw is written to ids[b, cur_len] when
+ * write_token != 0.  top_k <= 0 means no top-k filter.  probs_out (B,V fp32, optional) receives the sampling
+ * distribution.  seed_ptr (device uint64, optional) overrides seed so a captured graph can be re-seeded.
+ * advance_pos != 0: the last CTA increments *pos_ptr (ticket = zeroed device int32). */
+int i2t_sample(float* logits, int64_t ldl, int64_t B, int64_t V, int64_t* ids, int64_t ids_ld, int32_t* pos_ptr,
+               int advance_pos, int64_t cur_len, float temperature, int64_t top_k, const int32_t* ngrams,
+               int64_t n_ngrams, uint64_t seed, const uint64_t* seed_ptr, float* probs_out, int32_t* ticket, int write_token,
+               void* stream);
+
+/* ---- training-side memory-bound kernels ------------------------------------------------------------------------- */
+/* h = act(z) / dz = dh * act'(z): nn.GELU('tanh') models/layers.py:477,483; torchvision nn.GELU(); HF gelu_new.
+ * n (elements) must be a multiple of 4. */
+int i2t_act_fwd(const void* z, void* h, int64_t n, int act, int z_dtype, int h_dtype, void* stream);
+int i2t_act_bwd(const void* z, const void* dh, void* dz, int64_t n, int act, int z_dtype, int g_dtype, void* stream);
+/* dwte[ids[b,s],:] += dx[b, n_prompt+s, :]  (autograd of models/decoder.py:234 / vision_encoder_decoder.py:85-88) */
+int i2t_embed_bwd(const int64_t* ids, const float* dx, float* dwte, int64_t B, int64_t T, int64_t n_prompt, int64_t S,
+                  int64_t C, void* stream);
+/* out = g / (||g||_2 + 1e-6), norm over all n elements (models/functions.py:19-24).  acc: device double scratch. */
+int i2t_gradnorm_scale(const void* g, void* out, double* acc, int64_t n, int dtype, void* stream);
+/* Weighted (optionally distilled) LM loss, training/wrapper.py:80-96,120-151.  logits (B,T_logits,V); only the first
+ * Tl positions of every sequence are used (labels (B,ld_labels) int64).  weights (B*Tl) and loss_rows (B*Tl) are fp32
+ * scratch outputs; loss_out is a device fp32 scalar; dlogits (same shape/dtype as logits, optional) receives
+ * dLoss/dlogits for the first Tl positions (other positions must be zeroed by the caller). */
+int i2t_lm_loss(const void* logits, const void* teacher_logits, const int64_t* labels, float* weights, float* loss_rows,
+                float* loss_out, void* dlogits, int64_t B, int64_t T_logits, int64_t Tl, int64_t V, int64_t ld_labels,
+                float temperature, float alpha, int inv_sqrt_position, int use_eos_weight, float eos_weight,
+                int64_t eos_id, int64_t ignore_index, int dtype, void* stream);
+/* x *= *scale_ptr (device scalar) */
+int i2t_scale_inplace(void* x, const float* scale_ptr, int64_t n, int dtype, void* stream);
+
+/* ---- fused multi-tensor optimiser steps (fp32 state).  table: device int64[n_tensors*4] = {p, g, m, v} pointers per
+ *      tensor; chunk c updates elements [chunk_off[c], chunk_off[c]+chunk_len[c]) of tensor chunk_tensor[c];
+ *      step counts from 1; grad_scale multiplies the gradient on the fly (1.0 = reference semantics). ---------------- */
+/* torch.optim.AdamW as constructed at trainer.py:169-172 (eps 1e-8, amsgrad off) */
+int i2t_adamw_multi(const int64_t* table, const int32_t* chunk_tensor, const int64_t* chunk_off, const int32_t* chunk_len,
+                    int64_t n_chunks, double lr, double beta1, double beta2, double eps, double weight_decay,
+                    int64_t step, double grad_scale, void* stream);
+/* SNRAdam, models/optimizer.py:56-113 */
+int i2t_snradam_multi(const int64_t* table, const int32_t* chunk_tensor, const int64_t* chunk_off,
+                      const int32_t* chunk_len, int64_t n_chunks, double lr, double beta1, double beta2, double eps,
+                      double weight_decay, int64_t step, double grad_scale, void* stream);
+/* momentum-distillation teacher: p_m = p_m*momentum + p*(1-momentum), training/wrapper.py:53-60; table = {p_m, p, 0, 0} */
+int i2t_ema_multi(const int64_t* table, const int32_t* chunk_tensor, const int64_t* chunk_off, const int32_t* chunk_len,
+                  int64_t n_chunks, double momentum, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* I2T_H_ */
