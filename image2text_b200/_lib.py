@@ -17,6 +17,7 @@ SIGNATURES = {
     "i2t_last_error": (c_char_p, []),
     "i2t_launch_count": (c_int64, []),
     "i2t_set_tensor_core_gemm": (None, [I]),
+    "i2t_set_pdl": (None, [I]),
     "i2t_layernorm_fwd": (c_int, [P, P, P, P, P, P, L, L, L, F, I, I, P]),
     "i2t_layernorm_bwd": (c_int, [P, P, P, P, P, P, P, P, L, L, I, I, I, P]),
     "i2t_gemm": (c_int, [P, P, P, P, P, L, L, L, L, L, L, I, I, I, I, I, I, I, P]),
@@ -64,6 +65,10 @@ def lib() -> ctypes.CDLL:
             fn = getattr(handle, name)      # AttributeError if the library does not export a declared symbol
             fn.restype = res
             fn.argtypes = args
+        if os.environ.get("I2T_PDL") is not None:          # A/B switch for measurements
+            handle.i2t_set_pdl(int(os.environ["I2T_PDL"]))
+        if os.environ.get("I2T_TC_GEMM") is not None:
+            handle.i2t_set_tensor_core_gemm(int(os.environ["I2T_TC_GEMM"]))
         _lib = handle
     return _lib
 

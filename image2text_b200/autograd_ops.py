@@ -18,7 +18,7 @@ class LayerNormFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, gamma, beta, eps, out_dtype):
         x = x.contiguous()
-        need = torch.is_grad_enabled() and (x.requires_grad or gamma.requires_grad)
+        need = any(ctx.needs_input_grad)
         if need:
             y, mean, rstd = ops.layernorm(x, gamma, beta, eps, out_dtype, want_stats=True)
             ctx.save_for_backward(x, gamma, mean, rstd)
@@ -44,8 +44,7 @@ class LinearFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x2d, w, w_c, bias, residual, act, out_dtype):
-        need = torch.is_grad_enabled() and (x2d.requires_grad or w.requires_grad or
-                                            (residual is not None and residual.requires_grad))
+        need = any(ctx.needs_input_grad)      # grad mode is always off inside Function.forward
         if need and act != ops.ACT_NONE:
             z = ops.gemm(x2d, w_c, bias=bias, out_dtype=x2d.dtype)
             y = torch.empty(z.shape, device=z.device, dtype=out_dtype)
@@ -102,7 +101,7 @@ class AttnFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, qkv, B, T, H, mask_mode, n_prompt):
         qkv = qkv.contiguous()
-        if torch.is_grad_enabled() and qkv.requires_grad:
+        if any(ctx.needs_input_grad):
             out, lse = ops.attention_packed(qkv, B, T, H, mask_mode, n_prompt, want_lse=True)
             ctx.save_for_backward(qkv, out, lse)
             ctx.meta = (B, T, H, mask_mode, n_prompt)
@@ -124,7 +123,7 @@ class XAttnFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, kv, B, T, S, H):
         q, kv = q.contiguous(), kv.contiguous()
-        if torch.is_grad_enabled() and (q.requires_grad or kv.requires_grad):
+        if any(ctx.needs_input_grad):
             ctx.save_for_backward(q, kv)
             ctx.meta = (B, T, S, H)
         return ops.xattn(q, kv, B, T, S, H)
@@ -193,7 +192,7 @@ class LmLossFn(torch.autograd.Function):
         B, T_logits, V = logits.shape
         Tl = min(T_logits, labels.shape[1])
         labels = labels.contiguous()
-        need = torch.is_grad_enabled() and logits.requires_grad
+        need = ctx.needs_input_grad[0]
         weights = torch.empty(B * Tl, device=logits.device, dtype=torch.float32)
         rows = torch.empty(B * Tl, device=logits.device, dtype=torch.float32)
         loss = torch.empty((), device=logits.device, dtype=torch.float32)

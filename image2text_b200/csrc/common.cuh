@@ -25,15 +25,17 @@ extern std::atomic<int64_t> g_launches;
 #define I2T_CUDA(call)                                                                       \
   do {                                                                                       \
     cudaError_t e__ = (call);                                                                \
-    if (e__ != cudaSuccess)                                                                  \
+    if (e__ != cudaSuccess) {                                                                \
+      (void)cudaGetLastError(); /* do not leave a sticky error for unrelated later launches */ \
       return ::i2t::fail(I2T_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    }                                                                                        \
   } while (0)
 
 // call after every kernel launch
 #define I2T_LAUNCHED()                                                                        \
   do {                                                                                        \
     ::i2t::g_launches.fetch_add(1, std::memory_order_relaxed);                                \
-    cudaError_t e__ = cudaPeekAtLastError();                                                  \
+    cudaError_t e__ = cudaGetLastError();                                                     \
     if (e__ != cudaSuccess)                                                                   \
       return ::i2t::fail(I2T_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
   } while (0)

@@ -4,17 +4,72 @@
 //   * text rows never attend to the soft-prompt rows (reference :93-99 zeroes query rows), so the prompt
 //     rows are dropped entirely and text position i just uses wpe[n_prompt + i];
 //   * self K/V of earlier tokens and the cross K/V projections of the encoder output are cached.
-// Everything here is a batch-of-B (B <= 16) weight-streaming problem: HBM-bound on the weight bytes.
-// All kernels read the current position from DEVICE memory so that one captured CUDA graph replays every step.
+// Everything here is a batch-of-8 weight-streaming problem: HBM-bound on the weight bytes, so the design goal is
+// bytes in flight, not FLOPs:
+//   * every CTA of the skinny linear pulls its slab of weight rows with ONE bulk async copy per 8 rows
+//     (cp.async.bulk, the 1-D TMA path: no registers, completion on an mbarrier) issued before anything else;
+//   * programmatic dependent launch: the next kernel of the step starts while the previous one drains, issues its
+//     weight copies (weights never depend on the previous kernel) and only then waits on griddepcontrol.wait --
+//     the HBM stream continues across kernel boundaries;
+//   * all kernels read the current position from DEVICE memory so one captured CUDA graph replays every step.
 #include "common.cuh"
 
 namespace i2t {
+
+static std::atomic<int> g_pdl{1};
+
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl.load() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_addr(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// 1-D bulk async copy global -> shared (bytes % 16 == 0, both addresses 16-byte aligned), completes on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
+               "l"(src), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
 
 // x[b,:] = wte[ids[b, pos]] + wpe[n_prompt + pos]          (models/decoder.py:234-243)
 __global__ void __launch_bounds__(256) dec_embed_kernel(const int64_t* __restrict__ ids, const float* __restrict__ wte,
                                                         const float* __restrict__ wpe, float* __restrict__ x,
                                                         const int32_t* __restrict__ pos_ptr, int B, int C, int64_t ids_ld,
                                                         int n_prompt) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int pos = *pos_ptr;
   const int c4 = C / 4;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B * c4; i += gridDim.x * blockDim.x) {
@@ -27,28 +82,22 @@ __global__ void __launch_bounds__(256) dec_embed_kernel(const int64_t* __restric
   }
 }
 
-__global__ void dec_advance_kernel(int32_t* pos_ptr) { *pos_ptr += 1; }
-
-// one 16-byte global load of weights -> fp32 registers (4 x fp32 or 8 x bf16), streaming (read once)
-__device__ __forceinline__ void load_w16(const float* p, float (&o)[4]) {
-  const float4 a = __ldcs(reinterpret_cast<const float4*>(p));
-  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
-}
-__device__ __forceinline__ void load_w16(const __nv_bfloat16* p, float (&o)[8]) {
-  const uint4 raw = __ldcs(reinterpret_cast<const uint4*>(p));
-  const uint32_t u[4] = {raw.x, raw.y, raw.z, raw.w};
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    o[2 * i] = __uint_as_float(u[i] << 16);
-    o[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u);
-  }
+__global__ void dec_advance_kernel(int32_t* pos_ptr) {
+  pdl_launch_dependents();
+  pdl_wait();
+  *pos_ptr += 1;
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Skinny linear: out[b, n] = epi( sum_k LN?(x)[b,k] * W[n,k] + bias[n] ),  b < B <= MAXB.
-// CTA = 4 warps, each warp owns R = 4 consecutive output rows and the whole K; the (optionally layer-normed)
-// activations live in shared memory as fp32; weights stream from HBM with 128-bit loads, one pass, no reuse.
-// Epilogues: bias, activation, residual add (in place on the fp32 residual stream) and the fused KV-cache append.
+// Skinny linear: out[b, n] = epi( sum_k LN?(x)[b,k] * W[n,k] + bias[n] ),  b < B <= 8, W (N,K) row-major.
+// CTA = 256 threads, owns `rows_per_cta` (8, 16 or 32) consecutive weight rows = one contiguous slab of W.
+//   1. thread 0 arms one mbarrier per 8-row pass and issues the bulk copies of the whole slab (HBM -> smem);
+//   2. griddepcontrol.wait (the activations come from the previous kernel), then the 8 warps stage x into shared
+//      memory with the fused LayerNorm prologue (one batch row per warp, two-pass statistics, fp32);
+//   3. per pass: K is split over all 256 threads; each thread keeps its 16-byte chunk of x for all 8 batch rows in
+//      registers and walks the 8 weight rows in shared memory (1 LDS.128 per 32..64 FMAs);
+//   4. the 8x8 partial sums are reduced with a transposing shuffle tree (62 shuffles instead of 320), across warps
+//      through shared memory, and 64 threads apply bias / activation / residual / KV-cache append.
 // ---------------------------------------------------------------------------------------------------------
 struct DecLinearEpi {
   int mode;               // 0: out[b*ldo + n];  1: qkv split (q -> out, k/v -> caches at *pos_ptr)
@@ -63,19 +112,55 @@ struct DecLinearEpi {
   const int32_t* pos_ptr;
 };
 
-template <typename TW, int MAXB>
-__global__ void __launch_bounds__(128)
+constexpr int DL_THREADS = 256, DL_R = 8, DL_B = 8, DL_MAX_PASSES = 4;
+
+__device__ __forceinline__ void unpack16(const float4& raw, float (&o)[4]) {
+  o[0] = raw.x; o[1] = raw.y; o[2] = raw.z; o[3] = raw.w;
+}
+__device__ __forceinline__ void unpack16(const float4& raw, float (&o)[8]) {
+  const uint32_t u[4] = {__float_as_uint(raw.x), __float_as_uint(raw.y), __float_as_uint(raw.z), __float_as_uint(raw.w)};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    o[2 * i] = __uint_as_float(u[i] << 16);
+    o[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u);
+  }
+}
+
+template <typename TW>
+__global__ void __launch_bounds__(DL_THREADS)
 dec_linear_kernel(const float* __restrict__ x, const float* __restrict__ ln_g, const float* __restrict__ ln_b, float ln_eps,
-                  const TW* __restrict__ W, const float* __restrict__ bias, int B, int N, int K, int act, DecLinearEpi epi) {
-  extern __shared__ __align__(16) float xs[];  // [MAXB][K]
-  constexpr int R = 4;
-  constexpr int VEC = sizeof(TW) == 4 ? 4 : 8;  // elements per 16-byte load
+                  const TW* __restrict__ W, const float* __restrict__ bias, int B, int N, int K, int act, int rows_per_cta,
+                  DecLinearEpi epi) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[DL_MAX_PASSES];
+  constexpr int VEC = 16 / (int)sizeof(TW);        // weight elements per 16-byte chunk
+  TW* wslab = reinterpret_cast<TW*>(smem_raw);                                   // [rows_per_cta][K]
+  float* xs = reinterpret_cast<float*>(smem_raw + (size_t)rows_per_cta * K * sizeof(TW));   // [DL_B][K]
+  float* part = xs + DL_B * K;                                                   // [8 warps][64]
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-  // stage activations (+ LayerNorm prologue: one warp per batch row, two-pass statistics)
-  for (int b = w; b < MAXB; b += 4) {
-    float* xr = xs + b * K;
-    if (b < B) {
-      const float* src = x + (int64_t)b * K;
+  const int n0 = blockIdx.x * rows_per_cta;
+  const int nrows = min(rows_per_cta, N - n0);
+  const int passes = (nrows + DL_R - 1) / DL_R;
+
+  if (t == 0) {
+    for (int p = 0; p < passes; ++p) mbar_init(&bars[p], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    for (int p = 0; p < passes; ++p) {
+      const int rp = min(DL_R, nrows - p * DL_R);
+      const uint32_t bytes = (uint32_t)rp * (uint32_t)K * (uint32_t)sizeof(TW);
+      mbar_expect_tx(&bars[p], bytes);
+      bulk_g2s(wslab + (size_t)p * DL_R * K, W + ((size_t)n0 + (size_t)p * DL_R) * K, bytes, &bars[p]);
+    }
+  }
+  pdl_launch_dependents();
+  pdl_wait();                       // activations (x, residual, position) are produced by the previous kernels
+
+  // ---- stage activations with the LayerNorm prologue: warp w handles batch row w ----
+  {
+    float* xr = xs + w * K;
+    if (w < B) {
+      const float* src = x + (int64_t)w * K;
       float s = 0.f;
       for (int k = lane * 4; k < K; k += 128) {
         const float4 v = load4(src + k);
@@ -100,13 +185,10 @@ dec_linear_kernel(const float* __restrict__ x, const float* __restrict__ ln_g, c
             const float4 be = load4(ln_b + k);
             v.x += be.x; v.y += be.y; v.z += be.z; v.w += be.w;
           }
-          if (sizeof(TW) == 2) {  // autocast semantics: the Linear sees bf16 activations
-            v.x = __bfloat162float(__float2bfloat16_rn(v.x)); v.y = __bfloat162float(__float2bfloat16_rn(v.y));
-            v.z = __bfloat162float(__float2bfloat16_rn(v.z)); v.w = __bfloat162float(__float2bfloat16_rn(v.w));
-          }
           *reinterpret_cast<float4*>(xr + k) = v;
         }
-      } else if (sizeof(TW) == 2) {
+      }
+      if (sizeof(TW) == 2) {  // autocast semantics: the Linear sees bf16 activations
         for (int k = lane * 4; k < K; k += 128) {
           float4 v = *reinterpret_cast<const float4*>(xr + k);
           v.x = __bfloat162float(__float2bfloat16_rn(v.x)); v.y = __bfloat162float(__float2bfloat16_rn(v.y));
@@ -120,76 +202,85 @@ dec_linear_kernel(const float* __restrict__ x, const float* __restrict__ ln_g, c
   }
   __syncthreads();
 
-  const int n0 = (blockIdx.x * 4 + w) * R;
-  if (n0 >= N) return;
-  float acc[R][MAXB];
-#pragma unroll
-  for (int r = 0; r < R; ++r)
-#pragma unroll
-    for (int b = 0; b < MAXB; ++b) acc[r][b] = 0.f;
-  const TW* wrow[R];
-#pragma unroll
-  for (int r = 0; r < R; ++r) wrow[r] = W + (int64_t)min(n0 + r, N - 1) * K;
-
-  for (int k = lane * VEC; k < K; k += 32 * VEC) {
-    float wv[R][VEC];
-#pragma unroll
-    for (int r = 0; r < R; ++r) load_w16(wrow[r] + k, wv[r]);
-#pragma unroll
-    for (int b = 0; b < MAXB; ++b) {
-      float xv[VEC];
-#pragma unroll
-      for (int j = 0; j < VEC; j += 4) {
-        const float4 a = *reinterpret_cast<const float4*>(xs + b * K + k + j);
-        xv[j] = a.x; xv[j + 1] = a.y; xv[j + 2] = a.z; xv[j + 3] = a.w;
-      }
-#pragma unroll
-      for (int r = 0; r < R; ++r)
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) acc[r][b] = fmaf(wv[r][j], xv[j], acc[r][b]);
-    }
-  }
-#pragma unroll
-  for (int r = 0; r < R; ++r)
-#pragma unroll
-    for (int b = 0; b < MAXB; ++b) acc[r][b] = warp_sum(acc[r][b]);
-
-  // lane (r, b) = (lane / MAXB', lane % ...) writes one output: spread the R*MAXB results over the lanes
+  const int nchunks = K / VEC;
   const int pos = epi.mode == 1 ? *epi.pos_ptr : 0;
+  for (int p = 0; p < passes; ++p) {
+    float acc[DL_R * DL_B];
 #pragma unroll
-  for (int r = 0; r < R; ++r) {
+    for (int i = 0; i < DL_R * DL_B; ++i) acc[i] = 0.f;
+    mbar_wait(&bars[p], 0u);
+    const TW* wp = wslab + (size_t)p * DL_R * K;
+    const int rp = min(DL_R, nrows - p * DL_R);
+    for (int c = t; c < nchunks; c += DL_THREADS) {
+      float xv[DL_B][VEC];
 #pragma unroll
-    for (int b = 0; b < MAXB; ++b) {
-      if (lane == ((r * MAXB + b) & 31)) {
-        const int n = n0 + r;
-        if (n < N && b < B) {
-          float v = acc[r][b];
-          if (bias != nullptr) v += bias[n];
-          v = apply_act(v, act);
-          if (epi.mode == 0) {
-            if (epi.residual != nullptr) v += epi.residual[(int64_t)b * epi.ldo + n];
-            epi.out[(int64_t)b * epi.ldo + n] = v;
+      for (int b = 0; b < DL_B; ++b)
+#pragma unroll
+        for (int j = 0; j < VEC; j += 4) {
+          const float4 a = *reinterpret_cast<const float4*>(xs + b * K + c * VEC + j);
+          xv[b][j] = a.x; xv[b][j + 1] = a.y; xv[b][j + 2] = a.z; xv[b][j + 3] = a.w;
+        }
+#pragma unroll
+      for (int r = 0; r < DL_R; ++r) {
+        if (r < rp) {
+          float wv[VEC];
+          unpack16(*reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(wp + (size_t)r * K) + (size_t)c * 16), wv);
+#pragma unroll
+          for (int b = 0; b < DL_B; ++b)
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) acc[r * DL_B + b] = fmaf(wv[j], xv[b][j], acc[r * DL_B + b]);
+        }
+      }
+    }
+    // transposing shuffle reduction: afterwards lane l holds the warp totals of flat indices 2l and 2l+1
+#pragma unroll
+    for (int off = 16, n = DL_R * DL_B; off >= 1; off >>= 1, n >>= 1) {
+      const int half = n >> 1;
+      const bool upper = (lane & off) != 0;
+#pragma unroll
+      for (int i = 0; i < half; ++i) {
+        const float send = upper ? acc[i] : acc[i + half];
+        const float keep = upper ? acc[i + half] : acc[i];
+        acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
+    }
+    part[w * 64 + 2 * lane] = acc[0];
+    part[w * 64 + 2 * lane + 1] = acc[1];
+    __syncthreads();
+    if (t < DL_R * DL_B) {
+      float v = 0.f;
+#pragma unroll
+      for (int i = 0; i < DL_THREADS / 32; ++i) v += part[i * 64 + t];
+      const int r = t / DL_B, b = t % DL_B;
+      const int n = n0 + p * DL_R + r;
+      if (r < rp && b < B) {
+        if (bias != nullptr) v += bias[n];
+        v = apply_act(v, act);
+        if (epi.mode == 0) {
+          if (epi.residual != nullptr) v += epi.residual[(int64_t)b * epi.ldo + n];
+          epi.out[(int64_t)b * epi.ldo + n] = v;
+        } else {
+          const int seg = n / epi.C, nl = n % epi.C;
+          if (seg == 0) {
+            epi.out[(int64_t)b * epi.ldo + nl] = v;
           } else {
-            const int seg = n / epi.C, nl = n % epi.C;
-            if (seg == 0) {
-              epi.out[(int64_t)b * epi.ldo + nl] = v;
-            } else {
-              void* base = seg == 1 ? epi.kcache : epi.vcache;
-              const int64_t off = (int64_t)b * epi.cache_bs + (int64_t)pos * epi.C + nl;
-              if (epi.cache_dtype == I2T_F32) ((float*)base)[off] = v;
-              else ((__nv_bfloat16*)base)[off] = __float2bfloat16_rn(v);
-            }
+            void* base = seg == 1 ? epi.kcache : epi.vcache;
+            const int64_t off = (int64_t)b * epi.cache_bs + (int64_t)pos * epi.C + nl;
+            if (epi.cache_dtype == I2T_F32) ((float*)base)[off] = v;
+            else ((__nv_bfloat16*)base)[off] = __float2bfloat16_rn(v);
           }
         }
       }
     }
+    __syncthreads();   // `part` is reused by the next pass
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Single-query attention over a (B, Tmax, C) cache: grid (H, B), 4 warps; each warp takes keys w, w+4, ...
-// with its 32 lanes across the head dimension, keeps an online softmax, and the 4 partial states are merged
-// in shared memory.  len = *len_ptr + len_add (self: pos + 1) or the constant S (cross attention).
+// Single-query attention over a (B, Tmax, C) cache: grid (H, B), 4 warps; each warp takes keys in groups of 4
+// (4 independent row loads in flight) with its 32 lanes across the head dimension, keeps an online softmax, and
+// the 4 partial states are merged in shared memory.  len = *len_ptr + len_add (self: pos + 1) or the constant S
+// (cross attention over the cached K/V projections of the encoder output).
 // ---------------------------------------------------------------------------------------------------------
 template <typename TC, int HS>
 __global__ void __launch_bounds__(128)
@@ -197,10 +288,13 @@ dec_attn_kernel(const float* __restrict__ q, int64_t q_ld, const TC* __restrict_
                 int64_t cache_bs, int64_t cache_rs, float* __restrict__ out, int64_t out_ld,
                 const int32_t* __restrict__ len_ptr, int len_add, int round_q_bf16) {
   constexpr int EPL = HS / 32;
+  constexpr int G = 4;
   __shared__ float s_m[4], s_l[4], s_acc[4][HS];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int h = blockIdx.x;
   const int64_t b = blockIdx.y;
+  pdl_launch_dependents();
+  pdl_wait();
   const int len = (len_ptr != nullptr ? *len_ptr : 0) + len_add;
   const float scale = 1.0f / sqrtf((float)HS);
   float qv[EPL];
@@ -215,17 +309,45 @@ dec_attn_kernel(const float* __restrict__ q, int64_t q_ld, const TC* __restrict_
   float m = -INFINITY, l = 0.f, acc[EPL];
 #pragma unroll
   for (int e = 0; e < EPL; ++e) acc[e] = 0.f;
-  for (int j = w; j < len; j += 4) {
-    float d = 0.f;
+  for (int j0 = w * G; j0 < len; j0 += 4 * G) {
+    float kk[G][EPL], vv[G][EPL], d[G];
 #pragma unroll
-    for (int e = 0; e < EPL; ++e) d = fmaf(qv[e], to_f32(kb[(int64_t)j * cache_rs + lane + 32 * e]), d);
-    d = warp_sum(d);
-    const float m_new = fmaxf(m, d);
+    for (int g = 0; g < G; ++g) {
+      const int j = min(j0 + g, len - 1);
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        kk[g][e] = to_f32(kb[(int64_t)j * cache_rs + lane + 32 * e]);
+        vv[g][e] = to_f32(vb[(int64_t)j * cache_rs + lane + 32 * e]);
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      float s = 0.f;
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) s = fmaf(qv[e], kk[g][e], s);
+      d[g] = s;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int g = 0; g < G; ++g) d[g] += __shfl_xor_sync(0xffffffffu, d[g], o);
+    float m_new = m;
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+      if (j0 + g < len) m_new = fmaxf(m_new, d[g]);
     const float corr = expf(m - m_new);
-    const float p = expf(d - m_new);
-    l = l * corr + p;
+    l *= corr;
 #pragma unroll
-    for (int e = 0; e < EPL; ++e) acc[e] = fmaf(p, to_f32(vb[(int64_t)j * cache_rs + lane + 32 * e]), acc[e] * corr);
+    for (int e = 0; e < EPL; ++e) acc[e] *= corr;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      if (j0 + g < len) {
+        const float p = expf(d[g] - m_new);
+        l += p;
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) acc[e] = fmaf(p, vv[g][e], acc[e]);
+      }
+    }
     m = m_new;
   }
   if (lane == 0) { s_m[w] = m; s_l[w] = l; }
@@ -233,7 +355,7 @@ dec_attn_kernel(const float* __restrict__ q, int64_t q_ld, const TC* __restrict_
   for (int e = 0; e < EPL; ++e) s_acc[w][lane + 32 * e] = acc[e];
   __syncthreads();
   if (w == 0) {
-    float M = fmaxf(fmaxf(s_m[0], s_m[1]), fmaxf(s_m[2], s_m[3]));
+    const float M = fmaxf(fmaxf(s_m[0], s_m[1]), fmaxf(s_m[2], s_m[3]));
     float L = 0.f, o[EPL];
 #pragma unroll
     for (int e = 0; e < EPL; ++e) o[e] = 0.f;
@@ -254,20 +376,27 @@ dec_attn_kernel(const float* __restrict__ q, int64_t q_ld, const TC* __restrict_
 
 using namespace i2t;
 
+#define I2T_LAUNCH_CHECK(expr)                                                                              \
+  do {                                                                                                      \
+    cudaError_t e__ = (expr);                                                                               \
+    ::i2t::g_launches.fetch_add(1, std::memory_order_relaxed);                                              \
+    if (e__ != cudaSuccess) return ::i2t::fail(I2T_ERR_CUDA, "launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+extern "C" void i2t_set_pdl(int enabled) { g_pdl.store(enabled ? 1 : 0); }
+
 extern "C" int i2t_dec_embed(const int64_t* ids, const float* wte, const float* wpe, float* x, const int32_t* pos_ptr,
                              int64_t B, int64_t C, int64_t ids_ld, int64_t n_prompt, void* stream) {
   I2T_REQUIRE(ids && wte && wpe && x && pos_ptr && B > 0 && C % 4 == 0, "dec_embed: bad arguments");
   const int64_t n = B * C / 4;
-  dec_embed_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(ids, wte, wpe, x, pos_ptr, (int)B, (int)C,
-                                                                              ids_ld, (int)n_prompt);
-  I2T_LAUNCHED();
+  I2T_LAUNCH_CHECK(launch(dec_embed_kernel, dim3((unsigned)ceil_div(n, 256)), dim3(256), 0, (cudaStream_t)stream, ids, wte, wpe,
+                          x, pos_ptr, (int)B, (int)C, ids_ld, (int)n_prompt));
   return I2T_OK;
 }
 
 extern "C" int i2t_dec_advance(int32_t* pos_ptr, void* stream) {
   I2T_REQUIRE(pos_ptr, "dec_advance: null pointer");
-  dec_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(pos_ptr);
-  I2T_LAUNCHED();
+  I2T_LAUNCH_CHECK(launch(dec_advance_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, pos_ptr));
   return I2T_OK;
 }
 
@@ -282,35 +411,45 @@ extern "C" int i2t_dec_linear(const float* x, const float* ln_gamma, const float
   I2T_REQUIRE(valid_dtype(w_dtype) && aligned16(W) && aligned16(x), "dec_linear: dtype/alignment");
   I2T_REQUIRE(!qkv_split || (kcache && vcache && pos_ptr && C > 0 && N == 3 * C && valid_dtype(cache_dtype)),
               "dec_linear: qkv split needs caches, pos_ptr and N == 3C");
-  DecLinearEpi epi;
-  epi.mode = qkv_split ? 1 : 0;
-  epi.out = out;
-  epi.ldo = ldo;
-  epi.residual = residual;
-  epi.kcache = kcache;
-  epi.vcache = vcache;
-  epi.cache_bs = cache_batch_stride;
-  epi.C = (int)C;
-  epi.cache_dtype = cache_dtype;
-  epi.pos_ptr = pos_ptr;
   cudaStream_t st = (cudaStream_t)stream;
-  const unsigned grid = (unsigned)ceil_div(N, 16);
-  const int maxb = B <= 8 ? 8 : 16;
-  const size_t smem = (size_t)maxb * K * sizeof(float);
-  I2T_REQUIRE(smem <= 200 * 1024, "dec_linear: B*K too large for shared memory");
-#define I2T_DL(TW, MB)                                                                                              \
-  do {                                                                                                              \
-    auto kern = dec_linear_kernel<TW, MB>;                                                                          \
-    if (smem > 48 * 1024) I2T_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    kern<<<grid, 128, smem, st>>>(x, ln_gamma, ln_beta, ln_eps, (const TW*)W, bias, (int)B, (int)N, (int)K, act, epi); \
-  } while (0)
-  if (w_dtype == I2T_F32) {
-    if (maxb == 8) I2T_DL(float, 8); else I2T_DL(float, 16);
-  } else {
-    if (maxb == 8) I2T_DL(__nv_bfloat16, 8); else I2T_DL(__nv_bfloat16, 16);
+  const int64_t esz = w_dtype == I2T_F32 ? 4 : 2;
+  // slab height: as tall as 48 KB allows, but keep >= 2 CTAs per SM when the matrix is small
+  int rows = DL_R * DL_MAX_PASSES;
+  while (rows > DL_R && (rows * K * esz > 48 * 1024 || ceil_div(N, rows) < 2 * (int64_t)num_sms())) rows >>= 1;
+  const size_t smem = (size_t)rows * K * esz + (size_t)DL_B * K * sizeof(float) + (size_t)(DL_THREADS / 32) * 64 * sizeof(float);
+  // 227 KB per CTA is the opt-in ceiling for static + dynamic shared memory together
+  I2T_REQUIRE(smem <= 226 * 1024, "dec_linear: K=%lld too large for shared memory", (long long)K);
+  static std::atomic<size_t> attr_f32{0}, attr_bf16{0};
+  if (w_dtype == I2T_F32 && smem > attr_f32.load()) {
+    I2T_CUDA(cudaFuncSetAttribute(dec_linear_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_f32.store(smem);
   }
-#undef I2T_DL
-  I2T_LAUNCHED();
+  if (w_dtype == I2T_BF16 && smem > attr_bf16.load()) {
+    I2T_CUDA(cudaFuncSetAttribute(dec_linear_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_bf16.store(smem);
+  }
+  for (int64_t b0 = 0; b0 < B; b0 += DL_B) {     // batches above 8 re-stream the weights (second pass hits L2)
+    const int bn = (int)(B - b0 < DL_B ? B - b0 : DL_B);
+    DecLinearEpi epi;
+    epi.mode = qkv_split ? 1 : 0;
+    epi.out = out + b0 * ldo;
+    epi.ldo = ldo;
+    epi.residual = residual ? residual + b0 * ldo : nullptr;
+    const int64_t cesz = cache_dtype == I2T_F32 ? 4 : 2;
+    epi.kcache = kcache ? (void*)((uint8_t*)kcache + b0 * cache_batch_stride * cesz) : nullptr;
+    epi.vcache = vcache ? (void*)((uint8_t*)vcache + b0 * cache_batch_stride * cesz) : nullptr;
+    epi.cache_bs = cache_batch_stride;
+    epi.C = (int)C;
+    epi.cache_dtype = cache_dtype;
+    epi.pos_ptr = pos_ptr;
+    const dim3 grid((unsigned)ceil_div(N, rows));
+    if (w_dtype == I2T_F32)
+      I2T_LAUNCH_CHECK(launch(dec_linear_kernel<float>, grid, dim3(DL_THREADS), smem, st, x + b0 * K, ln_gamma, ln_beta, ln_eps,
+                              (const float*)W, bias, bn, (int)N, (int)K, act, rows, epi));
+    else
+      I2T_LAUNCH_CHECK(launch(dec_linear_kernel<__nv_bfloat16>, grid, dim3(DL_THREADS), smem, st, x + b0 * K, ln_gamma, ln_beta,
+                              ln_eps, (const __nv_bfloat16*)W, bias, bn, (int)N, (int)K, act, rows, epi));
+  }
   return I2T_OK;
 }
 
@@ -326,14 +465,13 @@ extern "C" int i2t_dec_attn(const float* q, int64_t q_ld, const void* kcache, co
   dim3 grid((unsigned)H, (unsigned)B);
   const int rq = cache_dtype == I2T_BF16 ? 1 : 0;
 #define I2T_DA(TC, HSV)                                                                                              \
-  dec_attn_kernel<TC, HSV><<<grid, 128, 0, st>>>(q, q_ld, (const TC*)kcache, (const TC*)vcache, cache_batch_stride,  \
-                                                 cache_row_stride, out, out_ld, len_ptr, (int)len_add, rq)
+  I2T_LAUNCH_CHECK(launch(dec_attn_kernel<TC, HSV>, grid, dim3(128), 0, st, q, q_ld, (const TC*)kcache, (const TC*)vcache, \
+                          cache_batch_stride, cache_row_stride, out, out_ld, len_ptr, (int)len_add, rq))
   if (cache_dtype == I2T_F32) {
     if (head_dim == 64) I2T_DA(float, 64); else I2T_DA(float, 32);
   } else {
     if (head_dim == 64) I2T_DA(__nv_bfloat16, 64); else I2T_DA(__nv_bfloat16, 32);
   }
 #undef I2T_DA
-  I2T_LAUNCHED();
   return I2T_OK;
 }

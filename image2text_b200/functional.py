@@ -95,7 +95,7 @@ class _LshTailFn(torch.autograd.Function):
         B, D = feat.shape
         n_res = len(num_bins)
         out = torch.empty((B, n_cls, E), device=feat.device, dtype=torch.float32)
-        need = torch.is_grad_enabled() and any(w.requires_grad for w in emb_weights)
+        need = any(ctx.needs_input_grad)
         idx = torch.empty((B, n_cls, n_res, n_proj), device=feat.device, dtype=torch.int32) if need else None
         call("i2t_lsh_tail", ptr(feat), ptr(tables["proj"]), ptr(tables["grid"]), ptr(tables["emb"]), ptr(tables["nb"]),
              ptr(out), ptr(idx), B, D, n_cls, n_res, n_proj, E, stream())

@@ -132,6 +132,9 @@ void i2t_set_tensor_core_gemm(int enabled);
 /* ---- KV-cached decode step (no counterpart in the reference, which recomputes the prefix every token:
  *      models/vision_encoder_decoder.py:144-150).  pos_ptr is a DEVICE int32: the index of the token being processed
  *      (also its KV-cache slot); every kernel reads it on the device so one CUDA graph replays all steps. ---------- */
+/* 1 (default): decode kernels are launched with programmatic dependent launch so that a kernel's weight copies overlap
+ * the tail of its predecessor; 0: plain stream order. */
+void i2t_set_pdl(int enabled);
 /* x[b,:] = wte[ids[b*ids_ld + pos]] + wpe[n_prompt + pos]            (models/decoder.py:234-243) */
 int i2t_dec_embed(const int64_t* ids, const float* wte, const float* wpe, float* x, const int32_t* pos_ptr, int64_t B,
                   int64_t C, int64_t ids_ld, int64_t n_prompt, void* stream);

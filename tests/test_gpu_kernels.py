@@ -73,20 +73,20 @@ def test_gemm_fp32_layouts(M, N, K, layout):
     A = a.to(DEV) if layout[0] == "n" else a.t().contiguous().to(DEV)
     Bm = b.to(DEV) if layout[1] == "t" else b.t().contiguous().to(DEV)
     out = ops.gemm(A, Bm, a_kmajor=layout[0] == "n", b_kmajor=layout[1] == "t")
-    assert relerr(out, ref) < 2e-6
+    assert relerr(out, ref) < 5e-6          # fp32 accumulation over K <= 3072 against an fp64 reference
     if layout == "nt":
         out = ops.gemm(A, Bm, bias=bias.to(DEV), residual=res.to(DEV), act=ops.ACT_GELU_TANH)
         ref2 = O.gelu_tanh(ref + bias.double()) + res.double()
-        assert relerr(out, ref2) < 3e-6
+        assert relerr(out, ref2) < 6e-6
         out = ops.gemm(A, Bm, bias=bias.to(DEV), act=ops.ACT_GELU_ERF)
-        assert relerr(out, O.gelu_erf(ref + bias.double())) < 3e-6
+        assert relerr(out, O.gelu_erf(ref + bias.double())) < 6e-6
         acc = res.to(DEV).clone()
         ops.gemm(A, Bm, out=acc, accumulate=True)
-        assert relerr(acc, ref + res.double()) < 3e-6
+        assert relerr(acc, ref + res.double()) < 6e-6
         # in-place residual (C aliases residual), as the residual stream is updated
         x = res.to(DEV).clone()
         ops.gemm(A, Bm, bias=bias.to(DEV), residual=x, out=x)
-        assert relerr(x, ref + bias.double() + res.double()) < 3e-6
+        assert relerr(x, ref + bias.double() + res.double()) < 6e-6
 
 
 @pytest.mark.parametrize("M,N,K", [(1576, 2304, 768), (128, 128, 64), (300, 50257, 768), (2048, 768, 3072), (1, 256, 768),
@@ -192,7 +192,8 @@ def test_lsh_tail_matches_oracle_indices_and_values():
     nb = torch.tensor([4, 8, 20], dtype=torch.int32, device=DEV)
     out = torch.empty(16, 3, 128, device=DEV)
     idx = torch.empty(16, 3, 3, 32, dtype=torch.int32, device=DEV)
-    call("i2t_lsh_tail", ptr(feat.to(DEV)), ptr(tab["proj"]), ptr(tab["grid"]), ptr(tab["emb"]), ptr(nb), ptr(out), ptr(idx),
+    featd = feat.to(DEV)
+    call("i2t_lsh_tail", ptr(featd), ptr(tab["proj"]), ptr(tab["grid"]), ptr(tab["emb"]), ptr(nb), ptr(out), ptr(idx),
          16, 768, 3, 3, 32, 128, stream())
     for s in range(3):
         for r, nbins in enumerate((4, 8, 20)):
@@ -226,16 +227,18 @@ def test_dec_linear(B, N, K, wdt):
         xn = xn.float().to(torch.bfloat16).double()
     ref = O.gelu_tanh(xn @ w.double().t() + bias.double()) + res.double()
     out = torch.empty(B, N, device=DEV)
-    call("i2t_dec_linear", ptr(x.to(DEV)), ptr(g.to(DEV)), ptr(be.to(DEV)), 1e-5, ptr(w.to(DEV)), ptr(bias.to(DEV)),
-         ptr(res.to(DEV)), ptr(out), N, B, N, K, ops.ACT_GELU_TANH, wcode, 0, None, None, 0, 0, 0, None, stream())
-    assert relerr(out, ref) < (3e-6 if wdt == torch.float32 else 3e-3)
+    # device copies are bound to names: a temporary would be recycled by the caching allocator before the launch
+    xd, gd, bed, wdev, biasd, resd = (t.to(DEV) for t in (x, g, be, w, bias, res))
+    call("i2t_dec_linear", ptr(xd), ptr(gd), ptr(bed), 1e-5, ptr(wdev), ptr(biasd), ptr(resd), ptr(out), N, B, N, K,
+         ops.ACT_GELU_TANH, wcode, 0, None, None, 0, 0, 0, None, stream())
+    assert relerr(out, ref) < (5e-6 if wdt == torch.float32 else 3e-3)
     # no LayerNorm, no bias, in-place residual
     xin = x.double() if wdt == torch.float32 else x.to(torch.bfloat16).double()
     ref2 = xin @ w.double().t() + res.double()
-    acc = res.to(DEV).clone()
-    call("i2t_dec_linear", ptr(x.to(DEV)), None, None, 1e-5, ptr(w.to(DEV)), None, ptr(acc), ptr(acc), N, B, N, K, 0, wcode, 0,
+    acc = resd.clone()
+    call("i2t_dec_linear", ptr(xd), None, None, 1e-5, ptr(wdev), None, ptr(acc), ptr(acc), N, B, N, K, 0, wcode, 0,
          None, None, 0, 0, 0, None, stream())
-    assert relerr(acc, ref2) < (3e-6 if wdt == torch.float32 else 3e-3)
+    assert relerr(acc, ref2) < (5e-6 if wdt == torch.float32 else 3e-3)
 
 
 @pytest.mark.parametrize("cdt", [torch.float32, torch.bfloat16])
@@ -250,7 +253,8 @@ def test_dec_qkv_append_and_attention(cdt):
     kc0, vc0 = kc.clone(), vc.clone()
     q = torch.empty(B, C, device=DEV)
     posd = torch.tensor([pos], dtype=torch.int32, device=DEV)
-    call("i2t_dec_linear", ptr(x.to(DEV)), None, None, 1e-5, ptr(w.to(DEV)), ptr(bias.to(DEV)), None, ptr(q), C, B, 3 * C, C, 0,
+    xd, wdev, biasd = x.to(DEV), w.to(DEV), bias.to(DEV)
+    call("i2t_dec_linear", ptr(xd), None, None, 1e-5, ptr(wdev), ptr(biasd), None, ptr(q), C, B, 3 * C, C, 0,
          code, 1, ptr(kc), ptr(vc), Tmax * C, C, code, ptr(posd), stream())
     xin = x.double() if cdt == torch.float32 else x.to(torch.bfloat16).double()
     qkv = xin @ w.double().t() + bias.double()
@@ -401,6 +405,7 @@ def test_ema_multi_and_actfn_and_gradnorm():
         h = torch.empty(64, 512, device=DEV)
         dz = torch.empty(64, 512, device=DEV)
         dh = torch.full((64, 512), 0.7, device=DEV)
-        call("i2t_act_fwd", ptr(z.to(DEV)), ptr(h), z.numel(), act, ops.F32, ops.F32, stream())
-        call("i2t_act_bwd", ptr(z.to(DEV)), ptr(dh), ptr(dz), z.numel(), act, ops.F32, ops.F32, stream())
+        zd = z.to(DEV)
+        call("i2t_act_fwd", ptr(zd), ptr(h), z.numel(), act, ops.F32, ops.F32, stream())
+        call("i2t_act_bwd", ptr(zd), ptr(dh), ptr(dz), z.numel(), act, ops.F32, ops.F32, stream())
         assert relerr(h, f(z.double())) < 2e-6 and relerr(dz, zr.grad) < 5e-6
