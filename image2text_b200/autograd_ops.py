@@ -144,13 +144,13 @@ class EmbedFn(torch.autograd.Function):
         B, S = ids.shape
         x = ops.embed(ids, prompt, wte, wpe, B, T, n_prompt, S)
         ctx.save_for_backward(ids)
-        ctx.meta = (B, T, n_prompt, S, wte.shape, prompt is not None)
+        ctx.meta = (B, T, n_prompt, S, wte.shape, prompt is not None, wpe.shape[0])
         return x
 
     @staticmethod
     def backward(ctx, dx):
         (ids,) = ctx.saved_tensors
-        B, T, n_prompt, S, wte_shape, has_prompt = ctx.meta
+        B, T, n_prompt, S, wte_shape, has_prompt, wpe_rows = ctx.meta
         dx = dx.contiguous()
         C = dx.shape[-1]
         dprompt = dwte = dwpe = None
@@ -160,9 +160,8 @@ class EmbedFn(torch.autograd.Function):
             dwte = torch.zeros(wte_shape, device=dx.device, dtype=torch.float32)
             call("i2t_embed_bwd", ptr(ids), ptr(dx), ptr(dwte), B, T, n_prompt, S, C, stream())
         if ctx.needs_input_grad[3]:
-            dwpe_t = torch.zeros(T * C, device=dx.device, dtype=torch.float32)
-            ops.colsum_(dx.view(B, T * C), dwpe_t)
-            dwpe = dwpe_t.view(T, C)
+            dwpe = torch.zeros((wpe_rows, C), device=dx.device, dtype=torch.float32)   # rows >= T stay zero
+            ops.colsum_(dx.view(B, T * C), dwpe.view(-1)[:T * C])
         return None, dprompt, dwte, dwpe, None, None
 
 

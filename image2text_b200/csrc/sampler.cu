@@ -211,6 +211,169 @@ sample_kernel(float* __restrict__ logits, int64_t ldl, int V, int64_t* __restric
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Shared-memory-resident variant (V floats fit in the CTA's shared memory, e.g. GPT-2's 50257): the vocabulary row is
+// read from memory ONCE; every later pass (radix select, max, sum, draw) runs on shared memory.  The top-k radix
+// select uses 8 group histograms so the few hot exponent bins contend less.  top_k == 1 (greedy) skips the radix
+// select: the threshold is the row maximum.  The draw walks the elements in (thread, stride) order -- any fixed order
+// yields the same categorical distribution.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int SAMP_HGROUPS = 8;
+
+__global__ void __launch_bounds__(SAMP_THREADS)
+sample_smem_kernel(float* __restrict__ logits, int64_t ldl, int V, int64_t* __restrict__ ids, int64_t ids_ld,
+                   const int32_t* pos_ptr_c, int32_t* pos_ptr_adv, int cur_len_const, float temperature, int top_k,
+                   const int32_t* __restrict__ ngrams, int n_ngrams, uint64_t seed_arg,
+                   const uint64_t* __restrict__ seed_ptr, float* __restrict__ probs_out, int32_t* __restrict__ ticket,
+                   int write_token) {
+  extern __shared__ __align__(16) float sv[];   // [V]
+  __shared__ int s_banned[SAMP_MAX_BANNED];
+  __shared__ int s_nbanned;
+  __shared__ uint32_t s_ghist[SAMP_HGROUPS][256];
+  __shared__ float s_redf[32];
+  __shared__ double s_redd[32];
+  __shared__ uint32_t s_prefix, s_kleft;
+  __shared__ double s_scan[SAMP_THREADS / 32];
+  __shared__ int s_choice, s_fallback;
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const int b = blockIdx.x;
+  const uint64_t seed = seed_ptr != nullptr ? *seed_ptr : seed_arg;
+  const int cur_len = pos_ptr_c != nullptr ? (*pos_ptr_c + 1) : cur_len_const;
+  float* row = logits + (int64_t)b * ldl;
+  const int64_t* idr = ids + (int64_t)b * ids_ld;
+
+  if (t == 0) { s_nbanned = 0; s_choice = 0x7fffffff; s_fallback = 0x7fffffff; }
+  __syncthreads();
+  for (int g = 0; g < n_ngrams; ++g) {
+    const int n = ngrams[g];
+    if (n <= 0 || cur_len + 1 < n) continue;
+    const int tail = cur_len + 1 - n;
+    for (int i = t; i <= cur_len - n; i += SAMP_THREADS) {
+      bool same = true;
+      for (int j = 0; j < n - 1; ++j) same = same && (idr[i + j] == idr[tail + j]);
+      if (same) {
+        const int slot = atomicAdd(&s_nbanned, 1);
+        if (slot < SAMP_MAX_BANNED) s_banned[slot] = (int)idr[i + n - 1];
+      }
+    }
+  }
+  // one pass over global memory: scale, keep in shared memory, track the maximum
+  float mx = -INFINITY;
+  for (int i = t; i < V; i += SAMP_THREADS) sv[i] = row[i] / temperature;
+  __syncthreads();
+  const int nb = min(s_nbanned, SAMP_MAX_BANNED);
+  for (int i = t; i < nb; i += SAMP_THREADS) {
+    const int tok = s_banned[i];
+    if (tok >= 0 && tok < V) sv[tok] = -INFINITY;
+  }
+  __syncthreads();
+  if (temperature != 1.0f || nb > 0) {      // keep the documented in-place contract (scaled / banned logits)
+    for (int i = t; i < V; i += SAMP_THREADS) row[i] = sv[i];
+  }
+  for (int i = t; i < V; i += SAMP_THREADS) mx = fmaxf(mx, sv[i]);
+  mx = block_reduce<float>(mx, s_redf, true);
+
+  float thr = -INFINITY;
+  if (top_k == 1) {
+    thr = mx;
+  } else if (top_k > 1 && top_k < V) {
+    if (t == 0) { s_prefix = 0u; s_kleft = (uint32_t)top_k; }
+    __syncthreads();
+    for (int pass = 0; pass < 4; ++pass) {
+      const int shift = 24 - 8 * pass;
+      for (int i = t; i < SAMP_HGROUPS * 256; i += SAMP_THREADS) (&s_ghist[0][0])[i] = 0u;
+      __syncthreads();
+      const uint32_t prefix = s_prefix;
+      const uint32_t mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+      uint32_t* hist = s_ghist[w & (SAMP_HGROUPS - 1)];
+      for (int i = t; i < V; i += SAMP_THREADS) {
+        const uint32_t key = float_key(sv[i]);
+        if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+      }
+      __syncthreads();
+      if (t < 256) {
+        uint32_t tot = 0;
+#pragma unroll
+        for (int i = 0; i < SAMP_HGROUPS; ++i) tot += s_ghist[i][t];
+        s_ghist[0][t] = tot;
+      }
+      __syncthreads();
+      if (t == 0) {
+        uint32_t left = s_kleft;
+        int bin = 255;
+        for (; bin > 0; --bin) {
+          if (s_ghist[0][bin] >= left) break;
+          left -= s_ghist[0][bin];
+        }
+        s_kleft = left;
+        s_prefix = prefix | ((uint32_t)bin << shift);
+      }
+      __syncthreads();
+    }
+    const uint32_t kk = s_prefix;
+    thr = __uint_as_float((kk & 0x80000000u) ? (kk & 0x7fffffffu) : ~kk);
+  }
+
+  double part = 0.0;
+  for (int i = t; i < V; i += SAMP_THREADS) {
+    const float x = sv[i];
+    if (x >= thr) part += (double)expf(x - mx);
+  }
+  const double total = block_reduce<double>(part, s_redd, false);
+  if (probs_out != nullptr) {
+    for (int i = t; i < V; i += SAMP_THREADS) {
+      const float x = sv[i];
+      probs_out[(int64_t)b * V + i] = x >= thr ? (float)((double)expf(x - mx) / total) : 0.f;
+    }
+  }
+  const double target = (double)philox_uniform(seed, (uint32_t)b, (uint32_t)cur_len) * total;
+  double incl = part;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double nbr = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += nbr;
+  }
+  if (lane == 31) s_scan[w] = incl;
+  __syncthreads();
+  double woff = 0.0;
+  for (int i = 0; i < w; ++i) woff += s_scan[i];
+  const double excl = woff + incl - part;
+  if (part > 0.0 && target > excl && target <= excl + part) {
+    double run = excl;
+    int pick = -1;
+    for (int i = t; i < V; i += SAMP_THREADS) {
+      const float x = sv[i];
+      if (x >= thr) {
+        run += (double)expf(x - mx);
+        pick = i;
+        if (run >= target) break;
+      }
+    }
+    if (pick >= 0) atomicMin(&s_choice, pick);
+  }
+  __syncthreads();
+  if (s_choice == 0x7fffffff) {
+    int best = 0x7fffffff;
+    for (int i = t; i < V; i += SAMP_THREADS)
+      if (sv[i] == mx) best = min(best, i);
+    if (best != 0x7fffffff) atomicMin(&s_fallback, best);
+    __syncthreads();
+    if (t == 0) s_choice = s_fallback;
+    __syncthreads();
+  }
+  if (t == 0) {
+    if (write_token) ids[(int64_t)b * ids_ld + cur_len] = (int64_t)s_choice;
+    if (pos_ptr_adv != nullptr) {
+      __threadfence();
+      const int fin = atomicAdd(ticket, 1);
+      if (fin == (int)gridDim.x - 1) {
+        *ticket = 0;
+        *pos_ptr_adv += 1;
+      }
+    }
+  }
+}
+
 }  // namespace i2t
 
 using namespace i2t;
@@ -224,9 +387,21 @@ extern "C" int i2t_sample(float* logits, int64_t ldl, int64_t B, int64_t V, int6
   I2T_REQUIRE(n_ngrams == 0 || ngrams, "sample: n-gram list missing");
   I2T_REQUIRE(!advance_pos || (pos_ptr && ticket), "sample: advancing the position needs pos_ptr and a ticket counter");
   I2T_REQUIRE(pos_ptr || cur_len > 0, "sample: need a position");
-  sample_kernel<<<(unsigned)B, SAMP_THREADS, 0, (cudaStream_t)stream>>>(
-      logits, ldl, (int)V, ids, ids_ld, pos_ptr, advance_pos ? pos_ptr : nullptr, (int)cur_len, temperature,
-      (int)(top_k > 0 ? top_k : 0), ngrams, (int)n_ngrams, seed, seed_ptr, probs_out, ticket, write_token);
+  const size_t row_bytes = (size_t)V * sizeof(float);
+  if (row_bytes <= 208 * 1024) {   // the row fits in shared memory next to ~17 KB of static scratch
+    static std::atomic<size_t> attr{0};
+    if (row_bytes > attr.load()) {
+      I2T_CUDA(cudaFuncSetAttribute(sample_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_bytes));
+      attr.store(row_bytes);
+    }
+    sample_smem_kernel<<<(unsigned)B, SAMP_THREADS, row_bytes, (cudaStream_t)stream>>>(
+        logits, ldl, (int)V, ids, ids_ld, pos_ptr, advance_pos ? pos_ptr : nullptr, (int)cur_len, temperature,
+        (int)(top_k > 0 ? top_k : 0), ngrams, (int)n_ngrams, seed, seed_ptr, probs_out, ticket, write_token);
+  } else {
+    sample_kernel<<<(unsigned)B, SAMP_THREADS, 0, (cudaStream_t)stream>>>(
+        logits, ldl, (int)V, ids, ids_ld, pos_ptr, advance_pos ? pos_ptr : nullptr, (int)cur_len, temperature,
+        (int)(top_k > 0 ? top_k : 0), ngrams, (int)n_ngrams, seed, seed_ptr, probs_out, ticket, write_token);
+  }
   I2T_LAUNCHED();
   return I2T_OK;
 }

@@ -1,0 +1,148 @@
+"""Data-parallel gradient exchange: one process per GPU, bucketed all-reduce overlapped with backward.
+
+The reference wraps the trainer in accelerate's DDP (trainer.py:173-174) but then calls ``.module.train_step``
+(training/utils.py:76-78), which bypasses ``DDP.forward`` -- DDP's reducer never arms, so no gradient is ever exchanged
+and replicas drift.  This module does the exchange the reference intends: the MEAN over ranks of the
+per-rank gradients (each rank's loss is already normalised by its local batch, training/wrapper.py:96).
+
+Mechanics: parameters that need a gradient are packed, in reverse registration order (the order backward produces
+them), into flat fp32 buckets of ~``bucket_mb``; ``register_post_accumulate_grad_hook`` counts arrivals; when a bucket is
+complete its gradients are copied into the flat buffer and an asynchronous ``all_reduce`` is launched on a side stream
+that waits only on that point of the compute stream -- the remaining backward kernels keep running.  ``finish()`` joins
+the side stream, scales by 1/world and scatters the averaged values back into ``.grad``.  With
+``gradient_accumulation_steps`` > 1 call ``no_sync()`` on the non-final micro-steps.  Collectives: NCCL over
+NVLink/NVSwitch on GPUs, gloo on CPU (tests).  Nothing here touches the data path of generation (captions shard by
+image, no collective).
+"""
+from __future__ import annotations
+
+import contextlib
+from typing import Iterable, List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+class GradientAllReducer:
+    def __init__(self, params: Iterable[torch.nn.Parameter], bucket_mb: float = 32.0, process_group=None,
+                 only_with_grad: bool = True):
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        seen, uniq = set(), []
+        for p in params:
+            if p.requires_grad and id(p) not in seen:
+                seen.add(id(p))
+                uniq.append(p)
+        self.params: List[torch.nn.Parameter] = list(reversed(uniq))
+        self.buckets: List[List[torch.nn.Parameter]] = []
+        cap = int(bucket_mb * 1024 * 1024 / 4)
+        cur, cur_n = [], 0
+        for p in self.params:
+            if cur and cur_n + p.numel() > cap:
+                self.buckets.append(cur)
+                cur, cur_n = [], 0
+            cur.append(p)
+            cur_n += p.numel()
+        if cur:
+            self.buckets.append(cur)
+        self.bucket_of = {id(p): bi for bi, b in enumerate(self.buckets) for p in b}
+        self.flat: List[Optional[torch.Tensor]] = [None] * len(self.buckets)
+        self.pending = [0] * len(self.buckets)
+        self.work = [None] * len(self.buckets)
+        self.launched = [False] * len(self.buckets)
+        self.sync_enabled = True
+        self.side_stream = None
+        self.hooks = [p.register_post_accumulate_grad_hook(self._hook) for p in self.params]
+        self.only_with_grad = only_with_grad
+        self._reset()
+
+    # -- public ------------------------------------------------------------------------------------------------
+    def broadcast_parameters(self, module: torch.nn.Module, src: int = 0):
+        """DDP-constructor equivalent (reference trainer.py:173-174): rank `src`'s parameters and buffers win."""
+        if self.world == 1:
+            return
+        with torch.no_grad():
+            for t in list(module.parameters()) + list(module.buffers()):
+                dist.broadcast(t.data, src=src, group=self.group)
+
+    @contextlib.contextmanager
+    def no_sync(self):
+        old = self.sync_enabled
+        self.sync_enabled = False
+        try:
+            yield
+        finally:
+            self.sync_enabled = old
+
+    def finish(self):
+        """Call after backward of the last micro-step, before optimizer.step()."""
+        if self.world == 1:
+            self._reset()
+            return
+        # buckets whose parameters did not all receive a gradient this step (unused parameters)
+        for bi in range(len(self.buckets)):
+            if not self.launched[bi] and any(p.grad is not None for p in self.buckets[bi]):
+                self._launch(bi)
+        for bi, w in enumerate(self.work):
+            if w is not None:
+                w.wait()
+        if self.side_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.side_stream)
+        inv = 1.0 / self.world
+        with torch.no_grad():
+            for bi, bucket in enumerate(self.buckets):
+                if not self.launched[bi]:
+                    continue
+                flat, off = self.flat[bi], 0
+                for p in bucket:
+                    n = p.numel()
+                    if p.grad is not None:
+                        p.grad.copy_(flat[off:off + n].view_as(p.grad))
+                        p.grad.mul_(inv)
+                    off += n
+        self._reset()
+
+    def remove(self):
+        for h in self.hooks:
+            h.remove()
+
+    # -- internals ---------------------------------------------------------------------------------------------
+    def _reset(self):
+        for bi, b in enumerate(self.buckets):
+            self.pending[bi] = len(b)
+            self.work[bi] = None
+            self.launched[bi] = False
+
+    def _hook(self, p: torch.nn.Parameter):
+        if not self.sync_enabled or self.world == 1:
+            return
+        bi = self.bucket_of[id(p)]
+        self.pending[bi] -= 1
+        if self.pending[bi] == 0:
+            self._launch(bi)
+
+    def _launch(self, bi: int):
+        bucket = self.buckets[bi]
+        dev = bucket[0].device
+        n = sum(p.numel() for p in bucket)
+        if self.flat[bi] is None:
+            self.flat[bi] = torch.zeros(n, device=dev, dtype=torch.float32)
+        flat = self.flat[bi]
+        with torch.no_grad():
+            off = 0
+            for p in bucket:
+                m = p.numel()
+                if p.grad is not None:
+                    flat[off:off + m].copy_(p.grad.reshape(-1))
+                else:
+                    flat[off:off + m].zero_()
+                off += m
+        if dev.type == "cuda":
+            if self.side_stream is None:
+                self.side_stream = torch.cuda.Stream(device=dev)
+            self.side_stream.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(self.side_stream):
+                self.work[bi] = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        else:
+            self.work[bi] = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self.launched[bi] = True

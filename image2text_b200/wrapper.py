@@ -1,0 +1,107 @@
+"""Mirror of the reference's ``training.wrapper.ModelTrainerWrapper`` (training/wrapper.py:13-214) over the B200 model.
+
+Same constructor arguments, same ``train_step`` / ``val_step`` / ``forward`` / ``forward_m`` / ``copy_momentum_params``
+surface, same loss definitions:
+  * token corruption (MLM) and BOS shift are integer bookkeeping on the id tensors (training/wrapper.py:154-196);
+  * the LM loss -- weighted CE, or the momentum-distillation soft-CE -- and its gradient w.r.t. the logits come from ONE
+    fused pass over the vocabulary (``i2t_lm_loss``), never materialising the (B,T,V+1) one-hot of :136-141;
+  * the EMA teacher update is one in-place multi-tensor launch (``i2t_ema_multi``) instead of a per-parameter
+    allocate-and-rebind loop (:53-60).  It runs every micro-step before backward, like the reference.
+The contrastive auxiliary loss (:98-118, off in every reference YAML) is not built.
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import torch
+import torch.nn as nn
+
+from .autograd_ops import LmLossFn
+from .config_schema import TrainerWrapperConfig, VisionEncoderDecoderConfig
+from .optimizer import EmaUpdater
+from .vision_encoder_decoder import VisionEncoderDecoder
+
+
+class ModelTrainerWrapper(nn.Module):
+    def __init__(self, model_config: VisionEncoderDecoderConfig, tokenizer, trainer_config: TrainerWrapperConfig,
+                 ignore_index: int = -100, device="cuda", compute_dtype: torch.dtype = torch.float32, **model_kw):
+        super().__init__()
+        if trainer_config.add_contrastive_loss:
+            raise NotImplementedError("contrastive auxiliary loss (reference training/wrapper.py:98-118) is not built")
+        self.model = VisionEncoderDecoder(config=model_config, device=device, compute_dtype=compute_dtype, **model_kw)
+        self.is_momentum = trainer_config.moco_momentum is not None and trainer_config.moco_alpha is not None
+        self.model_m = VisionEncoderDecoder(config=model_config, device=device, compute_dtype=compute_dtype, **model_kw) \
+            if self.is_momentum else None
+        self.tokenizer = tokenizer
+        self.ignore_index = ignore_index
+        self.temperature = trainer_config.training_temperature
+        self.weight_fn = trainer_config.weight_fn
+        if self.weight_fn not in ("constant", "inverse_sqrt_position"):
+            raise ValueError(f"unknown weight_fn: {self.weight_fn}")
+        self.mask_fraction = trainer_config.mask_fraction
+        self.random_mask_fraction = trainer_config.random_mask_fraction
+        self.eos_token_weight = trainer_config.eos_token_weight
+        self.momentum = trainer_config.moco_momentum
+        self.alpha = trainer_config.moco_alpha
+        self._ema = EmaUpdater()
+        self.copy_momentum_params()
+
+    @torch.no_grad()
+    def copy_momentum_params(self):
+        if self.is_momentum:
+            self.model_m.load_state_dict(self.model.state_dict())      # buffers too (training/wrapper.py:46-51)
+
+    @torch.no_grad()
+    def _momentum_update(self):
+        if not self.is_momentum:
+            return
+        ps = [p for _, p in self.model.named_parameters()]
+        pm = [p for _, p in self.model_m.named_parameters()]
+        self._ema(pm, ps, self.momentum)
+
+    def forward(self, images, input_ids, attn_msk=None) -> Tuple[torch.Tensor, torch.Tensor]:
+        out = self.model(images=images, ids=input_ids, attn_msk=attn_msk)
+        return out.logits, out.hidden_state
+
+    @torch.no_grad()
+    def forward_m(self, images, input_ids, attn_msk=None) -> Tuple[torch.Tensor, torch.Tensor]:
+        out = self.model_m(images=images, ids=input_ids, attn_msk=attn_msk)
+        return out.logits, out.hidden_state
+
+    def train_step(self, images, labels):
+        return self._step(images, labels, True)
+
+    def val_step(self, images, labels):
+        return self._step(images, labels, False)
+
+    def compute_lm_loss(self, lm_logits, labels, lm_logits_moco=None):
+        return LmLossFn.apply(lm_logits, lm_logits_moco, labels, self.temperature, self.alpha, self.weight_fn,
+                              self.eos_token_weight, self.tokenizer.eos_token_id, self.ignore_index)
+
+    def _step(self, images, labels, is_train: bool):
+        tok = self.tokenizer
+        keep = labels != self.ignore_index
+        input_ids = torch.where(keep, labels, torch.full_like(labels, tok.eos_token_id))
+        if is_train and self.mask_fraction > 0:
+            mask = torch.full_like(input_ids, tok.mask_token_id)
+            corrupted_mask = torch.where(torch.rand_like(input_ids, dtype=torch.float) <= self.random_mask_fraction,
+                                         torch.randint_like(input_ids, low=0, high=tok.vocab_size), mask)
+            corrupted = torch.where(torch.rand_like(input_ids, dtype=torch.float) <= self.mask_fraction, corrupted_mask,
+                                    input_ids)
+            corrupted = torch.where(keep, corrupted, torch.full_like(labels, tok.eos_token_id))
+        else:
+            corrupted = input_ids
+        bs, sl = corrupted.shape
+        bos = torch.full((bs, 1), tok.bos_token_id, device=corrupted.device, dtype=torch.long)
+        corrupted = torch.cat((bos, corrupted), dim=1)[:, :sl].contiguous()
+        attn_msk = torch.cat((torch.ones((bs, 1), device=keep.device, dtype=torch.bool), keep), dim=1)[:, :sl]
+        step = "train" if is_train else "val"
+        lm_logits, _ = self(images, corrupted, attn_msk)
+        lm_logits_moco = None
+        if self.is_momentum and is_train:
+            lm_logits_moco, _ = self.forward_m(images, corrupted, attn_msk)
+        loss = self.compute_lm_loss(lm_logits, labels, lm_logits_moco)
+        metrics = {f"{step}_loss_lm": loss.detach()}
+        if is_train:
+            self._momentum_update()
+        return loss, metrics

@@ -1,0 +1,123 @@
+"""Secondary benchmark (BASELINE.json configs[0]/[3] shape): nano.yaml training step on ONE or N GPUs.
+
+    python scripts/bench_train.py [--dtype fp32|bf16] [--steps K] [--moco] [--cpu-ref]
+    torchrun --nproc-per-node N scripts/bench_train.py ...
+
+One optimiser-visible step = gradient_accumulation_steps (4) micro-steps of batch 8 per GPU: train_step -> backward ->
+[DP all-reduce overlapped with backward] -> fused AdamW on the YAML's two parameter groups (reference trainer.py:145-172;
+loop restated from training/utils.py:85-101).  Dropout is NOT applied on the B200 path yet, so
+the number is reported as "dropout off" -- the reference's YAML value is 0.1.
+Prints one JSON line: img/s (all ranks), ms/step, achieved model TFLOP/s (243.4 GFLOP/img).
+"""
+import argparse
+import json
+import os
+import sys
+import time
+import types
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--dtype", default="fp32")
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=1)
+    ap.add_argument("--moco", action="store_true")
+    ap.add_argument("--cpu-ref", action="store_true", help="time the CPU oracle's train step instead")
+    args = ap.parse_args()
+    from image2text_b200 import load_training_config
+    from image2text_b200.config_schema import TrainerWrapperConfig
+    from image2text_b200.model_spec import spec_from_config, synth_state_dict
+    from image2text_b200.synthetic import synth_images, synth_labels
+    tc = load_training_config(os.path.join(ROOT, "configs", "nano.yaml"))
+    bs, accum = tc.batch_size, tc.gradient_accumulation_steps
+    if args.cpu_ref:
+        from oracle import i2t_oracle as O
+        spec = spec_from_config(tc.model)
+        sd = synth_state_dict(spec, seed=0)
+        train_keys = [k for k in sd if ("lsh_emb" in k and k.endswith("emb.weight")) or "wpe" in k or "cross_attn" in k or "ln_3" in k]
+        sd = {k: (v.clone().requires_grad_(True) if k in train_keys else v) for k, v in sd.items()}
+        images, labels = synth_images(bs, 224, seed=1234), synth_labels(bs, 256, seed=1234)
+        t0 = time.perf_counter()
+        loss = O.train_step_loss(sd, spec, images, labels)
+        loss.backward()
+        dt = time.perf_counter() - t0
+        print(json.dumps({"impl": "cpu oracle (port of the reference train step, dropout 0)", "img_per_s": round(bs / dt, 3),
+                          "s_per_micro_step": round(dt, 2), "threads": torch.get_num_threads(), "loss": float(loss)}))
+        return
+    from image2text_b200.dp import GradientAllReducer
+    from image2text_b200.optimizer import AdamW
+    from image2text_b200.wrapper import ModelTrainerWrapper
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cd = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    tok = types.SimpleNamespace(eos_token_id=50256, bos_token_id=50256, mask_token_id=None, vocab_size=50257)
+    tkw = dict(moco_momentum=0.995, moco_alpha=0.4) if args.moco else {}
+    w = ModelTrainerWrapper(tc.model, tok, TrainerWrapperConfig(**tkw), -100, device=f"cuda:{local}", compute_dtype=cd)
+    w.model.load_state_dict(synth_state_dict(w.model.spec, seed=0))
+    w.copy_momentum_params()
+    w.train()
+    # param groups exactly as reference trainer.py:145-172 (fnmatch on the name without the leading "model.")
+    import fnmatch
+    groups, chosen = [], set()
+    for oc in tc.optimizers:
+        ps = [p for n, p in w.named_parameters() if n.split(".", 1)[0] != "model_m" and
+              (oc.target_modules is None or any(fnmatch.fnmatch(n.split(".", 1)[-1], pat) for pat in oc.target_modules))]
+        groups.append(dict(params=ps, lr=oc.lr, weight_decay=oc.weight_decay, betas=oc.betas))
+        chosen.update(id(p) for p in ps)
+    # Q5: parameters outside every group never change; skipping their weight gradients is a pure saving
+    for n, p in w.model.named_parameters():
+        if id(p) not in chosen:
+            p.requires_grad_(False)
+    opt = AdamW(groups)
+    red = GradientAllReducer([p for g in groups for p in g["params"]])
+    red.broadcast_parameters(w.model)
+    images = synth_images(bs, 224, seed=1234 + rank).cuda()
+    labels = synth_labels(bs, 256, seed=1234 + rank).cuda()
+
+    def one_step():
+        for micro in range(accum):
+            ctx = red.no_sync() if micro < accum - 1 else torch.enable_grad()
+            with ctx:
+                loss, _ = w.train_step(images, labels)
+                (loss / accum).backward()
+        red.finish()
+        opt.step()
+        opt.zero_grad(set_to_none=False)
+        return loss
+
+    for _ in range(args.warmup):
+        one_step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = one_step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    imgs = bs * accum * args.steps * world
+    gflop_img = 243.4 + (104.5 if args.moco else 0.0)
+    if rank == 0:
+        print(json.dumps({"metric": "train img/s (nano.yaml, B=8/GPU, accum 4, AdamW 2 groups, dropout off)",
+                          "value": round(imgs / (ms / 1e3), 2), "n_gpus": world, "dtype": args.dtype, "moco": args.moco,
+                          "ms_per_step": round(ms / args.steps, 2), "model_tflops": round(imgs * gflop_img / (ms / 1e3) / 1e3, 2),
+                          "loss": float(loss), "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2)}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
