@@ -2,28 +2,33 @@
 
 What the reference does per new token (models/vision_encoder_decoder.py:144-180): a FULL decoder forward over the whole
 prefix, logits for every position, a python n-gram processor with a host sync, top-k / softmax / multinomial / cat.
-What this engine does per new token: ~8 fused kernels per layer that touch every decoder weight exactly once
-(weight-streaming, HBM-bound), an in-place KV-cache append, an on-device sampler that also advances the position
-counter -- the whole step is one CUDA-graph replay with no host round trip.
+What this engine does per new token: every decoder weight is touched exactly once (weight streaming, HBM-bound), the
+K/V rows are appended in place, the sampler runs on the device and advances the position counter -- one CUDA-graph
+replay per token, no host round trip.  Two executions of the same arithmetic:
 
-The result is the same sequence of token ids: text rows never see the soft-prompt rows, so the last-row
-logits of the cache-less forward equal the incremental ones (tests/test_gpu_generate.py checks bit-exact greedy ids
-against the oracle and the reference-made golden ids).
+  mode "mega"    (default, B <= 8): ONE cooperative launch per step (csrc/decode_mega.cu);
+  mode "kernels" : ~81 launches per step (csrc/decode.cu + sampler.cu), used for larger batches / wider models and as
+                   the cross-check of the megakernel.
+
+The result is the same sequence of token ids as the reference: text rows never see the soft-prompt rows,
+so the last-row logits of the cache-less forward equal the incremental ones (tests/test_gpu_model.py checks bit-exact
+greedy ids against the reference-made golden ids in both modes).
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
 
 from . import ops
-from ._lib import call
+from ._lib import I2TError, call, launch_count
 from .model_spec import layer_has_cross_attn
 from .ops import ptr, stream
 
 
 class DecodeEngine:
-    def __init__(self, model, batch: int):
+    def __init__(self, model, batch: int, mode: Optional[str] = None):
         spec = model.spec
         if spec["decoder"] != "transformer":
             raise NotImplementedError("KV-cached decode is built for TransformerDecoder only (HF GPT-2 layout: next)")
@@ -32,32 +37,118 @@ class DecodeEngine:
         dev = next(model.parameters()).device
         self.dev = dev
         C, L, V = spec["n_embd"], spec["n_layer"], spec["vocab_size"]
+        self.F = int(spec["ff_mult"] * C)
         self.n_prompt = spec["n_cls"] if spec["use_soft_prompting"] else 0
         self.Tmax = spec["block_size"] - self.n_prompt
+        # measured on B200 (profiles/r01_*): the megakernel wins in bf16, the separate kernels win in fp32
+        mode = mode or os.environ.get("I2T_DECODE", "mega" if self.cd == torch.bfloat16 else "kernels")
+        if batch > 8 or max(C, self.F) > 3072 or C > 1024:
+            mode = "kernels"
+        self.mode = mode
         self.ids = torch.zeros((batch, self.Tmax + 1), device=dev, dtype=torch.int64)
         self.pos = torch.zeros(1, device=dev, dtype=torch.int32)
         self.ticket = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.bar = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.err = torch.zeros(1, device=dev, dtype=torch.int32)
         self.kcache = torch.zeros((L, batch, self.Tmax, C), device=dev, dtype=self.cd)
         self.vcache = torch.zeros((L, batch, self.Tmax, C), device=dev, dtype=self.cd)
         self.cross_layers = [d for d in range(L) if spec["use_cross_attn"] and layer_has_cross_attn(spec, d)
                              and (d % 2 == 0 or not spec["skip_alternate_cross_attn"])]
-        S = spec["n_cls"]
-        self.S = S
-        self.xkv = torch.zeros((max(1, len(self.cross_layers)), batch * S, 2 * C), device=dev, dtype=self.cd)
+        self.S = spec["n_cls"]
+        self.xkv = torch.zeros((max(1, len(self.cross_layers)), batch * self.S, 2 * C), device=dev, dtype=self.cd)
         f32 = dict(device=dev, dtype=torch.float32)
         self.x = torch.zeros((batch, C), **f32)
         self.q = torch.zeros((batch, C), **f32)
         self.y = torch.zeros((batch, C), **f32)
-        self.h = torch.zeros((batch, int(spec["ff_mult"] * C)), **f32)
+        self.h = torch.zeros((batch, self.F), **f32)
         self.logits = torch.zeros((batch, V), **f32)
         self.ngrams = torch.tensor(list(spec["no_repeat_n_grams"]) or [0], device=dev, dtype=torch.int32)
         self.n_ngrams = len(spec["no_repeat_n_grams"])
         self.seed_dev = torch.zeros(1, device=dev, dtype=torch.int64)
         self.graphs = {}
         self.launches_per_step = None
+        self.replays_last = 0
+        self._mega = None
+        self.trace = None          # set to an int64 device tensor [n_sched * 4] to collect per-stage clock stamps
 
-    # one decode step for the token at position *pos (device).  sample=False: teacher-forced prompt token.
-    def _step(self, sample: bool, temperature: float, top_k: Optional[int], seed: int):
+    # ------------------------------------------------------------------ megakernel tables ---------------------
+    def _mega_tables(self):
+        """(lin, att, sched_sample, sched_prefill, keepalive) -- rebuilt when a weight (or shadow) pointer changes."""
+        W = self.model.weights()
+        spec, C, F, V = self.spec, self.spec["n_embd"], self.F, self.spec["vocab_size"]
+        dp = "decoder.transformer."
+        keep = []
+        lin, att = [], []
+        sample, prefill = [], []
+
+        def P(t):
+            return 0 if t is None else t.data_ptr()
+
+        def add_lin(wkey, bkey, ln, inp, out, residual, N, K, act=0, mode=0, kc=None, vc=None, in_mode=0, rows=None, ldo=None,
+                    wpe=None, both=True):
+            w = W.c(wkey)
+            b = W.get(bkey) if bkey else None
+            if rows is not None:
+                w = w[rows]
+                b = b[rows] if b is not None else None
+            keep.extend([w, b])
+            g = W[ln + ".weight"] if ln else None
+            be = W.get(ln + ".bias") if ln else None
+            lin.append([P(w), P(b), P(g), P(be), P(inp), P(out), P(residual), N, K, act, mode, P(kc), P(vc), in_mode, P(wpe),
+                        ldo if ldo is not None else N, self.Tmax * C, 0, 0, 0])
+            sample.append([0, len(lin) - 1, 0, 0])
+            if both:
+                prefill.append([0, len(lin) - 1, 0, 0])
+
+        def add_att(k_ptr, v_ptr, bs, rs, len_mode, len_const):
+            att.append([k_ptr, v_ptr, bs, rs, len_mode, len_const, 0, 0])
+            sample.append([1, len(att) - 1, 0, 0])
+            prefill.append([1, len(att) - 1, 0, 0])
+
+        xi = 0
+        for d in range(spec["n_layer"]):
+            lp = f"{dp}h.{d}."
+            if d == 0:
+                add_lin(lp + "attn.c_attn.weight", lp + "attn.c_attn.bias", lp + "ln_1", W[dp + "wte.weight"], self.q, self.x,
+                        3 * C, C, mode=1, kc=self.kcache[d], vc=self.vcache[d], in_mode=1, ldo=C, wpe=W[dp + "wpe.weight"])
+            else:
+                add_lin(lp + "attn.c_attn.weight", lp + "attn.c_attn.bias", lp + "ln_1", self.x, self.q, None, 3 * C, C, mode=1,
+                        kc=self.kcache[d], vc=self.vcache[d], ldo=C)
+            add_att(self.kcache[d].data_ptr(), self.vcache[d].data_ptr(), self.Tmax * C, C, 0, 0)
+            add_lin(lp + "attn.c_proj.weight", lp + "attn.c_proj.bias", None, self.y, self.x, self.x, C, C)
+            if d in self.cross_layers:
+                kw, kb = lp + "cross_attn.in_proj_weight", lp + "cross_attn.in_proj_bias"
+                add_lin(kw, kb, lp + "ln_3", self.x, self.q, None, C, C, rows=slice(0, C))
+                kv = self.xkv[xi]
+                add_att(kv.data_ptr(), kv.data_ptr() + C * kv.element_size(), self.S * 2 * C, 2 * C, 1, self.S)
+                add_lin(lp + "cross_attn.out_proj.weight", lp + "cross_attn.out_proj.bias", None, self.y, self.x, self.x, C, C)
+                xi += 1
+            add_lin(lp + "mlp.c_fc.weight", lp + "mlp.c_fc.bias", lp + "ln_2", self.x, self.h, None, F, C, act=ops.ACT_GELU_TANH)
+            add_lin(lp + "mlp.c_proj.weight", lp + "mlp.c_proj.bias", None, self.h, self.x, self.x, C, F)
+        add_lin("decoder.lm_head.weight", None, dp + "ln_f", self.x, self.logits, None, V, C, both=False)
+        sample.append([2, 0, 0, 0])
+        prefill.append([3, 0, 0, 0])
+        dev = self.dev
+        t64 = lambda rows: torch.tensor(rows, dtype=torch.int64, device=dev).contiguous()
+        t32 = lambda rows: torch.tensor(rows, dtype=torch.int32, device=dev).contiguous()
+        return dict(lin=t64(lin), att=t64(att), sample=t32(sample), prefill=t32(prefill), n_ops=len(lin), keep=keep,
+                    sig=tuple(r[0] for r in lin))
+
+    def _mega_step(self, sample: bool, temperature: float, top_k: Optional[int]):
+        if self._mega is None:
+            self._mega = self._mega_tables()
+        T = self._mega
+        sched = T["sample"] if sample else T["prefill"]
+        spec = self.spec
+        wd = ops.F32 if self.cd == torch.float32 else ops.BF16
+        call("i2t_decode_mega", ptr(T["lin"]), ptr(T["att"]), ptr(sched), sched.shape[0], T["n_ops"], self.B, spec["n_embd"],
+             spec["n_head"], spec["vocab_size"], self.n_prompt, wd, ptr(self.ids), self.ids.shape[1], ptr(self.pos), ptr(self.q),
+             ptr(self.y), ptr(self.logits), ptr(self.bar), ptr(self.err), temperature, int(top_k) if top_k is not None else 0,
+             ptr(self.ngrams), self.n_ngrams, ptr(self.seed_dev), ptr(self.ticket), max(spec["n_embd"], self.F),
+             ptr(self.trace) if sample else None, stream())
+
+    # ------------------------------------------------------------------ one step, separate kernels -------------
+    def _kernel_step(self, sample: bool, temperature: float, top_k: Optional[int]):
         m, spec, B = self.model, self.spec, self.B
         W = m.weights()
         C, H = spec["n_embd"], spec["n_head"]
@@ -83,6 +174,7 @@ class DecodeEngine:
                  wd, 1 if qkv else 0, kc, vc, cbs, C, wd, pos, st)
 
         xi = 0
+        F = self.F
         for d in range(spec["n_layer"]):
             lp = f"{dp}h.{d}."
             lin(self.x, lp + "ln_1", lp + "attn.c_attn.weight", lp + "attn.c_attn.bias", self.q, C, 3 * C, C,
@@ -100,16 +192,22 @@ class DecodeEngine:
                 lin(self.y, None, lp + "cross_attn.out_proj.weight", lp + "cross_attn.out_proj.bias", self.x, C, C, C,
                     residual=self.x)
                 xi += 1
-            F = self.h.shape[1]
             lin(self.x, lp + "ln_2", lp + "mlp.c_fc.weight", lp + "mlp.c_fc.bias", self.h, F, F, C, act=ops.ACT_GELU_TANH)
             lin(self.h, None, lp + "mlp.c_proj.weight", lp + "mlp.c_proj.bias", self.x, C, C, F, residual=self.x)
         if sample:
             V = spec["vocab_size"]
             lin(self.x, dp + "ln_f", "decoder.lm_head.weight", None, self.logits, V, V, C)
             call("i2t_sample", ptr(self.logits), V, B, V, ptr(self.ids), self.ids.shape[1], pos, 1, 0, temperature,
-                 int(top_k) if top_k is not None else 0, ptr(self.ngrams), self.n_ngrams, 0, ptr(self.seed_dev), None, ptr(self.ticket), 1, st)
+                 int(top_k) if top_k is not None else 0, ptr(self.ngrams), self.n_ngrams, 0, ptr(self.seed_dev), None,
+                 ptr(self.ticket), 1, st)
         else:
             call("i2t_dec_advance", pos, st)
+
+    def _step(self, sample: bool, temperature: float, top_k: Optional[int]):
+        if self.mode == "mega":
+            self._mega_step(sample, temperature, top_k)
+        else:
+            self._kernel_step(sample, temperature, top_k)
 
     def _prefill_cross(self, enc: torch.Tensor):
         """K/V projections of the (fixed) encoder output, once per generate call: the k,v rows of
@@ -127,31 +225,35 @@ class DecodeEngine:
     @torch.no_grad()
     def generate(self, images, prompt_ids, max_new_tokens: int, temperature: float, top_k: Optional[int], seed: int):
         from . import functional as Fn
-        from ._lib import launch_count
         m, B = self.model, self.B
         P = prompt_ids.shape[1]
         assert prompt_ids.shape[0] == B and P + max_new_tokens <= self.Tmax + 1
         enc = Fn.encoder_forward(m.weights(), self.spec, images, self.cd, train_trunk=False)
         self._prefill_cross(enc)
+        if self.mode == "mega":
+            W = m.weights()
+            sig = self._mega["sig"] if self._mega is not None else None
+            if sig is not None and sig[0] != W.c("decoder.transformer.h.0.attn.c_attn.weight").data_ptr():
+                self._mega, self.graphs = None, {}        # weights were re-materialised: rebuild tables and graphs
         self.ids[:, :P].copy_(prompt_ids)
         self.pos.zero_()
         self.ticket.zero_()
-        for _ in range(P - 1):
-            self._step(False, temperature, top_k, seed)
         self.seed_dev.fill_(int(seed) & 0x7FFFFFFFFFFFFFFF)
+        for _ in range(P - 1):
+            self._step(False, temperature, top_k)
         key = (float(temperature), top_k)
         g = self.graphs.get(key)
         if g is None:
             # first use: run one step eagerly (sets kernel attributes, loads modules), then capture the next one
             n0 = launch_count()
-            self._step(True, temperature, top_k, seed)
+            self._step(True, temperature, top_k)
             self.launches_per_step = launch_count() - n0
             done = 1
             if max_new_tokens > 1:
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    self._step(True, temperature, top_k, seed)
+                    self._step(True, temperature, top_k)
                 # capture does not execute: the graph now holds exactly one step
                 if len(self.graphs) > 16:
                     self.graphs.clear()
@@ -161,4 +263,7 @@ class DecodeEngine:
         self.replays_last = max_new_tokens - done
         for _ in range(max_new_tokens - done):
             g.replay()
-        return self.ids[:, :P + max_new_tokens].clone()
+        out = self.ids[:, :P + max_new_tokens].clone()
+        if self.mode == "mega" and int(self.err.item()) != 0:
+            raise I2TError(f"decode megakernel reported an internal wait timeout (code {int(self.err.item())})")
+        return out

@@ -152,6 +152,22 @@ int i2t_dec_attn(const float* q, int64_t q_ld, const void* kcache, const void* v
                  int64_t cache_row_stride, float* out, int64_t out_ld, const int32_t* len_ptr, int64_t len_add, int64_t B,
                  int64_t H, int64_t head_dim, int cache_dtype, void* stream);
 
+/* One whole decode step (every layer, LM head, sampler) as ONE cooperative launch: the same arithmetic as the
+ * i2t_dec_* sequence, with the weights streamed through a shared-memory ring by a producer warp per CTA and ~1 us grid
+ * barriers between the ~80 dependent stages (decode_mega.cu).  lin / att / sched are device tables of plain numbers:
+ *   lin[op][20]  = {W, bias, ln_gamma, ln_beta, in, out, residual, N, K, act, mode(0 plain | 1 qkv split + KV append),
+ *                   kcache, vcache, in_mode(0 buffer | 1 token embedding, in = wte), wpe, ldo, cache_batch_stride, 0,0,0}
+ *   att[a][8]    = {k, v, batch_stride, row_stride, len_mode(0: *pos+1 | 1: const), len_const, 0, 0}
+ *   sched[s][4]  = {kind(0 linear | 1 attention | 2 sample | 3 advance position), index, 0, 0}
+ * bar: device uint32 scratch; error_flag: device int32, non-zero if an internal wait timed out (results invalid).
+ * max_k: largest K of any linear (<= 3072).  B <= 8.  trace (optional, device int64[n_sched*4]): clock64 stamps of
+ * CTA 0 per stage (begin, activations staged, computed, barrier passed) for profiling. */
+int i2t_decode_mega(const int64_t* lin, const int64_t* att, const int32_t* sched, int64_t n_sched, int64_t n_ops, int64_t B,
+                    int64_t C, int64_t H, int64_t V, int64_t n_prompt, int w_dtype, int64_t* ids, int64_t ids_ld,
+                    int32_t* pos, float* q, float* y, float* logits, uint32_t* bar, int32_t* error_flag, float temperature,
+                    int64_t top_k, const int32_t* ngrams, int64_t n_ngrams, const uint64_t* seed_ptr, int32_t* ticket,
+                    int64_t max_k, int64_t* trace, void* stream);
+
 /* ---- sampler: models/vision_encoder_decoder.py:152-180 + transformers NoRepeatNGramLogitsProcessor ----------------
  * logits (B,ldl) fp32 are modified in place (/temperature, banned -> -inf).  Tokens ids[b, 0..cur_len) are the history
  * (cur_len = *pos_ptr + 1 when pos_ptr != NULL, else the cur_len argument); the draw is written to ids[b, cur_len] when
