@@ -43,8 +43,14 @@ class LinearFn(torch.autograd.Function):
     models/decoder.py:256, nn.MultiheadAttention projections.  `w_c` is the compute-dtype view of the master weight."""
 
     @staticmethod
-    def forward(ctx, x2d, w, w_c, bias, residual, act, out_dtype):
+    def forward(ctx, x2d, w, w_c, bias, residual, act, out_dtype, pad_rows=False):
         need = any(ctx.needs_input_grad)      # grad mode is always off inside Function.forward
+        out = None
+        if pad_rows and w_c.shape[0] % 8 != 0:
+            # rows padded to a multiple of 8 elements (e.g. V = 50257 -> pitch 50264): the output is a strided view, and
+            # the gradient that comes back with the same pitch satisfies TMA's 16-byte row-pitch rule for dgrad / wgrad
+            N = w_c.shape[0]
+            out = torch.empty((x2d.shape[0], (N + 7) // 8 * 8), device=x2d.device, dtype=out_dtype)[:, :N]
         if need and act != ops.ACT_NONE:
             z = ops.gemm(x2d, w_c, bias=bias, out_dtype=x2d.dtype)
             y = torch.empty(z.shape, device=z.device, dtype=out_dtype)
@@ -52,7 +58,7 @@ class LinearFn(torch.autograd.Function):
             assert residual is None
         else:
             z = None
-            y = ops.gemm(x2d, w_c, bias=bias, residual=residual, act=act, out_dtype=out_dtype)
+            y = ops.gemm(x2d, w_c, bias=bias, residual=residual, act=act, out_dtype=out_dtype, out=out)
         if need:
             ctx.save_for_backward(x2d, w_c, z)
             ctx.act = act
@@ -64,7 +70,8 @@ class LinearFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         x2d, w_c, z = ctx.saved_tensors
-        dy = dy.contiguous()
+        if not (dy.dim() == 2 and dy.stride(1) == 1 and dy.stride(0) % 8 == 0 and dy.stride(0) >= dy.shape[1]):
+            dy = dy.contiguous()      # row-padded gradients (LM head) are consumed in place
         dres = dy.to(ctx.res_dtype) if (ctx.has_res and ctx.needs_input_grad[4]) else None
         g = dy
         if g.dtype != x2d.dtype:
@@ -87,11 +94,11 @@ class LinearFn(torch.autograd.Function):
         if ctx.has_bias and ctx.needs_input_grad[3]:
             db = torch.zeros(g.shape[1], device=g.device, dtype=torch.float32)
             ops.colsum_(g, db)
-        return dx, dw, None, db, dres, None, None
+        return dx, dw, None, db, dres, None, None, None
 
 
-def linear(x2d, w, w_c, bias=None, residual=None, act=ops.ACT_NONE, out_dtype=torch.float32):
-    return LinearFn.apply(x2d, w, w_c, bias, residual, act, out_dtype)
+def linear(x2d, w, w_c, bias=None, residual=None, act=ops.ACT_NONE, out_dtype=torch.float32, pad_rows=False):
+    return LinearFn.apply(x2d, w, w_c, bias, residual, act, out_dtype, pad_rows)
 
 
 class AttnFn(torch.autograd.Function):
@@ -187,30 +194,41 @@ class LmLossFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, logits, teacher_logits, labels, temperature, alpha, weight_fn, eos_weight, eos_id, ignore_index):
-        logits = logits.contiguous()
         B, T_logits, V = logits.shape
+
+        def rows_ok(t):   # (B,T,V) view of a (B*T, pitch) buffer: what the LM head produces (pitch = V rounded up to 8)
+            return t.stride(2) == 1 and t.stride(1) >= V and t.stride(0) == T_logits * t.stride(1)
+        if not rows_ok(logits):
+            logits = logits.contiguous()
+        ld = logits.stride(1)
         Tl = min(T_logits, labels.shape[1])
         labels = labels.contiguous()
         need = ctx.needs_input_grad[0]
         weights = torch.empty(B * Tl, device=logits.device, dtype=torch.float32)
         rows = torch.empty(B * Tl, device=logits.device, dtype=torch.float32)
         loss = torch.empty((), device=logits.device, dtype=torch.float32)
-        dlogits = None
-        if need:
-            dlogits = torch.zeros_like(logits) if Tl < T_logits else torch.empty_like(logits)
+        dbuf = None
+        if need:    # same row pitch as the logits so the LM-head backward GEMMs read it in place
+            alloc = torch.zeros if Tl < T_logits else torch.empty
+            dbuf = alloc((B, T_logits, ld), device=logits.device, dtype=logits.dtype)
+        ld_t = 0
         if teacher_logits is not None:
-            teacher_logits = teacher_logits.contiguous().to(logits.dtype)
-        call("i2t_lm_loss", ptr(logits), ptr(teacher_logits), ptr(labels), ptr(weights), ptr(rows), ptr(loss), ptr(dlogits),
+            teacher_logits = teacher_logits.to(logits.dtype)
+            if not rows_ok(teacher_logits):
+                teacher_logits = teacher_logits.contiguous()
+            ld_t = teacher_logits.stride(1)
+        call("i2t_lm_loss", ptr(logits), ptr(teacher_logits), ptr(labels), ptr(weights), ptr(rows), ptr(loss), ptr(dbuf),
              B, T_logits, Tl, V, labels.shape[1], float(temperature), float(alpha if alpha is not None else 0.0),
              int(weight_fn == "inverse_sqrt_position"), int(eos_weight is not None),
-             float(eos_weight if eos_weight is not None else 0.0), int(eos_id), int(ignore_index), dt(logits), stream())
+             float(eos_weight if eos_weight is not None else 0.0), int(eos_id), int(ignore_index), ld, ld_t, dt(logits), stream())
         if need:
-            ctx.save_for_backward(dlogits)
+            ctx.save_for_backward(dbuf)
+            ctx.V = V
         return loss
 
     @staticmethod
     def backward(ctx, gloss):
-        (dlogits,) = ctx.saved_tensors
+        (dbuf,) = ctx.saved_tensors
         scale = gloss.reshape(1).to(torch.float32).contiguous()
-        call("i2t_scale_inplace", ptr(dlogits), ptr(scale), dlogits.numel(), dt(dlogits), stream())
-        return dlogits, None, None, None, None, None, None, None, None
+        call("i2t_scale_inplace", ptr(dbuf), ptr(scale), dbuf.numel(), dt(dbuf), stream())
+        return dbuf[..., :ctx.V], None, None, None, None, None, None, None, None

@@ -65,6 +65,18 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   d |= (uint64_t)2 << 61;            // SWIZZLE_128B
   return d;
 }
+// MN-major, 128-byte swizzle: the tile is stored [K rows][64 MN elements = 128 B]; a swizzle atom is 8 K-rows (1024 B).
+// Canonical layout ((T,8,m),(8,k)) with strides ((1,T,LBO),(8T,SBO)): LBO = distance between the two 64-wide MN halves
+// of the 128-wide tile (64 rows x 128 B = 8192 B), SBO = distance between consecutive 8-row K groups (1024 B).
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(8192 >> 4) << 16;  // leading byte offset
+  d |= (uint64_t)(1024 >> 4) << 32;  // stride byte offset
+  d |= (uint64_t)1 << 46;            // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;            // SWIZZLE_128B
+  return d;
+}
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -90,6 +102,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int num_k_blocks,
                TcEpilogue epi) {
@@ -134,25 +147,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t ph = (uint32_t)(kb / TC_STAGES) & 1u;
         mbar_wait(&empty_bar[s], ph ^ 1u);
         mbar_expect_tx(&full_bar[s], TC_A_BYTES + TC_B_BYTES);
-        tma_load_2d(smemA + s * TC_A_BYTES, &tmA, kb * TC_BK, m_blk * TC_BM, &full_bar[s]);
-        tma_load_2d(smemB + s * TC_B_BYTES, &tmB, kb * TC_BK, n_blk * TC_BN, &full_bar[s]);
+        // K-major operand ([rows][K], K contiguous): one box {64 k, 128 rows}.
+        // MN-major operand ([K][rows], rows contiguous): two boxes {64 rows, 64 k}, one per 64-wide half of the tile.
+        if (!A_MN) {
+          tma_load_2d(smemA + s * TC_A_BYTES, &tmA, kb * TC_BK, m_blk * TC_BM, &full_bar[s]);
+        } else {
+          tma_load_2d(smemA + s * TC_A_BYTES, &tmA, m_blk * TC_BM, kb * TC_BK, &full_bar[s]);
+          tma_load_2d(smemA + s * TC_A_BYTES + TC_A_BYTES / 2, &tmA, m_blk * TC_BM + 64, kb * TC_BK, &full_bar[s]);
+        }
+        if (!B_MN) {
+          tma_load_2d(smemB + s * TC_B_BYTES, &tmB, kb * TC_BK, n_blk * TC_BN, &full_bar[s]);
+        } else {
+          tma_load_2d(smemB + s * TC_B_BYTES, &tmB, n_blk * TC_BN, kb * TC_BK, &full_bar[s]);
+          tma_load_2d(smemB + s * TC_B_BYTES + TC_B_BYTES / 2, &tmB, n_blk * TC_BN + 64, kb * TC_BK, &full_bar[s]);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N=128, M=128 (cute::UMMA::InstrDescriptor)
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(A_MN ? 1u : 0u) << 15) |
+                             ((uint32_t)(B_MN ? 1u : 0u) << 16) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       for (int kb = 0; kb < num_k_blocks; ++kb) {
         const int s = kb % TC_STAGES;
         const uint32_t ph = (uint32_t)(kb / TC_STAGES) & 1u;
         mbar_wait(&full_bar[s], ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint64_t adesc = umma_desc_sw128(smem_u32(smemA + s * TC_A_BYTES));
-        const uint64_t bdesc = umma_desc_sw128(smem_u32(smemB + s * TC_B_BYTES));
+        const uint64_t adesc = A_MN ? umma_desc_sw128_mn(smem_u32(smemA + s * TC_A_BYTES)) : umma_desc_sw128(smem_u32(smemA + s * TC_A_BYTES));
+        const uint64_t bdesc = B_MN ? umma_desc_sw128_mn(smem_u32(smemB + s * TC_B_BYTES)) : umma_desc_sw128(smem_u32(smemB + s * TC_B_BYTES));
 #pragma unroll
         for (int k = 0; k < TC_BK / 16; ++k) {
-          // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle span: +2 in the (addr >> 4) field
-          umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          // one UMMA consumes 16 values of K.  K-major tile: 16 bf16 = 32 bytes inside the 128-byte swizzle span
+          // (+2 in the addr>>4 field).  MN-major tile: 16 K-rows of 128 bytes = 2 swizzle atoms = 2048 bytes (+128).
+          umma_bf16(tmem_base, adesc + (uint64_t)((A_MN ? 128 : 2) * k), bdesc + (uint64_t)((B_MN ? 128 : 2) * k), idesc,
+                    (kb | k) != 0 ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
       }
@@ -260,20 +288,24 @@ static EncodeTiledFn encode_fn() {
 struct MapKey {
   const void* p;
   int64_t rows, cols, ld;
-  bool operator==(const MapKey& o) const { return p == o.p && rows == o.rows && cols == o.cols && ld == o.ld; }
+  int box_rows;
+  bool operator==(const MapKey& o) const {
+    return p == o.p && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
+  }
 };
 struct MapKeyHash {
   size_t operator()(const MapKey& k) const {
     return std::hash<const void*>()(k.p) ^ (std::hash<int64_t>()(k.rows) * 1315423911u) ^
-           (std::hash<int64_t>()(k.cols) * 2654435761u) ^ (std::hash<int64_t>()(k.ld) << 7);
+           (std::hash<int64_t>()(k.cols) * 2654435761u) ^ (std::hash<int64_t>()(k.ld) << 7) ^ (size_t)k.box_rows;
   }
 };
 
-// 2-D bf16 [rows][cols] (cols contiguous, pitch ld elements), box 64 x 128, 128-byte swizzle, zero fill out of bounds
-static int make_map(const void* ptr, int64_t rows, int64_t cols, int64_t ld, CUtensorMap* out) {
+// 2-D bf16 [rows][cols] (cols contiguous, pitch ld elements), box {64 cols, box_rows}, 128-byte swizzle, zero fill out
+// of bounds.  K-major operand: cols = K, box_rows = 128.  MN-major operand: cols = MN, rows = K, box_rows = 64.
+static int make_map(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, CUtensorMap* out) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-  MapKey key{ptr, rows, cols, ld};
+  MapKey key{ptr, rows, cols, ld, box_rows};
   {
     std::lock_guard<std::mutex> g(mu);
     auto it = cache.find(key);
@@ -286,7 +318,7 @@ static int make_map(const void* ptr, int64_t rows, int64_t cols, int64_t ld, CUt
   if (fn == nullptr) return fail(I2T_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {TC_BK, TC_BM};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -300,23 +332,32 @@ static int make_map(const void* ptr, int64_t rows, int64_t cols, int64_t ld, CUt
   return I2T_OK;
 }
 
-int gemm_tc_try(const void* A, const void* B, const float* bias, const void* residual, void* C, int64_t M, int64_t N,
-                int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int a_kmajor, int b_kmajor, int act, int accumulate,
-                int res_dtype, int c_dtype, cudaStream_t st) {
-  if (!a_kmajor || !b_kmajor) return 0;
-  if (K % 8 != 0 || lda % 8 != 0 || ldb % 8 != 0 || !aligned16(A) || !aligned16(B)) return 0;
-  if (M > 128 * 65535LL || N > 128LL * 0x7fffffff) return 0;
-  CUtensorMap ma, mb;
-  int rc = make_map(A, M, K, lda, &ma);
-  if (rc != I2T_OK) return rc;
-  rc = make_map(B, N, K, ldb, &mb);
-  if (rc != I2T_OK) return rc;
+template <bool A_MN, bool B_MN>
+static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, int kblocks, const TcEpilogue& epi, dim3 grid, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
     if (e != cudaSuccess) return fail(I2T_ERR_CUDA, "cudaFuncSetAttribute(gemm_tc_kernel): %s", cudaGetErrorString(e));
     attr_set = true;
   }
+  gemm_tc_kernel<A_MN, B_MN><<<grid, TC_THREADS, TC_SMEM, st>>>(ma, mb, kblocks, epi);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(I2T_ERR_CUDA, "gemm_tc launch failed: %s", cudaGetErrorString(e));
+  return 1;
+}
+
+int gemm_tc_try(const void* A, const void* B, const float* bias, const void* residual, void* C, int64_t M, int64_t N,
+                int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int a_kmajor, int b_kmajor, int act, int accumulate,
+                int res_dtype, int c_dtype, cudaStream_t st) {
+  // leading dimensions are row pitches in elements: 16-byte multiples for TMA
+  if (lda % 8 != 0 || ldb % 8 != 0 || !aligned16(A) || !aligned16(B)) return 0;
+  if (M > 128 * 65535LL || N > 128LL * 0x7fffffff) return 0;
+  CUtensorMap ma, mb;
+  int rc = a_kmajor ? make_map(A, M, K, lda, TC_BM, &ma) : make_map(A, K, M, lda, 64, &ma);
+  if (rc != I2T_OK) return rc;
+  rc = b_kmajor ? make_map(B, N, K, ldb, TC_BN, &mb) : make_map(B, K, N, ldb, 64, &mb);
+  if (rc != I2T_OK) return rc;
   TcEpilogue epi;
   epi.bias = bias;
   epi.residual = residual;
@@ -329,11 +370,11 @@ int gemm_tc_try(const void* A, const void* B, const float* bias, const void* res
   epi.res_dtype = res_dtype;
   epi.c_dtype = c_dtype;
   dim3 grid((unsigned)ceil_div(N, TC_BN), (unsigned)ceil_div(M, TC_BM));
-  gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM, st>>>(ma, mb, (int)ceil_div(K, TC_BK), epi);
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  cudaError_t e = cudaPeekAtLastError();
-  if (e != cudaSuccess) return fail(I2T_ERR_CUDA, "gemm_tc launch failed: %s", cudaGetErrorString(e));
-  return 1;
+  const int kb = (int)ceil_div(K, TC_BK);
+  if (a_kmajor && b_kmajor) return launch_tc<false, false>(ma, mb, kb, epi, grid, st);
+  if (a_kmajor && !b_kmajor) return launch_tc<false, true>(ma, mb, kb, epi, grid, st);
+  if (!a_kmajor && b_kmajor) return launch_tc<true, false>(ma, mb, kb, epi, grid, st);
+  return launch_tc<true, true>(ma, mb, kb, epi, grid, st);
 }
 
 }  // namespace i2t

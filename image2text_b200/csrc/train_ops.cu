@@ -115,14 +115,15 @@ template <typename TL>
 __global__ void __launch_bounds__(512)
 lm_loss_kernel(const TL* __restrict__ logits, const TL* __restrict__ teacher, const int64_t* __restrict__ labels,
                const float* __restrict__ w, float* __restrict__ loss_rows, TL* __restrict__ dlogits, int V, int T_logits,
-               int Tl, int64_t ld_labels, float inv_tau, float alpha, int64_t ignore_index) {
+               int Tl, int64_t ld_labels, float inv_tau, float alpha, int64_t ignore_index, int64_t ld_logits,
+               int64_t ld_teacher) {
   __shared__ float redf[16];
   __shared__ float s_a, s_b;
   const int row = blockIdx.x;                 // row = b * Tl + t  (only the first Tl positions of each sequence)
   const int b = row / Tl, t = row % Tl;
-  const TL* z = logits + ((int64_t)b * T_logits + t) * V;
-  const TL* zm = teacher ? teacher + ((int64_t)b * T_logits + t) * V : nullptr;
-  TL* dz = dlogits ? dlogits + ((int64_t)b * T_logits + t) * V : nullptr;
+  const TL* z = logits + ((int64_t)b * T_logits + t) * ld_logits;
+  const TL* zm = teacher ? teacher + ((int64_t)b * T_logits + t) * ld_teacher : nullptr;
+  TL* dz = dlogits ? dlogits + ((int64_t)b * T_logits + t) * ld_logits : nullptr;
   const float wt = w[row];
   const int64_t y = labels[(int64_t)b * ld_labels + t];
   const bool valid = y != ignore_index;
@@ -281,11 +282,12 @@ extern "C" int i2t_gradnorm_scale(const void* g, void* out, double* acc, int64_t
 extern "C" int i2t_lm_loss(const void* logits, const void* teacher_logits, const int64_t* labels, float* weights,
                            float* loss_rows, float* loss_out, void* dlogits, int64_t B, int64_t T_logits, int64_t Tl,
                            int64_t V, int64_t ld_labels, float temperature, float alpha, int inv_sqrt_position,
-                           int use_eos_weight, float eos_weight, int64_t eos_id, int64_t ignore_index, int dtype,
-                           void* stream) {
+                           int use_eos_weight, float eos_weight, int64_t eos_id, int64_t ignore_index, int64_t ld_logits,
+                           int64_t ld_teacher, int dtype, void* stream) {
   I2T_REQUIRE(logits && labels && weights && loss_rows && loss_out, "lm_loss: null pointer");
   I2T_REQUIRE(B > 0 && Tl > 0 && Tl <= T_logits && Tl <= ld_labels && V > 1 && temperature > 0.f && valid_dtype(dtype),
               "lm_loss: bad sizes");
+  I2T_REQUIRE(ld_logits >= V && (teacher_logits == nullptr || ld_teacher >= V), "lm_loss: row pitch smaller than V");
   cudaStream_t st = (cudaStream_t)stream;
   loss_weights_kernel<<<(unsigned)B, 256, 0, st>>>(labels, weights, (int)Tl, ld_labels, inv_sqrt_position, eos_weight,
                                                   use_eos_weight, eos_id, ignore_index, (int)B);
@@ -293,11 +295,11 @@ extern "C" int i2t_lm_loss(const void* logits, const void* teacher_logits, const
   if (dtype == I2T_F32)
     lm_loss_kernel<float><<<(unsigned)(B * Tl), 512, 0, st>>>((const float*)logits, (const float*)teacher_logits, labels,
                                                               weights, loss_rows, (float*)dlogits, (int)V, (int)T_logits,
-                                                              (int)Tl, ld_labels, 1.0f / temperature, alpha, ignore_index);
+                                                              (int)Tl, ld_labels, 1.0f / temperature, alpha, ignore_index, ld_logits, ld_teacher);
   else
     lm_loss_kernel<__nv_bfloat16><<<(unsigned)(B * Tl), 512, 0, st>>>(
         (const __nv_bfloat16*)logits, (const __nv_bfloat16*)teacher_logits, labels, weights, loss_rows,
-        (__nv_bfloat16*)dlogits, (int)V, (int)T_logits, (int)Tl, ld_labels, 1.0f / temperature, alpha, ignore_index);
+        (__nv_bfloat16*)dlogits, (int)V, (int)T_logits, (int)Tl, ld_labels, 1.0f / temperature, alpha, ignore_index, ld_logits, ld_teacher);
   I2T_LAUNCHED();
   sum_rows_kernel<<<1, 256, 0, st>>>(loss_rows, loss_out, (int)(B * Tl));
   I2T_LAUNCHED();

@@ -194,6 +194,8 @@ def decoder_forward(W, spec, ids: torch.Tensor, encoder_output: torch.Tensor, cd
     # logits only for the text rows (the reference computes all rows, then slices [offset:], :132)
     text = hidden[:, n_prompt:, :].reshape(B * (T - n_prompt), C)
     text = text if cd == torch.float32 else text.to(cd)
+    # logits come out in the compute dtype (bf16 under the reference's autocast) with rows padded to a
+    # multiple of 8 elements; the (B, T, V) result is a strided view of that buffer
     logits = linear(text, W["decoder.lm_head.weight"], W.c("decoder.lm_head.weight"), None, None, ops.ACT_NONE,
-                    torch.float32).view(B, T - n_prompt, -1)
+                    cd, pad_rows=True).view(B, T - n_prompt, -1)
     return logits, hidden

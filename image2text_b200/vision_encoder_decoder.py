@@ -121,7 +121,7 @@ class VisionEncoderDecoder(nn.Module):
 
     # ------------------------------------------------------------------ forward -------------------------------
     def forward(self, images: Optional[torch.Tensor], ids: torch.Tensor, attn_msk: Optional[torch.Tensor] = None,
-                encoder_output: Optional[torch.Tensor] = None) -> VisionEncoderDecoderModelOutput:
+                encoder_output: Optional[torch.Tensor] = None, _padded_logits: bool = False) -> VisionEncoderDecoderModelOutput:
         from . import functional as Fn
         W = self.weights()
         if encoder_output is None:
@@ -129,6 +129,9 @@ class VisionEncoderDecoder(nn.Module):
                                                 train_trunk=self.training and self.spec["refine_base_model"])
         # attn_msk: accepted and ignored -- it has no effect in the reference either (D9)
         logits, hidden = Fn.decoder_forward(W, self.spec, ids, encoder_output, self.compute_dtype, training=self.training)
+        if not _padded_logits:
+            logits = logits.contiguous()      # the reference returns contiguous logits (vision_encoder_decoder.py:132);
+            # the trainer wrapper asks for the row-padded view instead so the LM-head backward runs in place
         return VisionEncoderDecoderModelOutput(encoder_output=encoder_output, logits=logits, hidden_state=hidden)
 
     @torch.no_grad()

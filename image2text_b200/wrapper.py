@@ -60,12 +60,12 @@ class ModelTrainerWrapper(nn.Module):
         self._ema(pm, ps, self.momentum)
 
     def forward(self, images, input_ids, attn_msk=None) -> Tuple[torch.Tensor, torch.Tensor]:
-        out = self.model(images=images, ids=input_ids, attn_msk=attn_msk)
+        out = self.model(images=images, ids=input_ids, attn_msk=attn_msk, _padded_logits=True)
         return out.logits, out.hidden_state
 
     @torch.no_grad()
     def forward_m(self, images, input_ids, attn_msk=None) -> Tuple[torch.Tensor, torch.Tensor]:
-        out = self.model_m(images=images, ids=input_ids, attn_msk=attn_msk)
+        out = self.model_m(images=images, ids=input_ids, attn_msk=attn_msk, _padded_logits=True)
         return out.logits, out.hidden_state
 
     def train_step(self, images, labels):

@@ -192,11 +192,13 @@ int i2t_gradnorm_scale(const void* g, void* out, double* acc, int64_t n, int dty
 /* Weighted (optionally distilled) LM loss, training/wrapper.py:80-96,120-151.  logits (B,T_logits,V); only the first
  * Tl positions of every sequence are used (labels (B,ld_labels) int64).  weights (B*Tl) and loss_rows (B*Tl) are fp32
  * scratch outputs; loss_out is a device fp32 scalar; dlogits (same shape/dtype as logits, optional) receives
- * dLoss/dlogits for the first Tl positions (other positions must be zeroed by the caller). */
+ * dLoss/dlogits for the first Tl positions (other positions must be zeroed by the caller).  ld_logits / ld_teacher: row
+ * pitch in elements (>= V) of logits+dlogits / teacher_logits -- the LM head writes rows padded to a multiple of 8 so that
+ * its backward GEMMs meet TMA's 16-byte pitch rule. */
 int i2t_lm_loss(const void* logits, const void* teacher_logits, const int64_t* labels, float* weights, float* loss_rows,
                 float* loss_out, void* dlogits, int64_t B, int64_t T_logits, int64_t Tl, int64_t V, int64_t ld_labels,
                 float temperature, float alpha, int inv_sqrt_position, int use_eos_weight, float eos_weight,
-                int64_t eos_id, int64_t ignore_index, int dtype, void* stream);
+                int64_t eos_id, int64_t ignore_index, int64_t ld_logits, int64_t ld_teacher, int dtype, void* stream);
 /* x *= *scale_ptr (device scalar) */
 int i2t_scale_inplace(void* x, const float* scale_ptr, int64_t n, int dtype, void* stream);
 

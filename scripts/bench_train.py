@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--moco", action="store_true")
+    ap.add_argument("--profile", action="store_true")
     ap.add_argument("--cpu-ref", action="store_true", help="time the CPU oracle's train step instead")
     args = ap.parse_args()
     from image2text_b200 import load_training_config
@@ -97,6 +98,12 @@ def main():
     for _ in range(args.warmup):
         one_step()
     torch.cuda.synchronize()
+    if args.profile and rank == 0:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            one_step()
+            torch.cuda.synchronize()
+        print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=70))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):

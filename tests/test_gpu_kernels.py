@@ -108,6 +108,26 @@ def test_gemm_bf16_tcgen05_and_fallback(M, N, K):
     lib().i2t_set_tensor_core_gemm(1)
 
 
+@pytest.mark.parametrize("M,N,K", [(2048, 768, 3072), (1984, 768, 768), (768, 3072, 2048), (200, 136, 264), (128, 64, 72)])
+@pytest.mark.parametrize("layout", ["nn", "tn", "tt"])
+def test_gemm_bf16_tcgen05_mn_major_layouts(M, N, K, layout):
+    """dgrad (A K-major, B MN-major), wgrad (both MN-major) and the A-transposed case on the tensor cores:
+    MN-major UMMA descriptors + TMA boxes over the K-row-major storage."""
+    a = rnd(M, K, seed=50).to(torch.bfloat16)
+    b = rnd(N, K, seed=51, scale=0.05).to(torch.bfloat16)
+    ref = a.double() @ b.double().t()
+    A = (a if layout[0] == "n" else a.t().contiguous()).to(DEV)
+    Bm = (b if layout[1] == "t" else b.t().contiguous()).to(DEV)
+    for tc in (1, 0):
+        lib().i2t_set_tensor_core_gemm(tc)
+        out = ops.gemm(A, Bm, a_kmajor=layout[0] == "n", b_kmajor=layout[1] == "t")
+        assert relerr(out, ref) < 1e-5, f"tc={tc}"
+    lib().i2t_set_tensor_core_gemm(1)
+    acc = torch.ones(M, N, device=DEV)
+    ops.gemm(A, Bm, out=acc, a_kmajor=layout[0] == "n", b_kmajor=layout[1] == "t", accumulate=True)
+    assert relerr(acc, ref + 1.0) < 1e-5
+
+
 def test_colsum():
     x = rnd(1000, 333, seed=13)
     out = torch.zeros(333, device=DEV)
