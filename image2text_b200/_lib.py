@@ -43,6 +43,8 @@ SIGNATURES = {
     "i2t_gradnorm_scale": (c_int, [P, P, P, L, I, P]),
     "i2t_lm_loss": (c_int, [P, P, P, P, P, P, P, L, L, L, L, L, F, F, I, I, F, L, L, L, L, I, P]),
     "i2t_scale_inplace": (c_int, [P, P, L, I, P]),
+    "i2t_l2norm_fwd": (c_int, [P, P, L, L, F, P]),
+    "i2t_l2norm_bwd": (c_int, [P, P, P, L, L, F, P]),
     "i2t_adamw_multi": (c_int, [P, P, P, P, L, D, D, D, D, D, L, D, P]),
     "i2t_snradam_multi": (c_int, [P, P, P, P, L, D, D, D, D, D, L, D, P]),
     "i2t_ema_multi": (c_int, [P, P, P, P, L, D, P]),

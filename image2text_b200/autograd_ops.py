@@ -232,3 +232,78 @@ class LmLossFn(torch.autograd.Function):
         scale = gloss.reshape(1).to(torch.float32).contiguous()
         call("i2t_scale_inplace", ptr(dbuf), ptr(scale), dbuf.numel(), dt(dbuf), stream())
         return dbuf[..., :ctx.V], None, None, None, None, None, None, None, None
+
+
+class L2NormFn(torch.autograd.Function):
+    """F.normalize(x, p=2, dim=-1): reference models/encoder.py:118-119."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous().float()
+        cols = x.shape[-1]
+        y = torch.empty_like(x)
+        call("i2t_l2norm_fwd", ptr(x), ptr(y), x.numel() // cols, cols, 1e-12, stream())
+        if any(ctx.needs_input_grad):
+            ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dy = dy.contiguous().float()
+        cols = x.shape[-1]
+        dx = torch.empty_like(x)
+        call("i2t_l2norm_bwd", ptr(x), ptr(dy), ptr(dx), x.numel() // cols, cols, 1e-12, stream())
+        return dx
+
+
+class Conv1DFn(torch.autograd.Function):
+    """HF GPT-2 `Conv1D`: y = act(x W + b) + residual with W stored (in, out) -- transformers/pytorch_utils.py Conv1D as
+    used by reference models/decoder.py:285-361.  The weight keeps its checkpoint layout; it is the MN-major B operand of
+    the forward GEMM and the K-major B operand of the data-gradient GEMM."""
+
+    @staticmethod
+    def forward(ctx, x2d, w, w_c, bias, residual, act, out_dtype):
+        need = any(ctx.needs_input_grad)
+        if need and act != ops.ACT_NONE:
+            z = ops.gemm(x2d, w_c, bias=bias, out_dtype=x2d.dtype, b_kmajor=False)
+            y = torch.empty(z.shape, device=z.device, dtype=out_dtype)
+            call("i2t_act_fwd", ptr(z), ptr(y), z.numel(), act, dt(z), dt(y), stream())
+            assert residual is None
+        else:
+            z = None
+            y = ops.gemm(x2d, w_c, bias=bias, residual=residual, act=act, out_dtype=out_dtype, b_kmajor=False)
+        if need:
+            ctx.save_for_backward(x2d, w_c, z)
+            ctx.act = act
+            ctx.has_bias = bias is not None
+            ctx.has_res = residual is not None
+            ctx.res_dtype = residual.dtype if residual is not None else None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2d, w_c, z = ctx.saved_tensors
+        dy = dy.contiguous()
+        dres = dy.to(ctx.res_dtype) if (ctx.has_res and ctx.needs_input_grad[4]) else None
+        g = dy if dy.dtype == x2d.dtype else dy.to(x2d.dtype)
+        if z is not None:
+            dz = torch.empty_like(z)
+            call("i2t_act_bwd", ptr(z), ptr(g), ptr(dz), z.numel(), ctx.act, dt(z), dt(g), stream())
+            g = dz
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.gemm(g, w_c, out_dtype=x2d.dtype, a_kmajor=True, b_kmajor=True)          # dX = dY W^T, W (K,N) is [n'][k']
+        if ctx.needs_input_grad[1]:
+            M, N = g.shape
+            K = x2d.shape[1]
+            dw = torch.empty((K, N), device=g.device, dtype=torch.float32)                    # dW (K,N) = X^T dY
+            ops.gemm(x2d, g, out=dw, a_kmajor=False, b_kmajor=False, M=K, N=N, K=M, lda=x2d.stride(0), ldb=g.stride(0), ldc=N)
+        if ctx.has_bias and ctx.needs_input_grad[3]:
+            db = torch.zeros(g.shape[1], device=g.device, dtype=torch.float32)
+            ops.colsum_(g, db)
+        return dx, dw, None, db, dres, None, None
+
+
+def conv1d(x2d, w, w_c, bias=None, residual=None, act=ops.ACT_NONE, out_dtype=torch.float32):
+    return Conv1DFn.apply(x2d, w, w_c, bias, residual, act, out_dtype)

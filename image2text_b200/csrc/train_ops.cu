@@ -315,3 +315,55 @@ extern "C" int i2t_scale_inplace(void* x, const float* scale_ptr, int64_t n, int
   I2T_LAUNCHED();
   return I2T_OK;
 }
+
+// ---- row-wise L2 normalisation: F.normalize(x, p=2, dim=-1) at reference models/encoder.py:118-119 ------------------
+namespace i2t {
+__global__ void __launch_bounds__(128) l2norm_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t rows,
+                                                         int cols, float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * 4 + warp;
+  if (r >= rows) return;
+  const float* xr = x + r * cols;
+  float s = 0.f;
+  for (int c = lane; c < cols; c += 32) s = fmaf(xr[c], xr[c], s);
+  const float n = fmaxf(sqrtf(warp_sum(s)), eps);
+  for (int c = lane; c < cols; c += 32) y[r * cols + c] = xr[c] / n;
+}
+
+// y = x / n, n = max(||x||, eps):  dx = dy / n - x * (x . dy) / n^3   (the second term vanishes when the clamp is active)
+__global__ void __launch_bounds__(128) l2norm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                         float* __restrict__ dx, int64_t rows, int cols, float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * 4 + warp;
+  if (r >= rows) return;
+  const float* xr = x + r * cols;
+  const float* gr = dy + r * cols;
+  float s = 0.f, d = 0.f;
+  for (int c = lane; c < cols; c += 32) {
+    s = fmaf(xr[c], xr[c], s);
+    d = fmaf(xr[c], gr[c], d);
+  }
+  s = warp_sum(s);
+  d = warp_sum(d);
+  const float nrm = sqrtf(s);
+  const float n = fmaxf(nrm, eps);
+  const float k = nrm >= eps ? d / (n * n * n) : 0.f;
+  for (int c = lane; c < cols; c += 32) dx[r * cols + c] = gr[c] / n - xr[c] * k;
+}
+}  // namespace i2t
+
+extern "C" int i2t_l2norm_fwd(const float* x, float* y, int64_t rows, int64_t cols, float eps, void* stream) {
+  I2T_REQUIRE(x && y && rows >= 0 && cols > 0, "l2norm_fwd: bad arguments");
+  if (rows == 0) return I2T_OK;
+  i2t::l2norm_fwd_kernel<<<(unsigned)i2t::ceil_div(rows, 4), 128, 0, (cudaStream_t)stream>>>(x, y, rows, (int)cols, eps);
+  I2T_LAUNCHED();
+  return I2T_OK;
+}
+
+extern "C" int i2t_l2norm_bwd(const float* x, const float* dy, float* dx, int64_t rows, int64_t cols, float eps, void* stream) {
+  I2T_REQUIRE(x && dy && dx && rows >= 0 && cols > 0, "l2norm_bwd: bad arguments");
+  if (rows == 0) return I2T_OK;
+  i2t::l2norm_bwd_kernel<<<(unsigned)i2t::ceil_div(rows, 4), 128, 0, (cudaStream_t)stream>>>(x, dy, dx, rows, (int)cols, eps);
+  I2T_LAUNCHED();
+  return I2T_OK;
+}

@@ -121,6 +121,29 @@ class _LshTailFn(torch.autograd.Function):
         return (None, None, None, None, None, None, *grads)
 
 
+def posbias_tail(W, spec, feat: torch.Tensor, cd: torch.dtype, pre: str) -> torch.Tensor:
+    """F.normalize -> one MLP (768 -> gate sizes -> out, GELU tanh) per summary slot + residual -> F.normalize:
+    reference models/encoder.py:118-119 + models/layers.py:617-638 (AdvancedPositionalBiasMLP) + :222-255 (MLP)."""
+    from .autograd_ops import L2NormFn
+    x = L2NormFn.apply(feat)                                   # (B, 768) fp32
+    xc = x if cd == torch.float32 else x.to(cd)
+    outs = []
+    n_lin = len(spec["gate_sizes"]) + 1
+    for s in range(spec["n_cls"]):
+        kp = f"{pre}{s}."
+        if (kp + "residual_connector.weight") in W:
+            res = _lin(W, kp + "residual_connector.weight", kp + "residual_connector.bias", xc)
+        else:
+            res = x
+        h = xc
+        for j in range(n_lin):
+            last = j == n_lin - 1
+            h = _lin(W, kp + f"model.{2 * j}.weight", kp + f"model.{2 * j}.bias", h, residual=res if last else None,
+                     act=ops.ACT_NONE if last else ops.ACT_GELU_TANH, out_dtype=torch.float32 if last else cd)
+        outs.append(h)
+    return L2NormFn.apply(torch.stack(outs, dim=1))
+
+
 def encoder_forward(W, spec, images: torch.Tensor, cd: torch.dtype, train_trunk: bool = False) -> torch.Tensor:
     bridged = "encoder.1.weight" in W
     pre = "encoder.0." if bridged else "encoder."
@@ -136,7 +159,7 @@ def encoder_forward(W, spec, images: torch.Tensor, cd: torch.dtype, train_trunk:
         out = _LshTailFn.apply(feat, tables, spec["lsh_num_bins"], spec["n_cls"], spec["lsh_num_proj"],
                                spec["n_embd_out_vit"], *embs)
     else:
-        raise NotImplementedError("per-slot MLP tail (reference models/layers.py:617-638) is not built yet")
+        out = posbias_tail(W, spec, feat, cd, pre + "proj.models.")
     if bridged:
         B, n, E = out.shape
         out = linear(out.view(B * n, E).to(cd), W["encoder.1.weight"], W.c("encoder.1.weight"), None, None, ops.ACT_NONE,
@@ -147,9 +170,54 @@ def encoder_forward(W, spec, images: torch.Tensor, cd: torch.dtype, train_trunk:
 # ------------------------------------------------------------------------------------------------------------
 # decoder: reference models/vision_encoder_decoder.py:84-134 + models/decoder.py:214-256 + models/layers.py:565-614
 # ------------------------------------------------------------------------------------------------------------
+def hf_gpt2_forward(W, spec, ids: torch.Tensor, encoder_output: torch.Tensor, cd: torch.dtype):
+    """transformers GPT2LMHeadModel with add_cross_attention=True exactly as the reference drives it
+    (models/decoder.py:335-361: attention_mask=None -> plain causal over prompt + text; every block has
+    ln_cross_attn + crossattention {q_attn, c_attn -> [k|v], c_proj}); Conv1D weights stay (in, out)."""
+    from .autograd_ops import conv1d
+    C, H = spec["n_embd"], spec["n_head"]
+    B, S = ids.shape
+    n_prompt = spec["n_cls"] if spec["use_soft_prompting"] else 0
+    T = min(n_prompt + S, 1024)
+    dp = "decoder.backbone.transformer."
+    prompt = encoder_output.contiguous().float() if n_prompt else None
+    x = EmbedFn.apply(ids.contiguous(), prompt, W[dp + "wte.weight"], W[dp + "wpe.weight"], T, n_prompt)
+    cross = spec["use_cross_attn"]
+    S_enc = encoder_output.shape[1]
+    enc_c = None
+    if cross:
+        enc_c = encoder_output.reshape(B * S_enc, C)
+        enc_c = enc_c if enc_c.dtype == cd else enc_c.to(cd)
+
+    def c1d(wkey, x2d, residual=None, act=ops.ACT_NONE, out_dtype=torch.float32):
+        return conv1d(x2d, W[wkey + ".weight"], W.c(wkey + ".weight"), W[wkey + ".bias"], residual, act, out_dtype)
+
+    for i in range(spec["n_layer"]):
+        lp = f"{dp}h.{i}."
+        y = _ln(W, lp + "ln_1.weight", lp + "ln_1.bias", x, 1e-5, cd)
+        qkv = c1d(lp + "attn.c_attn", y.view(B * T, C), out_dtype=cd)
+        a = AttnFn.apply(qkv, B, T, H, ops.MASK_CAUSAL, 0)
+        x = c1d(lp + "attn.c_proj", a, residual=x.view(B * T, C)).view(B, T, C)
+        if cross:
+            y = _ln(W, lp + "ln_cross_attn.weight", lp + "ln_cross_attn.bias", x, 1e-5, cd)
+            q = c1d(lp + "crossattention.q_attn", y.view(B * T, C), out_dtype=cd)
+            kv = c1d(lp + "crossattention.c_attn", enc_c, out_dtype=cd)
+            a = XAttnFn.apply(q, kv, B, T, S_enc, H)
+            x = c1d(lp + "crossattention.c_proj", a, residual=x.view(B * T, C)).view(B, T, C)
+        y = _ln(W, lp + "ln_2.weight", lp + "ln_2.bias", x, 1e-5, cd)
+        h = c1d(lp + "mlp.c_fc", y.view(B * T, C), act=ops.ACT_GELU_TANH, out_dtype=cd)
+        x = c1d(lp + "mlp.c_proj", h, residual=x.view(B * T, C)).view(B, T, C)
+    hidden = _ln(W, dp + "ln_f.weight", dp + "ln_f.bias", x, 1e-5, torch.float32)
+    text = hidden[:, n_prompt:, :].reshape(B * (T - n_prompt), C)
+    text = text if cd == torch.float32 else text.to(cd)
+    logits = linear(text, W["decoder.backbone.lm_head.weight"], W.c("decoder.backbone.lm_head.weight"), None, None,
+                    ops.ACT_NONE, cd, pad_rows=True).view(B, T - n_prompt, -1)
+    return logits, hidden
+
+
 def decoder_forward(W, spec, ids: torch.Tensor, encoder_output: torch.Tensor, cd: torch.dtype, training: bool = False):
-    if spec["decoder"] != "transformer":
-        raise NotImplementedError("HF GPT-2 layout decoder (reference models/decoder.py:285-377) is not built yet")
+    if spec["decoder"] == "hf_gpt2":
+        return hf_gpt2_forward(W, spec, ids, encoder_output, cd)
     C, H, blk = spec["n_embd"], spec["n_head"], spec["block_size"]
     B, S = ids.shape
     n_prompt = spec["n_cls"] if spec["use_soft_prompting"] else 0

@@ -199,6 +199,9 @@ int i2t_lm_loss(const void* logits, const void* teacher_logits, const int64_t* l
                 float* loss_out, void* dlogits, int64_t B, int64_t T_logits, int64_t Tl, int64_t V, int64_t ld_labels,
                 float temperature, float alpha, int inv_sqrt_position, int use_eos_weight, float eos_weight,
                 int64_t eos_id, int64_t ignore_index, int64_t ld_logits, int64_t ld_teacher, int dtype, void* stream);
+/* y = x / max(||x||_2, eps) per row and its backward: F.normalize(p=2, dim=-1) at models/encoder.py:118-119 */
+int i2t_l2norm_fwd(const float* x, float* y, int64_t rows, int64_t cols, float eps, void* stream);
+int i2t_l2norm_bwd(const float* x, const float* dy, float* dx, int64_t rows, int64_t cols, float eps, void* stream);
 /* x *= *scale_ptr (device scalar) */
 int i2t_scale_inplace(void* x, const float* scale_ptr, int64_t n, int dtype, void* stream);
 

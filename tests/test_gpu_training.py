@@ -115,3 +115,38 @@ def test_fused_optimizer_classes(cls, ref):
             assert rel_err(ps[i].detach().cpu(), cpu[i]) < 3e-6, (step, i)
     sd = opt.state_dict()
     assert len(sd["state"]) == 4 and "exp_avg" in sd["state"][0]
+
+
+def test_gpt2_hf_layout_forward_and_backward_match(golden):
+    """BASELINE configs[2]/[3] model: ViT-B/16 (trainable) + per-slot MLP tail + HF-layout GPT-2 with cross attention.
+    Forward against the reference-made fixture, gradients against the CPU oracle's autograd on the same weights."""
+    from image2text_b200 import VisionEncoderDecoder
+    g = golden("gpt2_fwd")
+    tc, spec, sd = spec_and_weights("gpt2")
+    m = VisionEncoderDecoder(tc.model, device="cuda")
+    m.load_state_dict(sd)
+    images = synth_images(2, 224, seed=31)
+    labels = T(g["labels"])
+    ids = torch.where(labels != -100, labels, torch.full_like(labels, 50256))
+    m.eval()
+    with torch.no_grad():
+        out = m(images=images.cuda(), ids=ids.cuda())
+    assert rel_err(out.encoder_output.cpu(), T(g["enc"])) < 1e-4
+    assert rel_err(out.hidden_state.cpu(), T(g["hidden"])) < 1e-4
+    assert rel_err(out.logits.cpu()[..., :256], T(g["logits_head"])) < 1e-4
+    assert np.array_equal(out.logits.argmax(-1).cpu().numpy(), g["logits_argmax"])
+    # gradients of a scalar loss w.r.t. a few tensors of every kind (Conv1D, cross attention, tail MLP, ViT trunk)
+    keys = ["decoder.backbone.transformer.h.0.attn.c_attn.weight", "decoder.backbone.transformer.h.3.crossattention.q_attn.weight",
+            "decoder.backbone.transformer.h.11.mlp.c_proj.bias", "decoder.backbone.transformer.h.5.crossattention.c_attn.weight",
+            "encoder.proj.models.3.model.0.weight", "encoder.model.encoder.layers.encoder_layer_11.mlp.3.weight",
+            "decoder.backbone.transformer.wpe.weight", "encoder.model.conv_proj.bias"]
+    m.train()
+    out = m(images=images.cuda(), ids=ids.cuda())
+    probe = torch.randn(out.logits.shape, generator=torch.Generator().manual_seed(5)).cuda()
+    (out.logits.float() * probe).sum().backward()
+    named = dict(m.named_parameters())
+    sdo = {k: (v.clone().requires_grad_(True) if k in keys else v) for k, v in sd.items()}
+    _, logits_o, _ = O.ved_forward(sdo, spec, images, ids)
+    (logits_o * probe.cpu()).sum().backward()
+    for k in keys:
+        assert rel_err(named[k].grad.cpu(), sdo[k].grad) < 5e-4, k
