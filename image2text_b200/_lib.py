@@ -18,6 +18,7 @@ SIGNATURES = {
     "i2t_launch_count": (c_int64, []),
     "i2t_set_tensor_core_gemm": (None, [I]),
     "i2t_set_pdl": (None, [I]),
+    "i2t_set_tensor_core_attention": (None, [I]),
     "i2t_layernorm_fwd": (c_int, [P, P, P, P, P, P, L, L, L, F, I, I, P]),
     "i2t_layernorm_bwd": (c_int, [P, P, P, P, P, P, P, P, L, L, I, I, I, P]),
     "i2t_gemm": (c_int, [P, P, P, P, P, L, L, L, L, L, L, I, I, I, I, I, I, I, P]),
@@ -37,6 +38,8 @@ SIGNATURES = {
     "i2t_dec_attn": (c_int, [P, L, P, P, L, L, P, L, P, L, L, L, L, I, P]),
     "i2t_sample": (c_int, [P, L, L, L, P, L, P, I, L, F, L, P, L, U64, P, P, P, I, P]),
     "i2t_decode_mega": (c_int, [P, P, P, L, L, L, L, L, L, L, I, P, L, P, P, P, P, P, P, F, L, P, L, P, P, L, P, P]),
+    "i2t_decode_mega2_max_keys": (c_int, []),
+    "i2t_decode_mega2": (c_int, [P, P, P, L, P, L, L, L, L, L, L, L, L, P, L, P, P, P, P, P, P, P, F, L, P, L, P, P, L, L, P, P]),
     "i2t_act_fwd": (c_int, [P, P, L, I, I, I, P]),
     "i2t_act_bwd": (c_int, [P, P, P, L, I, I, I, P]),
     "i2t_embed_bwd": (c_int, [P, P, P, L, L, L, L, L, P]),
@@ -72,6 +75,8 @@ def lib() -> ctypes.CDLL:
             handle.i2t_set_pdl(int(os.environ["I2T_PDL"]))
         if os.environ.get("I2T_TC_GEMM") is not None:
             handle.i2t_set_tensor_core_gemm(int(os.environ["I2T_TC_GEMM"]))
+        if os.environ.get("I2T_TC_ATTN") is not None:
+            handle.i2t_set_tensor_core_attention(int(os.environ["I2T_TC_ATTN"]))
         _lib = handle
     return _lib
 

@@ -423,9 +423,17 @@ static int launch_attn_fwd(const void* q, const void* k, const void* v, void* ou
   return I2T_OK;
 }
 
+// attention_tc.cu: bf16 tensor-core forward (returns 1 when it handled the call, 0 when the shape is not eligible)
+int attn_fwd_tc(const void* q, const void* k, const void* v, void* out, float* lse, int64_t B, int64_t H, int64_t Tq, int64_t Tk,
+                int64_t head_dim, int64_t q_bs, int64_t q_rs, int64_t kv_bs, int64_t kv_rs, int mode, int64_t n_prompt,
+                cudaStream_t st);
+static std::atomic<int> g_attn_tc{1};
+
 }  // namespace i2t
 
 using namespace i2t;
+
+extern "C" void i2t_set_tensor_core_attention(int enabled) { g_attn_tc.store(enabled ? 1 : 0); }
 
 extern "C" int i2t_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int64_t B, int64_t H,
                             int64_t Tq, int64_t Tk, int64_t head_dim, int64_t q_batch_stride, int64_t q_row_stride,
@@ -439,6 +447,11 @@ extern "C" int i2t_attn_fwd(const void* q, const void* k, const void* v, void* o
               "attn_fwd: strides must be multiples of 4 elements");
   I2T_REQUIRE(valid_dtype(in_dtype) && valid_dtype(out_dtype), "attn_fwd: bad dtype");
   cudaStream_t st = (cudaStream_t)stream;
+  if (in_dtype == I2T_BF16 && out_dtype == I2T_BF16 && g_attn_tc.load() == 1) {
+    const int r = attn_fwd_tc(q, k, v, out, lse, B, H, Tq, Tk, head_dim, q_batch_stride, q_row_stride, kv_batch_stride,
+                              kv_row_stride, mask_mode, n_prompt, st);
+    if (r != 0) return r < 0 ? r : I2T_OK;
+  }
 #define I2T_ATT(TI, TO, HSV) \
   return launch_attn_fwd<TI, TO, HSV>(q, k, v, out, lse, B, H, Tq, Tk, q_batch_stride, q_row_stride, kv_batch_stride, kv_row_stride, mask_mode, n_prompt, st)
   if (head_dim == 64) {

@@ -6,7 +6,9 @@ What this engine does per new token: every decoder weight is touched exactly onc
 K/V rows are appended in place, the sampler runs on the device and advances the position counter -- one CUDA-graph
 replay per token, no host round trip.  Two executions of the same arithmetic:
 
-  mode "mega"    (default, B <= 8): ONE cooperative launch per step (csrc/decode_mega.cu);
+  mode "mega2"   (default for bf16, B <= 8): ONE cooperative launch per generate() call -- the token loop, every layer,
+                 the LM head with the n-gram ban + arg-max fused (greedy) or the sampler (csrc/decode_mega2.cu);
+  mode "mega"    : ONE cooperative launch per step (csrc/decode_mega.cu), fp32 or bf16;
   mode "kernels" : ~81 launches per step (csrc/decode.cu + sampler.cu), used for larger batches / wider models and as
                    the cross-check of the megakernel.
 
@@ -41,15 +43,18 @@ class DecodeEngine:
         self.n_prompt = spec["n_cls"] if spec["use_soft_prompting"] else 0
         self.Tmax = spec["block_size"] - self.n_prompt
         # measured on B200 (profiles/r01_*): the megakernel wins in bf16, the separate kernels win in fp32
-        mode = mode or os.environ.get("I2T_DECODE", "mega" if self.cd == torch.bfloat16 else "kernels")
+        mode = mode or os.environ.get("I2T_DECODE", "mega2" if self.cd == torch.bfloat16 else "kernels")
         if batch > 8 or max(C, self.F) > 3072 or C > 1024:
             mode = "kernels"
+        if mode == "mega2" and (self.cd != torch.bfloat16 or C > 768 or C % 32 or self.F % 32 or self.Tmax > 256):
+            mode = "mega" if self.cd == torch.bfloat16 else "kernels"
         self.mode = mode
         self.ids = torch.zeros((batch, self.Tmax + 1), device=dev, dtype=torch.int64)
         self.pos = torch.zeros(1, device=dev, dtype=torch.int32)
         self.ticket = torch.zeros(1, device=dev, dtype=torch.int32)
         self.bar = torch.zeros(1, device=dev, dtype=torch.int32)
         self.err = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.keys = torch.zeros(24, device=dev, dtype=torch.int64)
         self.kcache = torch.zeros((L, batch, self.Tmax, C), device=dev, dtype=self.cd)
         self.vcache = torch.zeros((L, batch, self.Tmax, C), device=dev, dtype=self.cd)
         self.cross_layers = [d for d in range(L) if spec["use_cross_attn"] and layer_has_cross_attn(spec, d)
@@ -85,7 +90,7 @@ class DecodeEngine:
             return 0 if t is None else t.data_ptr()
 
         def add_lin(wkey, bkey, ln, inp, out, residual, N, K, act=0, mode=0, kc=None, vc=None, in_mode=0, rows=None, ldo=None,
-                    wpe=None, both=True):
+                    wpe=None, both=True, flags=0):
             w = W.c(wkey)
             b = W.get(bkey) if bkey else None
             if rows is not None:
@@ -95,7 +100,7 @@ class DecodeEngine:
             g = W[ln + ".weight"] if ln else None
             be = W.get(ln + ".bias") if ln else None
             lin.append([P(w), P(b), P(g), P(be), P(inp), P(out), P(residual), N, K, act, mode, P(kc), P(vc), in_mode, P(wpe),
-                        ldo if ldo is not None else N, self.Tmax * C, 0, 0, 0])
+                        ldo if ldo is not None else N, self.Tmax * C, flags, 0, 0])
             sample.append([0, len(lin) - 1, 0, 0])
             if both:
                 prefill.append([0, len(lin) - 1, 0, 0])
@@ -125,7 +130,7 @@ class DecodeEngine:
                 xi += 1
             add_lin(lp + "mlp.c_fc.weight", lp + "mlp.c_fc.bias", lp + "ln_2", self.x, self.h, None, F, C, act=ops.ACT_GELU_TANH)
             add_lin(lp + "mlp.c_proj.weight", lp + "mlp.c_proj.bias", None, self.h, self.x, self.x, C, F)
-        add_lin("decoder.lm_head.weight", None, dp + "ln_f", self.x, self.logits, None, V, C, both=False)
+        add_lin("decoder.lm_head.weight", None, dp + "ln_f", self.x, self.logits, None, V, C, both=False, flags=1)
         sample.append([2, 0, 0, 0])
         prefill.append([3, 0, 0, 0])
         dev = self.dev
@@ -146,6 +151,19 @@ class DecodeEngine:
              ptr(self.y), ptr(self.logits), ptr(self.bar), ptr(self.err), temperature, int(top_k) if top_k is not None else 0,
              ptr(self.ngrams), self.n_ngrams, ptr(self.seed_dev), ptr(self.ticket), max(spec["n_embd"], self.F),
              ptr(self.trace) if sample else None, stream())
+
+    def _mega2_run(self, n_prefill: int, n_sample: int, temperature: float, top_k: Optional[int]):
+        """n_prefill prompt steps + n_sample sampled steps in ONE launch (decode_mega2.cu)."""
+        if self._mega is None:
+            self._mega = self._mega_tables()
+        T = self._mega
+        spec = self.spec
+        call("i2t_decode_mega2", ptr(T["lin"]), ptr(T["att"]), ptr(T["sample"]), T["sample"].shape[0], ptr(T["prefill"]),
+             T["prefill"].shape[0], n_prefill, n_sample, self.B, spec["n_embd"], spec["n_head"], spec["vocab_size"],
+             self.n_prompt, ptr(self.ids), self.ids.shape[1], ptr(self.pos), ptr(self.q), ptr(self.y), ptr(self.logits),
+             ptr(self.bar), ptr(self.err), ptr(self.keys), temperature, int(top_k) if top_k is not None else 0,
+             ptr(self.ngrams), self.n_ngrams, ptr(self.seed_dev), ptr(self.ticket), max(spec["n_embd"], self.F),
+             max(self.Tmax, self.S), ptr(self.trace), stream())
 
     # ------------------------------------------------------------------ one step, separate kernels -------------
     def _kernel_step(self, sample: bool, temperature: float, top_k: Optional[int]):
@@ -230,7 +248,7 @@ class DecodeEngine:
         assert prompt_ids.shape[0] == B and P + max_new_tokens <= self.Tmax + 1
         enc = Fn.encoder_forward(m.weights(), self.spec, images, self.cd, train_trunk=False)
         self._prefill_cross(enc)
-        if self.mode == "mega":
+        if self.mode in ("mega", "mega2"):
             W = m.weights()
             sig = self._mega["sig"] if self._mega is not None else None
             if sig is not None and sig[0] != W.c("decoder.transformer.h.0.attn.c_attn.weight").data_ptr():
@@ -239,6 +257,16 @@ class DecodeEngine:
         self.pos.zero_()
         self.ticket.zero_()
         self.seed_dev.fill_(int(seed) & 0x7FFFFFFFFFFFFFFF)
+        if self.mode == "mega2":
+            n0 = launch_count()
+            self._mega2_run(P - 1, max_new_tokens, temperature, top_k)
+            self.launches_per_step = launch_count() - n0
+            self.replays_last = 0
+            out = self.ids[:, :P + max_new_tokens].clone()
+            if int(self.err.item()) != 0:
+                raise I2TError(f"decode megakernel reported an internal error (code {int(self.err.item())}: 2 = barrier "
+                               f"timeout, 5 = more than 256 banned tokens for one sequence)")
+            return out
         for _ in range(P - 1):
             self._step(False, temperature, top_k)
         key = (float(temperature), top_k)

@@ -29,14 +29,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--moco", action="store_true")
     ap.add_argument("--profile", action="store_true")
+    ap.add_argument("--config", default="nano", choices=["nano", "gpt2"])
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU micro-batch (0 = the YAML value)")
     ap.add_argument("--cpu-ref", action="store_true", help="time the CPU oracle's train step instead")
     args = ap.parse_args()
     from image2text_b200 import load_training_config
     from image2text_b200.config_schema import TrainerWrapperConfig
     from image2text_b200.model_spec import spec_from_config, synth_state_dict
     from image2text_b200.synthetic import synth_images, synth_labels
-    tc = load_training_config(os.path.join(ROOT, "configs", "nano.yaml"))
-    bs, accum = tc.batch_size, tc.gradient_accumulation_steps
+    tc = load_training_config(os.path.join(ROOT, "configs", args.config + ".yaml"))
+    bs, accum = (args.batch or tc.batch_size), tc.gradient_accumulation_steps
     if args.cpu_ref:
         from oracle import i2t_oracle as O
         spec = spec_from_config(tc.model)
@@ -116,9 +118,9 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t)
     imgs = bs * accum * args.steps * world
-    gflop_img = 243.4 + (104.5 if args.moco else 0.0)
+    gflop_img = (243.4 + (104.5 if args.moco else 0.0)) if args.config == "nano" else (340.0 + (113.4 if args.moco else 0.0))
     if rank == 0:
-        print(json.dumps({"metric": "train img/s (nano.yaml, B=8/GPU, accum 4, AdamW 2 groups, dropout off)",
+        print(json.dumps({"metric": f"train img/s ({args.config}.yaml, B={bs}/GPU, accum {accum}, AdamW, dropout off)",
                           "value": round(imgs / (ms / 1e3), 2), "n_gpus": world, "dtype": args.dtype, "moco": args.moco,
                           "ms_per_step": round(ms / args.steps, 2), "model_tflops": round(imgs * gflop_img / (ms / 1e3) / 1e3, 2),
                           "loss": float(loss), "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2)}))

@@ -1,4 +1,4 @@
-"""Per-stage timing of the decode megakernel (clock64 stamps of CTA 0): python scripts/trace_mega.py [fp32|bf16]"""
+"""Per-stage timing of the decode megakernel (clock64 stamps of CTA 0): python scripts/trace_mega.py [fp32|bf16] [mega|mega2]"""
 import os
 import sys
 
@@ -16,14 +16,18 @@ tc = load_training_config(os.path.join(ROOT, "configs", "nano.yaml"))
 m = VisionEncoderDecoder(tc.model, device="cuda", compute_dtype=dtype)
 m.load_state_dict(synth_state_dict(m.spec, seed=0))
 m.eval()
-eng = DecodeEngine(m, 8, mode="mega")
+mode = sys.argv[2] if len(sys.argv) > 2 else ("mega2" if dtype == torch.bfloat16 else "mega")
+eng = DecodeEngine(m, 8, mode=mode)
 images = synth_images(8, 224, seed=1234).cuda()
 prompt = torch.full((8, 1), 50256, dtype=torch.long, device="cuda")
 eng.generate(images, prompt, 8, 1.0, 1, seed=0)
 n_sched = eng._mega["sample"].shape[0]
 eng.trace = torch.zeros(n_sched * 4, dtype=torch.int64, device="cuda")
-for _ in range(3):
-    eng._mega_step(True, 1.0, 1)
+if mode == "mega2":
+    eng.generate(images, prompt, 32, 1.0, 1, seed=0)      # stamps of the LAST step (cache length 32)
+else:
+    for _ in range(3):
+        eng._mega_step(True, 1.0, 1)
 torch.cuda.synchronize()
 tr = eng.trace.view(n_sched, 4).cpu()
 sched = eng._mega["sample"].cpu()
