@@ -39,7 +39,7 @@ SIGNATURES = {
     "i2t_sample": (c_int, [P, L, L, L, P, L, P, I, L, F, L, P, L, U64, P, P, P, I, P]),
     "i2t_decode_mega": (c_int, [P, P, P, L, L, L, L, L, L, L, I, P, L, P, P, P, P, P, P, F, L, P, L, P, P, L, P, P]),
     "i2t_decode_mega2_max_keys": (c_int, []),
-    "i2t_decode_mega2": (c_int, [P, P, P, L, P, L, L, L, L, L, L, L, L, P, L, P, P, P, P, P, P, P, F, L, P, L, P, P, L, L, P, P]),
+    "i2t_decode_mega2": (c_int, [P, P, P, L, P, L, L, L, L, L, L, L, L, L, L, P, L, P, P, P, P, P, P, P, F, L, P, L, P, L, L, P, P]),
     "i2t_act_fwd": (c_int, [P, P, L, I, I, I, P]),
     "i2t_act_bwd": (c_int, [P, P, P, L, I, I, I, P]),
     "i2t_embed_bwd": (c_int, [P, P, P, L, L, L, L, L, P]),

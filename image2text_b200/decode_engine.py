@@ -46,7 +46,8 @@ class DecodeEngine:
         mode = mode or os.environ.get("I2T_DECODE", "mega2" if self.cd == torch.bfloat16 else "kernels")
         if batch > 8 or max(C, self.F) > 3072 or C > 1024:
             mode = "kernels"
-        if mode == "mega2" and (self.cd != torch.bfloat16 or C > 768 or C % 32 or self.F % 32 or self.Tmax > 256):
+        if mode == "mega2" and (self.cd != torch.bfloat16 or C > 768 or C % 64 or self.F % 64 or self.F > 3072
+                                or max(self.Tmax, spec["n_cls"]) > 256 or batch * spec["n_head"] > 132):
             mode = "mega" if self.cd == torch.bfloat16 else "kernels"
         self.mode = mode
         self.ids = torch.zeros((batch, self.Tmax + 1), device=dev, dtype=torch.int64)
@@ -159,11 +160,11 @@ class DecodeEngine:
         T = self._mega
         spec = self.spec
         call("i2t_decode_mega2", ptr(T["lin"]), ptr(T["att"]), ptr(T["sample"]), T["sample"].shape[0], ptr(T["prefill"]),
-             T["prefill"].shape[0], n_prefill, n_sample, self.B, spec["n_embd"], spec["n_head"], spec["vocab_size"],
-             self.n_prompt, ptr(self.ids), self.ids.shape[1], ptr(self.pos), ptr(self.q), ptr(self.y), ptr(self.logits),
-             ptr(self.bar), ptr(self.err), ptr(self.keys), temperature, int(top_k) if top_k is not None else 0,
-             ptr(self.ngrams), self.n_ngrams, ptr(self.seed_dev), ptr(self.ticket), max(spec["n_embd"], self.F),
-             max(self.Tmax, self.S), ptr(self.trace), stream())
+             T["prefill"].shape[0], T["n_ops"], T["att"].shape[0], n_prefill, n_sample, self.B, spec["n_embd"],
+             spec["n_head"], spec["vocab_size"], self.n_prompt, ptr(self.ids), self.ids.shape[1], ptr(self.pos), ptr(self.q),
+             ptr(self.y), ptr(self.logits), ptr(self.bar), ptr(self.err), ptr(self.keys), temperature,
+             int(top_k) if top_k is not None else 0, ptr(self.ngrams), self.n_ngrams, ptr(self.seed_dev),
+             max(spec["n_embd"], self.F), max(self.Tmax, self.S), ptr(self.trace), stream())
 
     # ------------------------------------------------------------------ one step, separate kernels -------------
     def _kernel_step(self, sample: bool, temperature: float, top_k: Optional[int]):

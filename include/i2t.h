@@ -175,15 +175,16 @@ int i2t_decode_mega(const int64_t* lin, const int64_t* att, const int32_t* sched
  * Same tables as i2t_decode_mega; lin[op][17] bit 0 marks the LM head: with top_k == 1 its epilogue applies the
  * no-repeat-n-gram ban and reduces the arg-max into `keys` (device uint64[24], scratch) instead of writing logits, and
  * the next step's embedding reads the pick from there.  Weights travel HBM -> registers as mma.sync A fragments,
- * prefetched before each grid barrier.  max_len: largest number of cached positions any step can see (<= 256).
+ * prefetched before each grid barrier.  max_len: largest number of cached positions any step can see
+ * (<= i2t_decode_mega2_max_keys()); max_k: widest linear input (<= 3072); n_embd <= 768.
  * Replaces models/vision_encoder_decoder.py:144-180 (the per-token loop, which re-runs the whole prefix). */
 int i2t_decode_mega2_max_keys(void);
 int i2t_decode_mega2(const int64_t* lin, const int64_t* att, const int32_t* sched_sample, int64_t n_sched_sample,
-                     const int32_t* sched_prefill, int64_t n_sched_prefill, int64_t n_prefill, int64_t n_sample, int64_t B,
-                     int64_t C, int64_t H, int64_t V, int64_t n_prompt, int64_t* ids, int64_t ids_ld, int32_t* pos, float* q,
-                     float* y, float* logits, uint32_t* bar, int32_t* error_flag, uint64_t* keys, float temperature,
-                     int64_t top_k, const int32_t* ngrams, int64_t n_ngrams, const uint64_t* seed_ptr, int32_t* ticket,
-                     int64_t max_k, int64_t max_len, int64_t* trace, void* stream);
+                     const int32_t* sched_prefill, int64_t n_sched_prefill, int64_t n_ops, int64_t n_att, int64_t n_prefill,
+                     int64_t n_sample, int64_t B, int64_t C, int64_t H, int64_t V, int64_t n_prompt, int64_t* ids,
+                     int64_t ids_ld, int32_t* pos, float* q, float* y, float* logits, uint32_t* bar, int32_t* error_flag,
+                     uint64_t* keys, float temperature, int64_t top_k, const int32_t* ngrams, int64_t n_ngrams,
+                     const uint64_t* seed_ptr, int64_t max_k, int64_t max_len, int64_t* trace, void* stream);
 
 /* ---- sampler: models/vision_encoder_decoder.py:152-180 + transformers NoRepeatNGramLogitsProcessor ----------------
  * logits (B,ldl) fp32 are modified in place (/temperature, banned -> -inf).  Tokens ids[b, 0..cur_len) are the history
