@@ -158,10 +158,10 @@ def run_ours(args):
     step_e2e()
     sampler = ClockSampler(local)
     sampler.start()
-    n0 = launch_count()
-    ms = timed(step_resident, args.steps)
-    eager_launches = launch_count() - n0
     eng = next(iter(model._decode_engines.values()))
+    n0, g0 = launch_count(), eng.graph_launches
+    ms = timed(step_resident, args.steps)
+    eager_launches = launch_count() - n0 + (eng.graph_launches - g0)
     # kernels launched through the library directly (encoder, cross-KV prefill) + kernels inside the replayed step graphs
     launches = eager_launches + args.steps * eng.replays_last * (eng.launches_per_step or 0)
     ms_e2e = timed(step_e2e, args.steps)

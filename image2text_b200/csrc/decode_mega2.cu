@@ -73,7 +73,7 @@ struct M2Args {
 };
 
 struct __align__(16) M2Fixed {
-  float red[2][M2_WARPS][M2_TILE];               // per-warp partial tiles, double buffered (8 KB)
+  float red[2][M2_WARPS][2 * M2_TILE];           // per-warp partial tiles (a pair of them), double buffered (16 KB)
   int banned[M2_B][M2_MAX_BANNED];
   int nbanned[M2_B];
   int hist[M2_B][M2_MAX_KEYS + 8];               // token history of every sequence (n-gram ban)
@@ -172,22 +172,29 @@ __device__ __forceinline__ int m2_lead_tiles(const M2Op& o, int u0) {
 }
 
 // issue the copies of one tile: this warp's blocks (strided over the 8 warps) x 2 rows, 16 bytes per thread each,
-// into ring vectors [vec0 .. vec0 + 2 * nb)
-__device__ __forceinline__ void m2_issue(const M2Op& o, const M2Sm& S, int tile, int vec0, int warp, int lane, int tid) {
-  const int nblk = o.K / M2_BLK;
+// into ring vectors [vec0 .. vec0 + 2 * nb).  One out-of-line copy: the hot loop must stay inside the instruction cache.
+__device__ __noinline__ void m2_issue_tile(const __nv_bfloat16* W, int N, int K, int nb, int tile, int vec0) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nblk = K / M2_BLK;
   const int g = lane >> 2, qd = lane & 3;
-  const int r0 = min(tile * M2_ROWS + g, o.N - 1), r1 = min(tile * M2_ROWS + g + 8, o.N - 1);
-  const __nv_bfloat16* p0 = o.W + (size_t)r0 * o.K + qd * 8;
-  const __nv_bfloat16* p1 = o.W + (size_t)r1 * o.K + qd * 8;
+  const int r0 = min(tile * M2_ROWS + g, N - 1), r1 = min(tile * M2_ROWS + g + 8, N - 1);
+  const __nv_bfloat16* p0 = W + (size_t)r0 * K + qd * 8;
+  const __nv_bfloat16* p1 = W + (size_t)r1 * K + qd * 8;
   uint4* dst = m2_ring() + (size_t)vec0 * M2_THREADS + tid;
-#pragma unroll 3
-  for (int i = 0; i < o.nb; ++i) {
-    const int blk = warp + M2_WARPS * i;
-    if (blk < nblk) {
-      m2_cp_async16(dst + (2 * i) * M2_THREADS, p0 + blk * M2_BLK);
-      m2_cp_async16(dst + (2 * i + 1) * M2_THREADS, p1 + blk * M2_BLK);
+#pragma unroll 1
+  for (int i0 = 0; i0 < nb; i0 += M2_NBA) {
+#pragma unroll
+    for (int ii = 0; ii < M2_NBA; ++ii) {
+      const int i = i0 + ii, blk = warp + M2_WARPS * i;
+      if (blk < nblk) {
+        m2_cp_async16(dst + (2 * i) * M2_THREADS, p0 + blk * M2_BLK);
+        m2_cp_async16(dst + (2 * i + 1) * M2_THREADS, p1 + blk * M2_BLK);
+      }
     }
   }
+}
+__device__ __forceinline__ void m2_issue(const M2Op& o, const M2Sm& S, int tile, int vec0, int warp, int lane, int tid) {
+  m2_issue_tile(o.W, o.N, o.K, o.nb, tile, vec0);
 }
 // everything a linear stage can fetch before the grid barrier in front of it: LayerNorm parameters + its first tiles
 __device__ __forceinline__ void m2_lead_issue(const M2Op& o, const int64_t* d, const M2Sm& S, int u0, int warp, int lane, int tid) {
@@ -331,21 +338,58 @@ __device__ __forceinline__ float m2_act(float x, int act) {
 }
 
 // ---- one linear stage.  `lead` = its first tiles (and LayerNorm parameters) were issued before the barrier. ----
+struct M2Epi {
+  const float* bias;
+  float* out;
+  const float* residual;
+  __nv_bfloat16* kcache;
+  __nv_bfloat16* vcache;
+  int64_t ldo, cache_bs;
+  int act, mode, in_mode, N;
+  bool argmax;
+};
+// epilogue of one output: v = reduced dot product of weight row n with batch row eb
+__device__ __forceinline__ void m2_epilogue(const M2Args& a, const M2Epi& e, float v, int n0, int n, int eb, int pos, float e_bias,
+                                            float e_res, float& best_v, int& best_n) {
+  v = m2_act(v + e_bias, e.act);
+  if (e.mode == 0) {
+    if (e.residual != nullptr && e.in_mode == 0) v += e_res;
+    if (e.argmax) {
+      bool ban = false;
+      const int nb = min(m2_f()->nbanned[eb], M2_MAX_BANNED);
+      for (int i = 0; i < nb; ++i) ban = ban || (m2_f()->banned[eb][i] == n);
+      if (!ban && (v > best_v || best_n == 0x7fffffff)) { best_v = v; best_n = n; }
+    } else {
+      e.out[(int64_t)eb * e.ldo + n] = v;
+    }
+  } else {   // packed q | k | v (a tile never straddles two of them): q to the scratch, k / v appended at `pos`
+    const int seg = n0 / a.C, nl = n - seg * a.C;
+    if (seg == 0) {
+      e.out[(int64_t)eb * e.ldo + nl] = v;
+    } else {
+      __nv_bfloat16* base = seg == 1 ? e.kcache : e.vcache;
+      base[(int64_t)eb * e.cache_bs + (int64_t)pos * a.C + nl] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
 __device__ __forceinline__ void m2_linear(const M2Args& a, int op, const M2Sm& S, bool lead, int pos, int keybuf, int keyout,
                                           int tid, long long* trace) {
   const int lane = tid & 31, warp = tid >> 5;
   const int64_t* d = m2_lin(S, op);
   const M2Op o = m2_op(d);
-  const float* bias = reinterpret_cast<const float*>(d[1]);
-  float* out = reinterpret_cast<float*>(d[5]);
-  const float* residual = reinterpret_cast<const float*>(d[6]);
-  const int act = (int)d[9], mode = (int)d[10], in_mode = (int)d[13];
-  const int64_t ldo = d[15];
-  const bool argmax = ((int)d[17] & 1) != 0 && a.top_k == 1;
+  M2Epi e;
+  e.bias = reinterpret_cast<const float*>(d[1]);
+  e.out = reinterpret_cast<float*>(d[5]);
+  e.residual = reinterpret_cast<const float*>(d[6]);
+  e.kcache = reinterpret_cast<__nv_bfloat16*>(d[11]);
+  e.vcache = reinterpret_cast<__nv_bfloat16*>(d[12]);
+  e.ldo = d[15]; e.cache_bs = d[16];
+  e.act = (int)d[9]; e.mode = (int)d[10]; e.in_mode = (int)d[13]; e.N = o.N;
+  e.argmax = ((int)d[17] & 1) != 0 && a.top_k == 1;
   const int G = gridDim.x;
   const int u0 = m2_first_unit(op);
   const int g = lane >> 2, qd = lane & 3;
-  const int er = tid >> 3, eb = tid & 7;       // epilogue position of threads 0..127: row er of the tile, batch eb
   float best_v = -INFINITY;
   int best_n = 0x7fffffff;
   if (u0 < o.total) {
@@ -355,74 +399,76 @@ __device__ __forceinline__ void m2_linear(const M2Args& a, int op, const M2Sm& S
     __syncthreads();                           // xs visible
     if (trace != nullptr) trace[1] = clock64();
     const int nblk = o.K / M2_BLK;
-    int j = 0;
-    for (int u = u0; u < o.total; u += G, ++j) {
-      const int slot = o.mode_b ? 0 : (j % M2_RING);
-      if (o.mode_b ? (j > 0) : (j >= M2_RING)) {
-        if (o.mode_b) { m2_issue(o, S, u, 0, warp, lane, tid); m2_commit(); m2_wait_group<0>(); }
-        else m2_wait_group<M2_RING - 1>();     // tile j was committed M2_RING iterations ago
+    const __nv_bfloat16* xp = m2_xs() + g * S.xpitch + qd * 8;
+    // Tiles are consumed in PAIRS when K <= 768 (two ring slots, one CTA barrier, 256 epilogue threads; a CTA with a single
+    // tile runs the same code with the second half switched off).  K > 768: one tile fills the whole ring.
+    const int half = tid >> 7, et = tid & 127;        // epilogue: threads 0..127 -> first tile, 128..255 -> second tile
+    const int er = et >> 3, eb = et & 7;
+    const int ustep = o.mode_b ? G : 2 * G;
+    int pidx = 0;
+#pragma unroll 1
+    for (int u = u0; u < o.total; u += ustep, ++pidx) {
+      const bool two = !o.mode_b && u + G < o.total;
+      int vec0 = 0;
+      if (o.mode_b) {
+        if (pidx > 0) { m2_issue(o, S, u, 0, warp, lane, tid); m2_commit(); m2_wait_group<0>(); }
+      } else {
+        if (pidx >= 2) m2_wait_group<1>();             // pair p was committed two iterations ago
+        vec0 = (pidx & 1) * 2 * M2_SLOT_VECS;
       }
-      const int n0 = u * M2_ROWS;
-      const bool e_on = tid < M2_TILE && n0 + er < o.N && eb < a.B;
-      float e_bias = 0.f, e_res = 0.f;         // epilogue operands do not depend on the MMAs: fetch them now
+      const int n0 = (u + half * G) * M2_ROWS;
+      const bool e_on = (half == 0 || two) && n0 + er < o.N && eb < a.B;
+      float e_bias = 0.f, e_res = 0.f;                 // epilogue operands do not depend on the MMAs: fetch them now
       if (e_on) {
-        if (bias != nullptr) e_bias = __ldcg(bias + n0 + er);
-        if (mode == 0 && residual != nullptr && in_mode == 0) e_res = __ldcg(residual + (int64_t)eb * ldo + n0 + er);
+        if (e.bias != nullptr) e_bias = __ldcg(e.bias + n0 + er);
+        if (e.mode == 0 && e.residual != nullptr && e.in_mode == 0) e_res = __ldcg(e.residual + (int64_t)eb * e.ldo + n0 + er);
       }
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-      const uint4* wv = m2_ring() + (size_t)(slot * M2_SLOT_VECS) * M2_THREADS + tid;
-      const __nv_bfloat16* xp = m2_xs() + g * S.xpitch + qd * 8;
-#pragma unroll 3
-      for (int i = 0; i < o.nb; ++i) {
-        const int blk = warp + M2_WARPS * i;
-        if (blk < nblk) {
-          const uint4 w0 = wv[(2 * i) * M2_THREADS], w1 = wv[(2 * i + 1) * M2_THREADS];
-          const uint4 xf = *reinterpret_cast<const uint4*>(xp + blk * M2_BLK);
-          m2_mma(acc, w0.x, w1.x, w0.y, w1.y, xf.x, xf.y);
-          m2_mma(acc, w0.z, w1.z, w0.w, w1.w, xf.z, xf.w);
+      float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      const uint4* wv = m2_ring() + (size_t)vec0 * M2_THREADS + tid;
+#pragma unroll 1
+      for (int i0 = 0; i0 < o.nb; i0 += M2_NBA) {
+#pragma unroll
+        for (int ii = 0; ii < M2_NBA; ++ii) {
+          const int i = i0 + ii, blk = warp + M2_WARPS * i;
+          if (blk < nblk) {
+            const uint4 xf = *reinterpret_cast<const uint4*>(xp + blk * M2_BLK);
+            const uint4 w0 = wv[(2 * i) * M2_THREADS], w1 = wv[(2 * i + 1) * M2_THREADS];
+            m2_mma(acc[0], w0.x, w1.x, w0.y, w1.y, xf.x, xf.y);
+            m2_mma(acc[0], w0.z, w1.z, w0.w, w1.w, xf.z, xf.w);
+            if (two) {
+              const uint4 v0 = wv[(M2_SLOT_VECS + 2 * i) * M2_THREADS], v1 = wv[(M2_SLOT_VECS + 2 * i + 1) * M2_THREADS];
+              m2_mma(acc[1], v0.x, v1.x, v0.y, v1.y, xf.x, xf.y);
+              m2_mma(acc[1], v0.z, v1.z, v0.w, v1.w, xf.z, xf.w);
+            }
+          }
         }
       }
-      if (trace != nullptr && j == 0) trace[7] = clock64() + (long long)(acc[0] == 123.f);
-      if (!o.mode_b) {                         // refill the slot with the tile M2_RING units ahead (thread-private data)
-        if (u + M2_RING * G < o.total) m2_issue(o, S, u + M2_RING * G, slot * M2_SLOT_VECS, warp, lane, tid);
+      if (trace != nullptr && pidx == 0) trace[7] = clock64() + (long long)(acc[0][0] == 123.f);
+      if (!o.mode_b) {   // refill both slots with the pair two iterations ahead (thread-private data: no barrier needed)
+        if (u + 4 * G < o.total) m2_issue(o, S, u + 4 * G, vec0, warp, lane, tid);
+        if (u + 5 * G < o.total) m2_issue(o, S, u + 5 * G, vec0 + M2_SLOT_VECS, warp, lane, tid);
         m2_commit();
       }
-      // acc: D[g][2qd], D[g][2qd+1], D[g+8][2qd], D[g+8][2qd+1]  ->  flat (row * 8 + batch)
-      float* red = m2_f()->red[j & 1][warp];
-      *reinterpret_cast<float2*>(red + lane * 2) = make_float2(acc[0], acc[1]);
-      *reinterpret_cast<float2*>(red + 64 + lane * 2) = make_float2(acc[2], acc[3]);
+      // acc: D[g][2qd], D[g][2qd+1], D[g+8][2qd], D[g+8][2qd+1]  ->  flat (row * 8 + batch), second tile at +128
+      float* red = &m2_f()->red[pidx & 1][warp][0];
+      *reinterpret_cast<float2*>(red + lane * 2) = make_float2(acc[0][0], acc[0][1]);
+      *reinterpret_cast<float2*>(red + 64 + lane * 2) = make_float2(acc[0][2], acc[0][3]);
+      if (two) {
+        *reinterpret_cast<float2*>(red + 128 + lane * 2) = make_float2(acc[1][0], acc[1][1]);
+        *reinterpret_cast<float2*>(red + 192 + lane * 2) = make_float2(acc[1][2], acc[1][3]);
+      }
       __syncthreads();
       if (e_on) {
-        const float* rp = &m2_f()->red[j & 1][0][tid];
+        const float* rp = &m2_f()->red[pidx & 1][0][tid];
         float v = 0.f;
 #pragma unroll
-        for (int i = 0; i < M2_WARPS; ++i) v += rp[i * M2_TILE];
-        const int n = n0 + er;
-        v = m2_act(v + e_bias, act);
-        if (mode == 0) {
-          if (residual != nullptr && in_mode == 0) v += e_res;
-          if (argmax) {
-            bool ban = false;
-            const int nb = min(m2_f()->nbanned[eb], M2_MAX_BANNED);
-            for (int i = 0; i < nb; ++i) ban = ban || (m2_f()->banned[eb][i] == n);
-            if (!ban && (v > best_v || best_n == 0x7fffffff)) { best_v = v; best_n = n; }
-          } else {
-            out[(int64_t)eb * ldo + n] = v;
-          }
-        } else {   // packed q | k | v (a tile never straddles two of them): q to the scratch, k / v appended at `pos`
-          const int seg = n0 / a.C, nl = n - seg * a.C;
-          if (seg == 0) {
-            out[(int64_t)eb * ldo + nl] = v;
-          } else {
-            __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(seg == 1 ? d[11] : d[12]);
-            base[(int64_t)eb * d[16] + (int64_t)pos * a.C + nl] = __float2bfloat16_rn(v);
-          }
-        }
+        for (int i = 0; i < M2_WARPS; ++i) v += rp[i * 2 * M2_TILE];
+        m2_epilogue(a, e, v, n0, n0 + er, eb, pos, e_bias, e_res, best_v, best_n);
       }
     }
   }
-  if (argmax) {
-    // CTA-level arg-max per sequence: rows of a warp (lane bits 3,4), then the epilogue warps, then one atomicMax
+  if (e.argmax) {
+    // CTA-level arg-max per sequence: rows of a warp (lane bits 3,4), then the 8 warps, then one atomicMax
     unsigned long long key = 0ull;
     if (best_n != 0x7fffffff)
       key = ((unsigned long long)float_key(best_v) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)best_n);

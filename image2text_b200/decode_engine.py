@@ -75,6 +75,8 @@ class DecodeEngine:
         self.launches_per_step = None
         self.replays_last = 0
         self._mega = None
+        self._enc_graph = None
+        self.graph_launches = 0     # kernels executed through graph replays (they bypass the library's launch counter)
         self.trace = None          # set to an int64 device tensor [n_sched * 4] to collect per-stage clock stamps
 
     # ------------------------------------------------------------------ megakernel tables ---------------------
@@ -241,14 +243,49 @@ class DecodeEngine:
             b = W[lp + "cross_attn.in_proj_bias"][C:]
             ops.gemm(e, w, bias=b, out=self.xkv[xi])
 
+    def _encode(self, images: torch.Tensor):
+        """ViT trunk + tail + cross K/V projections.  The ~200 launches are host-bound for a batch of 8 images, so the
+        sequence is captured into a CUDA graph on its second use with the same image shape (first use warms up kernel
+        attributes and TMA descriptors) and replayed from a static input buffer afterwards."""
+        from . import functional as Fn
+        W = self.model.weights()
+        key = (tuple(images.shape), images.dtype, W.c("decoder.transformer.h.0.attn.c_attn.weight").data_ptr())
+
+        def run(img):
+            enc = Fn.encoder_forward(W, self.spec, img, self.cd, train_trunk=False)
+            self._prefill_cross(enc)
+
+        st = self._enc_graph
+        if os.environ.get("I2T_ENCODER_GRAPH", "1") == "0" or (st is not None and st.get("failed")):
+            return run(images)
+        if st is None or st["key"] != key:
+            self._enc_graph = dict(key=key, calls=1, graph=None, static=None)
+            return run(images)
+        if st["graph"] is None:
+            try:
+                st["static"] = images.clone()
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                n0 = launch_count()
+                with torch.cuda.graph(g):
+                    run(st["static"])
+                st["launches"] = launch_count() - n0      # kernels inside the graph (capture does not execute them)
+                st["graph"] = g
+            except Exception:                      # capture is an optimisation only: keep the eager launches
+                st["failed"] = True
+                torch.cuda.synchronize()
+                return run(images)
+        st["static"].copy_(images)
+        st["graph"].replay()
+        self.graph_launches += st["launches"]
+
     @torch.no_grad()
     def generate(self, images, prompt_ids, max_new_tokens: int, temperature: float, top_k: Optional[int], seed: int):
         from . import functional as Fn
         m, B = self.model, self.B
         P = prompt_ids.shape[1]
         assert prompt_ids.shape[0] == B and P + max_new_tokens <= self.Tmax + 1
-        enc = Fn.encoder_forward(m.weights(), self.spec, images, self.cd, train_trunk=False)
-        self._prefill_cross(enc)
+        self._encode(images)
         if self.mode in ("mega", "mega2"):
             W = m.weights()
             sig = self._mega["sig"] if self._mega is not None else None
