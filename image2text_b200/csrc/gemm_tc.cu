@@ -1,12 +1,14 @@
 // bf16 x bf16 -> fp32 GEMM on the 5th-generation tensor cores (sm_100a): TMA (cp.async.bulk.tensor, 128-byte swizzle)
-// feeds a 3-stage shared-memory ring, ONE elected thread issues tcgen05.mma (M=128, N=128, K=16) with the accumulator
+// feeds a 6-stage shared-memory ring, ONE elected thread issues tcgen05.mma (M=128, N=128, K=16) with the accumulator
 // in TMEM, four epilogue warps read it back with tcgen05.ld and apply bias / GELU / residual / cast on the way out.
+// PERSISTENT: one CTA per SM loops over output tiles with a double-buffered TMEM accumulator, so a tile's epilogue and
+// the next tile's TMA prologue overlap the tensor-core main loop (the training shapes have K = 768: 12 k-blocks).
 //   C[M,N] = act(A[M,K] * B[N,K]^T + bias) + residual      (both operands K-major: activations x nn.Linear weight)
 // Warp roles (256 threads): 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4..7 = epilogue (TMEM lanes 32w..).
-// Two CTAs are resident per SM (97 KB of shared memory, 128 TMEM columns each) so one CTA's epilogue overlaps the
-// other's main loop.  M / N / K tails are handled by TMA zero fill on the way in and predicated stores on the way out.
+// M / N / K tails are handled by TMA zero fill on the way in and predicated stores on the way out.
 #include <cuda.h>
 
+#include <algorithm>
 #include <mutex>
 #include <unordered_map>
 
@@ -14,7 +16,7 @@
 
 namespace i2t {
 
-constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 64, TC_STAGES = 3, TC_THREADS = 256;
+constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 64, TC_STAGES = 6, TC_THREADS = 256;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2, TC_B_BYTES = TC_BN * TC_BK * 2;
 constexpr int TC_SMEM = TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + 1024;
 
@@ -102,21 +104,90 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// One epilogue chunk: 32 accumulator columns of this thread's row -> bias / activation / residual / cast -> global.
+__device__ __forceinline__ void tc_epilogue_chunk(const TcEpilogue& epi, const uint32_t (&r)[32], int64_t row, int64_t n0) {
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  const int nvalid = (int)min((int64_t)32, epi.N - n0);
+  if (epi.bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < nvalid) v[j] += epi.bias[n0 + j];
+  }
+  if (epi.act != I2T_ACT_NONE) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], epi.act);
+  }
+  const int64_t off = row * epi.ldc + n0;
+  if (epi.residual != nullptr) {
+    if (epi.res_dtype == I2T_F32) {
+      const float* rp = (const float*)epi.residual + off;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nvalid) v[j] += rp[j];
+    } else {
+      const __nv_bfloat16* rp = (const __nv_bfloat16*)epi.residual + off;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nvalid) v[j] += __bfloat162float(rp[j]);
+    }
+  }
+  if (epi.c_dtype == I2T_F32) {
+    float* cp = (float*)epi.C + off;
+    if (epi.accumulate) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nvalid) v[j] += cp[j];
+    }
+    if (nvalid == 32 && ((uintptr_t)cp & 15u) == 0) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nvalid) cp[j] = v[j];
+    }
+  } else {
+    __nv_bfloat16* cp = (__nv_bfloat16*)epi.C + off;
+    if (nvalid == 32 && ((uintptr_t)cp & 15u) == 0) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint4 pk;
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]), h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+        pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+        pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>(cp + j) = pk;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nvalid) cp[j] = __float2bfloat16_rn(v[j]);
+    }
+  }
+}
+
+// Persistent kernel: one CTA per SM walks the output tiles t = blockIdx.x, + gridDim.x, ... (m fastest, so concurrently
+// running CTAs share the weight tile in L2).  The TMA producer and the MMA issuer run ahead across tile boundaries
+// through the 6-stage ring; the accumulator is double buffered in TMEM (2 x 128 columns), so the four epilogue warps
+// drain tile i while the tensor core already works on tile i+1.
 template <bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(TC_THREADS, 2)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int num_k_blocks,
-               TcEpilogue epi) {
+               int m_tiles, int n_tiles, TcEpilogue epi) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[TC_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[TC_STAGES];
-  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_slot;
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
   uint8_t* smemA = smem;
   uint8_t* smemB = smem + TC_STAGES * TC_A_BYTES;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_blk = blockIdx.x, m_blk = blockIdx.y;
+  const int num_tiles = m_tiles * n_tiles;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -127,11 +198,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(&tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full_bar[b], 1);
+      mbar_init(&tmem_empty_bar[b], 4);      // one arrival per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(128u)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(256u)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -142,24 +216,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < num_k_blocks; ++kb) {
-        const int s = kb % TC_STAGES;
-        const uint32_t ph = (uint32_t)(kb / TC_STAGES) & 1u;
-        mbar_wait(&empty_bar[s], ph ^ 1u);
-        mbar_expect_tx(&full_bar[s], TC_A_BYTES + TC_B_BYTES);
-        // K-major operand ([rows][K], K contiguous): one box {64 k, 128 rows}.
-        // MN-major operand ([K][rows], rows contiguous): two boxes {64 rows, 64 k}, one per 64-wide half of the tile.
-        if (!A_MN) {
-          tma_load_2d(smemA + s * TC_A_BYTES, &tmA, kb * TC_BK, m_blk * TC_BM, &full_bar[s]);
-        } else {
-          tma_load_2d(smemA + s * TC_A_BYTES, &tmA, m_blk * TC_BM, kb * TC_BK, &full_bar[s]);
-          tma_load_2d(smemA + s * TC_A_BYTES + TC_A_BYTES / 2, &tmA, m_blk * TC_BM + 64, kb * TC_BK, &full_bar[s]);
-        }
-        if (!B_MN) {
-          tma_load_2d(smemB + s * TC_B_BYTES, &tmB, kb * TC_BK, n_blk * TC_BN, &full_bar[s]);
-        } else {
-          tma_load_2d(smemB + s * TC_B_BYTES, &tmB, n_blk * TC_BN, kb * TC_BK, &full_bar[s]);
-          tma_load_2d(smemB + s * TC_B_BYTES + TC_B_BYTES / 2, &tmB, n_blk * TC_BN + 64, kb * TC_BK, &full_bar[s]);
+      int it = 0;                                            // running k-block counter across tiles
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int m_blk = t % m_tiles, n_blk = t / m_tiles;
+        for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
+          const int s = it % TC_STAGES;
+          const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          mbar_expect_tx(&full_bar[s], TC_A_BYTES + TC_B_BYTES);
+          // K-major operand ([rows][K], K contiguous): one box {64 k, 128 rows}.
+          // MN-major operand ([K][rows], rows contiguous): two boxes {64 rows, 64 k}, one per 64-wide half of the tile.
+          if (!A_MN) {
+            tma_load_2d(smemA + s * TC_A_BYTES, &tmA, kb * TC_BK, m_blk * TC_BM, &full_bar[s]);
+          } else {
+            tma_load_2d(smemA + s * TC_A_BYTES, &tmA, m_blk * TC_BM, kb * TC_BK, &full_bar[s]);
+            tma_load_2d(smemA + s * TC_A_BYTES + TC_A_BYTES / 2, &tmA, m_blk * TC_BM + 64, kb * TC_BK, &full_bar[s]);
+          }
+          if (!B_MN) {
+            tma_load_2d(smemB + s * TC_B_BYTES, &tmB, kb * TC_BK, n_blk * TC_BN, &full_bar[s]);
+          } else {
+            tma_load_2d(smemB + s * TC_B_BYTES, &tmB, n_blk * TC_BN, kb * TC_BK, &full_bar[s]);
+            tma_load_2d(smemB + s * TC_B_BYTES + TC_B_BYTES / 2, &tmB, n_blk * TC_BN + 64, kb * TC_BK, &full_bar[s]);
+          }
         }
       }
     }
@@ -168,102 +246,61 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N=128, M=128 (cute::UMMA::InstrDescriptor)
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(A_MN ? 1u : 0u) << 15) |
                              ((uint32_t)(B_MN ? 1u : 0u) << 16) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      for (int kb = 0; kb < num_k_blocks; ++kb) {
-        const int s = kb % TC_STAGES;
-        const uint32_t ph = (uint32_t)(kb / TC_STAGES) & 1u;
-        mbar_wait(&full_bar[s], ph);
+      int it = 0, i = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++i) {
+        const int b = i & 1;
+        mbar_wait(&tmem_empty_bar[b], (((uint32_t)i >> 1) & 1u) ^ 1u);     // epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint64_t adesc = A_MN ? umma_desc_sw128_mn(smem_u32(smemA + s * TC_A_BYTES)) : umma_desc_sw128(smem_u32(smemA + s * TC_A_BYTES));
-        const uint64_t bdesc = B_MN ? umma_desc_sw128_mn(smem_u32(smemB + s * TC_B_BYTES)) : umma_desc_sw128(smem_u32(smemB + s * TC_B_BYTES));
+        const uint32_t tmem_d = tmem_base + (uint32_t)(b * TC_BN);
+        for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
+          const int s = it % TC_STAGES;
+          const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
+          mbar_wait(&full_bar[s], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t adesc = A_MN ? umma_desc_sw128_mn(smem_u32(smemA + s * TC_A_BYTES)) : umma_desc_sw128(smem_u32(smemA + s * TC_A_BYTES));
+          const uint64_t bdesc = B_MN ? umma_desc_sw128_mn(smem_u32(smemB + s * TC_B_BYTES)) : umma_desc_sw128(smem_u32(smemB + s * TC_B_BYTES));
 #pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k) {
-          // one UMMA consumes 16 values of K.  K-major tile: 16 bf16 = 32 bytes inside the 128-byte swizzle span
-          // (+2 in the addr>>4 field).  MN-major tile: 16 K-rows of 128 bytes = 2 swizzle atoms = 2048 bytes (+128).
-          umma_bf16(tmem_base, adesc + (uint64_t)((A_MN ? 128 : 2) * k), bdesc + (uint64_t)((B_MN ? 128 : 2) * k), idesc,
-                    (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            // one UMMA consumes 16 values of K.  K-major tile: 16 bf16 = 32 bytes inside the 128-byte swizzle span
+            // (+2 in the addr>>4 field).  MN-major tile: 16 K-rows of 128 bytes = 2 swizzle atoms = 2048 bytes (+128).
+            umma_bf16(tmem_d, adesc + (uint64_t)((A_MN ? 128 : 2) * k), bdesc + (uint64_t)((B_MN ? 128 : 2) * k), idesc,
+                      (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
         }
-        umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
+        umma_commit(&tmem_full_bar[b]);   // accumulator complete
       }
-      umma_commit(&tmem_full_bar);   // accumulator complete
     }
   } else if (warp >= 4) {
     const int wq = warp & 3;  // TMEM lane quarter this warp may touch
-    mbar_wait(&tmem_full_bar, 0u);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int64_t row = (int64_t)m_blk * TC_BM + wq * 32 + lane;
-    const bool row_ok = row < epi.M;
+    int i = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++i) {
+      const int m_blk = t % m_tiles, n_blk = t / m_tiles;
+      const int b = i & 1;
+      mbar_wait(&tmem_full_bar[b], ((uint32_t)i >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int64_t row = (int64_t)m_blk * TC_BM + wq * 32 + lane;
+      const bool row_ok = row < epi.M;
 #pragma unroll 1
-    for (int c = 0; c < TC_BN / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(c * 32), r);
-      const int64_t n0 = (int64_t)n_blk * TC_BN + c * 32;
-      if (!row_ok || n0 >= epi.N) continue;
-      float v[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-      const int nvalid = (int)min((int64_t)32, epi.N - n0);
-      if (epi.bias != nullptr) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j < nvalid) v[j] += epi.bias[n0 + j];
-      }
-      if (epi.act != I2T_ACT_NONE) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], epi.act);
-      }
-      const int64_t off = row * epi.ldc + n0;
-      if (epi.residual != nullptr) {
-        if (epi.res_dtype == I2T_F32) {
-          const float* rp = (const float*)epi.residual + off;
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < nvalid) v[j] += rp[j];
-        } else {
-          const __nv_bfloat16* rp = (const __nv_bfloat16*)epi.residual + off;
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < nvalid) v[j] += __bfloat162float(rp[j]);
+      for (int c = 0; c < TC_BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(b * TC_BN + c * 32), r);
+        if (c == TC_BN / 32 - 1) {
+          // the accumulator is in registers: hand the TMEM buffer back before the (slow) global stores
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[b])) : "memory");
         }
-      }
-      if (epi.c_dtype == I2T_F32) {
-        float* cp = (float*)epi.C + off;
-        if (epi.accumulate) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < nvalid) v[j] += cp[j];
-        }
-        if (nvalid == 32 && ((uintptr_t)cp & 15u) == 0) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < nvalid) cp[j] = v[j];
-        }
-      } else {
-        __nv_bfloat16* cp = (__nv_bfloat16*)epi.C + off;
-        if (nvalid == 32 && ((uintptr_t)cp & 15u) == 0) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 pk;
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]), h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-            pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-            pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-            *reinterpret_cast<uint4*>(cp + j) = pk;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < nvalid) cp[j] = __float2bfloat16_rn(v[j]);
-        }
+        const int64_t n0 = (int64_t)n_blk * TC_BN + c * 32;
+        if (!row_ok || n0 >= epi.N) continue;
+        tc_epilogue_chunk(epi, r, row, n0);
       }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
   }
 }
 
@@ -340,7 +377,9 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, int kblocks, 
     if (e != cudaSuccess) return fail(I2T_ERR_CUDA, "cudaFuncSetAttribute(gemm_tc_kernel): %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  gemm_tc_kernel<A_MN, B_MN><<<grid, TC_THREADS, TC_SMEM, st>>>(ma, mb, kblocks, epi);
+  const int m_tiles = (int)grid.y, n_tiles = (int)grid.x;
+  const int ctas = (int)std::min<int64_t>((int64_t)m_tiles * n_tiles, (int64_t)num_sms());
+  gemm_tc_kernel<A_MN, B_MN><<<ctas, TC_THREADS, TC_SMEM, st>>>(ma, mb, kblocks, m_tiles, n_tiles, epi);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(I2T_ERR_CUDA, "gemm_tc launch failed: %s", cudaGetErrorString(e));

@@ -74,6 +74,46 @@ class ModelTrainerWrapper(nn.Module):
     def val_step(self, images, labels):
         return self._step(images, labels, False)
 
+    def train_step_graphed(self, images, labels, loss_scale: float = 1.0):
+        """train_step + backward of (loss * loss_scale) as ONE CUDA-graph replay (no counterpart in the reference, whose
+        loop is `loss, _ = train_step(...); accelerator.backward(loss)`, training/utils.py:76-88).  A micro-step is ~1500
+        kernel launches; issued one by one from Python they leave the GPU idle half of the time, so the fixed-shape
+        forward + backward is captured once (third call: the first two run eagerly to create the .grad buffers and warm
+        up kernel attributes / TMA descriptors) and replayed from static input buffers.  Gradients ACCUMULATE into the
+        existing .grad tensors exactly like the eager path (keep `zero_grad(set_to_none=False)`).  Returns the detached
+        loss (a static tensor that the next replay overwrites)."""
+        key = (tuple(images.shape), images.dtype, tuple(labels.shape), float(loss_scale))
+        st = getattr(self, "_graph_state", None)
+        if st is None or st["key"] != key:
+            st = self._graph_state = dict(key=key, calls=0, graph=None)
+        st["calls"] += 1
+        if st["graph"] is None and (st["calls"] <= 2 or st.get("failed")):
+            loss, _ = self._step(images, labels, True)
+            (loss * loss_scale).backward()
+            return loss.detach()
+        if st["graph"] is None:
+            missing = [n for n, p in self.model.named_parameters() if p.requires_grad and p.grad is None]
+            if missing:
+                raise RuntimeError(f"train_step_graphed needs pre-allocated .grad tensors (zero_grad(set_to_none=False)); "
+                                   f"missing for {missing[:3]}...")
+            st["images"], st["labels"] = images.clone(), labels.clone()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            try:
+                with torch.cuda.graph(g):
+                    loss, _ = self._step(st["images"], st["labels"], True)
+                    (loss * loss_scale).backward()
+                    st["loss"] = loss.detach()
+            except Exception:
+                st["failed"] = True
+                torch.cuda.synchronize()
+                raise
+            st["graph"] = g
+        st["images"].copy_(images)
+        st["labels"].copy_(labels)
+        st["graph"].replay()
+        return st["loss"]
+
     def compute_lm_loss(self, lm_logits, labels, lm_logits_moco=None):
         return LmLossFn.apply(lm_logits, lm_logits_moco, labels, self.temperature, self.alpha, self.weight_fn,
                               self.eos_token_weight, self.tokenizer.eos_token_id, self.ignore_index)

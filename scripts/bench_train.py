@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--profile", action="store_true")
     ap.add_argument("--config", default="nano", choices=["nano", "gpt2"])
     ap.add_argument("--batch", type=int, default=0, help="per-GPU micro-batch (0 = the YAML value)")
+    ap.add_argument("--graph", type=int, default=1, help="1: forward+backward of a micro-step replayed as a CUDA graph")
     ap.add_argument("--cpu-ref", action="store_true", help="time the CPU oracle's train step instead")
     args = ap.parse_args()
     from image2text_b200 import load_training_config
@@ -88,10 +89,14 @@ def main():
 
     def one_step():
         for micro in range(accum):
-            ctx = red.no_sync() if micro < accum - 1 else torch.enable_grad()
+            last = micro == accum - 1
+            ctx = red.no_sync() if not last else torch.enable_grad()
             with ctx:
-                loss, _ = w.train_step(images, labels)
-                (loss / accum).backward()
+                if args.graph and (world == 1 or not last):     # the micro-step that fires the all-reduce hooks stays eager
+                    loss = w.train_step_graphed(images, labels, 1.0 / accum)
+                else:
+                    loss, _ = w.train_step(images, labels)
+                    (loss / accum).backward()
         red.finish()
         opt.step()
         opt.zero_grad(set_to_none=False)
@@ -121,7 +126,7 @@ def main():
     gflop_img = (243.4 + (104.5 if args.moco else 0.0)) if args.config == "nano" else (340.0 + (113.4 if args.moco else 0.0))
     if rank == 0:
         print(json.dumps({"metric": f"train img/s ({args.config}.yaml, B={bs}/GPU, accum {accum}, AdamW, dropout off)",
-                          "value": round(imgs / (ms / 1e3), 2), "n_gpus": world, "dtype": args.dtype, "moco": args.moco,
+                          "value": round(imgs / (ms / 1e3), 2), "n_gpus": world, "dtype": args.dtype, "moco": args.moco, "graph": args.graph,
                           "ms_per_step": round(ms / args.steps, 2), "model_tflops": round(imgs * gflop_img / (ms / 1e3) / 1e3, 2),
                           "loss": float(loss), "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2)}))
     if world > 1:
