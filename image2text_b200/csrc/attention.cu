@@ -427,6 +427,9 @@ static int launch_attn_fwd(const void* q, const void* k, const void* v, void* ou
 int attn_fwd_tc(const void* q, const void* k, const void* v, void* out, float* lse, int64_t B, int64_t H, int64_t Tq, int64_t Tk,
                 int64_t head_dim, int64_t q_bs, int64_t q_rs, int64_t kv_bs, int64_t kv_rs, int mode, int64_t n_prompt,
                 cudaStream_t st);
+int attn_bwd_tc(const void* q, const void* k, const void* v, const void* dout, const float* lse, const float* delta, float* dq_acc,
+                void* dk, void* dv, int64_t B, int64_t H, int64_t Tq, int64_t Tk, int64_t head_dim, int64_t q_bs, int64_t q_rs,
+                int64_t kv_bs, int64_t kv_rs, int mode, int64_t n_prompt, cudaStream_t st);
 static std::atomic<int> g_attn_tc{1};
 
 }  // namespace i2t
@@ -480,6 +483,18 @@ static int launch_attn_bwd(const void* q, const void* k, const void* v, const vo
   attn_delta_kernel<T, HS><<<(unsigned)ceil_div(rows, 4), 128, 0, st>>>((const T*)out, (const T*)dout, delta, (int)H,
                                                                         (int)Tq, rows);
   I2T_LAUNCHED();
+  if (sizeof(T) == 2 && g_attn_tc.load() == 1) {
+    const int r = attn_bwd_tc(q, k, v, dout, lse, delta, dq_acc, dk, dv, B, H, Tq, Tk, HS, q_bs, q_rs, kv_bs, kv_rs, mode,
+                              n_prompt, st);
+    if (r < 0) return r;
+    if (r == 1) {
+      const int64_t total_tc = B * H * Tq * (HS / 4);
+      attn_dq_scatter_kernel<T, HS><<<(unsigned)ceil_div(total_tc, 256), 256, 0, st>>>(dq_acc, (T*)dq, (int)H, (int)Tq, q_bs,
+                                                                                       q_rs, total_tc);
+      I2T_LAUNCHED();
+      return I2T_OK;
+    }
+  }
   const size_t smem = (size_t)(4 * HS * 64 + ATT_BQ * ATT_PSTRIDE + 3 * 64 * HS) * sizeof(float);
   auto kern = attn_bwd_kernel<T, HS>;
   I2T_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -175,6 +175,221 @@ attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __r
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Backward on the tensor cores.  CTA = (64-key tile, head, batch), 4 warps, each warp owns 16 keys; loop over
+// 64-query tiles.  Everything is computed TRANSPOSED (rows = keys) so that dK / dV accumulate in registers:
+//   S^T = K Q^T,  P^T = exp(S^T - lse[q]),  dP^T = V dO^T,  dS^T = P^T * (dP^T - delta[q]) * scale,
+//   dV += P^T dO,  dK += dS^T Q            (the S^T / dS^T accumulator fragments are re-used as A fragments)
+//   dQ[q,:] += dS K  over this CTA's 64 keys: dS^T goes through shared memory once, each warp takes 16 queries and
+//   adds its 16 x HS result to the fp32 dQ accumulator with atomics (other key tiles add to the same rows).
+// delta[q] = sum_e dO[q,e] O[q,e] comes from attn_delta_kernel (attention.cu).
+// ---------------------------------------------------------------------------------------------------------
+template <int HS>
+__global__ void __launch_bounds__(ATC_THREADS)
+attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v,
+                   const __nv_bfloat16* __restrict__ dout, const float* __restrict__ lse, const float* __restrict__ delta,
+                   float* __restrict__ dq_acc, __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv, int H, int Tq,
+                   int Tk, int64_t q_bs, int64_t q_rs, int64_t kv_bs, int64_t kv_rs, int mode, int n_prompt, float scale) {
+  constexpr int PITCH = HS + 8;
+  constexpr int KS = HS / 16, NT_O = HS / 8;
+  __shared__ __align__(16) __nv_bfloat16 Ks[ATC_BK][PITCH];
+  __shared__ __align__(16) __nv_bfloat16 Vs[ATC_BK][PITCH];
+  __shared__ __align__(16) __nv_bfloat16 Qs[ATC_BQ][PITCH];
+  __shared__ __align__(16) __nv_bfloat16 dOs[ATC_BQ][PITCH];
+  __shared__ __align__(16) __nv_bfloat16 dSs[ATC_BK][ATC_BQ + 8];     // dS^T: [key][query]
+  __shared__ float lse_s[ATC_BQ], delta_s[ATC_BQ];
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const int g = lane >> 2, tq = lane & 3;
+  const int mi = lane >> 3, r8 = lane & 7;
+  const int k0 = blockIdx.x * ATC_BK, h = blockIdx.y, b = blockIdx.z;
+  const __nv_bfloat16* qb = q + (int64_t)b * q_bs + (int64_t)h * HS;
+  const __nv_bfloat16* kb = k + (int64_t)b * kv_bs + (int64_t)h * HS;
+  const __nv_bfloat16* vb = v + (int64_t)b * kv_bs + (int64_t)h * HS;
+  const int64_t do_rs = (int64_t)H * HS;
+  const __nv_bfloat16* dob = dout + (int64_t)b * Tq * do_rs + (int64_t)h * HS;
+  const float LOG2E = 1.4426950408889634f;
+  const float scale_log2 = scale * LOG2E;
+
+  constexpr int CH = HS / 8;
+  for (int i = t; i < ATC_BK * CH; i += ATC_THREADS) {
+    const int r = i / CH, c = i % CH;
+    uint4 kv4 = make_uint4(0u, 0u, 0u, 0u), vv4 = kv4;
+    if (k0 + r < Tk) {
+      kv4 = *reinterpret_cast<const uint4*>(kb + (int64_t)(k0 + r) * kv_rs + c * 8);
+      vv4 = *reinterpret_cast<const uint4*>(vb + (int64_t)(k0 + r) * kv_rs + c * 8);
+    }
+    *reinterpret_cast<uint4*>(&Ks[r][c * 8]) = kv4;
+    *reinterpret_cast<uint4*>(&Vs[r][c * 8]) = vv4;
+  }
+  __syncthreads();
+  // A fragments of this warp's 16 keys (rows of K and V), kept in registers for the whole kernel
+  uint32_t kf[KS][4], vf[KS][4];
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+    ldsm_x4(kf[ks], &Ks[w * 16 + (mi & 1) * 8 + r8][ks * 16 + (mi >> 1) * 8]);
+    ldsm_x4(vf[ks], &Vs[w * 16 + (mi & 1) * 8 + r8][ks * 16 + (mi >> 1) * 8]);
+  }
+  float adk[NT_O][4], adv[NT_O][4];
+#pragma unroll
+  for (int i = 0; i < NT_O; ++i) adk[i][0] = adk[i][1] = adk[i][2] = adk[i][3] = adv[i][0] = adv[i][1] = adv[i][2] = adv[i][3] = 0.f;
+
+  int qstart = 0;
+  if (mode != I2T_MASK_NONE) qstart = (k0 / ATC_BQ) * ATC_BQ;       // queries before the key tile never see it
+  for (int q0 = qstart; q0 < Tq; q0 += ATC_BQ) {
+    __syncthreads();                                                  // previous tile's readers are done
+    for (int i = t; i < ATC_BQ * CH; i += ATC_THREADS) {
+      const int r = i / CH, c = i % CH;
+      uint4 q4 = make_uint4(0u, 0u, 0u, 0u), d4 = q4;
+      if (q0 + r < Tq) {
+        q4 = *reinterpret_cast<const uint4*>(qb + (int64_t)(q0 + r) * q_rs + c * 8);
+        d4 = *reinterpret_cast<const uint4*>(dob + (int64_t)(q0 + r) * do_rs + c * 8);
+      }
+      *reinterpret_cast<uint4*>(&Qs[r][c * 8]) = q4;
+      *reinterpret_cast<uint4*>(&dOs[r][c * 8]) = d4;
+    }
+    if (t < ATC_BQ) {
+      const bool ok = q0 + t < Tq;
+      const int64_t li = ((int64_t)b * H + h) * Tq + q0 + t;
+      lse_s[t] = ok ? lse[li] : -INFINITY;
+      delta_s[t] = ok ? delta[li] : 0.f;
+    }
+    __syncthreads();
+
+    // S^T = K Q^T and dP^T = V dO^T : rows = this warp's 16 keys, columns = the tile's 64 queries
+    float s[8][4], dp[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        uint32_t bq[4], bd[4];
+        ldsm_x4(bq, &Qs[(2 * np + (mi >> 1)) * 8 + r8][ks * 16 + (mi & 1) * 8]);
+        ldsm_x4(bd, &dOs[(2 * np + (mi >> 1)) * 8 + r8][ks * 16 + (mi & 1) * 8]);
+        mma_bf16(s[2 * np], kf[ks], bq[0], bq[1]);
+        mma_bf16(s[2 * np + 1], kf[ks], bq[2], bq[3]);
+        mma_bf16(dp[2 * np], vf[ks], bd[0], bd[1]);
+        mma_bf16(dp[2 * np + 1], vf[ks], bd[2], bd[3]);
+      }
+    }
+    // P^T and dS^T in place: s <- P^T, dp <- dS^T (scaled)
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int kj = k0 + w * 16 + g + (e >> 1) * 8;
+        const int ql = nt * 8 + tq * 2 + (e & 1);
+        const int qi = q0 + ql;
+        const float l = lse_s[ql];
+        float p = 0.f;
+        if (kj < Tk && qi < Tq && l != -INFINITY && atc_visible(mode, n_prompt, qi, kj)) p = exp2f(s[nt][e] * scale_log2 - l * LOG2E);
+        s[nt][e] = p;
+        dp[nt][e] = p * (dp[nt][e] - delta_s[ql]) * scale;
+      }
+    }
+    // dS^T -> shared memory [key][query] (for dQ), packed pairs along the query index
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      *reinterpret_cast<uint32_t*>(&dSs[w * 16 + g][nt * 8 + tq * 2]) = pack_bf16(dp[nt][0], dp[nt][1]);
+      *reinterpret_cast<uint32_t*>(&dSs[w * 16 + g + 8][nt * 8 + tq * 2]) = pack_bf16(dp[nt][2], dp[nt][3]);
+    }
+    // dV += P^T dO ; dK += dS^T Q   (k dimension = the 64 queries: 4 k-steps of 16)
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t pf[4], df[4];
+      pf[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
+      pf[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
+      pf[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+      pf[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+      df[0] = pack_bf16(dp[2 * kk][0], dp[2 * kk][1]);
+      df[1] = pack_bf16(dp[2 * kk][2], dp[2 * kk][3]);
+      df[2] = pack_bf16(dp[2 * kk + 1][0], dp[2 * kk + 1][1]);
+      df[3] = pack_bf16(dp[2 * kk + 1][2], dp[2 * kk + 1][3]);
+#pragma unroll
+      for (int np = 0; np < NT_O / 2; ++np) {
+        uint32_t bo[4], bqq[4];
+        ldsm_x4_t(bo, &dOs[kk * 16 + (mi & 1) * 8 + r8][(2 * np + (mi >> 1)) * 8]);
+        ldsm_x4_t(bqq, &Qs[kk * 16 + (mi & 1) * 8 + r8][(2 * np + (mi >> 1)) * 8]);
+        mma_bf16(adv[2 * np], pf, bo[0], bo[1]);
+        mma_bf16(adv[2 * np + 1], pf, bo[2], bo[3]);
+        mma_bf16(adk[2 * np], df, bqq[0], bqq[1]);
+        mma_bf16(adk[2 * np + 1], df, bqq[2], bqq[3]);
+      }
+    }
+    __syncthreads();                                                  // dS^T of all four warps is in shared memory
+    // dQ[q0 + w*16 .. +15][:] += dS[q][keys] K[keys][:]   (A = dS from the transposed tile, B = K)
+    {
+      float adq[NT_O][4];
+#pragma unroll
+      for (int i = 0; i < NT_O; ++i) adq[i][0] = adq[i][1] = adq[i][2] = adq[i][3] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < ATC_BK / 16; ++kk) {
+        uint32_t af[4];
+        // A[m = query][k = key] read from dSs[key][query]: matrices (q 0-7,k 0-7), (q 8-15,k 0-7), (q 0-7,k 8-15), (q 8-15,k 8-15)
+        ldsm_x4_t(af, &dSs[kk * 16 + (mi >> 1) * 8 + r8][w * 16 + (mi & 1) * 8]);
+#pragma unroll
+        for (int np = 0; np < NT_O / 2; ++np) {
+          uint32_t bk[4];
+          ldsm_x4_t(bk, &Ks[kk * 16 + (mi & 1) * 8 + r8][(2 * np + (mi >> 1)) * 8]);
+          mma_bf16(adq[2 * np], af, bk[0], bk[1]);
+          mma_bf16(adq[2 * np + 1], af, bk[2], bk[3]);
+        }
+      }
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int qi = q0 + w * 16 + g + half * 8;
+        if (qi >= Tq) continue;
+        float* dst = dq_acc + (((int64_t)b * H + h) * Tq + qi) * HS + tq * 2;
+#pragma unroll
+        for (int nt = 0; nt < NT_O; ++nt) {
+          atomicAdd(dst + nt * 8, adq[nt][half * 2]);
+          atomicAdd(dst + nt * 8 + 1, adq[nt][half * 2 + 1]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int kj = k0 + w * 16 + g + half * 8;
+    if (kj >= Tk) continue;
+    __nv_bfloat16* dkp = dk + (int64_t)b * kv_bs + (int64_t)kj * kv_rs + (int64_t)h * HS + tq * 2;
+    __nv_bfloat16* dvp = dv + (int64_t)b * kv_bs + (int64_t)kj * kv_rs + (int64_t)h * HS + tq * 2;
+#pragma unroll
+    for (int nt = 0; nt < NT_O; ++nt) {
+      *reinterpret_cast<uint32_t*>(dkp + nt * 8) = pack_bf16(adk[nt][half * 2], adk[nt][half * 2 + 1]);
+      *reinterpret_cast<uint32_t*>(dvp + nt * 8) = pack_bf16(adv[nt][half * 2], adv[nt][half * 2 + 1]);
+    }
+  }
+}
+
+// returns 1 when it handled the call, 0 when the shape is not eligible (the caller then runs the fp32-math kernel)
+int attn_bwd_tc(const void* q, const void* k, const void* v, const void* dout, const float* lse, const float* delta, float* dq_acc,
+                void* dk, void* dv, int64_t B, int64_t H, int64_t Tq, int64_t Tk, int64_t head_dim, int64_t q_bs, int64_t q_rs,
+                int64_t kv_bs, int64_t kv_rs, int mode, int64_t n_prompt, cudaStream_t st) {
+  if ((q_rs | q_bs | kv_rs | kv_bs) % 8 != 0 || !aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(dout) ||
+      (H * head_dim) % 8 != 0)
+    return 0;
+  if (((uintptr_t)dk & 3u) != 0 || ((uintptr_t)dv & 3u) != 0) return 0;
+  dim3 grid((unsigned)ceil_div(Tk, ATC_BK), (unsigned)H, (unsigned)B);
+  const float scale = 1.0f / sqrtf((float)head_dim);
+  if (head_dim == 64)
+    attn_bwd_tc_kernel<64><<<grid, ATC_THREADS, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v,
+                                                       (const __nv_bfloat16*)dout, lse, delta, dq_acc, (__nv_bfloat16*)dk,
+                                                       (__nv_bfloat16*)dv, (int)H, (int)Tq, (int)Tk, q_bs, q_rs, kv_bs, kv_rs, mode,
+                                                       (int)n_prompt, scale);
+  else if (head_dim == 32)
+    attn_bwd_tc_kernel<32><<<grid, ATC_THREADS, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v,
+                                                       (const __nv_bfloat16*)dout, lse, delta, dq_acc, (__nv_bfloat16*)dk,
+                                                       (__nv_bfloat16*)dv, (int)H, (int)Tq, (int)Tk, q_bs, q_rs, kv_bs, kv_rs, mode,
+                                                       (int)n_prompt, scale);
+  else
+    return 0;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(I2T_ERR_CUDA, "attn_bwd_tc launch failed: %s", cudaGetErrorString(e));
+  return 1;
+}
+
 int attn_fwd_tc(const void* q, const void* k, const void* v, void* out, float* lse, int64_t B, int64_t H, int64_t Tq, int64_t Tk,
                 int64_t head_dim, int64_t q_bs, int64_t q_rs, int64_t kv_bs, int64_t kv_rs, int mode, int64_t n_prompt,
                 cudaStream_t st) {

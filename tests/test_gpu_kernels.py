@@ -167,6 +167,23 @@ def test_attention_fwd_bwd(B, T, H, hs, mode, n_prompt):
     assert relerr(dqkv, qr.grad) < 2e-5
     out16 = ops.attention_packed(qkv.to(DEV).to(torch.bfloat16), B, T, H, mode, n_prompt)
     assert relerr(out16.float(), ref) < 2e-2
+    # bf16 backward on the tensor cores (attention_tc.cu) against the fp64 reference on the bf16-rounded inputs, and against
+    # the fp32-math kernel on the same bf16 inputs (A/B switch)
+    q16 = qkv.to(DEV).to(torch.bfloat16)
+    d16 = dout.to(DEV).to(torch.bfloat16)
+    qr16 = q16.double().cpu().requires_grad_(True)
+    ref16 = _ref_attention(qr16, B, T, H, mode, n_prompt)
+    ref16.backward(d16.double().cpu())
+    o16, lse16 = ops.attention_packed(q16, B, T, H, mode, n_prompt, want_lse=True)
+    g_tc = ops.attention_packed_bwd(q16, o16, d16, lse16, B, T, H, mode, n_prompt)
+    assert relerr(g_tc.float(), qr16.grad) < 2e-2
+    lib().i2t_set_tensor_core_attention(0)
+    try:
+        o_f, lse_f = ops.attention_packed(q16, B, T, H, mode, n_prompt, want_lse=True)
+        g_f = ops.attention_packed_bwd(q16, o_f, d16, lse_f, B, T, H, mode, n_prompt)
+    finally:
+        lib().i2t_set_tensor_core_attention(1)
+    assert relerr(g_tc.float(), g_f.float()) < 2e-2
 
 
 @pytest.mark.parametrize("B,T,S,H,hs", [(2, 256, 8, 12, 64), (3, 20, 4, 4, 32), (1, 33, 16, 12, 64), (1, 7, 64, 2, 64)])
