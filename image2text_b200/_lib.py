@@ -19,6 +19,7 @@ SIGNATURES = {
     "i2t_set_tensor_core_gemm": (None, [I]),
     "i2t_set_pdl": (None, [I]),
     "i2t_set_tensor_core_attention": (None, [I]),
+    "i2t_set_gemm_cta_pair": (None, [I]),
     "i2t_layernorm_fwd": (c_int, [P, P, P, P, P, P, L, L, L, F, I, I, P]),
     "i2t_layernorm_bwd": (c_int, [P, P, P, P, P, P, P, P, L, L, I, I, I, P]),
     "i2t_gemm": (c_int, [P, P, P, P, P, L, L, L, L, L, L, I, I, I, I, I, I, I, P]),
@@ -75,6 +76,8 @@ def lib() -> ctypes.CDLL:
             handle.i2t_set_pdl(int(os.environ["I2T_PDL"]))
         if os.environ.get("I2T_TC_GEMM") is not None:
             handle.i2t_set_tensor_core_gemm(int(os.environ["I2T_TC_GEMM"]))
+        if os.environ.get("I2T_GEMM_PAIR") is not None:
+            handle.i2t_set_gemm_cta_pair(int(os.environ["I2T_GEMM_PAIR"]))
         if os.environ.get("I2T_TC_ATTN") is not None:
             handle.i2t_set_tensor_core_attention(int(os.environ["I2T_TC_ATTN"]))
         _lib = handle

@@ -37,6 +37,7 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done;
+  uint32_t spins = 0;
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -45,6 +46,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(done)
         : "r"(addr), "r"(parity)
         : "memory");
+    if (!done && ++spins > (1u << 28)) asm volatile("trap;");   // a protocol bug must abort the launch, not hang the GPU
   } while (!done);
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
@@ -304,6 +306,205 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// CTA-PAIR kernel (tcgen05 cta_group::2): two CTAs of one cluster (one TPC) compute a 256 x BN tile together.
+// Each CTA stages ITS 128 rows of A and ITS half (BN/2 rows) of B; one thread of the leader CTA issues
+// tcgen05.mma.cta_group::2 (M = 256), which reads both CTAs' shared memory and writes each CTA's 128 accumulator rows
+// into that CTA's TMEM.  Per MAC this moves half the bytes through L2 / shared memory of the 128 x 128 single-CTA tile
+// (0.016 vs 0.031 B/MAC), which is what large GEMMs need to leave the L2-bandwidth bound.
+//   full[s]   : leader's barrier; BOTH CTAs' TMA loads complete_tx on it (the peer addresses it through mapa)
+//   empty[s], tmem_full[b] : per CTA; tcgen05.commit ... multicast::cluster arrives on both
+//   tmem_empty[b] : leader's; 8 arrivals (4 epilogue warps x 2 CTAs)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_cta0(uint32_t saddr) {    // same offset in the shared memory of cluster CTA 0
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(0u));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, int c0, int c1, uint32_t bar_cluster_addr) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {   // arrives on the barrier at this offset in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+
+template <int BN>
+struct PairCfg {
+  static constexpr int B_ROWS = BN / 2;                       // rows of B each CTA stages
+  static constexpr int B_BYTES = B_ROWS * TC_BK * 2;
+  static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
+  static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;    // 6 (BN 256) / 8 (BN 128)
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024;
+  static constexpr int TMEM_COLS = 2 * BN;                     // double-buffered accumulator
+};
+
+template <bool A_MN, bool B_MN, int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int num_k_blocks,
+                    int m_tiles, int n_tiles, TcEpilogue epi) {
+  using Cfg = PairCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_slot;
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  uint8_t* smemA = smem;
+  uint8_t* smemB = smem + STAGES * TC_A_BYTES;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_rank();
+  const bool leader = rank == 0;
+  const int num_tiles = m_tiles * n_tiles;
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full_bar[b], 1);
+      mbar_init(&tmem_empty_bar[b], 8);      // 4 epilogue warps of each CTA
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                 "r"((uint32_t)Cfg::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();                          // the peer's barriers are initialised before anything remote happens
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int t = pair; t < num_tiles; t += num_pairs) {
+        const int m_blk = t % m_tiles, n_blk = t / m_tiles;
+        const int m0 = m_blk * 256 + (int)rank * 128;            // this CTA's rows of A (and of the output)
+        const int n0 = n_blk * BN + (int)rank * Cfg::B_ROWS;     // this CTA's half of the B tile
+        for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          if (leader) mbar_expect_tx(&full_bar[s], 2 * Cfg::STAGE_BYTES);
+          const uint32_t fb = mapa_cta0(smem_u32(&full_bar[s]));
+          uint8_t* a_dst = smemA + s * TC_A_BYTES;
+          uint8_t* b_dst = smemB + s * Cfg::B_BYTES;
+          if (!A_MN) {
+            tma_load_2d_pair(a_dst, &tmA, kb * TC_BK, m0, fb);
+          } else {
+            tma_load_2d_pair(a_dst, &tmA, m0, kb * TC_BK, fb);
+            tma_load_2d_pair(a_dst + TC_A_BYTES / 2, &tmA, m0 + 64, kb * TC_BK, fb);
+          }
+          if (!B_MN) {
+            tma_load_2d_pair(b_dst, &tmB, kb * TC_BK, n0, fb);
+          } else {
+#pragma unroll
+            for (int hb = 0; hb < Cfg::B_ROWS / 64; ++hb)
+              tma_load_2d_pair(b_dst + hb * (64 * TC_BK * 2), &tmB, n0 + hb * 64, kb * TC_BK, fb);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      // instruction descriptor: D=f32, A=B=bf16, N = BN, M = 256 (the pair)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(A_MN ? 1u : 0u) << 15) |
+                             ((uint32_t)(B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      int it = 0, i = 0;
+      for (int t = pair; t < num_tiles; t += num_pairs, ++i) {
+        const int b = i & 1;
+        mbar_wait(&tmem_empty_bar[b], (((uint32_t)i >> 1) & 1u) ^ 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tmem_d = tmem_base + (uint32_t)(b * BN);
+        for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+          mbar_wait(&full_bar[s], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_addr = smem_u32(smemA + s * TC_A_BYTES), b_addr = smem_u32(smemB + s * Cfg::B_BYTES);
+          const uint64_t adesc = A_MN ? umma_desc_sw128_mn(a_addr) : umma_desc_sw128(a_addr);
+          const uint64_t bdesc = B_MN ? umma_desc_sw128_mn(b_addr) : umma_desc_sw128(b_addr);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k)
+            umma_bf16_pair(tmem_d, adesc + (uint64_t)((A_MN ? 128 : 2) * k), bdesc + (uint64_t)((B_MN ? 128 : 2) * k), idesc,
+                           (kb | k) != 0 ? 1u : 0u);
+          umma_commit_pair(&empty_bar[s]);     // both CTAs' producers may refill the slot
+        }
+        umma_commit_pair(&tmem_full_bar[b]);   // both CTAs' epilogues may read their half of the accumulator
+      }
+    }
+  } else if (warp >= 4) {
+    const int wq = warp & 3;
+    int i = 0;
+    for (int t = pair; t < num_tiles; t += num_pairs, ++i) {
+      const int m_blk = t % m_tiles, n_blk = t / m_tiles;
+      const int b = i & 1;
+      mbar_wait(&tmem_full_bar[b], ((uint32_t)i >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int64_t row = (int64_t)m_blk * 256 + (int64_t)rank * 128 + wq * 32 + lane;
+      const bool row_ok = row < epi.M;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(b * BN + c * 32), r);
+        if (c == BN / 32 - 1) {
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            const uint32_t eb = mapa_cta0(smem_u32(&tmem_empty_bar[b]));
+            asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(eb) : "memory");
+          }
+        }
+        const int64_t n0 = (int64_t)n_blk * BN + c * 32;
+        if (!row_ok || n0 >= epi.N) continue;
+        tc_epilogue_chunk(epi, r, row, n0);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();                          // nobody may still be reading our shared memory / signalling our barriers
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+  }
+}
+
 // ---- host side: tensor-map construction through the driver entry point (no link-time libcuda dependency) ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -386,17 +587,56 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, int kblocks, 
   return 1;
 }
 
+static std::atomic<int> g_pair_mode{1};   // 1: CTA-pair kernel where the problem has enough 256-row tiles; 0: never
+
+template <bool A_MN, bool B_MN, int BN>
+static int launch_pair(const CUtensorMap& ma, const CUtensorMap& mb, int kblocks, const TcEpilogue& epi, int m_tiles, int n_tiles,
+                       cudaStream_t st) {
+  using Cfg = PairCfg<BN>;
+  static bool attr_set = false;
+  auto kern = gemm_tc_pair_kernel<A_MN, B_MN, BN>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    if (e != cudaSuccess) return fail(I2T_ERR_CUDA, "cudaFuncSetAttribute(gemm_tc_pair_kernel): %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int pairs = (int)std::min<int64_t>((int64_t)m_tiles * n_tiles, (int64_t)(num_sms() / 2));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma, mb, kblocks, m_tiles, n_tiles, epi);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return fail(I2T_ERR_CUDA, "gemm_tc_pair launch failed: %s", cudaGetErrorString(e));
+  }
+  return 1;
+}
+
+template <int BN>
+static int launch_pair_layout(const CUtensorMap& ma, const CUtensorMap& mb, int kb, const TcEpilogue& epi, int mt, int nt,
+                              int a_kmajor, int b_kmajor, cudaStream_t st) {
+  if (a_kmajor && b_kmajor) return launch_pair<false, false, BN>(ma, mb, kb, epi, mt, nt, st);
+  if (a_kmajor && !b_kmajor) return launch_pair<false, true, BN>(ma, mb, kb, epi, mt, nt, st);
+  if (!a_kmajor && b_kmajor) return launch_pair<true, false, BN>(ma, mb, kb, epi, mt, nt, st);
+  return launch_pair<true, true, BN>(ma, mb, kb, epi, mt, nt, st);
+}
+
 int gemm_tc_try(const void* A, const void* B, const float* bias, const void* residual, void* C, int64_t M, int64_t N,
                 int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int a_kmajor, int b_kmajor, int act, int accumulate,
                 int res_dtype, int c_dtype, cudaStream_t st) {
   // leading dimensions are row pitches in elements: 16-byte multiples for TMA
   if (lda % 8 != 0 || ldb % 8 != 0 || !aligned16(A) || !aligned16(B)) return 0;
   if (M > 128 * 65535LL || N > 128LL * 0x7fffffff) return 0;
-  CUtensorMap ma, mb;
-  int rc = a_kmajor ? make_map(A, M, K, lda, TC_BM, &ma) : make_map(A, K, M, lda, 64, &ma);
-  if (rc != I2T_OK) return rc;
-  rc = b_kmajor ? make_map(B, N, K, ldb, TC_BN, &mb) : make_map(B, K, N, ldb, 64, &mb);
-  if (rc != I2T_OK) return rc;
   TcEpilogue epi;
   epi.bias = bias;
   epi.residual = residual;
@@ -408,8 +648,28 @@ int gemm_tc_try(const void* A, const void* B, const float* bias, const void* res
   epi.accumulate = accumulate;
   epi.res_dtype = res_dtype;
   epi.c_dtype = c_dtype;
-  dim3 grid((unsigned)ceil_div(N, TC_BN), (unsigned)ceil_div(M, TC_BM));
   const int kb = (int)ceil_div(K, TC_BK);
+  CUtensorMap ma, mb;
+  int rc = a_kmajor ? make_map(A, M, K, lda, TC_BM, &ma) : make_map(A, K, M, lda, 64, &ma);
+  if (rc != I2T_OK) return rc;
+  // CTA-pair tiles (256 x 256, else 256 x 128) when they fill at least ~3/4 of the 74 SM pairs; otherwise 128 x 128 tiles
+  if (g_pair_mode.load() == 1) {
+    const int64_t want = (int64_t)(num_sms() / 2) * 3 / 4;
+    const int64_t mt = ceil_div(M, 256);
+    int bn = 0;
+    if (mt * ceil_div(N, 256) >= want) bn = 256;
+    else if (mt * ceil_div(N, 128) >= want) bn = 128;
+    if (bn != 0) {
+      rc = b_kmajor ? make_map(B, N, K, ldb, bn / 2, &mb) : make_map(B, K, N, ldb, 64, &mb);
+      if (rc != I2T_OK) return rc;
+      const int nt = (int)ceil_div(N, bn);
+      return bn == 256 ? launch_pair_layout<256>(ma, mb, kb, epi, (int)mt, nt, a_kmajor, b_kmajor, st)
+                       : launch_pair_layout<128>(ma, mb, kb, epi, (int)mt, nt, a_kmajor, b_kmajor, st);
+    }
+  }
+  rc = b_kmajor ? make_map(B, N, K, ldb, TC_BN, &mb) : make_map(B, K, N, ldb, 64, &mb);
+  if (rc != I2T_OK) return rc;
+  dim3 grid((unsigned)ceil_div(N, TC_BN), (unsigned)ceil_div(M, TC_BM));
   if (a_kmajor && b_kmajor) return launch_tc<false, false>(ma, mb, kb, epi, grid, st);
   if (a_kmajor && !b_kmajor) return launch_tc<false, true>(ma, mb, kb, epi, grid, st);
   if (!a_kmajor && b_kmajor) return launch_tc<true, false>(ma, mb, kb, epi, grid, st);
@@ -417,3 +677,5 @@ int gemm_tc_try(const void* A, const void* B, const float* bias, const void* res
 }
 
 }  // namespace i2t
+
+extern "C" void i2t_set_gemm_cta_pair(int enabled) { i2t::g_pair_mode.store(enabled ? 1 : 0); }

@@ -128,6 +128,8 @@ int i2t_xattn_bwd(const void* q, const void* k, const void* v, const void* dout,
 
 /* 1 (default): bf16 contractions run on tcgen05 when the shape fits; 0: always the FMA kernel (A/B testing). */
 void i2t_set_tensor_core_gemm(int enabled);
+/* 1 (default): large bf16 GEMMs use the CTA-pair kernel (tcgen05 cta_group::2, 256-row tiles); 0: 128x128 tiles only. */
+void i2t_set_gemm_cta_pair(int enabled);
 /* 1 (default): bf16 attention forward runs on the tensor cores; 0: the fp32-math kernel (A/B testing). */
 void i2t_set_tensor_core_attention(int enabled);
 

@@ -128,6 +128,34 @@ def test_gemm_bf16_tcgen05_mn_major_layouts(M, N, K, layout):
     assert relerr(acc, ref + 1.0) < 1e-5
 
 
+@pytest.mark.parametrize("M,N,K", [(4096, 2304, 768), (2000, 4000, 200), (768, 3072, 2048), (16384, 776, 136)])
+@pytest.mark.parametrize("layout", ["nt", "nn", "tn", "tt"])
+def test_gemm_bf16_cta_pair(M, N, K, layout):
+    """CTA-pair kernel (tcgen05 cta_group::2, 256 x 256 and 256 x 128 tiles) in all four operand layouts, with M / N / K
+    tails, against fp64 and against the single-CTA kernel (A/B switch)."""
+    a = rnd(M, K, seed=60).to(torch.bfloat16)
+    b = rnd(N, K, seed=61, scale=0.05).to(torch.bfloat16)
+    bias, res = rnd(N, seed=62), rnd(M, N, seed=63)
+    ref = a.double() @ b.double().t()
+    A = (a if layout[0] == "n" else a.t().contiguous()).to(DEV)
+    Bm = (b if layout[1] == "t" else b.t().contiguous()).to(DEV)
+    kw = dict(a_kmajor=layout[0] == "n", b_kmajor=layout[1] == "t")
+    outs = {}
+    for pair in (1, 0):
+        lib().i2t_set_gemm_cta_pair(pair)
+        try:
+            out = ops.gemm(A, Bm, **kw)
+            assert relerr(out, ref) < 1e-5, f"pair={pair}"
+            outs[pair] = out
+            out2 = ops.gemm(A, Bm, bias=bias.to(DEV), residual=res.to(DEV), act=ops.ACT_GELU_TANH, **kw)
+            assert relerr(out2, O.gelu_tanh(ref + bias.double()) + res.double()) < 1e-5, f"pair={pair}"
+        finally:
+            lib().i2t_set_gemm_cta_pair(1)
+    assert relerr(outs[1], outs[0].double()) < 2e-6       # same products, fp32 accumulation in a different tile order
+    o16 = ops.gemm(A, Bm, bias=bias.to(DEV), out_dtype=torch.bfloat16, **kw)
+    assert relerr(o16.float(), ref + bias.double()) < 8e-3
+
+
 def test_colsum():
     x = rnd(1000, 333, seed=13)
     out = torch.zeros(333, device=DEV)
