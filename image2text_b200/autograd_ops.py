@@ -193,7 +193,10 @@ class LmLossFn(torch.autograd.Function):
     pass over the vocabulary that computes the loss."""
 
     @staticmethod
-    def forward(ctx, logits, teacher_logits, labels, temperature, alpha, weight_fn, eos_weight, eos_id, ignore_index):
+    def forward(ctx, logits, teacher_logits, labels, temperature, alpha, weight_fn, eos_weight, eos_id, ignore_index,
+                grad_prescale=1.0):
+        """grad_prescale != 1: the caller promises to back-propagate exactly `loss * grad_prescale`; the factor is folded
+        into the dlogits this pass writes and backward() skips the rescaling pass over the (B,T,V) gradient."""
         B, T_logits, V = logits.shape
 
         def rows_ok(t):   # (B,T,V) view of a (B*T, pitch) buffer: what the LM head produces (pitch = V rounded up to 8)
@@ -220,18 +223,21 @@ class LmLossFn(torch.autograd.Function):
         call("i2t_lm_loss", ptr(logits), ptr(teacher_logits), ptr(labels), ptr(weights), ptr(rows), ptr(loss), ptr(dbuf),
              B, T_logits, Tl, V, labels.shape[1], float(temperature), float(alpha if alpha is not None else 0.0),
              int(weight_fn == "inverse_sqrt_position"), int(eos_weight is not None),
-             float(eos_weight if eos_weight is not None else 0.0), int(eos_id), int(ignore_index), ld, ld_t, dt(logits), stream())
+             float(eos_weight if eos_weight is not None else 0.0), int(eos_id), int(ignore_index), ld, ld_t,
+             float(grad_prescale), dt(logits), stream())
         if need:
             ctx.save_for_backward(dbuf)
             ctx.V = V
+            ctx.prescaled = float(grad_prescale) != 1.0
         return loss
 
     @staticmethod
     def backward(ctx, gloss):
         (dbuf,) = ctx.saved_tensors
-        scale = gloss.reshape(1).to(torch.float32).contiguous()
-        call("i2t_scale_inplace", ptr(dbuf), ptr(scale), dbuf.numel(), dt(dbuf), stream())
-        return dbuf[..., :ctx.V], None, None, None, None, None, None, None, None
+        if not ctx.prescaled:
+            scale = gloss.reshape(1).to(torch.float32).contiguous()
+            call("i2t_scale_inplace", ptr(dbuf), ptr(scale), dbuf.numel(), dt(dbuf), stream())
+        return dbuf[..., :ctx.V], None, None, None, None, None, None, None, None, None
 
 
 class L2NormFn(torch.autograd.Function):

@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(512)
 lm_loss_kernel(const TL* __restrict__ logits, const TL* __restrict__ teacher, const int64_t* __restrict__ labels,
                const float* __restrict__ w, float* __restrict__ loss_rows, TL* __restrict__ dlogits, int V, int T_logits,
                int Tl, int64_t ld_labels, float inv_tau, float alpha, int64_t ignore_index, int64_t ld_logits,
-               int64_t ld_teacher) {
+               int64_t ld_teacher, float grad_scale) {
   __shared__ float redf[16];
   __shared__ float s_a, s_b;
   const int row = blockIdx.x;                 // row = b * Tl + t  (only the first Tl positions of each sequence)
@@ -178,7 +178,7 @@ lm_loss_kernel(const TL* __restrict__ logits, const TL* __restrict__ teacher, co
   else loss = valid ? -wt * (sy - lse) : 0.f;
   if (tid == 0) loss_rows[row] = loss;
   if (dz) {
-    const float scale = wt * inv_tau;
+    const float scale = wt * inv_tau * grad_scale;
     const float hard = zm ? (1.f - alpha) * (valid ? 1.f : 0.f) : (valid ? 1.f : 0.f);
     const float soft = zm ? alpha : 0.f;
     const float inv_sem = zm ? 1.0f / sem : 0.f;
@@ -283,7 +283,7 @@ extern "C" int i2t_lm_loss(const void* logits, const void* teacher_logits, const
                            float* loss_rows, float* loss_out, void* dlogits, int64_t B, int64_t T_logits, int64_t Tl,
                            int64_t V, int64_t ld_labels, float temperature, float alpha, int inv_sqrt_position,
                            int use_eos_weight, float eos_weight, int64_t eos_id, int64_t ignore_index, int64_t ld_logits,
-                           int64_t ld_teacher, int dtype, void* stream) {
+                           int64_t ld_teacher, float grad_scale, int dtype, void* stream) {
   I2T_REQUIRE(logits && labels && weights && loss_rows && loss_out, "lm_loss: null pointer");
   I2T_REQUIRE(B > 0 && Tl > 0 && Tl <= T_logits && Tl <= ld_labels && V > 1 && temperature > 0.f && valid_dtype(dtype),
               "lm_loss: bad sizes");
@@ -295,11 +295,11 @@ extern "C" int i2t_lm_loss(const void* logits, const void* teacher_logits, const
   if (dtype == I2T_F32)
     lm_loss_kernel<float><<<(unsigned)(B * Tl), 512, 0, st>>>((const float*)logits, (const float*)teacher_logits, labels,
                                                               weights, loss_rows, (float*)dlogits, (int)V, (int)T_logits,
-                                                              (int)Tl, ld_labels, 1.0f / temperature, alpha, ignore_index, ld_logits, ld_teacher);
+                                                              (int)Tl, ld_labels, 1.0f / temperature, alpha, ignore_index, ld_logits, ld_teacher, grad_scale);
   else
     lm_loss_kernel<__nv_bfloat16><<<(unsigned)(B * Tl), 512, 0, st>>>(
         (const __nv_bfloat16*)logits, (const __nv_bfloat16*)teacher_logits, labels, weights, loss_rows,
-        (__nv_bfloat16*)dlogits, (int)V, (int)T_logits, (int)Tl, ld_labels, 1.0f / temperature, alpha, ignore_index, ld_logits, ld_teacher);
+        (__nv_bfloat16*)dlogits, (int)V, (int)T_logits, (int)Tl, ld_labels, 1.0f / temperature, alpha, ignore_index, ld_logits, ld_teacher, grad_scale);
   I2T_LAUNCHED();
   sum_rows_kernel<<<1, 256, 0, st>>>(loss_rows, loss_out, (int)(B * Tl));
   I2T_LAUNCHED();

@@ -80,7 +80,8 @@ class ModelTrainerWrapper(nn.Module):
         kernel launches; issued one by one from Python they leave the GPU idle half of the time, so the fixed-shape
         forward + backward is captured once (third call: the first two run eagerly to create the .grad buffers and warm
         up kernel attributes / TMA descriptors) and replayed from static input buffers.  Gradients ACCUMULATE into the
-        existing .grad tensors exactly like the eager path (keep `zero_grad(set_to_none=False)`).  Returns the detached
+        existing .grad tensors exactly like the eager path (keep `zero_grad(set_to_none=False)`: the graph holds their
+        addresses; parameters that received no gradient in the two eager calls are unused and stay untouched).  Returns the detached
         loss (a static tensor that the next replay overwrites)."""
         key = (tuple(images.shape), images.dtype, tuple(labels.shape), float(loss_scale))
         st = getattr(self, "_graph_state", None)
@@ -92,14 +93,11 @@ class ModelTrainerWrapper(nn.Module):
             (loss * loss_scale).backward()
             return loss.detach()
         if st["graph"] is None:
-            missing = [n for n, p in self.model.named_parameters() if p.requires_grad and p.grad is None]
-            if missing:
-                raise RuntimeError(f"train_step_graphed needs pre-allocated .grad tensors (zero_grad(set_to_none=False)); "
-                                   f"missing for {missing[:3]}...")
             st["images"], st["labels"] = images.clone(), labels.clone()
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             try:
+                self._grad_prescale = float(loss_scale)       # folded into dlogits by the loss kernel (no rescale pass)
                 with torch.cuda.graph(g):
                     loss, _ = self._step(st["images"], st["labels"], True)
                     (loss * loss_scale).backward()
@@ -108,6 +106,8 @@ class ModelTrainerWrapper(nn.Module):
                 st["failed"] = True
                 torch.cuda.synchronize()
                 raise
+            finally:
+                self._grad_prescale = 1.0
             st["graph"] = g
         st["images"].copy_(images)
         st["labels"].copy_(labels)
@@ -116,7 +116,8 @@ class ModelTrainerWrapper(nn.Module):
 
     def compute_lm_loss(self, lm_logits, labels, lm_logits_moco=None):
         return LmLossFn.apply(lm_logits, lm_logits_moco, labels, self.temperature, self.alpha, self.weight_fn,
-                              self.eos_token_weight, self.tokenizer.eos_token_id, self.ignore_index)
+                              self.eos_token_weight, self.tokenizer.eos_token_id, self.ignore_index,
+                              getattr(self, "_grad_prescale", 1.0))
 
     def _step(self, images, labels, is_train: bool):
         tok = self.tokenizer

@@ -214,11 +214,13 @@ int i2t_gradnorm_scale(const void* g, void* out, double* acc, int64_t n, int dty
  * scratch outputs; loss_out is a device fp32 scalar; dlogits (same shape/dtype as logits, optional) receives
  * dLoss/dlogits for the first Tl positions (other positions must be zeroed by the caller).  ld_logits / ld_teacher: row
  * pitch in elements (>= V) of logits+dlogits / teacher_logits -- the LM head writes rows padded to a multiple of 8 so that
- * its backward GEMMs meet TMA's 16-byte pitch rule. */
+ * its backward GEMMs meet TMA's 16-byte pitch rule.  grad_scale multiplies dlogits only (the loss value is unscaled): the
+ * caller that will back-propagate `loss * s` passes s here and skips the rescaling pass over the (B,T,V) gradient. */
 int i2t_lm_loss(const void* logits, const void* teacher_logits, const int64_t* labels, float* weights, float* loss_rows,
                 float* loss_out, void* dlogits, int64_t B, int64_t T_logits, int64_t Tl, int64_t V, int64_t ld_labels,
                 float temperature, float alpha, int inv_sqrt_position, int use_eos_weight, float eos_weight,
-                int64_t eos_id, int64_t ignore_index, int64_t ld_logits, int64_t ld_teacher, int dtype, void* stream);
+                int64_t eos_id, int64_t ignore_index, int64_t ld_logits, int64_t ld_teacher, float grad_scale, int dtype,
+                void* stream);
 /* y = x / max(||x||_2, eps) per row and its backward: F.normalize(p=2, dim=-1) at models/encoder.py:118-119 */
 int i2t_l2norm_fwd(const float* x, float* y, int64_t rows, int64_t cols, float eps, void* stream);
 int i2t_l2norm_bwd(const float* x, const float* dy, float* dx, int64_t rows, int64_t cols, float eps, void* stream);

@@ -1,0 +1,2 @@
+timeout 600 python -m pytest tests/test_gpu_training.py tests/test_gpu_kernels.py -m gpu -q --timeout 300 -x -k "train or loss or graphed" 2>&1 | tail -5
+for b in 8 64; do timeout 600 python scripts/bench_train.py --dtype bf16 --steps 3 --warmup 2 --graph 1 --batch $b 2>&1 | tail -1 | cut -c1-400; done

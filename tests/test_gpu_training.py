@@ -150,3 +150,33 @@ def test_gpt2_hf_layout_forward_and_backward_match(golden):
     (logits_o * probe.cpu()).sum().backward()
     for k in keys:
         assert rel_err(named[k].grad.cpu(), sdo[k].grad) < 5e-4, k
+
+
+def test_graphed_micro_step_accumulates_the_same_gradients():
+    """train_step_graphed (forward + backward of one micro-step replayed as a CUDA graph, loss scale folded into the loss
+    kernel's dlogits) must leave the same accumulated .grad as `train_step` + `(loss * scale).backward()`."""
+    eager, spec, sd = make_wrapper("tiny", {}, eos=612)
+    graphed, _, _ = make_wrapper("tiny", {}, eos=612)
+    eager.train()
+    graphed.train()
+    scale = 0.25
+    batches = [(synth_images(3, 32, seed=30 + i).cuda(),
+                synth_labels(3, 20, spec["vocab_size"], seed=40 + i, min_len=3, max_len=14, eos=612).cuda()) for i in range(5)]
+    losses_e, losses_g = [], []
+    for i, (im, lb) in enumerate(batches):
+        le, _ = eager.train_step(im, lb)
+        (le * scale).backward()
+        losses_e.append(float(le))
+        lg = graphed.train_step_graphed(im, lb, scale)       # calls 1-2 eager, call 3 captures, 3-5 replay
+        losses_g.append(float(lg))
+    assert graphed._graph_state["graph"] is not None
+    for a, b in zip(losses_e, losses_g):
+        assert abs(a - b) < 1e-5 * abs(a)
+    pe, pg = dict(eager.model.named_parameters()), dict(graphed.model.named_parameters())
+    checked = 0
+    for k, p in pe.items():
+        if p.grad is None:
+            continue
+        assert rel_err(pg[k].grad.cpu(), p.grad.cpu()) < 2e-5, k
+        checked += 1
+    assert checked > 20
