@@ -37,7 +37,7 @@ SIGNATURES = {
     "i2t_dec_advance": (c_int, [P, P]),
     "i2t_dec_linear": (c_int, [P, P, P, F, P, P, P, P, L, L, L, L, I, I, I, P, P, L, L, I, P, P]),
     "i2t_dec_attn": (c_int, [P, L, P, P, L, L, P, L, P, L, L, L, L, I, P]),
-    "i2t_sample": (c_int, [P, L, L, L, P, L, P, I, L, F, L, P, L, U64, P, P, P, I, P]),
+    "i2t_sample": (c_int, [P, L, L, L, P, L, P, I, L, F, L, F, P, L, U64, P, P, P, I, P]),
     "i2t_decode_mega": (c_int, [P, P, P, L, L, L, L, L, L, L, I, P, L, P, P, P, P, P, P, F, L, P, L, P, P, L, P, P]),
     "i2t_decode_mega2_max_keys": (c_int, []),
     "i2t_decode_mega2": (c_int, [P, P, P, L, P, L, L, L, L, L, L, L, L, L, L, P, L, P, P, P, P, P, P, P, F, L, P, L, P, L, L, P, P]),

@@ -10,7 +10,7 @@ namespace i2t {
 
 __global__ void __launch_bounds__(SAMP_THREADS)
 sample_kernel(float* __restrict__ logits, int64_t ldl, int V, int64_t* __restrict__ ids, int64_t ids_ld,
-              const int32_t* pos_ptr_c, int32_t* pos_ptr_adv, int cur_len_const, float temperature, int top_k,
+              const int32_t* pos_ptr_c, int32_t* pos_ptr_adv, int cur_len_const, float temperature, int top_k, float nucleus_p,
               const int32_t* __restrict__ ngrams, int n_ngrams, uint64_t seed_arg, const uint64_t* __restrict__ seed_ptr,
               float* __restrict__ probs_out, int32_t* __restrict__ ticket, int write_token, int use_smem) {
   extern __shared__ __align__(16) float sv_smem[];
@@ -22,7 +22,7 @@ sample_kernel(float* __restrict__ logits, int64_t ldl, int V, int64_t* __restric
   float* row = logits + (int64_t)b * ldl;
   float* sv = use_smem ? sv_smem : row;
   const int choice = sample_row_smem(sv, S, row, V, ids + (int64_t)b * ids_ld, cur_len, temperature, top_k, ngrams, n_ngrams,
-                                     seed, b, probs_out ? probs_out + (int64_t)b * V : nullptr, t, SAMP_THREADS);
+                                     seed, b, probs_out ? probs_out + (int64_t)b * V : nullptr, t, SAMP_THREADS, nucleus_p);
   if (t == 0) {
     if (write_token) ids[(int64_t)b * ids_ld + cur_len] = (int64_t)choice;
     if (pos_ptr_adv != nullptr) {
@@ -41,11 +41,12 @@ sample_kernel(float* __restrict__ logits, int64_t ldl, int V, int64_t* __restric
 using namespace i2t;
 
 extern "C" int i2t_sample(float* logits, int64_t ldl, int64_t B, int64_t V, int64_t* ids, int64_t ids_ld,
-                          int32_t* pos_ptr, int advance_pos, int64_t cur_len, float temperature, int64_t top_k,
+                          int32_t* pos_ptr, int advance_pos, int64_t cur_len, float temperature, int64_t top_k, float nucleus_p,
                           const int32_t* ngrams, int64_t n_ngrams, uint64_t seed, const uint64_t* seed_ptr, float* probs_out,
                           int32_t* ticket, int write_token, void* stream) {
   I2T_REQUIRE(logits && ids && B > 0 && V > 1, "sample: bad arguments");
   I2T_REQUIRE(temperature > 0.f, "sample: temperature must be positive");
+  I2T_REQUIRE(nucleus_p >= 0.f && nucleus_p <= 1.f, "sample: nucleus_p must be in [0, 1] (0 or 1 = off)");
   I2T_REQUIRE(n_ngrams == 0 || ngrams, "sample: n-gram list missing");
   I2T_REQUIRE(!advance_pos || (pos_ptr && ticket), "sample: advancing the position needs pos_ptr and a ticket counter");
   I2T_REQUIRE(pos_ptr || cur_len > 0, "sample: need a position");
@@ -59,7 +60,7 @@ extern "C" int i2t_sample(float* logits, int64_t ldl, int64_t B, int64_t V, int6
   }
   sample_kernel<<<(unsigned)B, SAMP_THREADS, smem, (cudaStream_t)stream>>>(
       logits, ldl, (int)V, ids, ids_ld, pos_ptr, advance_pos ? pos_ptr : nullptr, (int)cur_len, temperature,
-      (int)(top_k > 0 ? top_k : 0), ngrams, (int)n_ngrams, seed, seed_ptr, probs_out, ticket, write_token, use_smem);
+      (int)(top_k > 0 ? top_k : 0), nucleus_p, ngrams, (int)n_ngrams, seed, seed_ptr, probs_out, ticket, write_token, use_smem);
   I2T_LAUNCHED();
   return I2T_OK;
 }

@@ -40,11 +40,14 @@ __device__ __forceinline__ float philox_uniform(uint64_t seed, uint32_t row, uin
 struct SampleScratch {
   int banned[SAMP_MAX_BANNED];
   uint32_t ghist[SAMP_HGROUPS][256];
+  float mhist[256];            // nucleus: probability mass per radix bin
   double redd[32];
   double scan[32];
   float redf[32];
   int nbanned;
   uint32_t prefix, kleft;
+  float nuc_above;             // nucleus: unnormalised mass of the keys above the boundary group
+  int nuc_found, nuc_first;
   int choice, fallback;
 };
 
@@ -74,7 +77,7 @@ __device__ __forceinline__ int sample_row_smem(float* __restrict__ sv, SampleScr
                                                const int64_t* __restrict__ idr, int cur_len, float temperature,
                                                int top_k, const int32_t* __restrict__ ngrams, int n_ngrams,
                                                uint64_t seed, int row_index, float* __restrict__ probs_row, int t,
-                                               int nthreads) {
+                                               int nthreads, float nucleus_p = 0.f) {
   const int lane = t & 31, w = t >> 5;
   if (t == 0) { S.nbanned = 0; S.choice = 0x7fffffff; S.fallback = 0x7fffffff; }
   samp_sync(nthreads);
@@ -154,16 +157,83 @@ __device__ __forceinline__ int sample_row_smem(float* __restrict__ sv, SampleScr
   //      chosen token does not depend on how many threads run the sampler ----
   const int chunk = (V + nthreads - 1) / nthreads;
   const int beg = min(V, t * chunk), end = min(V, beg + chunk);
+  // nucleus filter state (models/vision_encoder_decoder.py:160-172): a survivor stays iff its logit is ABOVE xk, or it is
+  // the designated first element of a tie group at the very top (the reference keeps exactly the first sorted entry then)
+  float xk = -INFINITY;
+  int tie_first = -1;
+  auto keep = [&](int i, float x) { return x >= thr && (x > xk || i == tie_first); };
   double part = 0.0;
   for (int i = beg; i < end; ++i) {
     const float x = sv[i];
-    if (x >= thr) part += (double)expf(x - mx);
+    if (keep(i, x)) part += (double)expf(x - mx);
   }
-  const double total = samp_block_reduce<double>(part, S.redd, false, t, nthreads);
+  double total = samp_block_reduce<double>(part, S.redd, false, t, nthreads);
+  if (nucleus_p > 0.f && nucleus_p < 1.f) {
+    // sorted descending, keep i iff cumsum_i <= max(p, p_max): find the boundary key by a radix descent over the
+    // order-preserving keys with per-bin probability MASS (unnormalised: p_max = 1, budget = max(p * total, 1))
+    const float budget = fmaxf(nucleus_p * (float)total, 1.0f);
+    if (t == 0) { S.prefix = 0u; S.nuc_above = 0.f; S.nuc_found = 0; S.nuc_first = 0x7fffffff; }
+    samp_sync(nthreads);
+    for (int pass = 0; pass < 4; ++pass) {
+      const int shift = 24 - 8 * pass;
+      for (int i = t; i < 256; i += nthreads) S.mhist[i] = 0.f;
+      samp_sync(nthreads);
+      const uint32_t prefix = S.prefix;
+      const uint32_t mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+      const bool live = pass == 0 || S.nuc_found;          // once every survivor fits there is nothing to refine
+      if (live) {
+        for (int i = t; i < V; i += nthreads) {
+          const float x = sv[i];
+          if (x >= thr) {
+            const uint32_t key = float_key(x);
+            if ((key & mask) == prefix) atomicAdd(&S.mhist[(key >> shift) & 255u], expf(x - mx));
+          }
+        }
+      }
+      samp_sync(nthreads);
+      if (t == 0 && live) {
+        float acc = S.nuc_above;
+        int bin = 255, found = 0;
+        for (; bin >= 0; --bin) {
+          if (acc + S.mhist[bin] > budget) { found = 1; break; }
+          acc += S.mhist[bin];
+        }
+        if (!found && pass > 0) {      // rounding: the sub-bins sum to less than their parent bin did -> lowest sub-bin is the boundary
+          found = 1;
+          bin = 0;
+          acc -= S.mhist[0];
+        }
+        S.nuc_found = found;
+        if (found) {
+          S.nuc_above = acc;
+          S.prefix = prefix | ((uint32_t)bin << shift);
+        }
+      }
+      samp_sync(nthreads);
+    }
+    if (S.nuc_found) {
+      const uint32_t kk = S.prefix;                         // key of the boundary group: it does not fit -> dropped
+      xk = __uint_as_float((kk & 0x80000000u) ? (kk & 0x7fffffffu) : ~kk);
+      if (S.nuc_above == 0.f) {                             // the boundary group IS the top (ties at the maximum): keep its first
+        int best = 0x7fffffff;
+        for (int i = t; i < V; i += nthreads)
+          if (sv[i] == xk) best = min(best, i);
+        if (best != 0x7fffffff) atomicMin(&S.nuc_first, best);
+        samp_sync(nthreads);
+        tie_first = S.nuc_first;
+      }
+      part = 0.0;
+      for (int i = beg; i < end; ++i) {
+        const float x = sv[i];
+        if (keep(i, x)) part += (double)expf(x - mx);
+      }
+      total = samp_block_reduce<double>(part, S.redd, false, t, nthreads);
+    }
+  }
   if (probs_row != nullptr) {
     for (int i = t; i < V; i += nthreads) {
       const float x = sv[i];
-      probs_row[i] = x >= thr ? (float)((double)expf(x - mx) / total) : 0.f;
+      probs_row[i] = keep(i, x) ? (float)((double)expf(x - mx) / total) : 0.f;
     }
   }
   const double target = (double)philox_uniform(seed, (uint32_t)row_index, (uint32_t)cur_len) * total;
@@ -183,7 +253,7 @@ __device__ __forceinline__ int sample_row_smem(float* __restrict__ sv, SampleScr
     int pick = -1;
     for (int i = beg; i < end; ++i) {
       const float x = sv[i];
-      if (x >= thr) {
+      if (keep(i, x)) {
         run += (double)expf(x - mx);
         pick = i;
         if (run >= target) break;

@@ -76,6 +76,7 @@ class DecodeEngine:
         self.replays_last = 0
         self._mega = None
         self._enc_graph = None
+        self.nucleus_p = None       # top-p filter (kernels mode only: the sampler kernel implements it)
         self.graph_launches = 0     # kernels executed through graph replays (they bypass the library's launch counter)
         self.trace = None          # set to an int64 device tensor [n_sched * 4] to collect per-stage clock stamps
 
@@ -219,7 +220,7 @@ class DecodeEngine:
             V = spec["vocab_size"]
             lin(self.x, dp + "ln_f", "decoder.lm_head.weight", None, self.logits, V, V, C)
             call("i2t_sample", ptr(self.logits), V, B, V, ptr(self.ids), self.ids.shape[1], pos, 1, 0, temperature,
-                 int(top_k) if top_k is not None else 0, ptr(self.ngrams), self.n_ngrams, 0, ptr(self.seed_dev), None,
+                 int(top_k) if top_k is not None else 0, float(self.nucleus_p or 0.0), ptr(self.ngrams), self.n_ngrams, 0, ptr(self.seed_dev), None,
                  ptr(self.ticket), 1, st)
         else:
             call("i2t_dec_advance", pos, st)
@@ -280,9 +281,15 @@ class DecodeEngine:
         self.graph_launches += st["launches"]
 
     @torch.no_grad()
-    def generate(self, images, prompt_ids, max_new_tokens: int, temperature: float, top_k: Optional[int], seed: int):
+    def generate(self, images, prompt_ids, max_new_tokens: int, temperature: float, top_k: Optional[int], seed: int,
+                 nucleus_p: Optional[float] = None):
         from . import functional as Fn
         m, B = self.model, self.B
+        if nucleus_p is not None and not (0.0 < nucleus_p < 1.0):
+            nucleus_p = None
+        if nucleus_p is not None and self.mode != "kernels":
+            raise I2TError("top-p sampling runs in the 'kernels' decode mode (VisionEncoderDecoder.generate selects it)")
+        self.nucleus_p = nucleus_p
         P = prompt_ids.shape[1]
         assert prompt_ids.shape[0] == B and P + max_new_tokens <= self.Tmax + 1
         self._encode(images)
@@ -307,7 +314,7 @@ class DecodeEngine:
             return out
         for _ in range(P - 1):
             self._step(False, temperature, top_k)
-        key = (float(temperature), top_k)
+        key = (float(temperature), top_k, nucleus_p)
         g = self.graphs.get(key)
         if g is None:
             # first use: run one step eagerly (sets kernel attributes, loads modules), then capture the next one

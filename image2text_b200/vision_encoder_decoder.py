@@ -140,19 +140,54 @@ class VisionEncoderDecoder(nn.Module):
         """reference models/vision_encoder_decoder.py:136-182, with a KV cache, an on-device sampler and one CUDA graph
         per step shape.  Returns (B, prompt + max_new_tokens) int64 including the prompt."""
         from .decode_engine import DecodeEngine
-        if nucleus_p is not None:
-            raise NotImplementedError("nucleus (top-p) sampling is a 'next' row (SURVEY.md 8f-3)")
         blk = self.spec["block_size"] - self.space_for_prompt
         assert max_new_tokens <= blk - prompt_ids.size(-1)
-        B = prompt_ids.shape[0]
-        key = (B, self.compute_dtype)
-        eng = self._decode_engines.get(key)
-        if eng is None:
-            eng = DecodeEngine(self, B)
-            self._decode_engines[key] = eng
         if seed is None:
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())   # torch's RNG seeds the device Philox stream
-        return eng.generate(images, prompt_ids, max_new_tokens, float(temperature), top_k, seed)
+        if nucleus_p is not None and not (0.0 < float(nucleus_p) < 1.0):
+            nucleus_p = None
+        if self.spec["decoder"] != "transformer":
+            return self._generate_cacheless(images, prompt_ids, max_new_tokens, float(temperature), top_k, nucleus_p, seed)
+        B = prompt_ids.shape[0]
+        key = (B, self.compute_dtype, nucleus_p is not None)
+        eng = self._decode_engines.get(key)
+        if eng is None:
+            # the top-p filter lives in the stand-alone sampler kernel: that request takes the per-stage kernels
+            eng = DecodeEngine(self, B, mode="kernels" if nucleus_p is not None else None)
+            self._decode_engines[key] = eng
+        return eng.generate(images, prompt_ids, max_new_tokens, float(temperature), top_k, seed, nucleus_p=nucleus_p)
+
+    @torch.no_grad()
+    def _generate_cacheless(self, images, prompt_ids, max_new_tokens, temperature, top_k, nucleus_p, seed):
+        """HF-layout decoders (GPT2HuggingfaceDecoder, models/decoder.py:335-361): the reference's own algorithm -- one full
+        decoder forward over the prefix per new token (vision_encoder_decoder.py:144-150) -- on the CUDA kernels, with the
+        device sampler (n-gram ban, top-k, top-p, Philox draw) instead of the host loop of :152-180.  The encoder runs once.
+        A KV-cached decode for the Conv1D weight layout is the next row; this path exists so that `generate` works for every
+        model the forward supports."""
+        from . import functional as Fn
+        from . import ops
+        from ._lib import call
+        spec = self.spec
+        W = self.weights()
+        enc = Fn.encoder_forward(W, spec, images, self.compute_dtype, train_trunk=False)
+        B, P = prompt_ids.shape
+        V = spec["vocab_size"]
+        blk = spec["block_size"] - self.space_for_prompt
+        dev = prompt_ids.device
+        ids = torch.zeros((B, P + max_new_tokens), device=dev, dtype=torch.int64)
+        ids[:, :P] = prompt_ids
+        ngrams = torch.tensor(list(spec["no_repeat_n_grams"]) or [0], device=dev, dtype=torch.int32)
+        n_ngrams = len(spec["no_repeat_n_grams"])
+        row = torch.empty((B, V), device=dev, dtype=torch.float32)
+        for t in range(max_new_tokens):
+            cur = P + t
+            cond = ids[:, max(0, cur - blk):cur].contiguous()
+            logits, _ = Fn.decoder_forward(W, spec, cond, enc, self.compute_dtype, training=False)
+            row.copy_(logits[:, -1, :V])
+            call("i2t_sample", ops.ptr(row), V, B, V, ops.ptr(ids), ids.shape[1], None, 0, cur, temperature,
+                 int(top_k) if top_k is not None else 0, float(nucleus_p or 0.0), ops.ptr(ngrams), n_ngrams,
+                 int(seed) & 0x7FFFFFFFFFFFFFFF, None, None, None, 1, ops.stream())
+        return ids
 
 
 class _Weights:

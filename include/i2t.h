@@ -192,10 +192,11 @@ int i2t_decode_mega2(const int64_t* lin, const int64_t* att, const int32_t* sche
  * logits (B,ldl) fp32 are modified in place (/temperature, banned -> -inf).  Tokens ids[b, 0..cur_len) are the history
  * (cur_len = *pos_ptr + 1 when pos_ptr != NULL, else the cur_len argument); the draw is written to ids[b, cur_len] when
  * write_token != 0.  top_k <= 0 means no top-k filter.  probs_out (B,V fp32, optional) receives the sampling
- * distribution.  seed_ptr (device uint64, optional) overrides seed so a captured graph can be re-seeded.
+ * distribution.  nucleus_p in (0,1): top-p filter of vision_encoder_decoder.py:160-172 after the top-k filter (sorted
+ * descending, keep while the cumulative probability <= max(p, p_max)); 0 or 1 = off.  seed_ptr (device uint64, optional) overrides seed so a captured graph can be re-seeded.
  * advance_pos != 0: the last CTA increments *pos_ptr (ticket = zeroed device int32). */
 int i2t_sample(float* logits, int64_t ldl, int64_t B, int64_t V, int64_t* ids, int64_t ids_ld, int32_t* pos_ptr,
-               int advance_pos, int64_t cur_len, float temperature, int64_t top_k, const int32_t* ngrams,
+               int advance_pos, int64_t cur_len, float temperature, int64_t top_k, float nucleus_p, const int32_t* ngrams,
                int64_t n_ngrams, uint64_t seed, const uint64_t* seed_ptr, float* probs_out, int32_t* ticket, int write_token,
                void* stream);
 

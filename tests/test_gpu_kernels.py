@@ -338,15 +338,35 @@ def test_dec_qkv_append_and_attention(cdt):
 
 
 # ------------------------------------------------------------------ sampler -----------------------------------
-def _run_sampler(logits, ids, cur_len, temperature, top_k, ngrams, seed=1, want_probs=True):
+def _run_sampler(logits, ids, cur_len, temperature, top_k, ngrams, seed=1, want_probs=True, nucleus_p=0.0):
     B, V = logits.shape
     lg = logits.to(DEV).clone()
     idd = ids.to(DEV).clone()
     ng = torch.tensor(list(ngrams) or [0], dtype=torch.int32, device=DEV)
     probs = torch.empty(B, V, device=DEV) if want_probs else None
-    call("i2t_sample", ptr(lg), V, B, V, ptr(idd), idd.shape[1], None, 0, cur_len, temperature, top_k or 0, ptr(ng), len(ngrams),
-         seed, None, ptr(probs), None, 1, stream())
+    call("i2t_sample", ptr(lg), V, B, V, ptr(idd), idd.shape[1], None, 0, cur_len, temperature, top_k or 0, float(nucleus_p),
+         ptr(ng), len(ngrams), seed, None, ptr(probs), None, 1, stream())
     return idd[:, cur_len].cpu(), (probs.cpu() if want_probs else None)
+
+
+@pytest.mark.parametrize("V,top_k,p", [(613, None, 0.9), (613, 40, 0.5), (50257, None, 0.95), (50257, 64, 0.3), (50257, None, 0.01)])
+def test_sampler_nucleus_matches_oracle(V, top_k, p):
+    """top-p filter (reference models/vision_encoder_decoder.py:160-172, restated in oracle.nucleus_filter): the device
+    sampler's distribution equals the reference's sorted / cumsum / renormalised one scattered back to token order."""
+    B = 4
+    logits = rnd(B, V, seed=70) * 3.0
+    ids = torch.zeros(B, 9, dtype=torch.int64)
+    ids[:, :8] = torch.randint(0, V, (B, 8), generator=torch.Generator().manual_seed(71))
+    spec = dict(no_repeat_n_grams=(2, 3, 4, 5))
+    base = O.next_token_probs(logits, ids[:, :8], spec, 0.8, top_k)
+    sp, si = O.nucleus_filter(base, p)
+    want = torch.zeros_like(base).scatter_(1, si, sp)
+    tok, probs = _run_sampler(logits, ids, 8, 0.8, top_k, (2, 3, 4, 5), nucleus_p=p)
+    assert float((probs - want).abs().max()) < 2e-6, float((probs - want).abs().max())
+    assert int((probs > 0).sum()) == int((want > 0).sum())
+    assert bool((want.gather(1, tok[:, None]) > 0).all())
+    if p == 0.01:                                       # p below the top probability: exactly the arg-max survives
+        assert torch.equal(tok, base.argmax(-1))
 
 
 def test_sampler_ngram_ban_topk_softmax_match_oracle(golden):

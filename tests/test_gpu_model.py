@@ -144,3 +144,36 @@ def test_nano_bf16_logits_within_2e_2(golden):
     assert torch.isfinite(full.logits).all()
     got = m.generate(images.repeat(4, 1, 1, 1), torch.full((8, 1), 50256, dtype=torch.long, device="cuda"), 8, top_k=1)
     assert got.shape == (8, 9)
+
+
+def test_tiny_nucleus_sampling_stays_in_reference_support():
+    """generate(nucleus_p=...) (reference models/vision_encoder_decoder.py:160-175): every sampled token must have non-zero
+    probability under the reference's top-k + top-p distribution given the same prefix; same seed -> same draw."""
+    m = build("tiny")
+    _, spec, sd = spec_and_weights("tiny")
+    images = synth_images(3, 32, seed=11)
+    eos = spec["vocab_size"] - 1
+    p1 = torch.full((3, 1), eos, dtype=torch.long)
+    got = m.generate(images.cuda(), p1.cuda(), max_new_tokens=14, temperature=0.9, top_k=50, nucleus_p=0.8, seed=3).cpu()
+    again = m.generate(images.cuda(), p1.cuda(), max_new_tokens=14, temperature=0.9, top_k=50, nucleus_p=0.8, seed=3).cpu()
+    assert torch.equal(got, again)
+    with torch.no_grad():
+        enc = None
+        for t in range(1, got.shape[1]):
+            enc, logits, _ = O.ved_forward(sd, spec, images, got[:, :t], encoder_output=enc, normalize_grads=False)
+            probs = O.next_token_probs(logits[:, -1], got[:, :t], spec, 0.9, 50)
+            sp, si = O.nucleus_filter(probs, 0.8)
+            kept = torch.zeros_like(probs).scatter_(1, si, sp)
+            assert bool((kept.gather(1, got[:, t:t + 1]) > 0).all()), t
+
+
+def test_gpt2hf_generate_matches_oracle_greedy():
+    """HF GPT-2 layout decoder (local/gpt2.yaml without LoRA): `generate` runs the reference's cache-less algorithm on the
+    CUDA kernels; greedy ids (top_k=1) equal the oracle's, fp32."""
+    m = build("gpt2")
+    _, spec, sd = spec_and_weights("gpt2")
+    images = synth_images(2, 224, seed=31)
+    prompt = torch.full((2, 1), 50256, dtype=torch.long)
+    got = m.generate(images.cuda(), prompt.cuda(), max_new_tokens=5, temperature=1.0, top_k=1).cpu()
+    want = O.generate(sd, spec, images, prompt, 5, top_k=1)
+    assert torch.equal(got, want)
