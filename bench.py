@@ -220,6 +220,24 @@ def run_ours(args):
     peak, peak_src = read_peaks()
     achieved = step_bytes / (step_ms / 1e3) / 1e9
     lm_bytes = V * C * esz + CAPTIONS * V * 4
+    lm = {"name": "dec_linear_kernel (LM head 50257x768 as a stand-alone launch; not on the mega2 path)",
+          "algorithmic_bytes": int(lm_bytes), "us": round(lm_ms * 1e3, 2), "achieved": round(lm_bytes / (lm_ms / 1e3) / 1e9, 1),
+          "frac": round(lm_bytes / (lm_ms / 1e3) / 1e9 / peak, 4)}
+    if eng.mode == "mega2":
+        # the dominant (only) decode kernel: one launch = NEW_TOKENS steps.  traffic: dram__bytes_read.sum + dram__bytes_write.sum
+        # of this kernel for this workload from the committed ncu --set full capture (profiles/r01_ncu_full_decode_mega2_bf16_raw.csv)
+        roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                    "traffic": 17455036456 if (cd == torch.bfloat16 and NEW_TOKENS == 64 and CAPTIONS == 8) else None,
+                    "traffic_source": "ncu --set full, profiles/r01_ncu_full_decode_mega2_bf16_raw.csv (per launch of 64 steps)",
+                    "peak_source": peak_src, "kernel": kernel_desc,
+                    "algorithmic_bytes_per_launch": int(step_bytes * NEW_TOKENS), "us_per_launch": round(step_ms * 1e3 * NEW_TOKENS, 1),
+                    "algorithmic_bytes_per_step": int(step_bytes), "us_per_step": round(step_ms * 1e3, 2),
+                    "note": "81 dependent stages per step separated by grid barriers (1.2 us floor each, scripts/micro/grid_barrier.cu): "
+                            "latency-bound, see DESIGN.md section 8; LM-head stage alone: 77 MB in ~15 us (profiles/r01_trace_mega2_bf16.txt)"}
+    else:
+        roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                    "traffic": None, "peak_source": peak_src, "kernel": kernel_desc, "algorithmic_bytes_per_launch": int(step_bytes),
+                    "us_per_launch": round(step_ms * 1e3, 2), "dominant_kernel": lm}
     line = {
         "metric": "decode tok/s (nano.yaml, 8 captions x 64 new tokens, greedy top_k=1, KV cache)",
         "value": round(value, 1), "unit": "tok/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -233,12 +251,7 @@ def run_ours(args):
         "e2e": {"value": round(e2e, 1), "unit": "tok/s", "h2d_bytes_per_step": int(images_host.numel() * 4 + prompt_host.numel() * 8),
                 "d2h_bytes_per_step": int(out_host.numel() * 8), "ms_per_step": round(ms_e2e / args.steps, 3)},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                     "traffic": None, "peak_source": peak_src, "kernel": kernel_desc,
-                     "algorithmic_bytes_per_launch": int(step_bytes), "us_per_launch": round(step_ms * 1e3, 2),
-                     "dominant_kernel": {"name": "dec_linear_kernel (LM head 50257x768 as a stand-alone launch)", "algorithmic_bytes": int(lm_bytes),
-                                         "us": round(lm_ms * 1e3, 2), "achieved": round(lm_bytes / (lm_ms / 1e3) / 1e9, 1),
-                                         "frac": round(lm_bytes / (lm_ms / 1e3) / 1e9 / peak, 4)}},
+        "roofline": roofline,
         "clocks": sampler.summary(),
     }
     if rank == 0:

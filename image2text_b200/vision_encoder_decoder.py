@@ -52,6 +52,40 @@ class _Side(ParamTree):
     def n_embd(self):
         return self._spec["n_embd"]
 
+    # Callable like the reference's sub-modules (BeamSearchTokenGenerator calls `model.encoder(images)`,
+    # models/generation_utils.py:37; the decoder API is models/decoder.py:214-256,150-157).
+    def _bind(self, owner):
+        import weakref
+        self.__dict__["_owner"] = weakref.ref(owner)      # not a registered sub-module: no cycle in state_dict()
+
+    def forward(self, *args, **kwargs):
+        from . import functional as Fn
+        m = self.__dict__["_owner"]()
+        W = m.weights()
+        if self._kind == "encoder":
+            images = args[0] if args else kwargs["images"]
+            return Fn.encoder_forward(W, self._spec, images, m.compute_dtype,
+                                      train_trunk=m.training and self._spec["refine_base_model"])
+        idx = kwargs.get("idx", args[0] if args else None)
+        cross = kwargs.get("cross_attn_embeds", args[2] if len(args) > 2 else None)
+        if kwargs.get("inputs_embeds", args[1] if len(args) > 1 else None) is not None or idx is None:
+            raise NotImplementedError("Decoder.forward(inputs_embeds=...) is composed inside VisionEncoderDecoder.forward here "
+                                      "(soft prompt + text rows are embedded by one kernel); pass idx")
+        # stand-alone decoder call: no soft prompt rows, cross attention iff embeddings are given (attn_msk: no-op, D9)
+        spec = dict(self._spec, use_soft_prompting=False, use_cross_attn=cross is not None)
+        enc = cross if cross is not None else torch.zeros((idx.shape[0], 1, spec["n_embd"]), device=idx.device)
+        logits, hidden = Fn.decoder_forward(W, spec, idx, enc, m.compute_dtype, training=m.training)
+        return logits[..., :spec["vocab_size"]], hidden
+
+    def get_inputs_embeds(self, idx):
+        m = self.__dict__["_owner"]()
+        key = "decoder.transformer.wte.weight" if self._spec["decoder"] == "transformer" else "decoder.backbone.transformer.wte.weight"
+        return m.weights()[key][idx]
+
+    def tie_weights(self):
+        """lm_head.weight and wte.weight are ONE storage by construction (both keys appear in the state dict)."""
+        return None
+
 
 class VisionEncoderDecoder(nn.Module):
     def __init__(self, config: VisionEncoderDecoderConfig, encoder=None, decoder=None, spec_overrides: Optional[dict] = None,
@@ -72,6 +106,8 @@ class VisionEncoderDecoder(nn.Module):
         self.compute_dtype = compute_dtype
         self.encoder = _Side("encoder", spec)
         self.decoder = _Side("decoder", spec)
+        self.encoder._bind(self)
+        self.decoder._bind(self)
         gen = None
         if seed is not None:
             gen = torch.Generator(device="cpu").manual_seed(seed)
@@ -87,6 +123,11 @@ class VisionEncoderDecoder(nn.Module):
             self.load_partial_checkpoint(config.chkpt_path)
 
     # ------------------------------------------------------------------ parameters ----------------------------
+    def __setstate__(self, state):
+        super().__setstate__(state)            # copy.deepcopy / pickle: re-point the sub-objects at THIS model
+        self.encoder._bind(self)
+        self.decoder._bind(self)
+
     def load_partial_checkpoint(self, path: str, map_location=None):
         """reference models/utils.py:31-36: state_dict().update(torch.load(path)); load_state_dict."""
         full = self.state_dict()

@@ -177,3 +177,20 @@ def test_gpt2hf_generate_matches_oracle_greedy():
     got = m.generate(images.cuda(), prompt.cuda(), max_new_tokens=5, temperature=1.0, top_k=1).cpu()
     want = O.generate(sd, spec, images, prompt, 5, top_k=1)
     assert torch.equal(got, want)
+
+
+def test_submodule_call_surface_matches_reference_api():
+    """`model.encoder(images)` (used by the reference's BeamSearchTokenGenerator, models/generation_utils.py:37) and the
+    stand-alone `model.decoder(idx=..., cross_attn_embeds=...)` / `get_inputs_embeds` (models/decoder.py:214-256,150-157)."""
+    m = build("tiny")
+    _, spec, sd = spec_and_weights("tiny")
+    images = synth_images(3, 32, seed=11)
+    with torch.no_grad():
+        enc = m.encoder(images.cuda())
+        ref_enc = O.encoder_forward(sd, spec, images)
+        assert rel_err(enc.cpu(), ref_enc) < 1e-4
+        out = m(images=None, ids=torch.randint(0, 600, (3, 7), generator=torch.Generator().manual_seed(2)).cuda(), encoder_output=enc)
+        assert out.logits.shape == (3, 7, spec["vocab_size"])
+        emb = m.decoder.get_inputs_embeds(torch.tensor([[5, 9]]).cuda())
+        assert torch.equal(emb.cpu(), sd["decoder.transformer.wte.weight"][[5, 9]][None])
+    assert m.decoder.block_size == spec["block_size"] and m.encoder.num_outputs == spec["n_cls"]
