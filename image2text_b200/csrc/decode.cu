@@ -12,6 +12,8 @@
 //     weight copies (weights never depend on the previous kernel) and only then waits on griddepcontrol.wait --
 //     the HBM stream continues across kernel boundaries;
 //   * all kernels read the current position from DEVICE memory so one captured CUDA graph replays every step.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace i2t {
@@ -391,6 +393,41 @@ extern "C" int i2t_dec_embed(const int64_t* ids, const float* wte, const float* 
   const int64_t n = B * C / 4;
   I2T_LAUNCH_CHECK(launch(dec_embed_kernel, dim3((unsigned)ceil_div(n, 256)), dim3(256), 0, (cudaStream_t)stream, ids, wte, wpe,
                           x, pos_ptr, (int)B, (int)C, ids_ld, (int)n_prompt));
+  return I2T_OK;
+}
+
+namespace i2t {
+// K / V rows of the token at *pos_ptr: columns [C,2C) and [2C,3C) of a packed (B, ld) fp32 qkv buffer -> row *pos_ptr of the
+// (B, Tmax, C) caches (large-batch decode: the projections run as GEMMs, this is the cache append of dec_linear's epilogue)
+template <typename TC>
+__global__ void __launch_bounds__(256) dec_kv_append_kernel(const float* __restrict__ qkv, int64_t ld, TC* __restrict__ kcache,
+                                                            TC* __restrict__ vcache, int64_t cache_bs, int C, int B,
+                                                            const int32_t* __restrict__ pos_ptr) {
+  const int pos = *pos_ptr;
+  const int c4 = C / 4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t)B * c4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / c4), cv = (int)(i % c4);
+    const float4 kx = load4(qkv + (int64_t)b * ld + C + cv * 4);
+    const float4 vx = load4(qkv + (int64_t)b * ld + 2 * C + cv * 4);
+    store4(kcache + (int64_t)b * cache_bs + (int64_t)pos * C + cv * 4, kx);
+    store4(vcache + (int64_t)b * cache_bs + (int64_t)pos * C + cv * 4, vx);
+  }
+}
+}  // namespace i2t
+
+extern "C" int i2t_dec_kv_append(const float* qkv, int64_t ld, void* kcache, void* vcache, int64_t cache_batch_stride, int64_t C,
+                                 int64_t B, int cache_dtype, const int32_t* pos_ptr, void* stream) {
+  I2T_REQUIRE(qkv && kcache && vcache && pos_ptr, "dec_kv_append: null pointer");
+  I2T_REQUIRE(B > 0 && C > 0 && C % 4 == 0 && ld >= 3 * C && ld % 4 == 0 && valid_dtype(cache_dtype), "dec_kv_append: bad sizes");
+  const int64_t n = B * (C / 4);
+  const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(n, 256), 4096);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cache_dtype == I2T_F32)
+    dec_kv_append_kernel<float><<<grid, 256, 0, st>>>(qkv, ld, (float*)kcache, (float*)vcache, cache_batch_stride, (int)C, (int)B, pos_ptr);
+  else
+    dec_kv_append_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(qkv, ld, (__nv_bfloat16*)kcache, (__nv_bfloat16*)vcache,
+                                                              cache_batch_stride, (int)C, (int)B, pos_ptr);
+  I2T_LAUNCHED();
   return I2T_OK;
 }
 

@@ -9,8 +9,10 @@ replay per token, no host round trip.  Two executions of the same arithmetic:
   mode "mega2"   (default for bf16, B <= 8): ONE cooperative launch per generate() call -- the token loop, every layer,
                  the LM head with the n-gram ban + arg-max fused (greedy) or the sampler (csrc/decode_mega2.cu);
   mode "mega"    : ONE cooperative launch per step (csrc/decode_mega.cu), fp32 or bf16;
-  mode "kernels" : ~81 launches per step (csrc/decode.cu + sampler.cu), used for larger batches / wider models and as
-                   the cross-check of the megakernel.
+  mode "kernels" : ~81 launches per step (csrc/decode.cu + sampler.cu), up to 16 sequences / wider models and as the
+                   cross-check of the megakernel;
+  mode "gemm"    : more than 16 sequences -- every projection is a tensor-core GEMM over the batch (i2t_gemm), KV append and
+                   single-query attention are the decode kernels, one CUDA graph per step.
 
 The result is the same sequence of token ids as the reference: text rows never see the soft-prompt rows,
 so the last-row logits of the cache-less forward equal the incremental ones (tests/test_gpu_model.py checks bit-exact
@@ -46,6 +48,8 @@ class DecodeEngine:
         mode = mode or os.environ.get("I2T_DECODE", "mega2" if self.cd == torch.bfloat16 else "kernels")
         if batch > 8 or max(C, self.F) > 3072 or C > 1024:
             mode = "kernels"
+        if batch > 16:
+            mode = "gemm"           # projections as tensor-core GEMMs over the batch
         if mode == "mega2" and (self.cd != torch.bfloat16 or C > 768 or C % 64 or self.F % 64 or self.F > 3072
                                 or max(self.Tmax, spec["n_cls"]) > 256 or batch * spec["n_head"] > 132):
             mode = "mega" if self.cd == torch.bfloat16 else "kernels"
@@ -67,6 +71,8 @@ class DecodeEngine:
         self.q = torch.zeros((batch, C), **f32)
         self.y = torch.zeros((batch, C), **f32)
         self.h = torch.zeros((batch, self.F), **f32)
+        self.qkv32 = torch.zeros((batch, 3 * C), **f32) if batch > 16 else None
+        self.y16 = torch.zeros((batch, C), device=dev, dtype=self.cd) if batch > 16 else None
         self.logits = torch.zeros((batch, V), **f32)
         self.ngrams = torch.tensor(list(spec["no_repeat_n_grams"]) or [0], device=dev, dtype=torch.int32)
         self.n_ngrams = len(spec["no_repeat_n_grams"])
@@ -225,7 +231,64 @@ class DecodeEngine:
         else:
             call("i2t_dec_advance", pos, st)
 
+    # ------------------------------------------------------------------ one step, large batch (GEMM path) -------
+    def _gemm_step(self, sample: bool, temperature: float, top_k: Optional[int]):
+        """More than 16 sequences: every projection is a tensor-core GEMM over the batch (M = B rows), the KV append and
+        the single-query attention are the decode kernels; same arithmetic, same device-side position / sampler."""
+        m, spec, B = self.model, self.spec, self.B
+        W = m.weights()
+        C, H, F, V = spec["n_embd"], spec["n_head"], self.F, spec["vocab_size"]
+        hs = C // H
+        cd = self.cd
+        wd = ops.F32 if cd == torch.float32 else ops.BF16
+        st = stream()
+        dp = "decoder.transformer."
+        pos = ptr(self.pos)
+        cbs = self.Tmax * C
+        call("i2t_dec_embed", ptr(self.ids), ptr(W[dp + "wte.weight"]), ptr(W[dp + "wpe.weight"]), ptr(self.x), pos, B, C,
+             self.ids.shape[1], self.n_prompt, st)
+
+        def ln(key):
+            return ops.layernorm(self.x, W[key + ".weight"], W.get(key + ".bias"), 1e-5, out_dtype=cd)
+
+        def att_out():          # attention output as the next GEMM's A operand
+            if cd == torch.float32:
+                return self.y
+            self.y16.copy_(self.y)
+            return self.y16
+
+        xi = 0
+        for d in range(spec["n_layer"]):
+            lp = f"{dp}h.{d}."
+            ops.gemm(ln(lp + "ln_1"), W.c(lp + "attn.c_attn.weight"), bias=W[lp + "attn.c_attn.bias"], out=self.qkv32)
+            call("i2t_dec_kv_append", ptr(self.qkv32), 3 * C, ptr(self.kcache[d]), ptr(self.vcache[d]), cbs, C, B, wd, pos, st)
+            call("i2t_dec_attn", ptr(self.qkv32), 3 * C, ptr(self.kcache[d]), ptr(self.vcache[d]), cbs, C, ptr(self.y), C, pos, 1,
+                 B, H, hs, wd, st)
+            ops.gemm(att_out(), W.c(lp + "attn.c_proj.weight"), bias=W[lp + "attn.c_proj.bias"], residual=self.x, out=self.x)
+            if d in self.cross_layers:
+                kw, kb = lp + "cross_attn.in_proj_weight", lp + "cross_attn.in_proj_bias"
+                ops.gemm(ln(lp + "ln_3"), W.c(kw)[0:C], bias=W[kb][0:C], out=self.q)
+                kv = self.xkv[xi]
+                es = kv.element_size()
+                call("i2t_dec_attn", ptr(self.q), C, kv.data_ptr(), kv.data_ptr() + C * es, self.S * 2 * C, 2 * C, ptr(self.y),
+                     C, None, self.S, B, H, hs, wd, st)
+                ops.gemm(att_out(), W.c(lp + "cross_attn.out_proj.weight"), bias=W[lp + "cross_attn.out_proj.bias"],
+                         residual=self.x, out=self.x)
+                xi += 1
+            h = ops.gemm(ln(lp + "ln_2"), W.c(lp + "mlp.c_fc.weight"), bias=W[lp + "mlp.c_fc.bias"], act=ops.ACT_GELU_TANH,
+                         out_dtype=cd)
+            ops.gemm(h, W.c(lp + "mlp.c_proj.weight"), bias=W[lp + "mlp.c_proj.bias"], residual=self.x, out=self.x)
+        if sample:
+            ops.gemm(ln(dp + "ln_f"), W.c("decoder.lm_head.weight"), out=self.logits)
+            call("i2t_sample", ptr(self.logits), V, B, V, ptr(self.ids), self.ids.shape[1], pos, 1, 0, temperature,
+                 int(top_k) if top_k is not None else 0, float(self.nucleus_p or 0.0), ptr(self.ngrams), self.n_ngrams, 0,
+                 ptr(self.seed_dev), None, ptr(self.ticket), 1, st)
+        else:
+            call("i2t_dec_advance", pos, st)
+
     def _step(self, sample: bool, temperature: float, top_k: Optional[int]):
+        if self.mode == "gemm":
+            return self._gemm_step(sample, temperature, top_k)
         if self.mode == "mega":
             self._mega_step(sample, temperature, top_k)
         else:
@@ -287,7 +350,7 @@ class DecodeEngine:
         m, B = self.model, self.B
         if nucleus_p is not None and not (0.0 < nucleus_p < 1.0):
             nucleus_p = None
-        if nucleus_p is not None and self.mode != "kernels":
+        if nucleus_p is not None and self.mode not in ("kernels", "gemm"):
             raise I2TError("top-p sampling runs in the 'kernels' decode mode (VisionEncoderDecoder.generate selects it)")
         self.nucleus_p = nucleus_p
         P = prompt_ids.shape[1]

@@ -143,6 +143,10 @@ void i2t_set_pdl(int enabled);
 int i2t_dec_embed(const int64_t* ids, const float* wte, const float* wpe, float* x, const int32_t* pos_ptr, int64_t B,
                   int64_t C, int64_t ids_ld, int64_t n_prompt, void* stream);
 int i2t_dec_advance(int32_t* pos_ptr, void* stream);
+/* large-batch decode (projections as GEMMs): append columns [C,2C) / [2C,3C) of the packed fp32 (B,ld) qkv rows to row
+ * *pos_ptr of the (B,Tmax,C) K / V caches (what i2t_dec_linear's qkv_split epilogue does for B <= 16) */
+int i2t_dec_kv_append(const float* qkv, int64_t ld, void* kcache, void* vcache, int64_t cache_batch_stride, int64_t C,
+                      int64_t B, int cache_dtype, const int32_t* pos_ptr, void* stream);
 /* out[b,n] = act(LN?(x)[b,:] . W[n,:] + bias[n]) (+ residual[b,n]);  B <= 16, W is (N,K) fp32 or bf16.
  * qkv_split=1 (N == 3C): columns [0,C) -> out (B,ldo), [C,2C) -> kcache, [2C,3C) -> vcache at row *pos_ptr of the
  * (B,Tmax,C) caches (fused KV-cache append).  Replaces c_attn/c_proj/c_fc/lm_head at models/layers.py:452,469,482,484

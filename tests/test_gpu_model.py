@@ -194,3 +194,19 @@ def test_submodule_call_surface_matches_reference_api():
         emb = m.decoder.get_inputs_embeds(torch.tensor([[5, 9]]).cuda())
         assert torch.equal(emb.cpu(), sd["decoder.transformer.wte.weight"][[5, 9]][None])
     assert m.decoder.block_size == spec["block_size"] and m.encoder.num_outputs == spec["n_cls"]
+
+
+def test_large_batch_generate_matches_reference(golden):
+    """More than 16 sequences take the GEMM decode path (projections as tensor-core / fp32 GEMMs over the batch): 24
+    sequences = the golden 8-caption workload three times; fp32 greedy ids must equal the reference's for every copy."""
+    g = golden("nano_generate")
+    m = build("nano")
+    images = synth_images(8, 224, seed=1234).cuda().repeat(3, 1, 1, 1)
+    prompt = torch.full((24, 1), 50256, dtype=torch.long, device="cuda")
+    got = m.generate(images, prompt, max_new_tokens=20, temperature=1.0, top_k=1).cpu().numpy()
+    assert m._decode_engines[(24, torch.float32, False)].mode == "gemm"
+    want = np.concatenate([g["greedy"][:, :21]] * 3, axis=0)
+    assert np.array_equal(got, want)
+    m16 = build("nano", torch.bfloat16)
+    out = m16.generate(images, prompt, max_new_tokens=6, temperature=0.9, top_k=16, nucleus_p=0.9, seed=5)
+    assert out.shape == (24, 7) and bool((out[:, 1:] >= 0).all()) and bool((out[:, 1:] < 50257).all())
