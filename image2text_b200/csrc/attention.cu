@@ -430,13 +430,17 @@ int attn_fwd_tc(const void* q, const void* k, const void* v, void* out, float* l
 int attn_bwd_tc(const void* q, const void* k, const void* v, const void* dout, const float* lse, const float* delta, float* dq_acc,
                 void* dk, void* dv, int64_t B, int64_t H, int64_t Tq, int64_t Tk, int64_t head_dim, int64_t q_bs, int64_t q_rs,
                 int64_t kv_bs, int64_t kv_rs, int mode, int64_t n_prompt, cudaStream_t st);
+int attn_fwd_tc5(const void* q, const void* k, const void* v, void* out, float* lse, int64_t B, int64_t H, int64_t Tq, int64_t Tk,
+                 int64_t head_dim, int64_t q_bs, int64_t q_rs, int64_t kv_bs, int64_t kv_rs, int mode, int64_t n_prompt,
+                 cudaStream_t st);
+// 0: fp32-math kernels; 1 (default): tensor cores -- tcgen05 forward where eligible, mma.sync otherwise; 2: mma.sync only
 static std::atomic<int> g_attn_tc{1};
 
 }  // namespace i2t
 
 using namespace i2t;
 
-extern "C" void i2t_set_tensor_core_attention(int enabled) { g_attn_tc.store(enabled ? 1 : 0); }
+extern "C" void i2t_set_tensor_core_attention(int mode) { g_attn_tc.store(mode < 0 ? 0 : (mode > 2 ? 1 : mode)); }
 
 extern "C" int i2t_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int64_t B, int64_t H,
                             int64_t Tq, int64_t Tk, int64_t head_dim, int64_t q_batch_stride, int64_t q_row_stride,
@@ -451,6 +455,11 @@ extern "C" int i2t_attn_fwd(const void* q, const void* k, const void* v, void* o
   I2T_REQUIRE(valid_dtype(in_dtype) && valid_dtype(out_dtype), "attn_fwd: bad dtype");
   cudaStream_t st = (cudaStream_t)stream;
   if (in_dtype == I2T_BF16 && out_dtype == I2T_BF16 && g_attn_tc.load() == 1) {
+    const int r5 = attn_fwd_tc5(q, k, v, out, lse, B, H, Tq, Tk, head_dim, q_batch_stride, q_row_stride, kv_batch_stride,
+                                kv_row_stride, mask_mode, n_prompt, st);
+    if (r5 != 0) return r5 < 0 ? r5 : I2T_OK;
+  }
+  if (in_dtype == I2T_BF16 && out_dtype == I2T_BF16 && g_attn_tc.load() != 0) {
     const int r = attn_fwd_tc(q, k, v, out, lse, B, H, Tq, Tk, head_dim, q_batch_stride, q_row_stride, kv_batch_stride,
                               kv_row_stride, mask_mode, n_prompt, st);
     if (r != 0) return r < 0 ? r : I2T_OK;
@@ -477,13 +486,13 @@ static int launch_attn_bwd(const void* q, const void* k, const void* v, const vo
                            int64_t n_prompt, cudaStream_t st) {
   // workspace: delta (B*H*Tq) then dq accumulator (B*H*Tq*HS), fp32
   float* delta = ws;
-  float* dq_acc = ws + B * H * Tq;
+  float* dq_acc = ws + (B * H * Tq + 3) / 4 * 4;      // keep the accumulator 16-byte aligned (float4 reads in the scatter)
   I2T_CUDA(cudaMemsetAsync(dq_acc, 0, (size_t)(B * H * Tq * HS) * sizeof(float), st));
   const int64_t rows = B * Tq * H;
   attn_delta_kernel<T, HS><<<(unsigned)ceil_div(rows, 4), 128, 0, st>>>((const T*)out, (const T*)dout, delta, (int)H,
                                                                         (int)Tq, rows);
   I2T_LAUNCHED();
-  if (sizeof(T) == 2 && g_attn_tc.load() == 1) {
+  if (sizeof(T) == 2 && g_attn_tc.load() != 0) {
     const int r = attn_bwd_tc(q, k, v, dout, lse, delta, dq_acc, dk, dv, B, H, Tq, Tk, HS, q_bs, q_rs, kv_bs, kv_rs, mode,
                               n_prompt, st);
     if (r < 0) return r;
@@ -512,7 +521,7 @@ static int launch_attn_bwd(const void* q, const void* k, const void* v, const vo
 }  // namespace i2t
 
 extern "C" int64_t i2t_attn_bwd_workspace_bytes(int64_t B, int64_t H, int64_t Tq, int64_t head_dim) {
-  return (B * H * Tq + B * H * Tq * head_dim) * (int64_t)sizeof(float);
+  return ((B * H * Tq + 3) / 4 * 4 + B * H * Tq * head_dim) * (int64_t)sizeof(float);
 }
 
 extern "C" int i2t_attn_bwd(const void* q, const void* k, const void* v, const void* out, const void* dout,

@@ -13,6 +13,7 @@
 #include <unordered_map>
 
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace i2t {
 
@@ -28,83 +29,6 @@ struct TcEpilogue {
   int M, N;
   int act, accumulate, res_dtype, c_dtype;
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t done;
-  uint32_t spins = 0;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (!done && ++spins > (1u << 28)) asm volatile("trap;");   // a protocol bug must abort the launch, not hang the GPU
-  } while (!done);
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-// K-major, 128-byte swizzle, rows of 64 bf16 (128 B), 8-row swizzle atoms 1024 B apart (cute::UMMA::SmemDescriptor)
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)1 << 16;            // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;  // stride byte offset between 8-row groups
-  d |= (uint64_t)1 << 46;            // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;            // SWIZZLE_128B
-  return d;
-}
-// MN-major, 128-byte swizzle: the tile is stored [K rows][64 MN elements = 128 B]; a swizzle atom is 8 K-rows (1024 B).
-// Canonical layout ((T,8,m),(8,k)) with strides ((1,T,LBO),(8T,SBO)): LBO = distance between the two 64-wide MN halves
-// of the 128-wide tile (64 rows x 128 B = 8192 B), SBO = distance between consecutive 8-row K groups (1024 B).
-__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)(8192 >> 4) << 16;  // leading byte offset
-  d |= (uint64_t)(1024 >> 4) << 32;  // stride byte offset
-  d |= (uint64_t)1 << 46;            // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;            // SWIZZLE_128B
-  return d;
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 // One epilogue chunk: 32 accumulator columns of this thread's row -> bias / activation / residual / cast -> global.
 __device__ __forceinline__ void tc_epilogue_chunk(const TcEpilogue& epi, const uint32_t (&r)[32], int64_t row, int64_t n0) {
@@ -540,7 +464,7 @@ struct MapKeyHash {
 
 // 2-D bf16 [rows][cols] (cols contiguous, pitch ld elements), box {64 cols, box_rows}, 128-byte swizzle, zero fill out
 // of bounds.  K-major operand: cols = K, box_rows = 128.  MN-major operand: cols = MN, rows = K, box_rows = 64.
-static int make_map(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, CUtensorMap* out) {
+int tc_make_map(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, CUtensorMap* out) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
   MapKey key{ptr, rows, cols, ld, box_rows};
@@ -650,7 +574,7 @@ int gemm_tc_try(const void* A, const void* B, const float* bias, const void* res
   epi.c_dtype = c_dtype;
   const int kb = (int)ceil_div(K, TC_BK);
   CUtensorMap ma, mb;
-  int rc = a_kmajor ? make_map(A, M, K, lda, TC_BM, &ma) : make_map(A, K, M, lda, 64, &ma);
+  int rc = a_kmajor ? tc_make_map(A, M, K, lda, TC_BM, &ma) : tc_make_map(A, K, M, lda, 64, &ma);
   if (rc != I2T_OK) return rc;
   // CTA-pair tiles (256 x 256, else 256 x 128) when they fill at least ~3/4 of the 74 SM pairs; otherwise 128 x 128 tiles
   if (g_pair_mode.load() == 1) {
@@ -660,14 +584,14 @@ int gemm_tc_try(const void* A, const void* B, const float* bias, const void* res
     if (mt * ceil_div(N, 256) >= want) bn = 256;
     else if (mt * ceil_div(N, 128) >= want) bn = 128;
     if (bn != 0) {
-      rc = b_kmajor ? make_map(B, N, K, ldb, bn / 2, &mb) : make_map(B, K, N, ldb, 64, &mb);
+      rc = b_kmajor ? tc_make_map(B, N, K, ldb, bn / 2, &mb) : tc_make_map(B, K, N, ldb, 64, &mb);
       if (rc != I2T_OK) return rc;
       const int nt = (int)ceil_div(N, bn);
       return bn == 256 ? launch_pair_layout<256>(ma, mb, kb, epi, (int)mt, nt, a_kmajor, b_kmajor, st)
                        : launch_pair_layout<128>(ma, mb, kb, epi, (int)mt, nt, a_kmajor, b_kmajor, st);
     }
   }
-  rc = b_kmajor ? make_map(B, N, K, ldb, TC_BN, &mb) : make_map(B, K, N, ldb, 64, &mb);
+  rc = b_kmajor ? tc_make_map(B, N, K, ldb, TC_BN, &mb) : tc_make_map(B, K, N, ldb, 64, &mb);
   if (rc != I2T_OK) return rc;
   dim3 grid((unsigned)ceil_div(N, TC_BN), (unsigned)ceil_div(M, TC_BM));
   if (a_kmajor && b_kmajor) return launch_tc<false, false>(ma, mb, kb, epi, grid, st);

@@ -130,8 +130,9 @@ int i2t_xattn_bwd(const void* q, const void* k, const void* v, const void* dout,
 void i2t_set_tensor_core_gemm(int enabled);
 /* 1 (default): large bf16 GEMMs use the CTA-pair kernel (tcgen05 cta_group::2, 256-row tiles); 0: 128x128 tiles only. */
 void i2t_set_gemm_cta_pair(int enabled);
-/* 1 (default): bf16 attention forward runs on the tensor cores; 0: the fp32-math kernel (A/B testing). */
-void i2t_set_tensor_core_attention(int enabled);
+/* bf16 attention: 1 (default) tensor cores -- tcgen05/TMEM forward when head_dim == 64 and <= 384 keys, mma.sync otherwise
+ * and for the backward; 2: mma.sync kernels only; 0: the fp32-math kernels (A/B testing). */
+void i2t_set_tensor_core_attention(int mode);
 
 /* ---- KV-cached decode step (no counterpart in the reference, which recomputes the prefix every token:
  *      models/vision_encoder_decoder.py:144-150).  pos_ptr is a DEVICE int32: the index of the token being processed

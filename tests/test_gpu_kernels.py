@@ -181,7 +181,8 @@ def _ref_attention(qkv, B, T, H, mode, n_prompt):
 
 
 @pytest.mark.parametrize("B,T,H,hs,mode,n_prompt", [(2, 197, 12, 64, 0, 0), (2, 256, 12, 64, 2, 8), (3, 70, 4, 32, 1, 0),
-                                                    (1, 64, 2, 64, 2, 4), (2, 48, 4, 32, 2, 4)])
+                                                    (1, 64, 2, 64, 2, 4), (2, 48, 4, 32, 2, 4), (2, 272, 12, 64, 1, 0),
+                                                    (1, 300, 4, 64, 0, 0), (3, 130, 3, 64, 2, 16)])
 def test_attention_fwd_bwd(B, T, H, hs, mode, n_prompt):
     C = H * hs
     qkv = rnd(B * T, 3 * C, seed=14)
@@ -212,6 +213,14 @@ def test_attention_fwd_bwd(B, T, H, hs, mode, n_prompt):
     finally:
         lib().i2t_set_tensor_core_attention(1)
     assert relerr(g_tc.float(), g_f.float()) < 2e-2
+    # forward A/B: tcgen05 kernel (default where eligible) vs the mma.sync kernel vs the fp32-math kernel, same bf16 inputs
+    lib().i2t_set_tensor_core_attention(2)
+    try:
+        o_mma, lse_mma = ops.attention_packed(q16, B, T, H, mode, n_prompt, want_lse=True)
+    finally:
+        lib().i2t_set_tensor_core_attention(1)
+    assert relerr(o16.float(), o_mma.float()) < 1e-2 and relerr(o16.float(), o_f.float()) < 1e-2
+    assert float((lse16 - lse_mma).abs().max()) < 2e-2 and float((lse16 - lse_f).abs().max()) < 2e-2
 
 
 @pytest.mark.parametrize("B,T,S,H,hs", [(2, 256, 8, 12, 64), (3, 20, 4, 4, 32), (1, 33, 16, 12, 64), (1, 7, 64, 2, 64)])
