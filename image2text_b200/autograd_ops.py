@@ -125,20 +125,33 @@ class AttnFn(torch.autograd.Function):
 
 
 class XAttnFn(torch.autograd.Function):
-    """Cross attention over S <= 64 encoder tokens: reference models/layers.py:537-542,600-605."""
+    """Cross attention over S <= 64 encoder tokens: reference models/layers.py:537-542,600-605.  bf16: the tensor-core
+    attention kernels with Tk = S (one key tile); fp32: the shared-memory K/V kernels of xattn.cu (parity anchor)."""
 
     @staticmethod
     def forward(ctx, q, kv, B, T, S, H):
         q, kv = q.contiguous(), kv.contiguous()
+        tc = q.dtype == torch.bfloat16 and (q.shape[1] // H) in (32, 64) and q.shape[1] % 8 == 0
+        if tc:
+            out, lse = ops.xattn_tc(q, kv, B, T, S, H)
+        else:
+            out, lse = ops.xattn(q, kv, B, T, S, H), None
         if any(ctx.needs_input_grad):
-            ctx.save_for_backward(q, kv)
-            ctx.meta = (B, T, S, H)
-        return ops.xattn(q, kv, B, T, S, H)
+            if tc:
+                ctx.save_for_backward(q, kv, out, lse)
+            else:
+                ctx.save_for_backward(q, kv)
+            ctx.meta = (B, T, S, H, tc)
+        return out
 
     @staticmethod
     def backward(ctx, dout):
+        B, T, S, H, tc = ctx.meta
+        if tc:
+            q, kv, out, lse = ctx.saved_tensors
+            dq, dkv = ops.xattn_tc_bwd(q, kv, out, dout.contiguous().to(q.dtype), lse, B, T, S, H)
+            return dq, dkv, None, None, None, None
         q, kv = ctx.saved_tensors
-        B, T, S, H = ctx.meta
         dq, dkv = ops.xattn_bwd(q, kv, dout.contiguous().to(q.dtype), B, T, S, H)
         return dq, dkv.to(kv.dtype), None, None, None, None
 

@@ -148,6 +148,33 @@ def xattn_bwd(q, kv, dout, B, T, S, H):
     return dq, dkv
 
 
+def xattn_tc(q: torch.Tensor, kv: torch.Tensor, B: int, T: int, S: int, H: int):
+    """bf16 cross attention on the tensor-core attention kernels (i2t_attn_fwd with Tk = S, no mask): q (B*T, C), kv (B*S, 2C)
+    packed [k | v].  Returns (out (B*T, C), lse (B, H, T))."""
+    C = q.shape[1]
+    hs = C // H
+    out = torch.empty_like(q)
+    lse = torch.empty((B, H, T), device=q.device, dtype=torch.float32)
+    es = kv.element_size()
+    call("i2t_attn_fwd", ptr(q), kv.data_ptr(), kv.data_ptr() + C * es, ptr(out), ptr(lse), B, H, T, S, hs, T * q.stride(0),
+         q.stride(0), S * 2 * C, 2 * C, MASK_NONE, 0, dt(q), dt(out), stream())
+    return out, lse
+
+
+def xattn_tc_bwd(q, kv, out, dout, lse, B, T, S, H):
+    C = q.shape[1]
+    hs = C // H
+    dq = torch.empty_like(q)
+    dkv = torch.empty_like(kv)
+    from ._lib import lib
+    ws = torch.empty(lib().i2t_attn_bwd_workspace_bytes(B, H, T, hs), device=q.device, dtype=torch.uint8)
+    es = kv.element_size()
+    call("i2t_attn_bwd", ptr(q), kv.data_ptr(), kv.data_ptr() + C * es, ptr(out), ptr(dout), ptr(lse), ptr(dq), dkv.data_ptr(),
+         dkv.data_ptr() + C * es, ptr(ws), B, H, T, S, hs, T * q.stride(0), q.stride(0), S * 2 * C, 2 * C, MASK_NONE, 0, dt(q),
+         stream())
+    return dq, dkv
+
+
 def patch_im2col(images: torch.Tensor, p: int, out_dtype) -> torch.Tensor:
     _need_cuda(images)
     assert images.dtype == torch.float32 and images.is_contiguous()

@@ -236,6 +236,16 @@ def test_xattn_fwd_bwd(B, T, S, H, hs):
     assert relerr(out, ref) < 3e-6
     dq, dkv = ops.xattn_bwd(q.to(DEV), kv.to(DEV), dout.to(DEV), B, T, S, H)
     assert relerr(dq, qr.grad) < 2e-5 and relerr(dkv, kvr.grad) < 2e-5
+    # bf16: the tensor-core attention kernels with Tk = S (what XAttnFn runs), against fp64 on the bf16-rounded inputs
+    q16, kv16, d16 = (t.to(DEV).to(torch.bfloat16) for t in (q, kv, dout))
+    qr2, kvr2 = q16.double().cpu().requires_grad_(True), kv16.double().cpu().requires_grad_(True)
+    k2, v2 = kvr2.view(B, S, 2 * C).split(C, dim=2)
+    ref2 = O.merge_heads(O.sdpa(O.split_heads(qr2.view(B, T, C), H), O.split_heads(k2, H), O.split_heads(v2, H), None)).reshape(B * T, C)
+    ref2.backward(d16.double().cpu())
+    o16, lse16 = ops.xattn_tc(q16, kv16, B, T, S, H)
+    assert relerr(o16.float(), ref2) < 1e-2
+    dq16, dkv16 = ops.xattn_tc_bwd(q16, kv16, o16, d16, lse16, B, T, S, H)
+    assert relerr(dq16.float(), qr2.grad) < 2e-2 and relerr(dkv16.float(), kvr2.grad) < 2e-2
 
 
 # ------------------------------------------------------------------ encoder pieces ----------------------------
