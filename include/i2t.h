@@ -130,6 +130,8 @@ int i2t_xattn_bwd(const void* q, const void* k, const void* v, const void* dout,
 void i2t_set_tensor_core_gemm(int enabled);
 /* 1 (default): large bf16 GEMMs use the CTA-pair kernel (tcgen05 cta_group::2, 256-row tiles); 0: 128x128 tiles only. */
 void i2t_set_gemm_cta_pair(int enabled);
+/* 1 (default): the CTA-pair kernel's output tile leaves through shared memory + cp.async.bulk.tensor stores; 0: row stores. */
+void i2t_set_gemm_tma_store(int enabled);
 /* bf16 attention: 1 (default) tensor cores -- tcgen05/TMEM forward when head_dim == 64 and <= 384 keys, mma.sync otherwise
  * and for the backward; 2: mma.sync kernels only; 0: the fp32-math kernels (A/B testing). */
 void i2t_set_tensor_core_attention(int mode);
