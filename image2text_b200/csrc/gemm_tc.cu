@@ -20,7 +20,7 @@ namespace i2t {
 
 constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 64, TC_STAGES = 6, TC_THREADS = 256;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2, TC_B_BYTES = TC_BN * TC_BK * 2;
-constexpr int TC_SMEM = TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + 1024;
+constexpr int TC_SMEM = TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + 2 * 128 * 128 + 1024;   // ring + 2 epilogue staging boxes
 
 struct TcEpilogue {
   const float* bias;
@@ -172,8 +172,8 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;"
 // drain tile i while the tensor core already works on tile i+1.
 template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int num_k_blocks,
-               int m_tiles, int n_tiles, TcEpilogue epi) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, int num_k_blocks, int m_tiles, int n_tiles, TcEpilogue epi) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[TC_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[TC_STAGES];
@@ -184,6 +184,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
   uint8_t* smemA = smem;
   uint8_t* smemB = smem + TC_STAGES * TC_A_BYTES;
+  uint8_t* smemC = smem + TC_STAGES * (TC_A_BYTES + TC_B_BYTES);     // 2 staging boxes for the TMA-store epilogue
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = m_tiles * n_tiles;
 
@@ -271,13 +272,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp >= 4) {
     const int wq = warp & 3;  // TMEM lane quarter this warp may touch
+    const int r_in_tile = wq * 32 + lane;
+    const bool issuer = warp == 4 && lane == 0;
+    if (issuer && epi.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
     int i = 0;
+    uint32_t box_count = 0;
+    const int chunks_per_box = epi.c_dtype == I2T_F32 ? 1 : 2;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++i) {
       const int m_blk = t % m_tiles, n_blk = t / m_tiles;
       const int b = i & 1;
       mbar_wait(&tmem_full_bar[b], ((uint32_t)i >> 1) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int64_t row = (int64_t)m_blk * TC_BM + wq * 32 + lane;
+      const int64_t row0 = (int64_t)m_blk * TC_BM;
+      const int64_t row = row0 + r_in_tile;
       const bool row_ok = row < epi.M;
 #pragma unroll 1
       for (int c = 0; c < TC_BN / 32; ++c) {
@@ -290,10 +297,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[b])) : "memory");
         }
         const int64_t n0 = (int64_t)n_blk * TC_BN + c * 32;
-        if (!row_ok || n0 >= epi.N) continue;
-        tc_epilogue_chunk(epi, r, row, n0);
+        if (!epi.tma_store) {
+          if (!row_ok || n0 >= epi.N) continue;
+          tc_epilogue_chunk(epi, r, row, n0);
+          continue;
+        }
+        float v[32];
+        tc_chunk_math(epi, r, v, row, n0, row_ok);
+        uint8_t* box = smemC + (box_count & 1u) * TC_STORE_BOX_BYTES;
+        tc_stage_chunk(box, r_in_tile, v, epi.c_dtype, c % chunks_per_box);
+        if ((c + 1) % chunks_per_box == 0) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          epi_bar_sync();
+          if (issuer) {
+            const int col0 = (int)((int64_t)n_blk * TC_BN + (c + 1 - chunks_per_box) * 32);
+            if (col0 < epi.N && row0 < epi.M) {
+              tma_store_2d(&tmC, box, col0, (int)row0);
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+          }
+          ++box_count;
+        }
       }
     }
+    if (issuer && epi.tma_store) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -603,7 +631,8 @@ static int make_map_dt(const void* ptr, int64_t rows, int64_t cols, int64_t ld, 
 }
 
 template <bool A_MN, bool B_MN>
-static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, int kblocks, const TcEpilogue& epi, dim3 grid, cudaStream_t st) {
+static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, int kblocks, const TcEpilogue& epi, dim3 grid,
+                     cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
@@ -612,7 +641,7 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, int kblocks, 
   }
   const int m_tiles = (int)grid.y, n_tiles = (int)grid.x;
   const int ctas = (int)std::min<int64_t>((int64_t)m_tiles * n_tiles, (int64_t)num_sms());
-  gemm_tc_kernel<A_MN, B_MN><<<ctas, TC_THREADS, TC_SMEM, st>>>(ma, mb, kblocks, m_tiles, n_tiles, epi);
+  gemm_tc_kernel<A_MN, B_MN><<<ctas, TC_THREADS, TC_SMEM, st>>>(ma, mb, mc, kblocks, m_tiles, n_tiles, epi);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(I2T_ERR_CUDA, "gemm_tc launch failed: %s", cudaGetErrorString(e));
@@ -713,11 +742,21 @@ int gemm_tc_try(const void* A, const void* B, const float* bias, const void* res
   }
   rc = b_kmajor ? tc_make_map(B, N, K, ldb, TC_BN, &mb) : tc_make_map(B, K, N, ldb, 64, &mb);
   if (rc != I2T_OK) return rc;
-  dim3 grid((unsigned)ceil_div(N, TC_BN), (unsigned)ceil_div(M, TC_BM));
-  if (a_kmajor && b_kmajor) return launch_tc<false, false>(ma, mb, kb, epi, grid, st);
-  if (a_kmajor && !b_kmajor) return launch_tc<false, true>(ma, mb, kb, epi, grid, st);
-  if (!a_kmajor && b_kmajor) return launch_tc<true, false>(ma, mb, kb, epi, grid, st);
-  return launch_tc<true, true>(ma, mb, kb, epi, grid, st);
+  {
+    const int esz = c_dtype == I2T_F32 ? 4 : 2;
+    CUtensorMap mc = ma;
+    epi.tma_store = 0;
+    if (!accumulate && aligned16(C) && (ldc * esz) % 16 == 0 && epi.debug == 0 && g_tma_store.load() == 1) {
+      rc = make_map_dt(C, M, N, ldc, 128, c_dtype == I2T_F32, &mc);
+      if (rc != I2T_OK) return rc;
+      epi.tma_store = 1;
+    }
+    dim3 grid((unsigned)ceil_div(N, TC_BN), (unsigned)ceil_div(M, TC_BM));
+    if (a_kmajor && b_kmajor) return launch_tc<false, false>(ma, mb, mc, kb, epi, grid, st);
+    if (a_kmajor && !b_kmajor) return launch_tc<false, true>(ma, mb, mc, kb, epi, grid, st);
+    if (!a_kmajor && b_kmajor) return launch_tc<true, false>(ma, mb, mc, kb, epi, grid, st);
+    return launch_tc<true, true>(ma, mb, mc, kb, epi, grid, st);
+  }
 }
 
 }  // namespace i2t
