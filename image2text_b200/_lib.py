@@ -36,6 +36,7 @@ SIGNATURES = {
     "i2t_xattn_bwd": (c_int, [P, P, P, P, P, P, P, L, L, L, L, L, L, L, L, L, L, I, P]),
     "i2t_dec_embed": (c_int, [P, P, P, P, P, L, L, L, L, P]),
     "i2t_dec_advance": (c_int, [P, P]),
+    "i2t_dec_embed_rows": (c_int, [P, L, P, P, P, L, L, P]),
     "i2t_dec_kv_append": (c_int, [P, L, P, P, L, L, L, I, P, P]),
     "i2t_dec_linear": (c_int, [P, P, P, F, P, P, P, P, L, L, L, L, I, I, I, P, P, L, L, I, P, P]),
     "i2t_dec_attn": (c_int, [P, L, P, P, L, L, P, L, P, L, L, L, L, I, P]),

@@ -415,6 +415,34 @@ __global__ void __launch_bounds__(256) dec_kv_append_kernel(const float* __restr
 }
 }  // namespace i2t
 
+namespace i2t {
+// x[b,:] = rows[b, *pos_ptr, :] + wpe[*pos_ptr, :]  -- a soft-prompt row as the decoder input of step *pos_ptr (HF decoders
+// see the prompt rows as ordinary positions, reference models/decoder.py:343-360)
+__global__ void __launch_bounds__(256) dec_embed_rows_kernel(const float* __restrict__ rows, int64_t batch_stride,
+                                                             const float* __restrict__ wpe, float* __restrict__ x,
+                                                             const int32_t* __restrict__ pos_ptr, int B, int C) {
+  const int pos = *pos_ptr;
+  const int c4 = C / 4;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B * c4; i += gridDim.x * blockDim.x) {
+    const int b = i / c4, cv = i % c4;
+    float4 v = load4(rows + (int64_t)b * batch_stride + (int64_t)pos * C + cv * 4);
+    const float4 pe = load4(wpe + (int64_t)pos * C + cv * 4);
+    v.x += pe.x; v.y += pe.y; v.z += pe.z; v.w += pe.w;
+    store4(x + (int64_t)b * C + cv * 4, v);
+  }
+}
+}  // namespace i2t
+
+extern "C" int i2t_dec_embed_rows(const float* rows, int64_t batch_stride, const float* wpe, float* x, const int32_t* pos_ptr,
+                                  int64_t B, int64_t C, void* stream) {
+  I2T_REQUIRE(rows && wpe && x && pos_ptr && B > 0 && C > 0 && C % 4 == 0, "dec_embed_rows: bad arguments");
+  const int64_t n = B * (C / 4);
+  dec_embed_rows_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n, 256), 4096), 256, 0, (cudaStream_t)stream>>>(
+      rows, batch_stride, wpe, x, pos_ptr, (int)B, (int)C);
+  I2T_LAUNCHED();
+  return I2T_OK;
+}
+
 extern "C" int i2t_dec_kv_append(const float* qkv, int64_t ld, void* kcache, void* vcache, int64_t cache_batch_stride, int64_t C,
                                  int64_t B, int cache_dtype, const int32_t* pos_ptr, void* stream) {
   I2T_REQUIRE(qkv && kcache && vcache && pos_ptr, "dec_kv_append: null pointer");

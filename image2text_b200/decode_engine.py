@@ -403,3 +403,160 @@ class DecodeEngine:
         if self.mode == "mega" and int(self.err.item()) != 0:
             raise I2TError(f"decode megakernel reported an internal wait timeout (code {int(self.err.item())})")
         return out
+
+
+class HFDecodeEngine:
+    """KV-cached decode for the HF GPT-2 layout decoder (GPT2HuggingfaceDecoder, reference models/decoder.py:335-361):
+    Conv1D weights (in, out) are read in place as MN-major GEMM operands, every block has cross attention, and the soft
+    prompt rows are ordinary causal positions 0..n_cls-1 (they are pushed through the decoder one step each to fill the
+    cache; token t then sits at position n_cls + t).  Every projection is an i2t_gemm over the batch; KV append, the
+    single-query attention and the sampler are the decode kernels; one CUDA graph per step kind."""
+
+    def __init__(self, model, batch: int, capacity: int):
+        spec = model.spec
+        assert spec["decoder"] == "hf_gpt2"
+        self.model, self.spec, self.B = model, spec, batch
+        self.cd = model.compute_dtype
+        dev = next(model.parameters()).device
+        C, L, V = spec["n_embd"], spec["n_layer"], spec["vocab_size"]
+        self.n_prompt = spec["n_cls"] if spec["use_soft_prompting"] else 0
+        self.S = spec["n_cls"]
+        self.cap = capacity                                   # cache rows: prompt rows + tokens
+        self.F = int(spec["ff_mult"] * C)
+        f32 = dict(device=dev, dtype=torch.float32)
+        self.ids = torch.zeros((batch, capacity + 1), device=dev, dtype=torch.int64)
+        self.pos = torch.zeros(1, device=dev, dtype=torch.int32)       # token index
+        self.ppos = torch.zeros(1, device=dev, dtype=torch.int32)      # prompt row index
+        self.ticket = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.seed_dev = torch.zeros(1, device=dev, dtype=torch.int64)
+        self.kcache = torch.zeros((L, batch, capacity, C), device=dev, dtype=self.cd)
+        self.vcache = torch.zeros((L, batch, capacity, C), device=dev, dtype=self.cd)
+        self.xkv = torch.zeros((L, batch * self.S, 2 * C), device=dev, dtype=self.cd)
+        self.enc = torch.zeros((batch, self.S, C), **f32)
+        self.x = torch.zeros((batch, C), **f32)
+        self.q = torch.zeros((batch, C), **f32)
+        self.y = torch.zeros((batch, C), **f32)
+        self.qkv32 = torch.zeros((batch, 3 * C), **f32)
+        self.y16 = torch.zeros((batch, C), device=dev, dtype=self.cd)
+        self.logits = torch.zeros((batch, V), **f32)
+        self.ngrams = torch.tensor(list(spec["no_repeat_n_grams"]) or [0], device=dev, dtype=torch.int32)
+        self.n_ngrams = len(spec["no_repeat_n_grams"])
+        self.graphs = {}
+        self.nucleus_p = None
+
+    def _layers(self, slot_ptr: int, row_offset: int, len_add: int):
+        """One position through all blocks: x (B, C) fp32 in place.  slot_ptr: device int32 whose value + row_offset is the
+        cache row of this position; keys visible = [0, value + len_add)."""
+        m, spec, B = self.model, self.spec, self.B
+        W = m.weights()
+        C, H = spec["n_embd"], spec["n_head"]
+        hs = C // H
+        cd = self.cd
+        wd = ops.F32 if cd == torch.float32 else ops.BF16
+        st = stream()
+        dp = "decoder.backbone.transformer."
+        cbs = self.cap * C
+        es = self.kcache.element_size()
+
+        def ln(key):
+            return ops.layernorm(self.x, W[key + ".weight"], W.get(key + ".bias"), 1e-5, out_dtype=cd)
+
+        def c1d(a, key, **kw):          # Conv1D: y = a @ W (in, out) + b
+            return ops.gemm(a, W.c(key + ".weight"), bias=W[key + ".bias"], b_kmajor=False, **kw)
+
+        def att_out():
+            if cd == torch.float32:
+                return self.y
+            self.y16.copy_(self.y)
+            return self.y16
+
+        for i in range(spec["n_layer"]):
+            lp = f"{dp}h.{i}."
+            c1d(ln(lp + "ln_1"), lp + "attn.c_attn", out=self.qkv32)
+            kbase = self.kcache[i].data_ptr() + row_offset * C * es
+            vbase = self.vcache[i].data_ptr() + row_offset * C * es
+            call("i2t_dec_kv_append", ptr(self.qkv32), 3 * C, kbase, vbase, cbs, C, B, wd, slot_ptr, st)
+            call("i2t_dec_attn", ptr(self.qkv32), 3 * C, ptr(self.kcache[i]), ptr(self.vcache[i]), cbs, C, ptr(self.y), C,
+                 slot_ptr, len_add, B, H, hs, wd, st)
+            c1d(att_out(), lp + "attn.c_proj", residual=self.x, out=self.x)
+            if spec["use_cross_attn"]:
+                c1d(ln(lp + "ln_cross_attn"), lp + "crossattention.q_attn", out=self.q)
+                kv = self.xkv[i]
+                call("i2t_dec_attn", ptr(self.q), C, kv.data_ptr(), kv.data_ptr() + C * kv.element_size(), self.S * 2 * C, 2 * C,
+                     ptr(self.y), C, None, self.S, B, H, hs, wd, st)
+                c1d(att_out(), lp + "crossattention.c_proj", residual=self.x, out=self.x)
+            h = c1d(ln(lp + "ln_2"), lp + "mlp.c_fc", act=ops.ACT_GELU_TANH, out_dtype=cd)
+            c1d(h, lp + "mlp.c_proj", residual=self.x, out=self.x)
+
+    def _prompt_step(self):
+        W = self.model.weights()
+        C = self.spec["n_embd"]
+        call("i2t_dec_embed_rows", ptr(self.enc), self.S * C, ptr(W["decoder.backbone.transformer.wpe.weight"]), ptr(self.x),
+             ptr(self.ppos), self.B, C, stream())
+        self._layers(ptr(self.ppos), 0, 1)
+        call("i2t_dec_advance", ptr(self.ppos), stream())
+
+    def _token_step(self, sample: bool, temperature: float, top_k):
+        W = self.model.weights()
+        spec, B = self.spec, self.B
+        C, V = spec["n_embd"], spec["vocab_size"]
+        dp = "decoder.backbone.transformer."
+        st = stream()
+        call("i2t_dec_embed", ptr(self.ids), ptr(W[dp + "wte.weight"]), ptr(W[dp + "wpe.weight"]), ptr(self.x), ptr(self.pos), B, C,
+             self.ids.shape[1], self.n_prompt, st)
+        self._layers(ptr(self.pos), self.n_prompt, self.n_prompt + 1)
+        if sample:
+            hid = ops.layernorm(self.x, W[dp + "ln_f.weight"], W.get(dp + "ln_f.bias"), 1e-5, out_dtype=self.cd)
+            ops.gemm(hid, W.c("decoder.backbone.lm_head.weight"), out=self.logits)
+            call("i2t_sample", ptr(self.logits), V, B, V, ptr(self.ids), self.ids.shape[1], ptr(self.pos), 1, 0, temperature,
+                 int(top_k) if top_k is not None else 0, float(self.nucleus_p or 0.0), ptr(self.ngrams), self.n_ngrams, 0,
+                 ptr(self.seed_dev), None, ptr(self.ticket), 1, st)
+        else:
+            call("i2t_dec_advance", ptr(self.pos), st)
+
+    def _run(self, key, fn, times: int):
+        """`fn` `times` times: first use eager (warm-up), second use captured, then graph replays."""
+        ent = self.graphs.get(key)
+        if ent is None:
+            ent = self.graphs[key] = dict(calls=0, graph=None)
+        for _ in range(times):
+            if ent["graph"] is None and ent["calls"] < 1:
+                fn()
+                ent["calls"] += 1
+                continue
+            if ent["graph"] is None:
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    fn()
+                ent["graph"] = g
+            ent["graph"].replay()
+
+    @torch.no_grad()
+    def generate(self, images, prompt_ids, max_new_tokens: int, temperature: float, top_k, seed: int, nucleus_p=None):
+        from . import functional as Fn
+        m, B, spec = self.model, self.B, self.spec
+        W = m.weights()
+        C = spec["n_embd"]
+        P = prompt_ids.shape[1]
+        assert prompt_ids.shape[0] == B and self.n_prompt + P + max_new_tokens <= self.cap + 1
+        self.nucleus_p = nucleus_p
+        enc = Fn.encoder_forward(W, spec, images, self.cd, train_trunk=False)
+        self.enc.copy_(enc)
+        if spec["use_cross_attn"]:
+            e = self.enc.reshape(B * self.S, C)
+            e = e if self.cd == torch.float32 else e.to(self.cd)
+            for i in range(spec["n_layer"]):
+                lp = f"decoder.backbone.transformer.h.{i}.crossattention.c_attn"
+                ops.gemm(e, W.c(lp + ".weight"), bias=W[lp + ".bias"], b_kmajor=False, out=self.xkv[i])
+        self.ids.zero_()
+        self.ids[:, :P].copy_(prompt_ids)
+        self.pos.zero_()
+        self.ppos.zero_()
+        self.ticket.zero_()
+        self.seed_dev.fill_(int(seed) & 0x7FFFFFFFFFFFFFFF)
+        self._run(("prompt",), self._prompt_step, self.n_prompt)
+        self._run(("prefill",), lambda: self._token_step(False, temperature, top_k), P - 1)
+        self._run(("sample", float(temperature), top_k, nucleus_p), lambda: self._token_step(True, temperature, top_k),
+                  max_new_tokens)
+        return self.ids[:, :P + max_new_tokens].clone()

@@ -13,6 +13,7 @@ Behavioural notes that parity depends on (all pinned by tests/golden, see DESIGN
 from __future__ import annotations
 
 from collections import namedtuple
+import os
 from typing import Dict, Optional
 
 import torch
@@ -188,7 +189,16 @@ class VisionEncoderDecoder(nn.Module):
         if nucleus_p is not None and not (0.0 < float(nucleus_p) < 1.0):
             nucleus_p = None
         if self.spec["decoder"] != "transformer":
-            return self._generate_cacheless(images, prompt_ids, max_new_tokens, float(temperature), top_k, nucleus_p, seed)
+            if os.environ.get("I2T_HF_DECODE", "cached") == "cacheless":
+                return self._generate_cacheless(images, prompt_ids, max_new_tokens, float(temperature), top_k, nucleus_p, seed)
+            from .decode_engine import HFDecodeEngine
+            need = self.space_for_prompt + prompt_ids.shape[1] + max_new_tokens
+            key = ("hf", prompt_ids.shape[0], self.compute_dtype)
+            eng = self._decode_engines.get(key)
+            if eng is None or eng.cap < need:
+                eng = HFDecodeEngine(self, prompt_ids.shape[0], capacity=max(need, 128))
+                self._decode_engines[key] = eng
+            return eng.generate(images, prompt_ids, max_new_tokens, float(temperature), top_k, seed, nucleus_p=nucleus_p)
         B = prompt_ids.shape[0]
         key = (B, self.compute_dtype, nucleus_p is not None)
         eng = self._decode_engines.get(key)

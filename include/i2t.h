@@ -146,6 +146,10 @@ void i2t_set_pdl(int enabled);
 int i2t_dec_embed(const int64_t* ids, const float* wte, const float* wpe, float* x, const int32_t* pos_ptr, int64_t B,
                   int64_t C, int64_t ids_ld, int64_t n_prompt, void* stream);
 int i2t_dec_advance(int32_t* pos_ptr, void* stream);
+/* x[b,:] = rows[b, *pos_ptr, :] + wpe[*pos_ptr, :]: a soft-prompt row as the input of decode step *pos_ptr (HF decoders
+ * treat the prompt rows as ordinary causal positions, models/decoder.py:343-360) */
+int i2t_dec_embed_rows(const float* rows, int64_t batch_stride, const float* wpe, float* x, const int32_t* pos_ptr, int64_t B,
+                       int64_t C, void* stream);
 /* large-batch decode (projections as GEMMs): append columns [C,2C) / [2C,3C) of the packed fp32 (B,ld) qkv rows to row
  * *pos_ptr of the (B,Tmax,C) K / V caches (what i2t_dec_linear's qkv_split epilogue does for B <= 16) */
 int i2t_dec_kv_append(const float* qkv, int64_t ld, void* kcache, void* vcache, int64_t cache_batch_stride, int64_t C,

@@ -210,3 +210,19 @@ def test_large_batch_generate_matches_reference(golden):
     m16 = build("nano", torch.bfloat16)
     out = m16.generate(images, prompt, max_new_tokens=6, temperature=0.9, top_k=16, nucleus_p=0.9, seed=5)
     assert out.shape == (24, 7) and bool((out[:, 1:] >= 0).all()) and bool((out[:, 1:] < 50257).all())
+
+
+def test_gpt2hf_cached_decode_equals_cacheless(monkeypatch):
+    """KV-cached HF decode (soft-prompt rows pushed through the cache, Conv1D weights as MN-major GEMM operands) must pick
+    the same greedy tokens as the reference-style cache-less loop on the same kernels; prompt of 3 tokens, fp32."""
+    m = build("gpt2")
+    images = synth_images(2, 224, seed=33).cuda()
+    prompt = torch.tensor([[50256, 11, 257], [50256, 318, 262]], dtype=torch.long, device="cuda")
+    cached = m.generate(images, prompt, max_new_tokens=10, temperature=1.0, top_k=1)
+    monkeypatch.setenv("I2T_HF_DECODE", "cacheless")
+    plain = m.generate(images, prompt, max_new_tokens=10, temperature=1.0, top_k=1)
+    assert torch.equal(cached, plain)
+    monkeypatch.delenv("I2T_HF_DECODE")
+    m16 = build("gpt2", torch.bfloat16)
+    out = m16.generate(images, prompt, max_new_tokens=8, temperature=0.8, top_k=20, nucleus_p=0.9, seed=4)
+    assert out.shape == (2, 11) and torch.equal(out[:, :3], prompt)
