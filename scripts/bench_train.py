@@ -90,9 +90,13 @@ def main():
     def one_step():
         for micro in range(accum):
             last = micro == accum - 1
-            ctx = red.no_sync() if not last else torch.enable_grad()
+            # graphed micro-steps never fire the all-reduce hooks (a replay runs no Python): with --graph every micro-step is
+            # a replay and red.finish() exchanges all buckets after the last backward (NVLink moves the ~0.1-1 GB of fp32
+            # gradients in a few ms; an eager last micro-step would cost 10x that in launch overhead).  --graph 0: eager
+            # micro-steps, bucketed all-reduce overlapped with the last backward.
+            ctx = red.no_sync() if (not last or args.graph) else torch.enable_grad()
             with ctx:
-                if args.graph and (world == 1 or not last):     # the micro-step that fires the all-reduce hooks stays eager
+                if args.graph:
                     loss = w.train_step_graphed(images, labels, 1.0 / accum)
                 else:
                     loss, _ = w.train_step(images, labels)

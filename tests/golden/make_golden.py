@@ -237,6 +237,31 @@ def case_gpt2(ref, out):
     out["gpt2_fwd"] = res
 
 
+def case_beam(ref, out):
+    """reference models/generation_utils.BeamSearchTokenGenerator on the tiny model, deterministic settings
+    (temperature 0 -> arg-top expansions, consolidation_temperature 0 -> top beams)."""
+    small_vit_patch(ref, layers=2, image=32)
+    over = dict(vit_layers=2, vit_image=32)
+    tc, mdl, spec, sd, model = build(ref, "tiny", over)
+    model.eval()
+    from models.generation_utils import BeamSearchTokenGenerator
+    images = synth_images(2, 32, seed=11)
+    eos = spec["vocab_size"] - 1
+    prompt = torch.full((2, 1), eos, dtype=torch.long)
+    g = {}
+    for name, kw in (("plain", dict(beam_width=3, temperature=0.0, top_k=None, max_new_tokens=10, beam_expansion_factor=4,
+                                    eos_token_id=611, consolidation_temperature=0.0, length_boost=1.0)),
+                     ("topk_eos", dict(beam_width=4, temperature=0.0, top_k=12, max_new_tokens=12, beam_expansion_factor=3,
+                                       eos_token_id=7, consolidation_temperature=0.0, length_boost=1.3))):
+        gen = BeamSearchTokenGenerator(model, **kw)
+        with torch.no_grad():
+            ids, scores = gen(images, prompt)
+        g[name + "_ids"] = ids.numpy()
+        g[name + "_scores"] = f32(scores)
+    out["tiny_beam"] = g
+    restore_vit_patch(ref)
+
+
 def main():
     torch.manual_seed(0)
     ref = ref_harness.load_reference()

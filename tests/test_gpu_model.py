@@ -226,3 +226,26 @@ def test_gpt2hf_cached_decode_equals_cacheless(monkeypatch):
     m16 = build("gpt2", torch.bfloat16)
     out = m16.generate(images, prompt, max_new_tokens=8, temperature=0.8, top_k=20, nucleus_p=0.9, seed=4)
     assert out.shape == (2, 11) and torch.equal(out[:, :3], prompt)
+
+
+def test_beam_search_matches_reference_golden(golden):
+    """image2text_b200.generation_utils.BeamSearchTokenGenerator vs the reference's class run on the reference model
+    (tests/golden/tiny_beam.npz; deterministic settings: temperature 0, consolidation_temperature 0)."""
+    from image2text_b200.generation_utils import BeamSearchTokenGenerator
+    g = golden("tiny_beam")
+    m = build("tiny")
+    images = synth_images(2, 32, seed=11).cuda()
+    eos = m.spec["vocab_size"] - 1
+    prompt = torch.full((2, 1), eos, dtype=torch.long, device="cuda")
+    for name, kw in (("plain", dict(beam_width=3, temperature=0.0, top_k=None, max_new_tokens=10, beam_expansion_factor=4,
+                                    eos_token_id=611, consolidation_temperature=0.0, length_boost=1.0)),
+                     ("topk_eos", dict(beam_width=4, temperature=0.0, top_k=12, max_new_tokens=12, beam_expansion_factor=3,
+                                       eos_token_id=7, consolidation_temperature=0.0, length_boost=1.3))):
+        ids, scores = BeamSearchTokenGenerator(m, **kw)(images, prompt)
+        assert np.array_equal(ids.cpu().numpy(), g[name + "_ids"]), name
+        assert float(np.abs(scores.cpu().numpy() - g[name + "_scores"]).max()) < 2e-3, name
+    # sampled expansions / consolidation: shapes, prompt kept, scores finite and sorted consistently with the API
+    ids, scores = BeamSearchTokenGenerator(m, beam_width=3, temperature=0.9, top_k=20, max_new_tokens=8, eos_token_id=611,
+                                           consolidation_temperature=0.7)(images, prompt)
+    assert ids.shape == (2, 3, 8) and scores.shape == (2, 3) and bool(torch.isfinite(scores).all())
+    assert bool((ids[:, :, 0] == eos).all())
