@@ -40,10 +40,13 @@ class LayerNormFn(torch.autograd.Function):
 
 class LinearFn(torch.autograd.Function):
     """y = act(x W^T + b) + residual with W an nn.Linear weight (N,K): reference models/layers.py:452,469,482,484,
-    models/decoder.py:256, nn.MultiheadAttention projections.  `w_c` is the compute-dtype view of the master weight."""
+    models/decoder.py:256, nn.MultiheadAttention projections.  `w_c` is the compute-dtype view of the master weight.
+    Training-mode dropout (ops.DropSite): `drop` = nn.Dropout on the projection before the residual add
+    (models/layers.py:469,485): y = residual + dropout(x W^T + b); `tok_drop` = the per-token q/k/v masks of
+    models/layers.py:454-461 applied to the packed c_attn output."""
 
     @staticmethod
-    def forward(ctx, x2d, w, w_c, bias, residual, act, out_dtype, pad_rows=False):
+    def forward(ctx, x2d, w, w_c, bias, residual, act, out_dtype, pad_rows=False, drop=None, tok_drop=None):
         need = any(ctx.needs_input_grad)      # grad mode is always off inside Function.forward
         out = None
         if pad_rows and w_c.shape[0] % 8 != 0:
@@ -51,7 +54,11 @@ class LinearFn(torch.autograd.Function):
             # the gradient that comes back with the same pitch satisfies TMA's 16-byte row-pitch rule for dgrad / wgrad
             N = w_c.shape[0]
             out = torch.empty((x2d.shape[0], (N + 7) // 8 * 8), device=x2d.device, dtype=out_dtype)[:, :N]
-        if need and act != ops.ACT_NONE:
+        if drop is not None:
+            assert act == ops.ACT_NONE and out is None and out_dtype == torch.float32
+            z = None
+            y = ops.dropout_add(ops.gemm(x2d, w_c, bias=bias, out_dtype=x2d.dtype), residual, drop)
+        elif need and act != ops.ACT_NONE:
             z = ops.gemm(x2d, w_c, bias=bias, out_dtype=x2d.dtype)
             y = torch.empty(z.shape, device=z.device, dtype=out_dtype)
             call("i2t_act_fwd", ptr(z), ptr(y), z.numel(), act, dt(z), dt(y), stream())
@@ -59,12 +66,16 @@ class LinearFn(torch.autograd.Function):
         else:
             z = None
             y = ops.gemm(x2d, w_c, bias=bias, residual=residual, act=act, out_dtype=out_dtype, out=out)
+        if tok_drop is not None:
+            site, seg, nseg = tok_drop
+            ops.token_dropout_(y, seg, nseg, site)
         if need:
             ctx.save_for_backward(x2d, w_c, z)
             ctx.act = act
             ctx.has_bias = bias is not None
             ctx.has_res = residual is not None
             ctx.res_dtype = residual.dtype if residual is not None else None
+            ctx.drop, ctx.tok_drop = drop, tok_drop
         return y
 
     @staticmethod
@@ -73,9 +84,7 @@ class LinearFn(torch.autograd.Function):
         if not (dy.dim() == 2 and dy.stride(1) == 1 and dy.stride(0) % 8 == 0 and dy.stride(0) >= dy.shape[1]):
             dy = dy.contiguous()      # row-padded gradients (LM head) are consumed in place
         dres = dy.to(ctx.res_dtype) if (ctx.has_res and ctx.needs_input_grad[4]) else None
-        g = dy
-        if g.dtype != x2d.dtype:
-            g = g.to(x2d.dtype)      # autocast: the linear's grad flows in the activation dtype
+        g = _grad_in(dy, x2d.dtype, ctx.drop, ctx.tok_drop)
         if z is not None:
             dz = torch.empty_like(z)
             call("i2t_act_bwd", ptr(z), ptr(g), ptr(dz), z.numel(), ctx.act, dt(z), dt(g), stream())
@@ -94,46 +103,65 @@ class LinearFn(torch.autograd.Function):
         if ctx.has_bias and ctx.needs_input_grad[3]:
             db = torch.zeros(g.shape[1], device=g.device, dtype=torch.float32)
             ops.colsum_(g, db)
-        return dx, dw, None, db, dres, None, None, None
+        return dx, dw, None, db, dres, None, None, None, None, None
 
 
-def linear(x2d, w, w_c, bias=None, residual=None, act=ops.ACT_NONE, out_dtype=torch.float32, pad_rows=False):
-    return LinearFn.apply(x2d, w, w_c, bias, residual, act, out_dtype, pad_rows)
+def _grad_in(dy, cd, drop, tok_drop):
+    """The gradient w.r.t. the GEMM output in the compute dtype: the dropout multiplier and the autocast cast are one
+    pass; the token-level q/k/v masks scale the (freshly produced) gradient of the packed buffer in place."""
+    if drop is not None:
+        g = ops.dropout_bwd(dy.contiguous(), cd, drop)
+    else:
+        g = dy if dy.dtype == cd else dy.to(cd)      # autocast: the linear's grad flows in the activation dtype
+    if tok_drop is not None:
+        site, seg, nseg = tok_drop      # dy is the attention backward's freshly written dqkv: scaled in place
+        ops.token_dropout_(g, seg, nseg, site)
+    return g
+
+
+def linear(x2d, w, w_c, bias=None, residual=None, act=ops.ACT_NONE, out_dtype=torch.float32, pad_rows=False, drop=None,
+           tok_drop=None):
+    return LinearFn.apply(x2d, w, w_c, bias, residual, act, out_dtype, pad_rows, drop, tok_drop)
 
 
 class AttnFn(torch.autograd.Function):
     """Self attention on a packed (B*T, 3C) qkv buffer: reference models/layers.py:465 (+ the mask algebra of
-    vision_encoder_decoder.py:75-111 / layers.py:581-595 folded into `mask_mode`), torchvision :113."""
+    vision_encoder_decoder.py:75-111 / layers.py:581-595 folded into `mask_mode`), torchvision :113.
+    `drop`: dropout_p of the SDPA call (training mode), regenerated -- not stored -- by the backward kernel."""
 
     @staticmethod
-    def forward(ctx, qkv, B, T, H, mask_mode, n_prompt):
+    def forward(ctx, qkv, B, T, H, mask_mode, n_prompt, drop=None):
         qkv = qkv.contiguous()
         if any(ctx.needs_input_grad):
-            out, lse = ops.attention_packed(qkv, B, T, H, mask_mode, n_prompt, want_lse=True)
+            out, lse = ops.attention_packed(qkv, B, T, H, mask_mode, n_prompt, want_lse=True, drop=drop)
             ctx.save_for_backward(qkv, out, lse)
-            ctx.meta = (B, T, H, mask_mode, n_prompt)
+            ctx.meta = (B, T, H, mask_mode, n_prompt, drop)
         else:
-            out = ops.attention_packed(qkv, B, T, H, mask_mode, n_prompt)
+            out = ops.attention_packed(qkv, B, T, H, mask_mode, n_prompt, drop=drop)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         qkv, out, lse = ctx.saved_tensors
-        B, T, H, mask_mode, n_prompt = ctx.meta
-        dqkv = ops.attention_packed_bwd(qkv, out, dout.contiguous().to(qkv.dtype), lse, B, T, H, mask_mode, n_prompt)
-        return dqkv, None, None, None, None, None
+        B, T, H, mask_mode, n_prompt, drop = ctx.meta
+        dqkv = ops.attention_packed_bwd(qkv, out, dout.contiguous().to(qkv.dtype), lse, B, T, H, mask_mode, n_prompt, drop=drop)
+        return dqkv, None, None, None, None, None, None
 
 
 class XAttnFn(torch.autograd.Function):
     """Cross attention over S <= 64 encoder tokens: reference models/layers.py:537-542,600-605.  bf16: the tensor-core
-    attention kernels with Tk = S (one key tile); fp32: the shared-memory K/V kernels of xattn.cu (parity anchor)."""
+    attention kernels with Tk = S (one key tile); fp32: the shared-memory K/V kernels of xattn.cu (parity anchor).
+    With dropout on the probabilities (nn.MultiheadAttention(dropout=), HF attn_pdrop) both dtypes run the general
+    attention kernels, which regenerate the mask in the backward."""
 
     @staticmethod
-    def forward(ctx, q, kv, B, T, S, H):
+    def forward(ctx, q, kv, B, T, S, H, drop=None):
         q, kv = q.contiguous(), kv.contiguous()
-        tc = q.dtype == torch.bfloat16 and (q.shape[1] // H) in (32, 64) and q.shape[1] % 8 == 0
+        tc = (q.dtype == torch.bfloat16 or drop is not None) and (q.shape[1] // H) in (32, 64) and q.shape[1] % 8 == 0
+        if drop is not None and not tc:
+            raise RuntimeError("cross-attention dropout needs head_dim 32 or 64")
         if tc:
-            out, lse = ops.xattn_tc(q, kv, B, T, S, H)
+            out, lse = ops.xattn_tc(q, kv, B, T, S, H, drop=drop)
         else:
             out, lse = ops.xattn(q, kv, B, T, S, H), None
         if any(ctx.needs_input_grad):
@@ -141,37 +169,41 @@ class XAttnFn(torch.autograd.Function):
                 ctx.save_for_backward(q, kv, out, lse)
             else:
                 ctx.save_for_backward(q, kv)
-            ctx.meta = (B, T, S, H, tc)
+            ctx.meta = (B, T, S, H, tc, drop)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        B, T, S, H, tc = ctx.meta
+        B, T, S, H, tc, drop = ctx.meta
         if tc:
             q, kv, out, lse = ctx.saved_tensors
-            dq, dkv = ops.xattn_tc_bwd(q, kv, out, dout.contiguous().to(q.dtype), lse, B, T, S, H)
-            return dq, dkv, None, None, None, None
+            dq, dkv = ops.xattn_tc_bwd(q, kv, out, dout.contiguous().to(q.dtype), lse, B, T, S, H, drop=drop)
+            return dq, dkv, None, None, None, None, None
         q, kv = ctx.saved_tensors
         dq, dkv = ops.xattn_bwd(q, kv, dout.contiguous().to(q.dtype), B, T, S, H)
-        return dq, dkv.to(kv.dtype), None, None, None, None
+        return dq, dkv.to(kv.dtype), None, None, None, None, None
 
 
 class EmbedFn(torch.autograd.Function):
     """cat(prompt, wte[ids])[:T] + wpe[:T]: reference vision_encoder_decoder.py:84-88 + decoder.py:234-243."""
 
     @staticmethod
-    def forward(ctx, ids, prompt, wte, wpe, T, n_prompt):
+    def forward(ctx, ids, prompt, wte, wpe, T, n_prompt, drop=None):
         B, S = ids.shape
         x = ops.embed(ids, prompt, wte, wpe, B, T, n_prompt, S)
+        if drop is not None:                                  # transformer.drop, models/decoder.py:236-243
+            x = ops.dropout_add(x, None, drop)
         ctx.save_for_backward(ids)
-        ctx.meta = (B, T, n_prompt, S, wte.shape, prompt is not None, wpe.shape[0])
+        ctx.meta = (B, T, n_prompt, S, wte.shape, prompt is not None, wpe.shape[0], drop)
         return x
 
     @staticmethod
     def backward(ctx, dx):
         (ids,) = ctx.saved_tensors
-        B, T, n_prompt, S, wte_shape, has_prompt, wpe_rows = ctx.meta
+        B, T, n_prompt, S, wte_shape, has_prompt, wpe_rows, drop = ctx.meta
         dx = dx.contiguous()
+        if drop is not None:
+            dx = ops.dropout_bwd(dx, torch.float32, drop)
         C = dx.shape[-1]
         dprompt = dwte = dwpe = None
         if has_prompt and ctx.needs_input_grad[1]:
@@ -182,7 +214,7 @@ class EmbedFn(torch.autograd.Function):
         if ctx.needs_input_grad[3]:
             dwpe = torch.zeros((wpe_rows, C), device=dx.device, dtype=torch.float32)   # rows >= T stay zero
             ops.colsum_(dx.view(B, T * C), dwpe.view(-1)[:T * C])
-        return None, dprompt, dwte, dwpe, None, None
+        return None, dprompt, dwte, dwpe, None, None, None
 
 
 class NormalizeGradientsFn(torch.autograd.Function):
@@ -282,9 +314,13 @@ class Conv1DFn(torch.autograd.Function):
     the forward GEMM and the K-major B operand of the data-gradient GEMM."""
 
     @staticmethod
-    def forward(ctx, x2d, w, w_c, bias, residual, act, out_dtype):
+    def forward(ctx, x2d, w, w_c, bias, residual, act, out_dtype, drop=None):
         need = any(ctx.needs_input_grad)
-        if need and act != ops.ACT_NONE:
+        if drop is not None:                                  # HF resid_pdrop before the residual add
+            assert act == ops.ACT_NONE and out_dtype == torch.float32
+            z = None
+            y = ops.dropout_add(ops.gemm(x2d, w_c, bias=bias, out_dtype=x2d.dtype, b_kmajor=False), residual, drop)
+        elif need and act != ops.ACT_NONE:
             z = ops.gemm(x2d, w_c, bias=bias, out_dtype=x2d.dtype, b_kmajor=False)
             y = torch.empty(z.shape, device=z.device, dtype=out_dtype)
             call("i2t_act_fwd", ptr(z), ptr(y), z.numel(), act, dt(z), dt(y), stream())
@@ -298,6 +334,7 @@ class Conv1DFn(torch.autograd.Function):
             ctx.has_bias = bias is not None
             ctx.has_res = residual is not None
             ctx.res_dtype = residual.dtype if residual is not None else None
+            ctx.drop = drop
         return y
 
     @staticmethod
@@ -305,7 +342,7 @@ class Conv1DFn(torch.autograd.Function):
         x2d, w_c, z = ctx.saved_tensors
         dy = dy.contiguous()
         dres = dy.to(ctx.res_dtype) if (ctx.has_res and ctx.needs_input_grad[4]) else None
-        g = dy if dy.dtype == x2d.dtype else dy.to(x2d.dtype)
+        g = _grad_in(dy, x2d.dtype, ctx.drop, None)
         if z is not None:
             dz = torch.empty_like(z)
             call("i2t_act_bwd", ptr(z), ptr(g), ptr(dz), z.numel(), ctx.act, dt(z), dt(g), stream())
@@ -321,8 +358,8 @@ class Conv1DFn(torch.autograd.Function):
         if ctx.has_bias and ctx.needs_input_grad[3]:
             db = torch.zeros(g.shape[1], device=g.device, dtype=torch.float32)
             ops.colsum_(g, db)
-        return dx, dw, None, db, dres, None, None
+        return dx, dw, None, db, dres, None, None, None
 
 
-def conv1d(x2d, w, w_c, bias=None, residual=None, act=ops.ACT_NONE, out_dtype=torch.float32):
-    return Conv1DFn.apply(x2d, w, w_c, bias, residual, act, out_dtype)
+def conv1d(x2d, w, w_c, bias=None, residual=None, act=ops.ACT_NONE, out_dtype=torch.float32, drop=None):
+    return Conv1DFn.apply(x2d, w, w_c, bias, residual, act, out_dtype, drop)

@@ -9,6 +9,7 @@
 //             atomically adds dQ (fp32 buffer zeroed by the caller through the host wrapper).
 // This file is the fp32 parity path and the bf16-IO fallback; tensor-core tiles live in attention_tc.cu.
 #include "common.cuh"
+#include "rng.cuh"
 
 namespace i2t {
 
@@ -25,7 +26,7 @@ template <typename TIN, typename TOUT, int HS>
 __global__ void __launch_bounds__(ATT_THREADS)
 attn_fwd_kernel(const TIN* __restrict__ q, const TIN* __restrict__ k, const TIN* __restrict__ v, TOUT* __restrict__ out,
                 float* __restrict__ lse, int H, int Tq, int Tk, int64_t q_bs, int64_t q_rs, int64_t kv_bs,
-                int64_t kv_rs, int mode, int n_prompt, float scale) {
+                int64_t kv_rs, int mode, int n_prompt, float scale, DropArgs drop) {
   extern __shared__ __align__(16) float smem[];
   float* Qt = smem;                       // [HS][64]  (transposed, pre-scaled)
   float* Kt = Qt + HS * ATT_BQ;           // [HS][64]
@@ -37,6 +38,8 @@ attn_fwd_kernel(const TIN* __restrict__ q, const TIN* __restrict__ k, const TIN*
   const TIN* qb = q + (int64_t)b * q_bs + (int64_t)h * HS;
   const TIN* kb = k + (int64_t)b * kv_bs + (int64_t)h * HS;
   const TIN* vb = v + (int64_t)b * kv_bs + (int64_t)h * HS;
+  DropKey dkey{0u, 0u, 0u};
+  if (drop.thr != 0u) dkey = drop_key(drop);
 
   // load Q tile transposed: thread -> (row = t % 64, 4-wide e chunk = t / 64 + 2*i)
   for (int c = t >> 6; c < HS / 4; c += ATT_THREADS / 64) {
@@ -126,6 +129,12 @@ attn_fwd_kernel(const TIN* __restrict__ q, const TIN* __restrict__ k, const TIN*
       rs += __shfl_xor_sync(0xffffffffu, rs, 4);
       l_i[i] = l_i[i] * corr + rs;
       m_i[i] = m_new;
+      if (drop.thr != 0u) {   // dropout on the probabilities: the denominator keeps every key, dropped terms leave the sum
+        const uint32_t row = (uint32_t)(((int64_t)b * H + h) * Tq + qi);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (!drop_attn_keep(drop, dkey, row, k0 + tx * 8 + j)) s[i][j] = 0.f;
+      }
 #pragma unroll
       for (int e = 0; e < EC; ++e) o[i][e] *= corr;
       float* pr = Ps + (ty * 4 + i) * ATT_PSTRIDE + tx * 8;
@@ -162,7 +171,7 @@ attn_fwd_kernel(const TIN* __restrict__ q, const TIN* __restrict__ k, const TIN*
   for (int i = 0; i < 4; ++i) {
     const int qi = q0 + ty * 4 + i;
     if (qi >= Tq) continue;
-    const float inv = l_i[i] > 0.f ? 1.0f / l_i[i] : 0.f;
+    const float inv = l_i[i] > 0.f ? drop.inv_keep / l_i[i] : 0.f;
     TOUT* op = out + ((int64_t)b * Tq + qi) * ((int64_t)H * HS) + (int64_t)h * HS + tx * EC;
 #pragma unroll
     for (int e = 0; e < EC; e += 4)
@@ -200,7 +209,7 @@ __global__ void __launch_bounds__(ATT_THREADS)
 attn_bwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, const T* __restrict__ dout,
                 const float* __restrict__ lse, const float* __restrict__ delta, float* __restrict__ dq,
                 T* __restrict__ dk, T* __restrict__ dv, int H, int Tq, int Tk, int64_t q_bs, int64_t q_rs, int64_t kv_bs,
-                int64_t kv_rs, int mode, int n_prompt, float scale) {
+                int64_t kv_rs, int mode, int n_prompt, float scale, DropArgs drop) {
   extern __shared__ __align__(16) float smem[];
   float* Kt = smem;                        // [HS][64]   K^T (key tile, fixed)
   float* Vt = Kt + HS * ATT_BK;            // [HS][64]   V^T
@@ -218,6 +227,8 @@ attn_bwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __res
   const T* vb = v + (int64_t)b * kv_bs + (int64_t)h * HS;
   const T* dob = dout + (int64_t)b * Tq * ((int64_t)H * HS) + (int64_t)h * HS;
   const int64_t do_rs = (int64_t)H * HS;
+  DropKey dkey{0u, 0u, 0u};
+  if (drop.thr != 0u) dkey = drop_key(drop);
 
   for (int c = t >> 6; c < HS / 4; c += ATT_THREADS / 64) {
     const int r = t & 63;
@@ -298,8 +309,11 @@ attn_bwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __res
         const int kj = k0 + tx * 8 + j;
         float p = 0.f;
         if (qok && kj < Tk && key_visible(mode, n_prompt, qi, kj) && L != -INFINITY) p = expf(s[i][j] * scale - L);
-        s[i][j] = p;
-        dp[i][j] = p * (dp[i][j] - D) * scale;  // dS (already carries the 1/sqrt(hs) of S = scale * q.k)
+        float mk = 1.f;       // dropout multiplier of P[q][key]: dV sees P*mk, dP = (dO V^T)*mk, delta already is sum P*dP
+        if (drop.thr != 0u && p != 0.f)
+          mk = drop_attn_keep(drop, dkey, (uint32_t)(((int64_t)b * H + h) * Tq + qi), kj) ? drop.inv_keep : 0.f;
+        s[i][j] = p * mk;
+        dp[i][j] = p * (dp[i][j] * mk - D) * scale;  // dS (already carries the 1/sqrt(hs) of S = scale * q.k)
       }
       float* pr = Ps + (ty * 4 + i) * ATT_PSTRIDE + tx * 8;
       *reinterpret_cast<float4*>(pr) = make_float4(s[i][0], s[i][1], s[i][2], s[i][3]);
@@ -411,14 +425,14 @@ __global__ void attn_dq_scatter_kernel(const float* __restrict__ acc, T* __restr
 template <typename TIN, typename TOUT, int HS>
 static int launch_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int64_t B, int64_t H,
                            int64_t Tq, int64_t Tk, int64_t q_bs, int64_t q_rs, int64_t kv_bs, int64_t kv_rs, int mode,
-                           int64_t n_prompt, cudaStream_t st) {
+                           int64_t n_prompt, DropArgs drop, cudaStream_t st) {
   const size_t smem = (size_t)(HS * ATT_BQ + HS * ATT_BK + ATT_BK * HS + ATT_BQ * ATT_PSTRIDE) * sizeof(float);
   auto kern = attn_fwd_kernel<TIN, TOUT, HS>;
   I2T_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)ceil_div(Tq, ATT_BQ), (unsigned)H, (unsigned)B);
   kern<<<grid, ATT_THREADS, smem, st>>>((const TIN*)q, (const TIN*)k, (const TIN*)v, (TOUT*)out, lse, (int)H, (int)Tq,
                                         (int)Tk, q_bs, q_rs, kv_bs, kv_rs, mode, (int)n_prompt,
-                                        1.0f / sqrtf((float)HS));
+                                        1.0f / sqrtf((float)HS), drop);
   I2T_LAUNCHED();
   return I2T_OK;
 }
@@ -426,13 +440,13 @@ static int launch_attn_fwd(const void* q, const void* k, const void* v, void* ou
 // attention_tc.cu: bf16 tensor-core forward (returns 1 when it handled the call, 0 when the shape is not eligible)
 int attn_fwd_tc(const void* q, const void* k, const void* v, void* out, float* lse, int64_t B, int64_t H, int64_t Tq, int64_t Tk,
                 int64_t head_dim, int64_t q_bs, int64_t q_rs, int64_t kv_bs, int64_t kv_rs, int mode, int64_t n_prompt,
-                cudaStream_t st);
+                DropArgs drop, cudaStream_t st);
 int attn_bwd_tc(const void* q, const void* k, const void* v, const void* dout, const float* lse, const float* delta, float* dq_acc,
                 void* dk, void* dv, int64_t B, int64_t H, int64_t Tq, int64_t Tk, int64_t head_dim, int64_t q_bs, int64_t q_rs,
-                int64_t kv_bs, int64_t kv_rs, int mode, int64_t n_prompt, cudaStream_t st);
+                int64_t kv_bs, int64_t kv_rs, int mode, int64_t n_prompt, DropArgs drop, cudaStream_t st);
 int attn_fwd_tc5(const void* q, const void* k, const void* v, void* out, float* lse, int64_t B, int64_t H, int64_t Tq, int64_t Tk,
                  int64_t head_dim, int64_t q_bs, int64_t q_rs, int64_t kv_bs, int64_t kv_rs, int mode, int64_t n_prompt,
-                 cudaStream_t st);
+                 DropArgs drop, cudaStream_t st);
 // 0: fp32-math kernels; 1 (default): tensor cores -- tcgen05 forward where eligible, mma.sync otherwise; 2: mma.sync only
 static std::atomic<int> g_attn_tc{1};
 
@@ -442,10 +456,10 @@ using namespace i2t;
 
 extern "C" void i2t_set_tensor_core_attention(int mode) { g_attn_tc.store(mode < 0 ? 0 : (mode > 2 ? 1 : mode)); }
 
-extern "C" int i2t_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int64_t B, int64_t H,
-                            int64_t Tq, int64_t Tk, int64_t head_dim, int64_t q_batch_stride, int64_t q_row_stride,
-                            int64_t kv_batch_stride, int64_t kv_row_stride, int mask_mode, int64_t n_prompt,
-                            int in_dtype, int out_dtype, void* stream) {
+static int attn_fwd_impl(const void* q, const void* k, const void* v, void* out, float* lse, int64_t B, int64_t H,
+                         int64_t Tq, int64_t Tk, int64_t head_dim, int64_t q_batch_stride, int64_t q_row_stride,
+                         int64_t kv_batch_stride, int64_t kv_row_stride, int mask_mode, int64_t n_prompt,
+                         int in_dtype, int out_dtype, DropArgs drop, void* stream) {
   I2T_REQUIRE(q && k && v && out, "attn_fwd: null pointer");
   I2T_REQUIRE(B > 0 && H > 0 && Tq > 0 && Tk > 0 && B <= 65535 && H <= 65535, "attn_fwd: bad sizes");
   I2T_REQUIRE(head_dim == 64 || head_dim == 32, "attn_fwd: head_dim %lld not built (32, 64)", (long long)head_dim);
@@ -453,19 +467,20 @@ extern "C" int i2t_attn_fwd(const void* q, const void* k, const void* v, void* o
   I2T_REQUIRE(q_row_stride % 4 == 0 && kv_row_stride % 4 == 0 && q_batch_stride % 4 == 0 && kv_batch_stride % 4 == 0,
               "attn_fwd: strides must be multiples of 4 elements");
   I2T_REQUIRE(valid_dtype(in_dtype) && valid_dtype(out_dtype), "attn_fwd: bad dtype");
+  I2T_REQUIRE(B * H * Tq < (int64_t)1 << 32, "attn_fwd: more than 2^32 query rows");
   cudaStream_t st = (cudaStream_t)stream;
   if (in_dtype == I2T_BF16 && out_dtype == I2T_BF16 && g_attn_tc.load() == 1) {
     const int r5 = attn_fwd_tc5(q, k, v, out, lse, B, H, Tq, Tk, head_dim, q_batch_stride, q_row_stride, kv_batch_stride,
-                                kv_row_stride, mask_mode, n_prompt, st);
+                                kv_row_stride, mask_mode, n_prompt, drop, st);
     if (r5 != 0) return r5 < 0 ? r5 : I2T_OK;
   }
   if (in_dtype == I2T_BF16 && out_dtype == I2T_BF16 && g_attn_tc.load() != 0) {
     const int r = attn_fwd_tc(q, k, v, out, lse, B, H, Tq, Tk, head_dim, q_batch_stride, q_row_stride, kv_batch_stride,
-                              kv_row_stride, mask_mode, n_prompt, st);
+                              kv_row_stride, mask_mode, n_prompt, drop, st);
     if (r != 0) return r < 0 ? r : I2T_OK;
   }
 #define I2T_ATT(TI, TO, HSV) \
-  return launch_attn_fwd<TI, TO, HSV>(q, k, v, out, lse, B, H, Tq, Tk, q_batch_stride, q_row_stride, kv_batch_stride, kv_row_stride, mask_mode, n_prompt, st)
+  return launch_attn_fwd<TI, TO, HSV>(q, k, v, out, lse, B, H, Tq, Tk, q_batch_stride, q_row_stride, kv_batch_stride, kv_row_stride, mask_mode, n_prompt, drop, st)
   if (head_dim == 64) {
     if (in_dtype == I2T_F32 && out_dtype == I2T_F32) I2T_ATT(float, float, 64);
     if (in_dtype == I2T_BF16 && out_dtype == I2T_BF16) I2T_ATT(__nv_bfloat16, __nv_bfloat16, 64);
@@ -478,12 +493,31 @@ extern "C" int i2t_attn_fwd(const void* q, const void* k, const void* v, void* o
   return fail(I2T_ERR_INVALID, "attn_fwd: dtype combination (%d,%d) not built", in_dtype, out_dtype);
 }
 
+extern "C" int i2t_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int64_t B, int64_t H,
+                            int64_t Tq, int64_t Tk, int64_t head_dim, int64_t q_batch_stride, int64_t q_row_stride,
+                            int64_t kv_batch_stride, int64_t kv_row_stride, int mask_mode, int64_t n_prompt,
+                            int in_dtype, int out_dtype, void* stream) {
+  return attn_fwd_impl(q, k, v, out, lse, B, H, Tq, Tk, head_dim, q_batch_stride, q_row_stride, kv_batch_stride, kv_row_stride,
+                       mask_mode, n_prompt, in_dtype, out_dtype, make_drop(0.f, nullptr, 0), stream);
+}
+
+extern "C" int i2t_attn_fwd_dropout(const void* q, const void* k, const void* v, void* out, float* lse, int64_t B, int64_t H,
+                                    int64_t Tq, int64_t Tk, int64_t head_dim, int64_t q_batch_stride, int64_t q_row_stride,
+                                    int64_t kv_batch_stride, int64_t kv_row_stride, int mask_mode, int64_t n_prompt,
+                                    int in_dtype, int out_dtype, float p_drop, const void* rng_state, int64_t site,
+                                    void* stream) {
+  I2T_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "attn_fwd_dropout: p must be in [0,1)");
+  I2T_REQUIRE(p_drop == 0.f || rng_state != nullptr, "attn_fwd_dropout: rng_state is null");
+  return attn_fwd_impl(q, k, v, out, lse, B, H, Tq, Tk, head_dim, q_batch_stride, q_row_stride, kv_batch_stride, kv_row_stride,
+                       mask_mode, n_prompt, in_dtype, out_dtype, make_drop(p_drop, rng_state, site), stream);
+}
+
 namespace i2t {
 template <typename T, int HS>
 static int launch_attn_bwd(const void* q, const void* k, const void* v, const void* out, const void* dout,
                            const float* lse, void* dq, void* dk, void* dv, float* ws, int64_t B, int64_t H, int64_t Tq,
                            int64_t Tk, int64_t q_bs, int64_t q_rs, int64_t kv_bs, int64_t kv_rs, int mode,
-                           int64_t n_prompt, cudaStream_t st) {
+                           int64_t n_prompt, DropArgs drop, cudaStream_t st) {
   // workspace: delta (B*H*Tq) then dq accumulator (B*H*Tq*HS), fp32
   float* delta = ws;
   float* dq_acc = ws + (B * H * Tq + 3) / 4 * 4;      // keep the accumulator 16-byte aligned (float4 reads in the scatter)
@@ -494,7 +528,7 @@ static int launch_attn_bwd(const void* q, const void* k, const void* v, const vo
   I2T_LAUNCHED();
   if (sizeof(T) == 2 && g_attn_tc.load() != 0) {
     const int r = attn_bwd_tc(q, k, v, dout, lse, delta, dq_acc, dk, dv, B, H, Tq, Tk, HS, q_bs, q_rs, kv_bs, kv_rs, mode,
-                              n_prompt, st);
+                              n_prompt, drop, st);
     if (r < 0) return r;
     if (r == 1) {
       const int64_t total_tc = B * H * Tq * (HS / 4);
@@ -510,7 +544,7 @@ static int launch_attn_bwd(const void* q, const void* k, const void* v, const vo
   dim3 grid((unsigned)ceil_div(Tk, ATT_BK), (unsigned)H, (unsigned)B);
   kern<<<grid, ATT_THREADS, smem, st>>>((const T*)q, (const T*)k, (const T*)v, (const T*)dout, lse, delta, dq_acc,
                                         (T*)dk, (T*)dv, (int)H, (int)Tq, (int)Tk, q_bs, q_rs, kv_bs, kv_rs, mode,
-                                        (int)n_prompt, 1.0f / sqrtf((float)HS));
+                                        (int)n_prompt, 1.0f / sqrtf((float)HS), drop);
   I2T_LAUNCHED();
   const int64_t total = B * H * Tq * (HS / 4);
   attn_dq_scatter_kernel<T, HS><<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(dq_acc, (T*)dq, (int)H, (int)Tq, q_bs,
@@ -524,11 +558,11 @@ extern "C" int64_t i2t_attn_bwd_workspace_bytes(int64_t B, int64_t H, int64_t Tq
   return ((B * H * Tq + 3) / 4 * 4 + B * H * Tq * head_dim) * (int64_t)sizeof(float);
 }
 
-extern "C" int i2t_attn_bwd(const void* q, const void* k, const void* v, const void* out, const void* dout,
-                            const float* lse, void* dq, void* dk, void* dv, void* workspace, int64_t B, int64_t H,
-                            int64_t Tq, int64_t Tk, int64_t head_dim, int64_t q_batch_stride, int64_t q_row_stride,
-                            int64_t kv_batch_stride, int64_t kv_row_stride, int mask_mode, int64_t n_prompt, int dtype,
-                            void* stream) {
+static int attn_bwd_impl(const void* q, const void* k, const void* v, const void* out, const void* dout,
+                         const float* lse, void* dq, void* dk, void* dv, void* workspace, int64_t B, int64_t H,
+                         int64_t Tq, int64_t Tk, int64_t head_dim, int64_t q_batch_stride, int64_t q_row_stride,
+                         int64_t kv_batch_stride, int64_t kv_row_stride, int mask_mode, int64_t n_prompt, int dtype,
+                         DropArgs drop, void* stream) {
   I2T_REQUIRE(q && k && v && out && dout && lse && dq && dk && dv && workspace, "attn_bwd: null pointer");
   I2T_REQUIRE(B > 0 && H > 0 && Tq > 0 && Tk > 0 && B <= 65535 && H <= 65535, "attn_bwd: bad sizes");
   I2T_REQUIRE(head_dim == 64 || head_dim == 32, "attn_bwd: head_dim %lld not built (32, 64)", (long long)head_dim);
@@ -538,7 +572,7 @@ extern "C" int i2t_attn_bwd(const void* q, const void* k, const void* v, const v
   cudaStream_t st = (cudaStream_t)stream;
   float* ws = (float*)workspace;
 #define I2T_ATTB(T, HSV) \
-  return launch_attn_bwd<T, HSV>(q, k, v, out, dout, lse, dq, dk, dv, ws, B, H, Tq, Tk, q_batch_stride, q_row_stride, kv_batch_stride, kv_row_stride, mask_mode, n_prompt, st)
+  return launch_attn_bwd<T, HSV>(q, k, v, out, dout, lse, dq, dk, dv, ws, B, H, Tq, Tk, q_batch_stride, q_row_stride, kv_batch_stride, kv_row_stride, mask_mode, n_prompt, drop, st)
   if (dtype == I2T_F32) {
     if (head_dim == 64) I2T_ATTB(float, 64);
     I2T_ATTB(float, 32);
@@ -548,4 +582,24 @@ extern "C" int i2t_attn_bwd(const void* q, const void* k, const void* v, const v
   }
 #undef I2T_ATTB
   return fail(I2T_ERR_INVALID, "attn_bwd: bad dtype %d", dtype);
+}
+
+extern "C" int i2t_attn_bwd(const void* q, const void* k, const void* v, const void* out, const void* dout,
+                            const float* lse, void* dq, void* dk, void* dv, void* workspace, int64_t B, int64_t H,
+                            int64_t Tq, int64_t Tk, int64_t head_dim, int64_t q_batch_stride, int64_t q_row_stride,
+                            int64_t kv_batch_stride, int64_t kv_row_stride, int mask_mode, int64_t n_prompt, int dtype,
+                            void* stream) {
+  return attn_bwd_impl(q, k, v, out, dout, lse, dq, dk, dv, workspace, B, H, Tq, Tk, head_dim, q_batch_stride, q_row_stride,
+                       kv_batch_stride, kv_row_stride, mask_mode, n_prompt, dtype, make_drop(0.f, nullptr, 0), stream);
+}
+
+extern "C" int i2t_attn_bwd_dropout(const void* q, const void* k, const void* v, const void* out, const void* dout,
+                                    const float* lse, void* dq, void* dk, void* dv, void* workspace, int64_t B, int64_t H,
+                                    int64_t Tq, int64_t Tk, int64_t head_dim, int64_t q_batch_stride, int64_t q_row_stride,
+                                    int64_t kv_batch_stride, int64_t kv_row_stride, int mask_mode, int64_t n_prompt,
+                                    int dtype, float p_drop, const void* rng_state, int64_t site, void* stream) {
+  I2T_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "attn_bwd_dropout: p must be in [0,1)");
+  I2T_REQUIRE(p_drop == 0.f || rng_state != nullptr, "attn_bwd_dropout: rng_state is null");
+  return attn_bwd_impl(q, k, v, out, dout, lse, dq, dk, dv, workspace, B, H, Tq, Tk, head_dim, q_batch_stride, q_row_stride,
+                       kv_batch_stride, kv_row_stride, mask_mode, n_prompt, dtype, make_drop(p_drop, rng_state, site), stream);
 }

@@ -7,6 +7,7 @@
 // bf16 autocast.  (The sequence lengths here -- 197..272 -- make this kernel latency- not throughput-bound; a tcgen05
 // version would not change its duration, so the legacy MMA path is the pragmatic choice for these shapes.)
 #include "common.cuh"
+#include "rng.cuh"
 
 namespace i2t {
 
@@ -41,7 +42,7 @@ template <int HS>
 __global__ void __launch_bounds__(ATC_THREADS)
 attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v,
                    __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int H, int Tq, int Tk, int64_t q_bs, int64_t q_rs,
-                   int64_t kv_bs, int64_t kv_rs, int mode, int n_prompt, float scale_log2) {
+                   int64_t kv_bs, int64_t kv_rs, int mode, int n_prompt, float scale_log2, DropArgs drop) {
   constexpr int PITCH = HS + 8;               // bf16 elements per shared-memory row (16 bytes of padding)
   constexpr int KS = HS / 16;                 // k-steps over the head dimension
   constexpr int NT_O = HS / 8;                // 8-wide output column tiles
@@ -55,6 +56,8 @@ attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __r
   const __nv_bfloat16* qb = q + (int64_t)b * q_bs + (int64_t)h * HS;
   const __nv_bfloat16* kb = k + (int64_t)b * kv_bs + (int64_t)h * HS;
   const __nv_bfloat16* vb = v + (int64_t)b * kv_bs + (int64_t)h * HS;
+  DropKey dkey{0u, 0u, 0u};
+  if (drop.thr != 0u) dkey = drop_key(drop);
 
   constexpr int CH = HS / 8;                  // 16-byte chunks per row
   for (int i = t; i < ATC_BQ * CH; i += ATC_THREADS) {
@@ -142,6 +145,18 @@ attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __r
         o[nt][half * 2] *= corr;
         o[nt][half * 2 + 1] *= corr;
       }
+      if (drop.thr != 0u) {   // dropout on the probabilities (the row sum above keeps every key); one Philox call per
+                              // 16-key block = this thread's four columns {2tq, 2tq+1, 8+2tq, 9+2tq} of the block
+        const uint32_t row = (uint32_t)(((int64_t)b * H + h) * Tq + qi);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const Philox4 r = drop_attn4(drop, dkey, row, (uint32_t)(k0 >> 4) + kk, (uint32_t)tq);
+          if (r.x < drop.thr) s[2 * kk][half * 2] = 0.f;
+          if (r.y < drop.thr) s[2 * kk][half * 2 + 1] = 0.f;
+          if (r.z < drop.thr) s[2 * kk + 1][half * 2] = 0.f;
+          if (r.w < drop.thr) s[2 * kk + 1][half * 2 + 1] = 0.f;
+        }
+      }
     }
     // O += P V : the S accumulators of key tiles (2kk, 2kk+1) are exactly the A fragment of key k-step kk
 #pragma unroll
@@ -165,7 +180,7 @@ attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __r
   for (int half = 0; half < 2; ++half) {
     const int qi = q0 + w * 16 + g + half * 8;
     if (qi >= Tq) continue;
-    const float inv = l_i[half] > 0.f ? 1.0f / l_i[half] : 0.f;
+    const float inv = l_i[half] > 0.f ? drop.inv_keep / l_i[half] : 0.f;
     __nv_bfloat16* op = out + ((int64_t)b * Tq + qi) * ((int64_t)H * HS) + (int64_t)h * HS;
 #pragma unroll
     for (int nt = 0; nt < NT_O; ++nt)
@@ -189,7 +204,8 @@ __global__ void __launch_bounds__(ATC_THREADS)
 attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v,
                    const __nv_bfloat16* __restrict__ dout, const float* __restrict__ lse, const float* __restrict__ delta,
                    float* __restrict__ dq_acc, __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv, int H, int Tq,
-                   int Tk, int64_t q_bs, int64_t q_rs, int64_t kv_bs, int64_t kv_rs, int mode, int n_prompt, float scale) {
+                   int Tk, int64_t q_bs, int64_t q_rs, int64_t kv_bs, int64_t kv_rs, int mode, int n_prompt, float scale,
+                   DropArgs drop) {
   constexpr int PITCH = HS + 8;
   constexpr int KS = HS / 16, NT_O = HS / 8;
   __shared__ __align__(16) __nv_bfloat16 Ks[ATC_BK][PITCH];
@@ -209,6 +225,8 @@ attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __r
   const __nv_bfloat16* dob = dout + (int64_t)b * Tq * do_rs + (int64_t)h * HS;
   const float LOG2E = 1.4426950408889634f;
   const float scale_log2 = scale * LOG2E;
+  DropKey dkey{0u, 0u, 0u};
+  if (drop.thr != 0u) dkey = drop_key(drop);
 
   constexpr int CH = HS / 8;
   for (int i = t; i < ATC_BK * CH; i += ATC_THREADS) {
@@ -272,9 +290,22 @@ attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __r
         mma_bf16(dp[2 * np + 1], vf[ks], bd[2], bd[3]);
       }
     }
-    // P^T and dS^T in place: s <- P^T, dp <- dS^T (scaled)
+    // P^T and dS^T in place: s <- P^T (with the dropout multiplier: it feeds dV), dp <- dS^T (scaled)
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
+      float mk[4] = {1.f, 1.f, 1.f, 1.f};
+      if (drop.thr != 0u) {
+        // the forward's mask: for query qi the words of block (keys k0 + w*16 ..+15), pair (g >> 1) cover keys g and g + 8
+        // of this thread at lanes (g & 1) and 2 + (g & 1)
+#pragma unroll
+        for (int e1 = 0; e1 < 2; ++e1) {
+          const int qi = q0 + nt * 8 + tq * 2 + e1;
+          const Philox4 r = drop_attn4(drop, dkey, (uint32_t)(((int64_t)b * H + h) * Tq + qi), (uint32_t)((k0 + w * 16) >> 4),
+                                       (uint32_t)(g >> 1) & 3u);
+          mk[e1] = philox_word(r, g & 1) >= drop.thr ? drop.inv_keep : 0.f;
+          mk[2 + e1] = philox_word(r, 2 + (g & 1)) >= drop.thr ? drop.inv_keep : 0.f;
+        }
+      }
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int kj = k0 + w * 16 + g + (e >> 1) * 8;
@@ -283,8 +314,8 @@ attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __r
         const float l = lse_s[ql];
         float p = 0.f;
         if (kj < Tk && qi < Tq && l != -INFINITY && atc_visible(mode, n_prompt, qi, kj)) p = exp2f(s[nt][e] * scale_log2 - l * LOG2E);
-        s[nt][e] = p;
-        dp[nt][e] = p * (dp[nt][e] - delta_s[ql]) * scale;
+        s[nt][e] = p * mk[e];
+        dp[nt][e] = p * (dp[nt][e] * mk[e] - delta_s[ql]) * scale;
       }
     }
     // dS^T -> shared memory [key][query] (for dQ), packed pairs along the query index
@@ -365,7 +396,7 @@ attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __r
 // returns 1 when it handled the call, 0 when the shape is not eligible (the caller then runs the fp32-math kernel)
 int attn_bwd_tc(const void* q, const void* k, const void* v, const void* dout, const float* lse, const float* delta, float* dq_acc,
                 void* dk, void* dv, int64_t B, int64_t H, int64_t Tq, int64_t Tk, int64_t head_dim, int64_t q_bs, int64_t q_rs,
-                int64_t kv_bs, int64_t kv_rs, int mode, int64_t n_prompt, cudaStream_t st) {
+                int64_t kv_bs, int64_t kv_rs, int mode, int64_t n_prompt, DropArgs drop, cudaStream_t st) {
   if ((q_rs | q_bs | kv_rs | kv_bs) % 8 != 0 || !aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(dout) ||
       (H * head_dim) % 8 != 0)
     return 0;
@@ -376,12 +407,12 @@ int attn_bwd_tc(const void* q, const void* k, const void* v, const void* dout, c
     attn_bwd_tc_kernel<64><<<grid, ATC_THREADS, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v,
                                                        (const __nv_bfloat16*)dout, lse, delta, dq_acc, (__nv_bfloat16*)dk,
                                                        (__nv_bfloat16*)dv, (int)H, (int)Tq, (int)Tk, q_bs, q_rs, kv_bs, kv_rs, mode,
-                                                       (int)n_prompt, scale);
+                                                       (int)n_prompt, scale, drop);
   else if (head_dim == 32)
     attn_bwd_tc_kernel<32><<<grid, ATC_THREADS, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v,
                                                        (const __nv_bfloat16*)dout, lse, delta, dq_acc, (__nv_bfloat16*)dk,
                                                        (__nv_bfloat16*)dv, (int)H, (int)Tq, (int)Tk, q_bs, q_rs, kv_bs, kv_rs, mode,
-                                                       (int)n_prompt, scale);
+                                                       (int)n_prompt, scale, drop);
   else
     return 0;
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -392,7 +423,7 @@ int attn_bwd_tc(const void* q, const void* k, const void* v, const void* dout, c
 
 int attn_fwd_tc(const void* q, const void* k, const void* v, void* out, float* lse, int64_t B, int64_t H, int64_t Tq, int64_t Tk,
                 int64_t head_dim, int64_t q_bs, int64_t q_rs, int64_t kv_bs, int64_t kv_rs, int mode, int64_t n_prompt,
-                cudaStream_t st) {
+                DropArgs drop, cudaStream_t st) {
   // 16-byte vector loads: strides and head offsets must be multiples of 8 bf16 elements
   if ((q_rs | q_bs | kv_rs | kv_bs) % 8 != 0 || !aligned16(q) || !aligned16(k) || !aligned16(v)) return 0;
   dim3 grid((unsigned)ceil_div(Tq, ATC_BQ), (unsigned)H, (unsigned)B);
@@ -400,11 +431,11 @@ int attn_fwd_tc(const void* q, const void* k, const void* v, void* out, float* l
   if (head_dim == 64)
     attn_fwd_tc_kernel<64><<<grid, ATC_THREADS, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v,
                                                        (__nv_bfloat16*)out, lse, (int)H, (int)Tq, (int)Tk, q_bs, q_rs, kv_bs, kv_rs,
-                                                       mode, (int)n_prompt, scale_log2);
+                                                       mode, (int)n_prompt, scale_log2, drop);
   else if (head_dim == 32)
     attn_fwd_tc_kernel<32><<<grid, ATC_THREADS, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v,
                                                        (__nv_bfloat16*)out, lse, (int)H, (int)Tq, (int)Tk, q_bs, q_rs, kv_bs, kv_rs,
-                                                       mode, (int)n_prompt, scale_log2);
+                                                       mode, (int)n_prompt, scale_log2, drop);
   else
     return 0;
   g_launches.fetch_add(1, std::memory_order_relaxed);

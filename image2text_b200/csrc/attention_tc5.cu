@@ -16,6 +16,7 @@
 // Keys beyond the causal diagonal of the tile are never loaded.  2 CTAs per SM when the sequence has <= 256 keys
 // (113 KB of shared memory, 256 TMEM columns each).
 #include "common.cuh"
+#include "rng.cuh"
 #include "tc_common.cuh"
 
 namespace i2t {
@@ -41,7 +42,7 @@ template <int NB>     // key blocks the kernel can hold (2 or 3)
 __global__ void __launch_bounds__(A5_THREADS, NB == 2 ? 2 : 1)
 attn_fwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int H,
-                    int Tq, int Tk, int mode, int n_prompt, float scale_log2) {
+                    int Tq, int Tk, int mode, int n_prompt, float scale_log2, DropArgs drop) {
   constexpr uint32_t TMEM_COLS = NB == 2 ? 256 : 512;
   // no static shared memory: two CTAs of the 2-block variant must fit one SM, so the barriers live behind the tiles and
   // the 1024-byte alignment of the swizzled tiles may cost at most A5_SLACK bytes
@@ -176,6 +177,21 @@ attn_fwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           p[i] = vis ? exp2f((__uint_as_float(v[i]) - m_use) * scale_log2) : 0.f;
           l += p[i];
         }
+        if (drop.thr != 0u) {   // dropout on the probabilities (l keeps every key): 8 Philox calls per 32 keys
+          const DropKey dkey = drop_key(drop);
+          const uint32_t row = (uint32_t)(((int64_t)b * H + h) * Tq + qi);
+#pragma unroll
+          for (int bl = 0; bl < 2; ++bl) {
+#pragma unroll
+            for (int pr = 0; pr < 4; ++pr) {
+              const Philox4 rr = drop_attn4(drop, dkey, row, (uint32_t)((j * A5_BK + c * 32) >> 4) + bl, (uint32_t)pr);
+              if (rr.x < drop.thr) p[bl * 16 + 2 * pr] = 0.f;
+              if (rr.y < drop.thr) p[bl * 16 + 2 * pr + 1] = 0.f;
+              if (rr.z < drop.thr) p[bl * 16 + 8 + 2 * pr] = 0.f;
+              if (rr.w < drop.thr) p[bl * 16 + 9 + 2 * pr] = 0.f;
+            }
+          }
+        }
         // 32 keys = four 16-byte chunks of the (c / 2)-th 64-key sub-block, chunk index (c % 2) * 4 + t, XOR-swizzled by row
         uint8_t* sub = sP + (c >> 1) * (A5_P_BYTES / 2) + r * 128;
 #pragma unroll
@@ -197,7 +213,7 @@ attn_fwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     // ---- epilogue: O / l ----
     mbar_wait(&bar_o, 0u);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const float inv = l > 0.f ? 1.0f / l : 0.f;
+    const float inv = l > 0.f ? drop.inv_keep / l : 0.f;
     __nv_bfloat16* op = out + ((int64_t)b * Tq + qi) * ((int64_t)H * A5_HS) + (int64_t)h * A5_HS;
 #pragma unroll 1
     for (int c = 0; c < A5_HS / 32; ++c) {
@@ -228,7 +244,7 @@ attn_fwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 // returns 1 when it handled the call, 0 when the shape is not eligible (the caller then runs the mma.sync kernel)
 int attn_fwd_tc5(const void* q, const void* k, const void* v, void* out, float* lse, int64_t B, int64_t H, int64_t Tq, int64_t Tk,
                  int64_t head_dim, int64_t q_bs, int64_t q_rs, int64_t kv_bs, int64_t kv_rs, int mode, int64_t n_prompt,
-                 cudaStream_t st) {
+                 DropArgs drop, cudaStream_t st) {
   if (head_dim != A5_HS || Tk > 3 * A5_BK) return 0;
   if (q_bs != Tq * q_rs || kv_bs != Tk * kv_rs) return 0;                // batches must be row-contiguous for one 2-D tensor map
   if (q_rs % 8 != 0 || kv_rs % 8 != 0 || !aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(out)) return 0;
@@ -252,7 +268,7 @@ int attn_fwd_tc5(const void* q, const void* k, const void* v, void* out, float* 
       attr2 = true;
     }
     attn_fwd_tc5_kernel<2><<<grid, A5_THREADS, SMEM, st>>>(mq, mk, mv, (__nv_bfloat16*)out, lse, (int)H, (int)Tq, (int)Tk, mode,
-                                                         (int)n_prompt, scale_log2);
+                                                         (int)n_prompt, scale_log2, drop);
   } else {
     constexpr int SMEM = a5_smem(3);
     if (!attr3) {
@@ -261,7 +277,7 @@ int attn_fwd_tc5(const void* q, const void* k, const void* v, void* out, float* 
       attr3 = true;
     }
     attn_fwd_tc5_kernel<3><<<grid, A5_THREADS, SMEM, st>>>(mq, mk, mv, (__nv_bfloat16*)out, lse, (int)H, (int)Tq, (int)Tk, mode,
-                                                         (int)n_prompt, scale_log2);
+                                                         (int)n_prompt, scale_log2, drop);
   }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();

@@ -21,14 +21,20 @@ def _ln(W, key_w, key_b, x, eps, out_dtype):
     return LayerNormFn.apply(x, W[key_w], W.get(key_b), eps, out_dtype)
 
 
-def _lin(W, key_w, key_b, x2d, residual=None, act=ops.ACT_NONE, out_dtype=torch.float32, rows: Optional[slice] = None):
+def _lin(W, key_w, key_b, x2d, residual=None, act=ops.ACT_NONE, out_dtype=torch.float32, rows: Optional[slice] = None,
+         drop=None, tok_drop=None):
     w = W[key_w]
     wc = W.c(key_w)
     b = W.get(key_b) if key_b else None
     if rows is not None:
         w, wc = w[rows], wc[rows]
         b = b[rows] if b is not None else None
-    return linear(x2d, w, wc, b, residual, act, out_dtype)
+    return linear(x2d, w, wc, b, residual, act, out_dtype, drop=drop, tok_drop=tok_drop)
+
+
+def _site(drop, p):
+    """Next dropout site of this forward pass (None when not training or p == 0)."""
+    return drop.site(p) if drop is not None else None
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -170,7 +176,7 @@ def encoder_forward(W, spec, images: torch.Tensor, cd: torch.dtype, train_trunk:
 # ------------------------------------------------------------------------------------------------------------
 # decoder: reference models/vision_encoder_decoder.py:84-134 + models/decoder.py:214-256 + models/layers.py:565-614
 # ------------------------------------------------------------------------------------------------------------
-def hf_gpt2_forward(W, spec, ids: torch.Tensor, encoder_output: torch.Tensor, cd: torch.dtype):
+def hf_gpt2_forward(W, spec, ids: torch.Tensor, encoder_output: torch.Tensor, cd: torch.dtype, drop=None):
     """transformers GPT2LMHeadModel with add_cross_attention=True exactly as the reference drives it
     (models/decoder.py:335-361: attention_mask=None -> plain causal over prompt + text; every block has
     ln_cross_attn + crossattention {q_attn, c_attn -> [k|v], c_proj}); Conv1D weights stay (in, out)."""
@@ -181,7 +187,8 @@ def hf_gpt2_forward(W, spec, ids: torch.Tensor, encoder_output: torch.Tensor, cd
     T = min(n_prompt + S, 1024)
     dp = "decoder.backbone.transformer."
     prompt = encoder_output.contiguous().float() if n_prompt else None
-    x = EmbedFn.apply(ids.contiguous(), prompt, W[dp + "wte.weight"], W[dp + "wpe.weight"], T, n_prompt)
+    pd = spec.get("dropout", 0.0)              # GPT2Config embd_pdrop = attn_pdrop = resid_pdrop (training mode only)
+    x = EmbedFn.apply(ids.contiguous(), prompt, W[dp + "wte.weight"], W[dp + "wpe.weight"], T, n_prompt, _site(drop, pd))
     cross = spec["use_cross_attn"]
     S_enc = encoder_output.shape[1]
     enc_c = None
@@ -189,24 +196,24 @@ def hf_gpt2_forward(W, spec, ids: torch.Tensor, encoder_output: torch.Tensor, cd
         enc_c = encoder_output.reshape(B * S_enc, C)
         enc_c = enc_c if enc_c.dtype == cd else enc_c.to(cd)
 
-    def c1d(wkey, x2d, residual=None, act=ops.ACT_NONE, out_dtype=torch.float32):
-        return conv1d(x2d, W[wkey + ".weight"], W.c(wkey + ".weight"), W[wkey + ".bias"], residual, act, out_dtype)
+    def c1d(wkey, x2d, residual=None, act=ops.ACT_NONE, out_dtype=torch.float32, dsite=None):
+        return conv1d(x2d, W[wkey + ".weight"], W.c(wkey + ".weight"), W[wkey + ".bias"], residual, act, out_dtype, dsite)
 
     for i in range(spec["n_layer"]):
         lp = f"{dp}h.{i}."
         y = _ln(W, lp + "ln_1.weight", lp + "ln_1.bias", x, 1e-5, cd)
         qkv = c1d(lp + "attn.c_attn", y.view(B * T, C), out_dtype=cd)
-        a = AttnFn.apply(qkv, B, T, H, ops.MASK_CAUSAL, 0)
-        x = c1d(lp + "attn.c_proj", a, residual=x.view(B * T, C)).view(B, T, C)
+        a = AttnFn.apply(qkv, B, T, H, ops.MASK_CAUSAL, 0, _site(drop, pd))
+        x = c1d(lp + "attn.c_proj", a, residual=x.view(B * T, C), dsite=_site(drop, pd)).view(B, T, C)
         if cross:
             y = _ln(W, lp + "ln_cross_attn.weight", lp + "ln_cross_attn.bias", x, 1e-5, cd)
             q = c1d(lp + "crossattention.q_attn", y.view(B * T, C), out_dtype=cd)
             kv = c1d(lp + "crossattention.c_attn", enc_c, out_dtype=cd)
-            a = XAttnFn.apply(q, kv, B, T, S_enc, H)
-            x = c1d(lp + "crossattention.c_proj", a, residual=x.view(B * T, C)).view(B, T, C)
+            a = XAttnFn.apply(q, kv, B, T, S_enc, H, _site(drop, pd))
+            x = c1d(lp + "crossattention.c_proj", a, residual=x.view(B * T, C), dsite=_site(drop, pd)).view(B, T, C)
         y = _ln(W, lp + "ln_2.weight", lp + "ln_2.bias", x, 1e-5, cd)
         h = c1d(lp + "mlp.c_fc", y.view(B * T, C), act=ops.ACT_GELU_TANH, out_dtype=cd)
-        x = c1d(lp + "mlp.c_proj", h, residual=x.view(B * T, C)).view(B, T, C)
+        x = c1d(lp + "mlp.c_proj", h, residual=x.view(B * T, C), dsite=_site(drop, pd)).view(B, T, C)
     hidden = _ln(W, dp + "ln_f.weight", dp + "ln_f.bias", x, 1e-5, torch.float32)
     text = hidden[:, n_prompt:, :].reshape(B * (T - n_prompt), C)
     text = text if cd == torch.float32 else text.to(cd)
@@ -215,16 +222,21 @@ def hf_gpt2_forward(W, spec, ids: torch.Tensor, encoder_output: torch.Tensor, cd
     return logits, hidden
 
 
-def decoder_forward(W, spec, ids: torch.Tensor, encoder_output: torch.Tensor, cd: torch.dtype, training: bool = False):
+def decoder_forward(W, spec, ids: torch.Tensor, encoder_output: torch.Tensor, cd: torch.dtype, training: bool = False,
+                    drop=None):
+    """`drop` (ops.DropCtx) switches the training-mode dropouts on: transformer.drop (models/decoder.py:236-243), the
+    per-token q/k/v masks + SDPA dropout_p + resid_dropout of models/layers.py:454-469, nn.MultiheadAttention's dropout
+    (:537-542) and _MLP.dropout (:485).  Site order = call order below (the oracle's mask provider counts the same way)."""
     if spec["decoder"] == "hf_gpt2":
-        return hf_gpt2_forward(W, spec, ids, encoder_output, cd)
+        return hf_gpt2_forward(W, spec, ids, encoder_output, cd, drop)
     C, H, blk = spec["n_embd"], spec["n_head"], spec["block_size"]
     B, S = ids.shape
     n_prompt = spec["n_cls"] if spec["use_soft_prompting"] else 0
     T = min(n_prompt + S, blk)
     dp = "decoder.transformer."
     prompt = encoder_output.contiguous().float() if n_prompt else None
-    x = EmbedFn.apply(ids.contiguous(), prompt, W[dp + "wte.weight"], W[dp + "wpe.weight"], T, n_prompt)
+    pd, pa = spec.get("dropout", 0.0), spec.get("attn_dropout", 0.0)
+    x = EmbedFn.apply(ids.contiguous(), prompt, W[dp + "wte.weight"], W[dp + "wpe.weight"], T, n_prompt, _site(drop, pd))
     if n_prompt:
         mask_mode = ops.MASK_PROMPT
     else:
@@ -239,9 +251,12 @@ def decoder_forward(W, spec, ids: torch.Tensor, encoder_output: torch.Tensor, cd
     for depth in range(spec["n_layer"]):
         lp = f"{dp}h.{depth}."
         y = _ln(W, lp + "ln_1.weight", lp + "ln_1.bias", x, 1e-5, cd)
-        qkv = _lin(W, lp + "attn.c_attn.weight", lp + "attn.c_attn.bias", y.view(B * T, C), out_dtype=cd)
-        a = AttnFn.apply(qkv, B, T, H, mask_mode, n_prompt)
-        x = _lin(W, lp + "attn.c_proj.weight", lp + "attn.c_proj.bias", a, residual=x.view(B * T, C)).view(B, T, C)
+        ts = _site(drop, pa)
+        qkv = _lin(W, lp + "attn.c_attn.weight", lp + "attn.c_attn.bias", y.view(B * T, C), out_dtype=cd,
+                   tok_drop=(ts, C, 3) if ts is not None else None)
+        a = AttnFn.apply(qkv, B, T, H, mask_mode, n_prompt, _site(drop, pd))
+        x = _lin(W, lp + "attn.c_proj.weight", lp + "attn.c_proj.bias", a, residual=x.view(B * T, C),
+                 drop=_site(drop, pd)).view(B, T, C)
         use_cross = cross is not None and (depth % 2 == 0 if spec["skip_alternate_cross_attn"] else True)
         if use_cross:
             if not layer_has_cross_attn(spec, depth):
@@ -250,12 +265,13 @@ def decoder_forward(W, spec, ids: torch.Tensor, encoder_output: torch.Tensor, cd
             kw, kb = lp + "cross_attn.in_proj_weight", lp + "cross_attn.in_proj_bias"
             q = _lin(W, kw, kb, y.view(B * T, C), out_dtype=cd, rows=slice(0, C))
             kv = _lin(W, kw, kb, enc_c, out_dtype=cd, rows=slice(C, 3 * C))            # raw encoder output, no LN
-            a = XAttnFn.apply(q, kv, B, T, S_enc, H)
+            a = XAttnFn.apply(q, kv, B, T, S_enc, H, _site(drop, pd))
             x = _lin(W, lp + "cross_attn.out_proj.weight", lp + "cross_attn.out_proj.bias", a,
                      residual=x.view(B * T, C)).view(B, T, C)
         y = _ln(W, lp + "ln_2.weight", lp + "ln_2.bias", x, 1e-5, cd)
         h = _lin(W, lp + "mlp.c_fc.weight", lp + "mlp.c_fc.bias", y.view(B * T, C), act=ops.ACT_GELU_TANH, out_dtype=cd)
-        x = _lin(W, lp + "mlp.c_proj.weight", lp + "mlp.c_proj.bias", h, residual=x.view(B * T, C)).view(B, T, C)
+        x = _lin(W, lp + "mlp.c_proj.weight", lp + "mlp.c_proj.bias", h, residual=x.view(B * T, C),
+                 drop=_site(drop, pd)).view(B, T, C)
         if grads and x.requires_grad:
             x = NormalizeGradientsFn.apply(x)                                          # models/layers.py:607-608
     hidden = _ln(W, dp + "ln_f.weight", dp + "ln_f.bias", x, 1e-5, torch.float32)

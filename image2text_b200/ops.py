@@ -2,7 +2,7 @@
 and streams only; every arithmetic operation below is a libi2t kernel."""
 from __future__ import annotations
 
-from typing import Optional
+from typing import NamedTuple, Optional
 
 import torch
 
@@ -11,6 +11,31 @@ from ._lib import call
 F32, BF16 = 0, 1
 ACT_NONE, ACT_GELU_TANH, ACT_GELU_ERF = 0, 1, 2
 MASK_NONE, MASK_CAUSAL, MASK_PROMPT = 0, 1, 2
+
+
+class DropSite(NamedTuple):
+    """One dropout call of a training forward pass: probability, the device rng state (uint64 {seed, step offset},
+    stored as an int64[2] tensor) and the site index.  The mask is a pure function of these (csrc/rng.cuh)."""
+    p: float
+    state: torch.Tensor
+    site: int
+
+
+class DropCtx:
+    """Hands out consecutive site indices over one forward pass.  `base` separates passes that run on the same step
+    offset (student forward = 0, EMA-teacher forward = 1 << 20)."""
+
+    def __init__(self, state: torch.Tensor, base: int = 0):
+        assert state.dtype == torch.int64 and state.numel() == 2 and state.is_cuda
+        self.state = state
+        self.base = base
+        self.n = 0
+
+    def site(self, p: float) -> Optional[DropSite]:
+        """Next site; None when p == 0 (the index is consumed either way so site numbering does not depend on p)."""
+        i = self.base + self.n
+        self.n += 1
+        return DropSite(float(p), self.state, i) if p > 0.0 else None
 
 
 def dt(t: torch.Tensor) -> int:
@@ -99,7 +124,22 @@ def colsum_(x2d: torch.Tensor, out: torch.Tensor):
     call("i2t_colsum", ptr(x2d), ptr(out), x2d.shape[0], x2d.shape[1], x2d.stride(0), dt(x2d), stream())
 
 
-def attention_packed(qkv: torch.Tensor, B: int, T: int, H: int, mask_mode: int, n_prompt: int = 0, want_lse: bool = False):
+def _attn_fwd(drop: Optional[DropSite], *args):
+    if drop is None:
+        call("i2t_attn_fwd", *args, stream())
+    else:
+        call("i2t_attn_fwd_dropout", *args, drop.p, ptr(drop.state), drop.site, stream())
+
+
+def _attn_bwd(drop: Optional[DropSite], *args):
+    if drop is None:
+        call("i2t_attn_bwd", *args, stream())
+    else:
+        call("i2t_attn_bwd_dropout", *args, drop.p, ptr(drop.state), drop.site, stream())
+
+
+def attention_packed(qkv: torch.Tensor, B: int, T: int, H: int, mask_mode: int, n_prompt: int = 0, want_lse: bool = False,
+                     drop: Optional[DropSite] = None):
     """qkv: (B*T, 3C) packed [q | k | v] as c_attn / in_proj produce it.  Returns (B*T, C) in qkv's dtype."""
     C = qkv.shape[1] // 3
     hs = C // H
@@ -107,12 +147,12 @@ def attention_packed(qkv: torch.Tensor, B: int, T: int, H: int, mask_mode: int, 
     lse = torch.empty((B, H, T), device=qkv.device, dtype=torch.float32) if want_lse else None
     es = qkv.element_size()
     base = qkv.data_ptr()
-    call("i2t_attn_fwd", base, base + C * es, base + 2 * C * es, ptr(out), ptr(lse), B, H, T, T, hs, T * 3 * C, 3 * C,
-         T * 3 * C, 3 * C, mask_mode, n_prompt, dt(qkv), dt(out), stream())
+    _attn_fwd(drop, base, base + C * es, base + 2 * C * es, ptr(out), ptr(lse), B, H, T, T, hs, T * 3 * C, 3 * C,
+              T * 3 * C, 3 * C, mask_mode, n_prompt, dt(qkv), dt(out))
     return (out, lse) if want_lse else out
 
 
-def attention_packed_bwd(qkv, out, dout, lse, B, T, H, mask_mode, n_prompt):
+def attention_packed_bwd(qkv, out, dout, lse, B, T, H, mask_mode, n_prompt, drop: Optional[DropSite] = None):
     C = qkv.shape[1] // 3
     hs = C // H
     dqkv = torch.empty_like(qkv)
@@ -121,8 +161,8 @@ def attention_packed_bwd(qkv, out, dout, lse, B, T, H, mask_mode, n_prompt):
     ws = torch.empty(ws_bytes, device=qkv.device, dtype=torch.uint8)
     es = qkv.element_size()
     b0, d0 = qkv.data_ptr(), dqkv.data_ptr()
-    call("i2t_attn_bwd", b0, b0 + C * es, b0 + 2 * C * es, ptr(out), ptr(dout), ptr(lse), d0, d0 + C * es, d0 + 2 * C * es,
-         ptr(ws), B, H, T, T, hs, T * 3 * C, 3 * C, T * 3 * C, 3 * C, mask_mode, n_prompt, dt(qkv), stream())
+    _attn_bwd(drop, b0, b0 + C * es, b0 + 2 * C * es, ptr(out), ptr(dout), ptr(lse), d0, d0 + C * es, d0 + 2 * C * es,
+              ptr(ws), B, H, T, T, hs, T * 3 * C, 3 * C, T * 3 * C, 3 * C, mask_mode, n_prompt, dt(qkv))
     return dqkv
 
 
@@ -148,20 +188,20 @@ def xattn_bwd(q, kv, dout, B, T, S, H):
     return dq, dkv
 
 
-def xattn_tc(q: torch.Tensor, kv: torch.Tensor, B: int, T: int, S: int, H: int):
-    """bf16 cross attention on the tensor-core attention kernels (i2t_attn_fwd with Tk = S, no mask): q (B*T, C), kv (B*S, 2C)
-    packed [k | v].  Returns (out (B*T, C), lse (B, H, T))."""
+def xattn_tc(q: torch.Tensor, kv: torch.Tensor, B: int, T: int, S: int, H: int, drop: Optional[DropSite] = None):
+    """Cross attention on the general attention kernels (i2t_attn_fwd with Tk = S, no mask; tensor cores for bf16):
+    q (B*T, C), kv (B*S, 2C) packed [k | v].  Returns (out (B*T, C), lse (B, H, T))."""
     C = q.shape[1]
     hs = C // H
     out = torch.empty_like(q)
     lse = torch.empty((B, H, T), device=q.device, dtype=torch.float32)
     es = kv.element_size()
-    call("i2t_attn_fwd", ptr(q), kv.data_ptr(), kv.data_ptr() + C * es, ptr(out), ptr(lse), B, H, T, S, hs, T * q.stride(0),
-         q.stride(0), S * 2 * C, 2 * C, MASK_NONE, 0, dt(q), dt(out), stream())
+    _attn_fwd(drop, ptr(q), kv.data_ptr(), kv.data_ptr() + C * es, ptr(out), ptr(lse), B, H, T, S, hs, T * q.stride(0),
+              q.stride(0), S * 2 * C, 2 * C, MASK_NONE, 0, dt(q), dt(out))
     return out, lse
 
 
-def xattn_tc_bwd(q, kv, out, dout, lse, B, T, S, H):
+def xattn_tc_bwd(q, kv, out, dout, lse, B, T, S, H, drop: Optional[DropSite] = None):
     C = q.shape[1]
     hs = C // H
     dq = torch.empty_like(q)
@@ -169,10 +209,38 @@ def xattn_tc_bwd(q, kv, out, dout, lse, B, T, S, H):
     from ._lib import lib
     ws = torch.empty(lib().i2t_attn_bwd_workspace_bytes(B, H, T, hs), device=q.device, dtype=torch.uint8)
     es = kv.element_size()
-    call("i2t_attn_bwd", ptr(q), kv.data_ptr(), kv.data_ptr() + C * es, ptr(out), ptr(dout), ptr(lse), ptr(dq), dkv.data_ptr(),
-         dkv.data_ptr() + C * es, ptr(ws), B, H, T, S, hs, T * q.stride(0), q.stride(0), S * 2 * C, 2 * C, MASK_NONE, 0, dt(q),
-         stream())
+    _attn_bwd(drop, ptr(q), kv.data_ptr(), kv.data_ptr() + C * es, ptr(out), ptr(dout), ptr(lse), ptr(dq), dkv.data_ptr(),
+              dkv.data_ptr() + C * es, ptr(ws), B, H, T, S, hs, T * q.stride(0), q.stride(0), S * 2 * C, 2 * C, MASK_NONE, 0,
+              dt(q))
     return dq, dkv
+
+
+def dropout_add(y: torch.Tensor, residual: Optional[torch.Tensor], drop: DropSite) -> torch.Tensor:
+    """residual + dropout(y) as one pass (fp32 out); y in the compute dtype."""
+    assert y.is_contiguous() and (residual is None or (residual.is_contiguous() and residual.dtype == torch.float32))
+    out = torch.empty(y.shape, device=y.device, dtype=torch.float32)
+    call("i2t_dropout_add_fwd", ptr(y), ptr(residual), ptr(out), y.numel(), drop.p, ptr(drop.state), drop.site, dt(y), stream())
+    return out
+
+
+def dropout_bwd(dy: torch.Tensor, out_dtype, drop: DropSite) -> torch.Tensor:
+    """keep * dy / (1-p), written in `out_dtype` (the cast the linear's backward needs anyway)."""
+    assert dy.is_contiguous()
+    g = torch.empty(dy.shape, device=dy.device, dtype=out_dtype)
+    call("i2t_dropout_bwd", ptr(dy), ptr(g), dy.numel(), drop.p, ptr(drop.state), drop.site, dt(dy), dt(g), stream())
+    return g
+
+
+def token_dropout_(x2d: torch.Tensor, seg: int, nseg: int, drop: DropSite) -> torch.Tensor:
+    """In place: one Bernoulli per (row, segment) of a packed (rows, nseg*seg) buffer (reference models/layers.py:454-461)."""
+    assert x2d.dim() == 2 and x2d.stride(1) == 1
+    call("i2t_token_dropout", ptr(x2d), x2d.shape[0], x2d.stride(0), seg, nseg, drop.p, ptr(drop.state), drop.site, dt(x2d),
+         stream())
+    return x2d
+
+
+def rng_advance(state: torch.Tensor):
+    call("i2t_rng_advance", ptr(state), stream())
 
 
 def patch_im2col(images: torch.Tensor, p: int, out_dtype) -> torch.Tensor:

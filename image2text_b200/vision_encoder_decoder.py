@@ -75,7 +75,7 @@ class _Side(ParamTree):
         # stand-alone decoder call: no soft prompt rows, cross attention iff embeddings are given (attn_msk: no-op, D9)
         spec = dict(self._spec, use_soft_prompting=False, use_cross_attn=cross is not None)
         enc = cross if cross is not None else torch.zeros((idx.shape[0], 1, spec["n_embd"]), device=idx.device)
-        logits, hidden = Fn.decoder_forward(W, spec, idx, enc, m.compute_dtype, training=m.training)
+        logits, hidden = Fn.decoder_forward(W, spec, idx, enc, m.compute_dtype, training=m.training, drop=m._drop_ctx())
         return logits[..., :spec["vocab_size"]], hidden
 
     def get_inputs_embeds(self, idx):
@@ -120,6 +120,8 @@ class VisionEncoderDecoder(nn.Module):
         self._shadow: Dict[str, tuple] = {}
         self._ptr_tables = None
         self._decode_engines = {}
+        self._rng = None               # device int64[2] {seed, step offset} of the training-mode dropout masks
+        self._drop_seed = 0x1234ABCD if seed is None else int(seed)
         if config.chkpt_path is not None:
             self.load_partial_checkpoint(config.chkpt_path)
 
@@ -156,6 +158,25 @@ class VisionEncoderDecoder(nn.Module):
             self._ptr_tables = (sig, tabs)
         return self._ptr_tables[1]
 
+    # ------------------------------------------------------------------ dropout ------------------------------
+    def set_dropout_seed(self, seed: int):
+        """Seed of the counter-based dropout masks (csrc/rng.cuh); the step offset restarts at 0."""
+        self._drop_seed = int(seed)
+        self._rng = None
+
+    def _drop_ctx(self):
+        """Mask context of ONE training-mode forward pass, or None (eval mode / every p == 0).  The shared step offset is
+        bumped on the stream and snapshotted, so the autograd nodes of this pass regenerate exactly its masks however many
+        other passes run before their backward (and a CUDA-graph replay of forward + backward draws fresh masks)."""
+        from . import ops
+        if not self.training or (self.spec.get("dropout", 0.0) <= 0.0 and self.spec.get("attn_dropout", 0.0) <= 0.0):
+            return None
+        dev = next(self.parameters()).device
+        if self._rng is None or self._rng.device != dev:
+            self._rng = torch.tensor([self._drop_seed & 0x7FFFFFFFFFFFFFFF, 0], dtype=torch.int64, device=dev)
+        ops.rng_advance(self._rng)
+        return ops.DropCtx(self._rng.clone())
+
     def weights(self):
         """key -> tensor accessor; `.c(key)` returns the tensor in the compute dtype (bf16 shadows are cached and
         refreshed when the fp32 master changes version, i.e. after an optimiser step or load_state_dict)."""
@@ -170,7 +191,8 @@ class VisionEncoderDecoder(nn.Module):
             encoder_output = Fn.encoder_forward(W, self.spec, images, self.compute_dtype,
                                                 train_trunk=self.training and self.spec["refine_base_model"])
         # attn_msk: accepted and ignored -- it has no effect in the reference either (D9)
-        logits, hidden = Fn.decoder_forward(W, self.spec, ids, encoder_output, self.compute_dtype, training=self.training)
+        logits, hidden = Fn.decoder_forward(W, self.spec, ids, encoder_output, self.compute_dtype, training=self.training,
+                                            drop=self._drop_ctx())
         if not _padded_logits:
             logits = logits.contiguous()      # the reference returns contiguous logits (vision_encoder_decoder.py:132);
             # the trainer wrapper asks for the row-padded view instead so the LM-head backward runs in place

@@ -44,6 +44,8 @@ class ModelTrainerWrapper(nn.Module):
         self.momentum = trainer_config.moco_momentum
         self.alpha = trainer_config.moco_alpha
         self._ema = EmaUpdater()
+        if self.model_m is not None:          # the teacher runs in train mode too: its own mask stream
+            self.model_m.set_dropout_seed(self.model._drop_seed + 1)
         self.copy_momentum_params()
 
     @torch.no_grad()

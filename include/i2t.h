@@ -239,6 +239,36 @@ int i2t_l2norm_bwd(const float* x, const float* dy, float* dx, int64_t rows, int
 /* x *= *scale_ptr (device scalar) */
 int i2t_scale_inplace(void* x, const float* scale_ptr, int64_t n, int dtype, void* stream);
 
+/* ---- training-mode dropout ------------------------------------------------------------------------------
+ * Masks are a pure function of (rng_state, site, element coordinates) -- Philox4x32-10, csrc/rng.cuh -- so nothing is
+ * stored for the backward.  rng_state: device uint64[2] = {seed, step offset}; site: index of the dropout call inside one
+ * forward pass.  The reference draws from torch's generator instead: same Bernoulli(1-p) / (1-p) scaling, another stream. */
+/* Same contract as i2t_attn_fwd / i2t_attn_bwd with dropout on the attention probabilities (dropout_p of
+ * F.scaled_dot_product_attention at reference models/layers.py:465; nn.MultiheadAttention(dropout=) at :537-542; HF
+ * attn_pdrop).  Row index (b*H + h)*Tq + i and key j select the mask word (see csrc/rng.cuh drop_attn4). */
+int i2t_attn_fwd_dropout(const void* q, const void* k, const void* v, void* out, float* lse, int64_t B, int64_t H,
+                         int64_t Tq, int64_t Tk, int64_t head_dim, int64_t q_batch_stride, int64_t q_row_stride,
+                         int64_t kv_batch_stride, int64_t kv_row_stride, int mask_mode, int64_t n_prompt, int in_dtype,
+                         int out_dtype, float p_drop, const void* rng_state, int64_t site, void* stream);
+int i2t_attn_bwd_dropout(const void* q, const void* k, const void* v, const void* out, const void* dout, const float* lse,
+                         void* dq, void* dk, void* dv, void* workspace, int64_t B, int64_t H, int64_t Tq, int64_t Tk,
+                         int64_t head_dim, int64_t q_batch_stride, int64_t q_row_stride, int64_t kv_batch_stride,
+                         int64_t kv_row_stride, int mask_mode, int64_t n_prompt, int dtype, float p_drop,
+                         const void* rng_state, int64_t site, void* stream);
+/* out[i] = residual[i] + keep(i) * y[i] / (1-p)   (residual optional; out fp32; n % 4 == 0): resid_dropout
+ * models/layers.py:469 + the residual add :596, _MLP.dropout :485 + :606, transformer.drop models/decoder.py:236-243 */
+int i2t_dropout_add_fwd(const void* y, const float* residual, float* out, int64_t n, float p, const void* rng_state,
+                        int64_t site, int y_dtype, void* stream);
+/* g[i] = keep(i) * dy[i] / (1-p), cast to g_dtype: backward of the above w.r.t. y */
+int i2t_dropout_bwd(const void* dy, void* g, int64_t n, float p, const void* rng_state, int64_t site, int dy_dtype,
+                    int g_dtype, void* stream);
+/* In place: x[row, s*seg + c] *= keep(row, s) / (1-p) for s < nseg: the (B,1,T,1) q/k/v masks of models/layers.py:454-461
+ * on the packed (rows, 3C) buffer (forward), and on its gradient (backward). */
+int i2t_token_dropout(void* x, int64_t rows, int64_t ld, int64_t seg, int64_t nseg, float p, const void* rng_state,
+                      int64_t site, int dtype, void* stream);
+/* rng_state[1] += 1 on the stream (fresh masks for the next step, also under CUDA-graph replay) */
+int i2t_rng_advance(void* rng_state, void* stream);
+
 /* ---- fused multi-tensor optimiser steps (fp32 state).  table: device int64[n_tensors*4] = {p, g, m, v} pointers per
  *      tensor; chunk c updates elements [chunk_off[c], chunk_off[c]+chunk_len[c]) of tensor chunk_tensor[c];
  *      step counts from 1; grad_scale multiplies the gradient on the fly (1.0 = reference semantics). ---------------- */

@@ -70,8 +70,10 @@ def gelu_erf(x: Tensor) -> Tensor:
     return 0.5 * x * (1.0 + torch.erf(x / math.sqrt(2.0)))
 
 
-def sdpa(q: Tensor, k: Tensor, v: Tensor, mask: Optional[Tensor]) -> Tensor:
-    """softmax(q k^T / sqrt(hs) + mask) v; a fully masked row yields 0 (torch>=2.5 SDPA)."""
+def sdpa(q: Tensor, k: Tensor, v: Tensor, mask: Optional[Tensor], pmul: Optional[Tensor] = None) -> Tensor:
+    """softmax(q k^T / sqrt(hs) + mask) v; a fully masked row yields 0 (torch>=2.5 SDPA).
+    pmul: training-mode dropout on the probabilities (dropout_p of models/layers.py:465) as an explicit multiplier
+    tensor (0 or 1/(1-p)) so that the caller controls the mask."""
     hs = q.shape[-1]
     s = (q @ k.transpose(-1, -2)) / math.sqrt(hs)
     if mask is not None:
@@ -82,6 +84,8 @@ def sdpa(q: Tensor, k: Tensor, v: Tensor, mask: Optional[Tensor]) -> Tensor:
     p = torch.exp(s - m)
     den = p.sum(dim=-1, keepdim=True)
     p = torch.where(dead, torch.zeros_like(p), p / torch.where(dead, torch.ones_like(den), den))
+    if pmul is not None:
+        p = p * pmul
     return p @ v
 
 
@@ -95,15 +99,16 @@ def merge_heads(x: Tensor) -> Tensor:
     return x.transpose(1, 2).reshape(b, t, h * e)
 
 
-def packed_mha(sd: Dict[str, Tensor], prefix: str, query: Tensor, kv: Tensor, n_head: int) -> Tensor:
-    """torch.nn.MultiheadAttention(batch_first=True), packed in_proj rows [q;k;v], no mask,
-    eval mode (models/layers.py:537-542,600-605; tv:103,113)."""
+def packed_mha(sd: Dict[str, Tensor], prefix: str, query: Tensor, kv: Tensor, n_head: int,
+               pmul: Optional[Tensor] = None) -> Tensor:
+    """torch.nn.MultiheadAttention(batch_first=True), packed in_proj rows [q;k;v], no mask
+    (models/layers.py:537-542,600-605; tv:103,113); pmul = its training-mode dropout on the probabilities."""
     w, b = sd[prefix + "in_proj_weight"], sd[prefix + "in_proj_bias"]
     c = query.shape[-1]
     q = F.linear(query, w[:c], b[:c])
     k = F.linear(kv, w[c:2 * c], b[c:2 * c])
     v = F.linear(kv, w[2 * c:], b[2 * c:])
-    y = sdpa(split_heads(q, n_head), split_heads(k, n_head), split_heads(v, n_head), None)
+    y = sdpa(split_heads(q, n_head), split_heads(k, n_head), split_heads(v, n_head), None, pmul)
     return F.linear(merge_heads(y), sd[prefix + "out_proj.weight"], sd[prefix + "out_proj.bias"])
 
 
@@ -214,10 +219,19 @@ def layer_has_cross_attn(spec: dict, depth: int) -> bool:
     return not (spec["skip_alternate_cross_attn"] and depth % 2 == 1)
 
 
+def _mul(x: Tensor, m: Optional[Tensor]) -> Tensor:
+    return x if m is None else x * m
+
+
 def transformer_block(sd, spec, lp: str, x: Tensor, cross: Optional[Tensor], attn_mask: Optional[Tensor],
-                      has_cross: bool, normalize_grads: bool) -> Tensor:
-    """models/layers.py:565-614 dense path; attention models/layers.py:447-470; MLP :481-486."""
+                      has_cross: bool, normalize_grads: bool, drop=None) -> Tensor:
+    """models/layers.py:565-614 dense path; attention models/layers.py:447-470; MLP :481-486.
+    drop (training mode): a provider of explicit dropout multipliers, asked in call order -- tokens() for the (B,1,T,1)
+    q/k/v masks of :454-461, attn() for SDPA's dropout_p :465, elem() for resid_dropout :469, attn() for
+    nn.MultiheadAttention's dropout :537-542, elem() for _MLP.dropout :485."""
     nh = spec["n_head"]
+    pd, pa = spec.get("dropout", 0.0), spec.get("attn_dropout", 0.0)
+    bs, tl = x.shape[0], x.shape[1]
     b_ = (lambda k: sd.get(k)) if spec["bias"] else (lambda k: None)
     if spec["is_causal"]:
         L = x.shape[-2]
@@ -227,44 +241,56 @@ def transformer_block(sd, spec, lp: str, x: Tensor, cross: Optional[Tensor], att
     y = layer_norm(x, sd[lp + "ln_1.weight"], b_(lp + "ln_1.bias"), 1e-5)
     qkv = F.linear(y, sd[lp + "attn.c_attn.weight"], b_(lp + "attn.c_attn.bias"))
     q, k, v = qkv.split(spec["n_embd"], dim=2)
-    y = sdpa(split_heads(q, nh), split_heads(k, nh), split_heads(v, nh), attn_mask)
-    x = x + F.linear(merge_heads(y), sd[lp + "attn.c_proj.weight"], b_(lp + "attn.c_proj.bias"))
+    pmul = None
+    if drop is not None:
+        tok = drop.tokens(pa, bs * tl)
+        if tok is not None:
+            tok = tok.view(bs, tl, 3)
+            q, k, v = q * tok[..., 0:1], k * tok[..., 1:2], v * tok[..., 2:3]
+        pmul = drop.attn(pd, bs, nh, tl, tl)
+    y = sdpa(split_heads(q, nh), split_heads(k, nh), split_heads(v, nh), attn_mask, pmul)
+    y = F.linear(merge_heads(y), sd[lp + "attn.c_proj.weight"], b_(lp + "attn.c_proj.bias"))
+    x = x + _mul(y, drop.elem(pd, y.shape) if drop is not None else None)
     if cross is not None:
         if not has_cross:
             raise ValueError("Model not configured for cross attn inputs!!!")
         y = layer_norm(x, sd[lp + "ln_3.weight"], b_(lp + "ln_3.bias"), 1e-5)
-        x = x + packed_mha(sd, lp + "cross_attn.", y, cross, nh)
+        pmul = drop.attn(pd, bs, nh, tl, cross.shape[1]) if drop is not None else None
+        x = x + packed_mha(sd, lp + "cross_attn.", y, cross, nh, pmul)
     y = layer_norm(x, sd[lp + "ln_2.weight"], b_(lp + "ln_2.bias"), 1e-5)
     y = gelu_tanh(F.linear(y, sd[lp + "mlp.c_fc.weight"], b_(lp + "mlp.c_fc.bias")))
-    x = x + F.linear(y, sd[lp + "mlp.c_proj.weight"], b_(lp + "mlp.c_proj.bias"))
+    y = F.linear(y, sd[lp + "mlp.c_proj.weight"], b_(lp + "mlp.c_proj.bias"))
+    x = x + _mul(y, drop.elem(pd, y.shape) if drop is not None else None)
     if normalize_grads:
         x = _NormalizeGradients.apply(x)
     return x
 
 
 def transformer_decoder_forward(sd, spec, idx=None, inputs_embeds=None, cross_attn_embeds=None, attn_msk=None,
-                                prefix: str = "decoder.", normalize_grads: bool = True):
-    """models/decoder.py:214-256 (dropout inactive: eval / p=0)."""
+                                prefix: str = "decoder.", normalize_grads: bool = True, drop=None):
+    """models/decoder.py:214-256; drop=None: eval / p=0, else explicit multipliers (transformer.drop :236-243 first)."""
     assert (idx is None) != (inputs_embeds is None)
     if inputs_embeds is None:
         inputs_embeds = sd[prefix + "transformer.wte.weight"][idx]
     t = inputs_embeds.shape[1]
     assert t <= spec["block_size"]
     x = inputs_embeds + sd[prefix + "transformer.wpe.weight"][:t]
+    if drop is not None:
+        x = _mul(x, drop.elem(spec.get("dropout", 0.0), x.shape))
     for depth in range(spec["n_layer"]):
         if spec["skip_alternate_cross_attn"]:
             cross = cross_attn_embeds if depth % 2 == 0 else None
         else:
             cross = cross_attn_embeds
         x = transformer_block(sd, spec, f"{prefix}transformer.h.{depth}.", x, cross, attn_msk,
-                              layer_has_cross_attn(spec, depth), normalize_grads)
+                              layer_has_cross_attn(spec, depth), normalize_grads, drop)
     b_ = sd.get(prefix + "transformer.ln_f.bias") if spec["bias"] else None
     x = layer_norm(x, sd[prefix + "transformer.ln_f.weight"], b_, 1e-5)
     return F.linear(x, sd[prefix + "lm_head.weight"]), x
 
 
 def hf_gpt2_forward(sd, spec, idx=None, inputs_embeds=None, cross_attn_embeds=None,
-                    prefix: str = "decoder.backbone."):
+                    prefix: str = "decoder.backbone.", drop=None):
     """transformers GPT2LMHeadModel with add_cross_attention=True as the reference calls it
     (models/decoder.py:335-361: attention_mask=None -> plain causal; hf: GPT2Block.forward,
     GPT2Attention.forward).  Conv1D weights are stored (in, out): y = x @ W + b."""
@@ -274,6 +300,11 @@ def hf_gpt2_forward(sd, spec, idx=None, inputs_embeds=None, cross_attn_embeds=No
         inputs_embeds = sd[prefix + "transformer.wte.weight"][idx]
     t = inputs_embeds.shape[1]
     x = inputs_embeds + sd[prefix + "transformer.wpe.weight"][:t]
+    pd = spec.get("dropout", 0.0)          # GPT2Config embd_pdrop = attn_pdrop = resid_pdrop (training mode, drop given)
+    bs = x.shape[0]
+    dm = (lambda shape: drop.elem(pd, shape)) if drop is not None else (lambda shape: None)
+    da = (lambda tk: drop.attn(pd, bs, nh, t, tk)) if drop is not None else (lambda tk: None)
+    x = _mul(x, dm(x.shape))
     causal = torch.ones((t, t), dtype=torch.bool, device=x.device).tril()
     mask = torch.zeros((t, t), dtype=x.dtype, device=x.device).masked_fill(~causal, NEG_INF)[None, None]
     for i in range(spec["n_layer"]):
@@ -281,18 +312,22 @@ def hf_gpt2_forward(sd, spec, idx=None, inputs_embeds=None, cross_attn_embeds=No
         y = layer_norm(x, sd[lp + "ln_1.weight"], sd[lp + "ln_1.bias"], 1e-5)
         qkv = y @ sd[lp + "attn.c_attn.weight"] + sd[lp + "attn.c_attn.bias"]
         q, k, v = qkv.split(c, dim=2)
-        y = merge_heads(sdpa(split_heads(q, nh), split_heads(k, nh), split_heads(v, nh), mask))
-        x = x + (y @ sd[lp + "attn.c_proj.weight"] + sd[lp + "attn.c_proj.bias"])
+        y = merge_heads(sdpa(split_heads(q, nh), split_heads(k, nh), split_heads(v, nh), mask, da(t)))
+        y = y @ sd[lp + "attn.c_proj.weight"] + sd[lp + "attn.c_proj.bias"]
+        x = x + _mul(y, dm(y.shape))
         if cross_attn_embeds is not None:
             y = layer_norm(x, sd[lp + "ln_cross_attn.weight"], sd[lp + "ln_cross_attn.bias"], 1e-5)
             q = y @ sd[lp + "crossattention.q_attn.weight"] + sd[lp + "crossattention.q_attn.bias"]
             kv = cross_attn_embeds @ sd[lp + "crossattention.c_attn.weight"] + sd[lp + "crossattention.c_attn.bias"]
             k, v = kv.split(c, dim=2)
-            y = merge_heads(sdpa(split_heads(q, nh), split_heads(k, nh), split_heads(v, nh), None))
-            x = x + (y @ sd[lp + "crossattention.c_proj.weight"] + sd[lp + "crossattention.c_proj.bias"])
+            y = merge_heads(sdpa(split_heads(q, nh), split_heads(k, nh), split_heads(v, nh), None,
+                                 da(cross_attn_embeds.shape[1])))
+            y = y @ sd[lp + "crossattention.c_proj.weight"] + sd[lp + "crossattention.c_proj.bias"]
+            x = x + _mul(y, dm(y.shape))
         y = layer_norm(x, sd[lp + "ln_2.weight"], sd[lp + "ln_2.bias"], 1e-5)
         y = gelu_tanh(y @ sd[lp + "mlp.c_fc.weight"] + sd[lp + "mlp.c_fc.bias"])
-        x = x + (y @ sd[lp + "mlp.c_proj.weight"] + sd[lp + "mlp.c_proj.bias"])
+        y = y @ sd[lp + "mlp.c_proj.weight"] + sd[lp + "mlp.c_proj.bias"]
+        x = x + _mul(y, dm(y.shape))
     x = layer_norm(x, sd[prefix + "transformer.ln_f.weight"], sd[prefix + "transformer.ln_f.bias"], 1e-5)
     return F.linear(x, sd[prefix + "lm_head.weight"]), x
 
@@ -334,7 +369,7 @@ def _bool_mask_to_float(attn_msk: Tensor) -> Tensor:
 
 
 def ved_forward(sd, spec, images: Optional[Tensor], ids: Tensor, attn_msk: Optional[Tensor] = None,
-                encoder_output: Optional[Tensor] = None, normalize_grads: bool = True):
+                encoder_output: Optional[Tensor] = None, normalize_grads: bool = True, drop=None):
     """Returns (encoder_output, logits, hidden_state) like VisionEncoderDecoderModelOutput."""
     if encoder_output is None:
         encoder_output = encoder_forward(sd, spec, images)
@@ -362,11 +397,12 @@ def ved_forward(sd, spec, images: Optional[Tensor], ids: Tensor, attn_msk: Optio
         mask = _bool_mask_to_float(attn_msk)
     cross = encoder_output if spec["use_cross_attn"] else None
     if spec["decoder"] == "hf_gpt2":
-        logits, hidden = hf_gpt2_forward(sd, spec, idx=dec_ids, inputs_embeds=inputs_embeds, cross_attn_embeds=cross)
+        logits, hidden = hf_gpt2_forward(sd, spec, idx=dec_ids, inputs_embeds=inputs_embeds, cross_attn_embeds=cross,
+                                         drop=drop)
     else:
         logits, hidden = transformer_decoder_forward(sd, spec, idx=dec_ids, inputs_embeds=inputs_embeds,
                                                      cross_attn_embeds=cross, attn_msk=mask, prefix=dec_prefix,
-                                                     normalize_grads=normalize_grads)
+                                                     normalize_grads=normalize_grads, drop=drop)
     return encoder_output, logits[..., offset:, :].contiguous(), hidden
 
 

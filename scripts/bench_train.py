@@ -5,8 +5,8 @@
 
 One optimiser-visible step = gradient_accumulation_steps (4) micro-steps of batch 8 per GPU: train_step -> backward ->
 [DP all-reduce overlapped with backward] -> fused AdamW on the YAML's two parameter groups (reference trainer.py:145-172;
-loop restated from training/utils.py:85-101).  Dropout is NOT applied on the B200 path yet, so
-the number is reported as "dropout off" -- the reference's YAML value is 0.1.
+loop restated from training/utils.py:85-101).  Dropout runs at the YAML's values (0.1: transformer.drop, token-level q/k/v,
+SDPA dropout_p, resid / MLP dropout, cross-attention dropout) unless --no-dropout is given.
 Prints one JSON line: img/s (all ranks), ms/step, achieved model TFLOP/s (243.4 GFLOP/img).
 """
 import argparse
@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--moco", action="store_true")
+    ap.add_argument("--no-dropout", action="store_true", help="switch every dropout off (the parity configuration)")
     ap.add_argument("--profile", action="store_true")
     ap.add_argument("--config", default="nano", choices=["nano", "gpt2"])
     ap.add_argument("--batch", type=int, default=0, help="per-GPU micro-batch (0 = the YAML value)")
@@ -65,7 +66,10 @@ def main():
     cd = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     tok = types.SimpleNamespace(eos_token_id=50256, bos_token_id=50256, mask_token_id=None, vocab_size=50257)
     tkw = dict(moco_momentum=0.995, moco_alpha=0.4) if args.moco else {}
-    w = ModelTrainerWrapper(tc.model, tok, TrainerWrapperConfig(**tkw), -100, device=f"cuda:{local}", compute_dtype=cd)
+    over = dict(dropout=0.0, attn_dropout=0.0) if args.no_dropout else {}
+    w = ModelTrainerWrapper(tc.model, tok, TrainerWrapperConfig(**tkw), -100, device=f"cuda:{local}", compute_dtype=cd,
+                            spec_overrides=over)
+    w.model.set_dropout_seed(1234 + rank)
     w.model.load_state_dict(synth_state_dict(w.model.spec, seed=0))
     w.copy_momentum_params()
     w.train()
@@ -129,7 +133,8 @@ def main():
     imgs = bs * accum * args.steps * world
     gflop_img = (243.4 + (104.5 if args.moco else 0.0)) if args.config == "nano" else (340.0 + (113.4 if args.moco else 0.0))
     if rank == 0:
-        print(json.dumps({"metric": f"train img/s ({args.config}.yaml, B={bs}/GPU, accum {accum}, AdamW, dropout off)",
+        print(json.dumps({"metric": f"train img/s ({args.config}.yaml, B={bs}/GPU, accum {accum}, AdamW, dropout "
+                                    f"{'off' if args.no_dropout else w.model.spec['dropout']})",
                           "value": round(imgs / (ms / 1e3), 2), "n_gpus": world, "dtype": args.dtype, "moco": args.moco, "graph": args.graph,
                           "ms_per_step": round(ms / args.steps, 2), "model_tflops": round(imgs * gflop_img / (ms / 1e3) / 1e3, 2),
                           "loss": float(loss), "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2)}))

@@ -10,7 +10,10 @@ from image2text_b200.model_spec import spec_from_config, synth_state_dict  # noq
 
 _CACHE = {}
 
-SPEC_OVERRIDES = {"tiny": dict(vit_layers=2, vit_image=32), "nano": {}, "gpt2": {}}
+# the reference-made goldens were produced with every dropout at 0 (tests/golden/make_golden.py: zero_dropout / .eval()),
+# so the parity models switch the YAML's p = 0.1 off; the dropout tests switch it back on explicitly
+NO_DROPOUT = dict(dropout=0.0, attn_dropout=0.0)
+SPEC_OVERRIDES = {"tiny": dict(vit_layers=2, vit_image=32), "nano": dict(NO_DROPOUT), "gpt2": dict(NO_DROPOUT)}
 
 
 def spec_and_weights(name: str, seed: int = 0):
@@ -26,3 +29,82 @@ def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     """max |a-b| / max |b|  (the '1e-4 relative' of BASELINE.json is read as relative to the tensor scale)."""
     a, b = a.double(), b.double()
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+# --------------------------------------------------------------------------------------------------------------
+# numpy restatement of the library's counter-based dropout masks (image2text_b200/csrc/rng.cuh): Philox4x32-10
+# (Salmon, Moraes, Dror, Shaw, SC'11; known-answer vectors from Random123's kat_vectors in test_oracle_golden.py)
+# and the element -> (counter, word) maps of the three kinds of site.  Test infrastructure only.
+# --------------------------------------------------------------------------------------------------------------
+import numpy as np  # noqa: E402
+
+
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Vectorised over numpy uint32 arrays (broadcast); returns the four output words."""
+    M0, M1, W0, W1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), 0x9E3779B9, 0xBB67AE85
+    mask = np.uint64(0xFFFFFFFF)
+    c0, c1, c2, c3 = (np.asarray(c, dtype=np.uint64) & mask for c in np.broadcast_arrays(c0, c1, c2, c3))
+    k0, k1 = int(k0) & 0xFFFFFFFF, int(k1) & 0xFFFFFFFF
+    for _ in range(10):
+        p0, p1 = M0 * c0, M1 * c2
+        n0 = (p1 >> np.uint64(32)) ^ c1 ^ np.uint64(k0)
+        n2 = (p0 >> np.uint64(32)) ^ c3 ^ np.uint64(k1)
+        c0, c1, c2, c3 = n0, p1 & mask, n2, p0 & mask
+        k0, k1 = (k0 + W0) & 0xFFFFFFFF, (k1 + W1) & 0xFFFFFFFF
+    return [c.astype(np.uint32) for c in (c0, c1, c2, c3)]
+
+
+class DropMasks:
+    """Multipliers (0 or 1/(1-p)) of successive dropout sites, for the oracle's `drop=` hooks: the same (seed, offset,
+    site) -> mask function the CUDA kernels evaluate.  One call = one site, also when p == 0 (returns None)."""
+
+    def __init__(self, seed: int, offset: int, base: int = 0):
+        self.k0 = seed & 0xFFFFFFFF
+        self.k1 = ((seed >> 32) ^ (offset >> 32)) & 0xFFFFFFFF
+        self.off = offset & 0xFFFFFFFF
+        self.n = base
+
+    def _next(self):
+        s = self.n
+        self.n += 1
+        return s
+
+    @staticmethod
+    def _thr(p):
+        return min(int(p * 4294967296.0 + 0.5), 4294967295)
+
+    def _mult(self, words, p):
+        keep = words >= np.uint32(self._thr(p))
+        return torch.from_numpy(np.where(keep, np.float32(1.0 / (1.0 - p)), np.float32(0.0)).astype(np.float32))
+
+    def elem(self, p, shape):
+        site = self._next()
+        if p <= 0:
+            return None
+        n = int(np.prod(shape))
+        e4 = np.arange((n + 3) // 4, dtype=np.uint64)
+        w = philox4x32_10(e4 & np.uint64(0xFFFFFFFF), e4 >> np.uint64(32), site, self.off, self.k0, self.k1)
+        flat = np.stack(w, axis=1).reshape(-1)[:n]
+        return self._mult(flat, p).reshape(tuple(shape))
+
+    def tokens(self, p, rows):
+        """(rows, 3) multipliers for the q, k, v segments of a packed row (words 0..2 of counter = row)."""
+        site = self._next()
+        if p <= 0:
+            return None
+        r = np.arange(rows, dtype=np.uint64)
+        w = philox4x32_10(r, 0, site, self.off, self.k0, self.k1)
+        return self._mult(np.stack(w[:3], axis=1), p)
+
+    def attn(self, p, B, H, Tq, Tk):
+        site = self._next()
+        if p <= 0:
+            return None
+        row = np.arange(B * H * Tq, dtype=np.uint64)[:, None]
+        kj = np.arange(Tk, dtype=np.uint64)[None, :]
+        c1 = (kj >> np.uint64(4)) * np.uint64(4) + ((kj >> np.uint64(1)) & np.uint64(3))
+        lane = (((kj >> np.uint64(3)) & np.uint64(1)) * np.uint64(2) + (kj & np.uint64(1))).astype(np.int64)
+        w = philox4x32_10(row, c1, site | 0x80000000, self.off, self.k0, self.k1)
+        stacked = np.stack(w, axis=-1)                                   # (rows, Tk, 4)
+        words = np.take_along_axis(stacked, np.broadcast_to(lane[..., None], stacked.shape[:2] + (1,)), axis=-1)[..., 0]
+        return self._mult(words, p).reshape(B, H, Tq, Tk)

@@ -123,7 +123,7 @@ def test_gpt2_hf_layout_forward_and_backward_match(golden):
     from image2text_b200 import VisionEncoderDecoder
     g = golden("gpt2_fwd")
     tc, spec, sd = spec_and_weights("gpt2")
-    m = VisionEncoderDecoder(tc.model, device="cuda")
+    m = VisionEncoderDecoder(tc.model, device="cuda", spec_overrides=SPEC_OVERRIDES["gpt2"])
     m.load_state_dict(sd)
     images = synth_images(2, 224, seed=31)
     labels = T(g["labels"])
