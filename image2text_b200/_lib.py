@@ -21,6 +21,7 @@ SIGNATURES = {
     "i2t_set_tensor_core_attention": (None, [I]),
     "i2t_set_gemm_cta_pair": (None, [I]),
     "i2t_set_gemm_tma_store": (None, [I]),
+    "i2t_set_gemm_split_k": (None, [I]),
     "i2t_layernorm_fwd": (c_int, [P, P, P, P, P, P, L, L, L, F, I, I, P]),
     "i2t_layernorm_bwd": (c_int, [P, P, P, P, P, P, P, P, L, L, I, I, I, P]),
     "i2t_gemm": (c_int, [P, P, P, P, P, L, L, L, L, L, L, I, I, I, I, I, I, I, P]),
@@ -87,6 +88,8 @@ def lib() -> ctypes.CDLL:
             handle.i2t_set_tensor_core_gemm(int(os.environ["I2T_TC_GEMM"]))
         if os.environ.get("I2T_GEMM_TMA_STORE") is not None:
             handle.i2t_set_gemm_tma_store(int(os.environ["I2T_GEMM_TMA_STORE"]))
+        if os.environ.get("I2T_GEMM_SPLITK") is not None:
+            handle.i2t_set_gemm_split_k(int(os.environ["I2T_GEMM_SPLITK"]))
         if os.environ.get("I2T_GEMM_PAIR") is not None:
             handle.i2t_set_gemm_cta_pair(int(os.environ["I2T_GEMM_PAIR"]))
         if os.environ.get("I2T_TC_ATTN") is not None:

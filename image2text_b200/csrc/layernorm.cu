@@ -16,15 +16,23 @@ __global__ void __launch_bounds__(128) ln_fwd_kernel(const TX* __restrict__ x, c
   if (row >= rows) return;
   const TX* xr = x + row * xstride;
   const int nvec = cols >> 2;
-  float4 v[MAXV];
+  float4 v[MAXV], gm[MAXV], bt[MAXV];
   float s = 0.f;
+  // x, gamma and beta are requested together: with a handful of rows (decode: one row per sequence) the kernel is one
+  // chain of memory latencies, and the parameters would otherwise wait for both reductions
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     const int c = lane + i * 32;
     if (c < nvec) {
       v[i] = load4(xr + c * 4);
-      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      gm[i] = load4(gamma + c * 4);
+      bt[i] = beta ? load4(beta + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+  }
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = lane + i * 32;
+    if (c < nvec) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   }
   const float mu = warp_sum(s) / (float)cols;
   float q = 0.f;
@@ -46,16 +54,11 @@ __global__ void __launch_bounds__(128) ln_fwd_kernel(const TX* __restrict__ x, c
   for (int i = 0; i < MAXV; ++i) {
     const int c = lane + i * 32;
     if (c < nvec) {
-      const float4 g = load4(gamma + c * 4);
       float4 o;
-      o.x = (v[i].x - mu) * rs * g.x;
-      o.y = (v[i].y - mu) * rs * g.y;
-      o.z = (v[i].z - mu) * rs * g.z;
-      o.w = (v[i].w - mu) * rs * g.w;
-      if (beta) {
-        const float4 b = load4(beta + c * 4);
-        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-      }
+      o.x = (v[i].x - mu) * rs * gm[i].x + bt[i].x;
+      o.y = (v[i].y - mu) * rs * gm[i].y + bt[i].y;
+      o.z = (v[i].z - mu) * rs * gm[i].z + bt[i].z;
+      o.w = (v[i].w - mu) * rs * gm[i].w + bt[i].w;
       store4(yr + c * 4, o);
     }
   }

@@ -73,7 +73,11 @@ class DecodeEngine:
         self.h = torch.zeros((batch, self.F), **f32)
         self.qkv32 = torch.zeros((batch, 3 * C), **f32) if batch > 16 else None
         self.y16 = torch.zeros((batch, C), device=dev, dtype=self.cd) if batch > 16 else None
-        self.logits = torch.zeros((batch, V), **f32)
+        self.h16 = torch.zeros((batch, self.F), device=dev, dtype=self.cd) if batch > 16 else None
+        # GEMM mode: rows pitched to 16 bytes so the LM-head tile leaves through TMA stores (V = 50257 floats per row would
+        # force scalar, sector-splitting stores); the kernels / megakernel modes address logits with pitch V
+        self.ldl = (V + 3) // 4 * 4 if mode == "gemm" else V
+        self.logits = torch.zeros((batch, self.ldl), **f32)[:, :V]
         self.ngrams = torch.tensor(list(spec["no_repeat_n_grams"]) or [0], device=dev, dtype=torch.int32)
         self.n_ngrams = len(spec["no_repeat_n_grams"])
         self.seed_dev = torch.zeros(1, device=dev, dtype=torch.int64)
@@ -275,12 +279,18 @@ class DecodeEngine:
                 ops.gemm(att_out(), W.c(lp + "cross_attn.out_proj.weight"), bias=W[lp + "cross_attn.out_proj.bias"],
                          residual=self.x, out=self.x)
                 xi += 1
-            h = ops.gemm(ln(lp + "ln_2"), W.c(lp + "mlp.c_fc.weight"), bias=W[lp + "mlp.c_fc.bias"], act=ops.ACT_GELU_TANH,
-                         out_dtype=cd)
+            if cd == torch.float32:
+                h = ops.gemm(ln(lp + "ln_2"), W.c(lp + "mlp.c_fc.weight"), bias=W[lp + "mlp.c_fc.bias"], act=ops.ACT_GELU_TANH,
+                             out_dtype=cd)
+            else:
+                # fp32 pre-activation (the few-tile GEMM splits K over the idle SMs), then GELU + cast in one small pass
+                ops.gemm(ln(lp + "ln_2"), W.c(lp + "mlp.c_fc.weight"), bias=W[lp + "mlp.c_fc.bias"], out=self.h)
+                call("i2t_act_fwd", ptr(self.h), ptr(self.h16), self.h.numel(), ops.ACT_GELU_TANH, ops.F32, ops.BF16, st)
+                h = self.h16
             ops.gemm(h, W.c(lp + "mlp.c_proj.weight"), bias=W[lp + "mlp.c_proj.bias"], residual=self.x, out=self.x)
         if sample:
             ops.gemm(ln(dp + "ln_f"), W.c("decoder.lm_head.weight"), out=self.logits)
-            call("i2t_sample", ptr(self.logits), V, B, V, ptr(self.ids), self.ids.shape[1], pos, 1, 0, temperature,
+            call("i2t_sample", ptr(self.logits), self.ldl, B, V, ptr(self.ids), self.ids.shape[1], pos, 1, 0, temperature,
                  int(top_k) if top_k is not None else 0, float(self.nucleus_p or 0.0), ptr(self.ngrams), self.n_ngrams, 0,
                  ptr(self.seed_dev), None, ptr(self.ticket), 1, st)
         else:
@@ -438,7 +448,8 @@ class HFDecodeEngine:
         self.y = torch.zeros((batch, C), **f32)
         self.qkv32 = torch.zeros((batch, 3 * C), **f32)
         self.y16 = torch.zeros((batch, C), device=dev, dtype=self.cd)
-        self.logits = torch.zeros((batch, V), **f32)
+        self.ldl = (V + 3) // 4 * 4                      # 16-byte row pitch: TMA-store epilogue of the LM-head GEMM
+        self.logits = torch.zeros((batch, self.ldl), **f32)[:, :V]
         self.ngrams = torch.tensor(list(spec["no_repeat_n_grams"]) or [0], device=dev, dtype=torch.int32)
         self.n_ngrams = len(spec["no_repeat_n_grams"])
         self.graphs = {}
@@ -508,7 +519,7 @@ class HFDecodeEngine:
         if sample:
             hid = ops.layernorm(self.x, W[dp + "ln_f.weight"], W.get(dp + "ln_f.bias"), 1e-5, out_dtype=self.cd)
             ops.gemm(hid, W.c("decoder.backbone.lm_head.weight"), out=self.logits)
-            call("i2t_sample", ptr(self.logits), V, B, V, ptr(self.ids), self.ids.shape[1], ptr(self.pos), 1, 0, temperature,
+            call("i2t_sample", ptr(self.logits), self.ldl, B, V, ptr(self.ids), self.ids.shape[1], ptr(self.pos), 1, 0, temperature,
                  int(top_k) if top_k is not None else 0, float(self.nucleus_p or 0.0), ptr(self.ngrams), self.n_ngrams, 0,
                  ptr(self.seed_dev), None, ptr(self.ticket), 1, st)
         else:

@@ -132,6 +132,9 @@ void i2t_set_tensor_core_gemm(int enabled);
 void i2t_set_gemm_cta_pair(int enabled);
 /* 1 (default): the CTA-pair kernel's output tile leaves through shared memory + cp.async.bulk.tensor stores; 0: row stores. */
 void i2t_set_gemm_tma_store(int enabled);
+/* 1 (default): bf16 GEMMs with few output tiles and fp32 output (decode projections over a batch, weight gradients) split K
+ * over the idle SMs and add the partial tiles with fp32 atomics (summation order not fixed); 0: never. */
+void i2t_set_gemm_split_k(int enabled);
 /* bf16 attention: 1 (default) tensor cores -- tcgen05/TMEM forward when head_dim == 64 and <= 384 keys, mma.sync otherwise
  * and for the backward; 2: mma.sync kernels only; 0: the fp32-math kernels (A/B testing). */
 void i2t_set_tensor_core_attention(int mode);

@@ -156,6 +156,42 @@ def test_gemm_bf16_cta_pair(M, N, K, layout):
     assert relerr(o16.float(), ref + bias.double()) < 8e-3
 
 
+@pytest.mark.parametrize("M,N,K,layout", [(64, 768, 3072, "nt"), (64, 2304, 768, "nt"), (512, 768, 768, "nt"), (40, 776, 1000, "nt"),
+                                            (768, 768, 8192, "tn"), (2304, 768, 4096, "tn"), (64, 768, 3072, "nn")])
+def test_gemm_bf16_split_k(M, N, K, layout):
+    """Few output tiles + long K (decode projections over a batch of sequences, weight gradients): K slices on otherwise
+    idle SMs, partial tiles added with fp32 atomics.  Plain (zeroed C + bias on slice 0), in-place residual and accumulate
+    forms, against fp64 and against the unsplit kernel (A/B switch)."""
+    a = rnd(M, K, seed=70).to(torch.bfloat16)
+    b = rnd(N, K, seed=71, scale=0.05).to(torch.bfloat16)
+    bias, res = rnd(N, seed=72), rnd(M, N, seed=73)
+    ref = a.double() @ b.double().t()
+    A = (a if layout[0] == "n" else a.t().contiguous()).to(DEV)
+    Bm = (b if layout[1] == "t" else b.t().contiguous()).to(DEV)
+    kw = dict(a_kmajor=layout[0] == "n", b_kmajor=layout[1] == "t")
+    outs = {}
+    tol = 1e-5 if K <= 4096 else 3e-5        # fp32 accumulation over K products (unsplit kernel: 1.02e-5 at K = 8192)
+    for split in (1, 0):
+        lib().i2t_set_gemm_split_k(split)
+        try:
+            out = torch.full((M, N), 7.0, device=DEV)                      # stale contents must not leak into the result
+            ops.gemm(A, Bm, bias=bias.to(DEV), out=out, **kw)
+            assert relerr(out, ref + bias.double()) < tol, f"split={split}"
+            outs[split] = out
+            x = res.to(DEV).clone()
+            ops.gemm(A, Bm, bias=bias.to(DEV), residual=x, out=x, **kw)    # x += a b^T + bias, in place (decode residual stream)
+            assert relerr(x, ref + bias.double() + res.double()) < tol, f"split={split}"
+            acc = res.to(DEV).clone()
+            ops.gemm(A, Bm, out=acc, accumulate=True, **kw)                # dW += ...
+            assert relerr(acc, ref + res.double()) < tol, f"split={split}"
+            pitched = torch.zeros((M, N + 12), device=DEV)[:, :N]
+            ops.gemm(A, Bm, out=pitched, **kw)
+            assert relerr(pitched, ref) < tol and float(pitched.untyped_storage().nbytes()) > 0
+        finally:
+            lib().i2t_set_gemm_split_k(1)
+    assert relerr(outs[1], outs[0].double()) < tol       # fp32 partial sums added in a different (and not fixed) order
+
+
 def test_colsum():
     x = rnd(1000, 333, seed=13)
     out = torch.zeros(333, device=DEV)
