@@ -48,7 +48,9 @@ class DecodeEngine:
         mode = mode or os.environ.get("I2T_DECODE", "mega2" if self.cd == torch.bfloat16 else "kernels")
         if batch > 8 or max(C, self.F) > 3072 or C > 1024:
             mode = "kernels"
-        if batch > 16:
+        # bf16, more sequences than the megakernel's 8: split-K tensor-core GEMMs over the batch beat the per-stage FMA
+        # kernels from 9 sequences on (16 sequences: 24.4k vs 11.4k tok/s); fp32 keeps the exact-FMA kernels up to 16
+        if (batch >= int(os.environ.get("I2T_DECODE_GEMM_MIN", "9")) and self.cd == torch.bfloat16) or batch > 16:
             mode = "gemm"           # projections as tensor-core GEMMs over the batch
         if mode == "mega2" and (self.cd != torch.bfloat16 or C > 768 or C % 64 or self.F % 64 or self.F > 3072
                                 or max(self.Tmax, spec["n_cls"]) > 256 or batch * spec["n_head"] > 132):
@@ -71,9 +73,9 @@ class DecodeEngine:
         self.q = torch.zeros((batch, C), **f32)
         self.y = torch.zeros((batch, C), **f32)
         self.h = torch.zeros((batch, self.F), **f32)
-        self.qkv32 = torch.zeros((batch, 3 * C), **f32) if batch > 16 else None
-        self.y16 = torch.zeros((batch, C), device=dev, dtype=self.cd) if batch > 16 else None
-        self.h16 = torch.zeros((batch, self.F), device=dev, dtype=self.cd) if batch > 16 else None
+        self.qkv32 = torch.zeros((batch, 3 * C), **f32) if mode == "gemm" else None
+        self.y16 = torch.zeros((batch, C), device=dev, dtype=self.cd) if mode == "gemm" else None
+        self.h16 = torch.zeros((batch, self.F), device=dev, dtype=self.cd) if mode == "gemm" else None
         # GEMM mode: rows pitched to 16 bytes so the LM-head tile leaves through TMA stores (V = 50257 floats per row would
         # force scalar, sector-splitting stores); the kernels / megakernel modes address logits with pitch V
         self.ldl = (V + 3) // 4 * 4 if mode == "gemm" else V

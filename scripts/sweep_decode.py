@@ -18,7 +18,10 @@ tc = load_training_config(os.path.join(ROOT, "configs", "nano.yaml"))
 m = VisionEncoderDecoder(tc.model, device="cuda", compute_dtype=dtype)
 m.load_state_dict(synth_state_dict(m.spec, seed=0))
 m.eval()
-for n_img, top_k in ((1, 1), (8, 1), (8, 16), (32, 1), (64, 1), (64, 50)):
+POINTS = ((1, 1), (2, 1), (4, 1), (8, 1), (8, 16), (32, 1), (64, 1), (64, 50))
+if len(sys.argv) > 2:
+    POINTS = tuple((int(x), 1) for x in sys.argv[2].split(","))
+for n_img, top_k in POINTS:
     B = n_img * 8
     images = synth_images(n_img, 224, seed=1234).cuda().repeat_interleave(8, dim=0)
     prompt = torch.full((B, 1), 50256, dtype=torch.long, device="cuda")
