@@ -22,9 +22,11 @@ SIGNATURES = {
     "i2t_set_gemm_cta_pair": (None, [I]),
     "i2t_set_gemm_tma_store": (None, [I]),
     "i2t_set_gemm_split_k": (None, [I]),
+    "i2t_set_sampler_greedy_fast_path": (None, [I]),
     "i2t_layernorm_fwd": (c_int, [P, P, P, P, P, P, L, L, L, F, I, I, P]),
     "i2t_layernorm_bwd": (c_int, [P, P, P, P, P, P, P, P, L, L, I, I, I, P]),
     "i2t_gemm": (c_int, [P, P, P, P, P, L, L, L, L, L, L, I, I, I, I, I, I, I, P]),
+    "i2t_gemm_ex": (c_int, [P, P, P, P, P, L, L, L, L, L, L, I, I, I, I, I, I, I, I, P]),
     "i2t_colsum": (c_int, [P, P, L, L, L, I, P]),
     "i2t_attn_fwd": (c_int, [P, P, P, P, P, L, L, L, L, L, L, L, L, L, I, L, I, I, P]),
     "i2t_attn_bwd_workspace_bytes": (c_int64, [L, L, L, L]),
@@ -41,6 +43,9 @@ SIGNATURES = {
     "i2t_dec_kv_append": (c_int, [P, L, P, P, L, L, L, I, P, P]),
     "i2t_dec_linear": (c_int, [P, P, P, F, P, P, P, P, L, L, L, L, I, I, I, P, P, L, L, I, P, P]),
     "i2t_dec_attn": (c_int, [P, L, P, P, L, L, P, L, P, L, L, L, L, I, P]),
+    "i2t_dec_attn_append": (c_int, [P, L, P, P, L, L, P, L, P, L, L, L, L, I, P, P, L, I, P]),
+    "i2t_dec_layernorm": (c_int, [P, P, P, P, L, L, F, I, P, L, P]),
+    "i2t_dec_act": (c_int, [P, P, L, I, I, P]),
     "i2t_sample": (c_int, [P, L, L, L, P, L, P, I, L, F, L, F, P, L, U64, P, P, P, I, P]),
     "i2t_decode_mega": (c_int, [P, P, P, L, L, L, L, L, L, L, I, P, L, P, P, P, P, P, P, F, L, P, L, P, P, L, P, P]),
     "i2t_decode_mega2_max_keys": (c_int, []),

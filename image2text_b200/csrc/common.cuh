@@ -40,6 +40,28 @@ extern std::atomic<int64_t> g_launches;
       return ::i2t::fail(I2T_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
   } while (0)
 
+// ---- programmatic dependent launch (PDL): a kernel launched through launch_pdl may start while its predecessor in the
+// stream is still running; it must call pdl_wait() before it touches anything the predecessor wrote (or overwrites anything
+// the predecessor reads), and calls pdl_launch_dependents() early so that ITS successor can do the same.  Weights never
+// depend on a predecessor: the decode step's kernels fetch them before pdl_wait().  i2t_set_pdl(0) switches the attribute off.
+extern std::atomic<int> g_pdl;
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl.load() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline bool valid_dtype(int d) { return d == I2T_F32 || d == I2T_BF16; }
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

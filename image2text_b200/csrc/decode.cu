@@ -18,24 +18,9 @@
 
 namespace i2t {
 
-static std::atomic<int> g_pdl{1};
-
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-
 template <typename... KArgs, typename... Args>
 static cudaError_t launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid;
-  cfg.blockDim = block;
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = g_pdl.load() ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+  return launch_pdl(kern, grid, block, smem, st, args...);
 }
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -288,7 +273,12 @@ template <typename TC, int HS>
 __global__ void __launch_bounds__(128)
 dec_attn_kernel(const float* __restrict__ q, int64_t q_ld, const TC* __restrict__ kc, const TC* __restrict__ vc,
                 int64_t cache_bs, int64_t cache_rs, float* __restrict__ out, int64_t out_ld,
-                const int32_t* __restrict__ len_ptr, int len_add, int round_q_bf16) {
+                const int32_t* __restrict__ len_ptr, int len_add, int round_q_bf16,
+                const float* __restrict__ knew, const float* __restrict__ vnew, int64_t new_ld, TC* __restrict__ kc_w,
+                TC* __restrict__ vc_w, __nv_bfloat16* __restrict__ out16) {
+  // knew / vnew (optional): the K / V row of the token being decoded, still in the projection's fp32 output.  It is key
+  // len - 1: rounded to the cache dtype, used from registers and stored into the cache by this CTA (the separate append
+  // launch disappears).  out16 (optional): the result is written as bf16, ready to be the next GEMM's A operand.
   constexpr int EPL = HS / 32;
   constexpr int G = 4;
   __shared__ float s_m[4], s_l[4], s_acc[4][HS];
@@ -311,11 +301,12 @@ dec_attn_kernel(const float* __restrict__ q, int64_t q_ld, const TC* __restrict_
   float m = -INFINITY, l = 0.f, acc[EPL];
 #pragma unroll
   for (int e = 0; e < EPL; ++e) acc[e] = 0.f;
-  for (int j0 = w * G; j0 < len; j0 += 4 * G) {
+  const int len_c = knew != nullptr ? len - 1 : len;      // keys read from the cache (the new key comes from knew / vnew)
+  for (int j0 = w * G; j0 < len_c; j0 += 4 * G) {
     float kk[G][EPL], vv[G][EPL], d[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) {
-      const int j = min(j0 + g, len - 1);
+      const int j = min(j0 + g, len_c - 1);
 #pragma unroll
       for (int e = 0; e < EPL; ++e) {
         kk[g][e] = to_f32(kb[(int64_t)j * cache_rs + lane + 32 * e]);
@@ -336,20 +327,42 @@ dec_attn_kernel(const float* __restrict__ q, int64_t q_ld, const TC* __restrict_
     float m_new = m;
 #pragma unroll
     for (int g = 0; g < G; ++g)
-      if (j0 + g < len) m_new = fmaxf(m_new, d[g]);
+      if (j0 + g < len_c) m_new = fmaxf(m_new, d[g]);
     const float corr = expf(m - m_new);
     l *= corr;
 #pragma unroll
     for (int e = 0; e < EPL; ++e) acc[e] *= corr;
 #pragma unroll
     for (int g = 0; g < G; ++g) {
-      if (j0 + g < len) {
+      if (j0 + g < len_c) {
         const float p = expf(d[g] - m_new);
         l += p;
 #pragma unroll
         for (int e = 0; e < EPL; ++e) acc[e] = fmaf(p, vv[g][e], acc[e]);
       }
     }
+    m = m_new;
+  }
+  if (knew != nullptr && w == 0 && len > 0) {
+    // key len - 1 = the token being decoded: rounded to the cache dtype, folded into warp 0's running softmax, appended
+    float k1[EPL], v1[EPL], d = 0.f;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+      const TC kq = from_f32<TC>(knew[b * new_ld + (int64_t)h * HS + lane + 32 * e]);
+      const TC vq = from_f32<TC>(vnew[b * new_ld + (int64_t)h * HS + lane + 32 * e]);
+      kc_w[b * cache_bs + (int64_t)(len - 1) * cache_rs + (int64_t)h * HS + lane + 32 * e] = kq;
+      vc_w[b * cache_bs + (int64_t)(len - 1) * cache_rs + (int64_t)h * HS + lane + 32 * e] = vq;
+      k1[e] = to_f32(kq);
+      v1[e] = to_f32(vq);
+      d = fmaf(qv[e], k1[e], d);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    const float m_new = fmaxf(m, d);
+    const float corr = expf(m - m_new), p = expf(d - m_new);
+    l = l * corr + p;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) acc[e] = fmaf(p, v1[e], acc[e] * corr);
     m = m_new;
   }
   if (lane == 0) { s_m[w] = m; s_l[w] = l; }
@@ -370,7 +383,10 @@ dec_attn_kernel(const float* __restrict__ q, int64_t q_ld, const TC* __restrict_
     }
     const float inv = L > 0.f ? 1.0f / L : 0.f;
 #pragma unroll
-    for (int e = 0; e < EPL; ++e) out[b * out_ld + (int64_t)h * HS + lane + 32 * e] = o[e] * inv;
+    for (int e = 0; e < EPL; ++e) {
+      if (out16 != nullptr) out16[b * out_ld + (int64_t)h * HS + lane + 32 * e] = __float2bfloat16_rn(o[e] * inv);
+      else out[b * out_ld + (int64_t)h * HS + lane + 32 * e] = o[e] * inv;
+    }
   }
 }
 
@@ -385,7 +401,6 @@ using namespace i2t;
     if (e__ != cudaSuccess) return ::i2t::fail(I2T_ERR_CUDA, "launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
   } while (0)
 
-extern "C" void i2t_set_pdl(int enabled) { g_pdl.store(enabled ? 1 : 0); }
 
 extern "C" int i2t_dec_embed(const int64_t* ids, const float* wte, const float* wpe, float* x, const int32_t* pos_ptr,
                              int64_t B, int64_t C, int64_t ids_ld, int64_t n_prompt, void* stream) {
@@ -459,6 +474,114 @@ extern "C" int i2t_dec_kv_append(const float* qkv, int64_t ld, void* kcache, voi
   return I2T_OK;
 }
 
+namespace i2t {
+// LayerNorm of the (B, C) residual stream for the batched decode step, PDL-aware: gamma / beta (weights) are fetched before
+// the dependency wait; optionally zero-fills `zero_ptr` (the fp32 output of the split-K projection that consumes this
+// LayerNorm: its partial tiles are ADDED, and a memset node would break the programmatic launch chain).
+template <typename TY, int MAXV>
+__global__ void __launch_bounds__(128) dec_ln_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, TY* __restrict__ y, int rows, int cols,
+                                                     float eps, float* __restrict__ zero_ptr, int64_t zero_n4) {
+  pdl_launch_dependents();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 4 + warp;
+  const int nvec = cols >> 2;
+  float4 v[MAXV], gm[MAXV], bt[MAXV];
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = lane + i * 32;
+    if (c < nvec) {
+      gm[i] = load4(gamma + c * 4);
+      bt[i] = beta ? load4(beta + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  pdl_wait();                 // x was written by the previous kernel; zero_ptr may still be read by an earlier one
+  if (zero_ptr != nullptr) {
+    float4* z4 = reinterpret_cast<float4*>(zero_ptr);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < zero_n4; i += (int64_t)gridDim.x * blockDim.x)
+      z4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (row >= rows) return;
+  const float* xr = x + (int64_t)row * cols;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = lane + i * 32;
+    if (c < nvec) {
+      v[i] = load4(xr + c * 4);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  const float mu = warp_sum(s) / (float)cols;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = lane + i * 32;
+    if (c < nvec) {
+      float a = v[i].x - mu, b = v[i].y - mu, cc = v[i].z - mu, d = v[i].w - mu;
+      q += (a * a + b * b) + (cc * cc + d * d);
+    }
+  }
+  const float rs = 1.0f / sqrtf(warp_sum(q) / (float)cols + eps);
+  TY* yr = y + (int64_t)row * cols;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = lane + i * 32;
+    if (c < nvec) {
+      float4 o;
+      o.x = (v[i].x - mu) * rs * gm[i].x + bt[i].x;
+      o.y = (v[i].y - mu) * rs * gm[i].y + bt[i].y;
+      o.z = (v[i].z - mu) * rs * gm[i].z + bt[i].z;
+      o.w = (v[i].w - mu) * rs * gm[i].w + bt[i].w;
+      store4(yr + c * 4, o);
+    }
+  }
+}
+
+// h = act(z) with a cast, PDL-aware (the GELU between the split-K FC and the MLP down projection of the batched decode step)
+template <typename TO>
+__global__ void __launch_bounds__(256) dec_act_kernel(const float* __restrict__ z, TO* __restrict__ h, int64_t n4, int act) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = load4(z + i * 4);
+    v.x = apply_act(v.x, act); v.y = apply_act(v.y, act); v.z = apply_act(v.z, act); v.w = apply_act(v.w, act);
+    store4(h + i * 4, v);
+  }
+}
+}  // namespace i2t
+
+extern "C" int i2t_dec_layernorm(const float* x, const float* gamma, const float* beta, void* y, int64_t rows, int64_t cols,
+                                 float eps, int y_dtype, float* zero_ptr, int64_t zero_count, void* stream) {
+  I2T_REQUIRE(x && gamma && y && rows > 0, "dec_layernorm: bad arguments");
+  I2T_REQUIRE(cols > 0 && cols % 4 == 0 && cols <= 2048, "dec_layernorm: cols=%lld must be a multiple of 4, <= 2048", (long long)cols);
+  I2T_REQUIRE(valid_dtype(y_dtype) && aligned16(x) && aligned16(gamma) && (beta == nullptr || aligned16(beta)) && aligned16(y),
+              "dec_layernorm: alignment / dtype");
+  I2T_REQUIRE(zero_ptr == nullptr || (zero_count % 4 == 0 && aligned16(zero_ptr)), "dec_layernorm: zero-fill range must be 16-byte granular");
+  cudaStream_t st = (cudaStream_t)stream;
+  const dim3 grid((unsigned)ceil_div(rows, 4)), block(128);
+  const int64_t z4 = zero_ptr ? zero_count / 4 : 0;
+#define I2T_DLN(TY, MV) I2T_LAUNCH_CHECK(launch(dec_ln_kernel<TY, MV>, grid, block, 0, st, x, gamma, beta, (TY*)y, (int)rows, (int)cols, eps, zero_ptr, z4))
+  if (y_dtype == I2T_F32) {
+    if (cols <= 1024) I2T_DLN(float, 8); else I2T_DLN(float, 16);
+  } else {
+    if (cols <= 1024) I2T_DLN(__nv_bfloat16, 8); else I2T_DLN(__nv_bfloat16, 16);
+  }
+#undef I2T_DLN
+  return I2T_OK;
+}
+
+extern "C" int i2t_dec_act(const float* z, void* h, int64_t n, int act, int h_dtype, void* stream) {
+  I2T_REQUIRE(z && h && n > 0 && n % 4 == 0 && valid_dtype(h_dtype), "dec_act: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t blocks = std::min<int64_t>(ceil_div(n / 4, 256), (int64_t)num_sms() * 8);
+  if (h_dtype == I2T_F32)
+    I2T_LAUNCH_CHECK(launch(dec_act_kernel<float>, dim3((unsigned)blocks), dim3(256), 0, st, z, (float*)h, n / 4, act));
+  else
+    I2T_LAUNCH_CHECK(launch(dec_act_kernel<__nv_bfloat16>, dim3((unsigned)blocks), dim3(256), 0, st, z, (__nv_bfloat16*)h, n / 4, act));
+  return I2T_OK;
+}
+
 extern "C" int i2t_dec_advance(int32_t* pos_ptr, void* stream) {
   I2T_REQUIRE(pos_ptr, "dec_advance: null pointer");
   I2T_LAUNCH_CHECK(launch(dec_advance_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, pos_ptr));
@@ -518,20 +641,24 @@ extern "C" int i2t_dec_linear(const float* x, const float* ln_gamma, const float
   return I2T_OK;
 }
 
-extern "C" int i2t_dec_attn(const float* q, int64_t q_ld, const void* kcache, const void* vcache,
-                            int64_t cache_batch_stride, int64_t cache_row_stride, float* out, int64_t out_ld,
-                            const int32_t* len_ptr, int64_t len_add, int64_t B, int64_t H, int64_t head_dim,
-                            int cache_dtype, void* stream) {
+static int dec_attn_impl(const float* q, int64_t q_ld, const void* kcache, const void* vcache, int64_t cache_batch_stride,
+                         int64_t cache_row_stride, void* out, int64_t out_ld, const int32_t* len_ptr, int64_t len_add, int64_t B,
+                         int64_t H, int64_t head_dim, int cache_dtype, const float* knew, const float* vnew, int64_t new_ld,
+                         int out_dtype, void* stream) {
   I2T_REQUIRE(q && kcache && vcache && out, "dec_attn: null pointer");
   I2T_REQUIRE(B > 0 && B <= 65535 && H > 0, "dec_attn: bad sizes");
   I2T_REQUIRE(head_dim == 64 || head_dim == 32, "dec_attn: head_dim %lld not built (32, 64)", (long long)head_dim);
-  I2T_REQUIRE(valid_dtype(cache_dtype), "dec_attn: bad dtype");
+  I2T_REQUIRE(valid_dtype(cache_dtype) && valid_dtype(out_dtype), "dec_attn: bad dtype");
+  I2T_REQUIRE((knew == nullptr) == (vnew == nullptr), "dec_attn: knew and vnew go together");
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid((unsigned)H, (unsigned)B);
   const int rq = cache_dtype == I2T_BF16 ? 1 : 0;
+  float* o32 = out_dtype == I2T_F32 ? (float*)out : nullptr;
+  __nv_bfloat16* o16 = out_dtype == I2T_BF16 ? (__nv_bfloat16*)out : nullptr;
 #define I2T_DA(TC, HSV)                                                                                              \
   I2T_LAUNCH_CHECK(launch(dec_attn_kernel<TC, HSV>, grid, dim3(128), 0, st, q, q_ld, (const TC*)kcache, (const TC*)vcache, \
-                          cache_batch_stride, cache_row_stride, out, out_ld, len_ptr, (int)len_add, rq))
+                          cache_batch_stride, cache_row_stride, o32, out_ld, len_ptr, (int)len_add, rq, knew, vnew, new_ld,  \
+                          (TC*)const_cast<void*>(kcache), (TC*)const_cast<void*>(vcache), o16))
   if (cache_dtype == I2T_F32) {
     if (head_dim == 64) I2T_DA(float, 64); else I2T_DA(float, 32);
   } else {
@@ -539,4 +666,20 @@ extern "C" int i2t_dec_attn(const float* q, int64_t q_ld, const void* kcache, co
   }
 #undef I2T_DA
   return I2T_OK;
+}
+
+extern "C" int i2t_dec_attn(const float* q, int64_t q_ld, const void* kcache, const void* vcache,
+                            int64_t cache_batch_stride, int64_t cache_row_stride, float* out, int64_t out_ld,
+                            const int32_t* len_ptr, int64_t len_add, int64_t B, int64_t H, int64_t head_dim,
+                            int cache_dtype, void* stream) {
+  return dec_attn_impl(q, q_ld, kcache, vcache, cache_batch_stride, cache_row_stride, out, out_ld, len_ptr, len_add, B, H,
+                       head_dim, cache_dtype, nullptr, nullptr, 0, I2T_F32, stream);
+}
+
+extern "C" int i2t_dec_attn_append(const float* q, int64_t q_ld, void* kcache, void* vcache, int64_t cache_batch_stride,
+                                   int64_t cache_row_stride, void* out, int64_t out_ld, const int32_t* len_ptr, int64_t len_add,
+                                   int64_t B, int64_t H, int64_t head_dim, int cache_dtype, const float* knew,
+                                   const float* vnew, int64_t new_ld, int out_dtype, void* stream) {
+  return dec_attn_impl(q, q_ld, kcache, vcache, cache_batch_stride, cache_row_stride, out, out_ld, len_ptr, len_add, B, H,
+                       head_dim, cache_dtype, knew, vnew, new_ld, out_dtype, stream);
 }

@@ -215,7 +215,8 @@ __device__ __forceinline__ void tc_stage_bias(const TcEpilogue& epi, float* sbia
 template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmC, int num_k_blocks, int m_tiles, int n_tiles, int splits, TcEpilogue epi) {
+               const __grid_constant__ CUtensorMap tmC, int num_k_blocks, int m_tiles, int n_tiles, int splits, int b_is_weight,
+               TcEpilogue epi) {
   // splits > 1 (split-K, for problems with few output tiles): work item w = (tile w % num_tiles, K slice w / num_tiles);
   // a slice covers k-blocks [slice * kpb, min(+kpb, num_k_blocks)) and its partial tile is added atomically (fp32 C only)
   extern __shared__ uint8_t smem_raw[];
@@ -260,31 +261,54 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_slot;
 
+  pdl_launch_dependents();                                       // the next kernel may start staging ITS weights
   if (warp == 0) {
     if (lane == 0) {
+      // K-major operand ([rows][K], K contiguous): one box {64 k, 128 rows}.
+      // MN-major operand ([K][rows], rows contiguous): two boxes {64 rows, 64 k}, one per 64-wide half of the tile.
+      auto load_a = [&](int s, int kb, int m_blk) {
+        if (!A_MN) {
+          tma_load_2d(smemA + s * TC_A_BYTES, &tmA, kb * TC_BK, m_blk * TC_BM, &full_bar[s]);
+        } else {
+          tma_load_2d(smemA + s * TC_A_BYTES, &tmA, m_blk * TC_BM, kb * TC_BK, &full_bar[s]);
+          tma_load_2d(smemA + s * TC_A_BYTES + TC_A_BYTES / 2, &tmA, m_blk * TC_BM + 64, kb * TC_BK, &full_bar[s]);
+        }
+      };
+      auto load_b = [&](int s, int kb, int n_blk) {
+        if (!B_MN) {
+          tma_load_2d(smemB + s * TC_B_BYTES, &tmB, kb * TC_BK, n_blk * TC_BN, &full_bar[s]);
+        } else {
+          tma_load_2d(smemB + s * TC_B_BYTES, &tmB, n_blk * TC_BN, kb * TC_BK, &full_bar[s]);
+          tma_load_2d(smemB + s * TC_B_BYTES + TC_B_BYTES / 2, &tmB, n_blk * TC_BN + 64, kb * TC_BK, &full_bar[s]);
+        }
+      };
       int it = 0;                                            // running k-block counter across tiles
+      bool first = true;
       for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
         const int t = w % num_tiles, kb0 = (w / num_tiles) * kpb, kb1 = min(kb0 + kpb, num_k_blocks);
         const int m_blk = t % m_tiles, n_blk = t / m_tiles;
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        int kb = kb0;
+        if (first) {
+          // Programmatic dependent launch: B (`b_is_weight`: a weight matrix) does not depend on the previous kernel, so the
+          // first ring-full of B tiles is requested BEFORE waiting for it; A (activations) follows after the wait.
+          first = false;
+          const int npre = b_is_weight ? min(TC_STAGES, kb1 - kb0) : 0;
+          for (int i = 0; i < npre; ++i) {
+            mbar_expect_tx(&full_bar[i], TC_A_BYTES + TC_B_BYTES);           // all slots are free at kernel start
+            load_b(i, kb0 + i, n_blk);
+          }
+          pdl_wait();
+          for (int i = 0; i < npre; ++i) load_a(i, kb0 + i, m_blk);
+          it = npre;
+          kb = kb0 + npre;
+        }
+        for (; kb < kb1; ++kb, ++it) {
           const int s = it % TC_STAGES;
           const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
           mbar_wait(&empty_bar[s], ph ^ 1u);
           mbar_expect_tx(&full_bar[s], TC_A_BYTES + TC_B_BYTES);
-          // K-major operand ([rows][K], K contiguous): one box {64 k, 128 rows}.
-          // MN-major operand ([K][rows], rows contiguous): two boxes {64 rows, 64 k}, one per 64-wide half of the tile.
-          if (!A_MN) {
-            tma_load_2d(smemA + s * TC_A_BYTES, &tmA, kb * TC_BK, m_blk * TC_BM, &full_bar[s]);
-          } else {
-            tma_load_2d(smemA + s * TC_A_BYTES, &tmA, m_blk * TC_BM, kb * TC_BK, &full_bar[s]);
-            tma_load_2d(smemA + s * TC_A_BYTES + TC_A_BYTES / 2, &tmA, m_blk * TC_BM + 64, kb * TC_BK, &full_bar[s]);
-          }
-          if (!B_MN) {
-            tma_load_2d(smemB + s * TC_B_BYTES, &tmB, kb * TC_BK, n_blk * TC_BN, &full_bar[s]);
-          } else {
-            tma_load_2d(smemB + s * TC_B_BYTES, &tmB, n_blk * TC_BN, kb * TC_BK, &full_bar[s]);
-            tma_load_2d(smemB + s * TC_B_BYTES + TC_B_BYTES / 2, &tmB, n_blk * TC_BN + 64, kb * TC_BK, &full_bar[s]);
-          }
+          load_a(s, kb, m_blk);
+          load_b(s, kb, n_blk);
         }
       }
     }
@@ -324,6 +348,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int r_in_tile = wq * 32 + lane;
     const bool issuer = warp == 4 && lane == 0;
     if (issuer && epi.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
+    pdl_wait();               // C / residual belong to the previous kernels (the bias does not, but it is staged per tile)
     int i = 0;
     uint32_t box_count = 0;
     const int chunks_per_box = epi.c_dtype == I2T_F32 ? 1 : 2;
@@ -688,7 +713,7 @@ static int make_map_dt(const void* ptr, int64_t rows, int64_t cols, int64_t ld, 
 
 template <bool A_MN, bool B_MN>
 static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, int kblocks, const TcEpilogue& epi, dim3 grid,
-                     int splits, cudaStream_t st) {
+                     int splits, int b_is_weight, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
@@ -697,10 +722,14 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const CUtenso
   }
   const int m_tiles = (int)grid.y, n_tiles = (int)grid.x;
   const int ctas = (int)std::min<int64_t>((int64_t)m_tiles * n_tiles * splits, (int64_t)num_sms());
-  gemm_tc_kernel<A_MN, B_MN><<<ctas, TC_THREADS, TC_SMEM, st>>>(ma, mb, mc, kblocks, m_tiles, n_tiles, splits, epi);
+  // programmatic stream serialization: the kernel calls griddepcontrol.wait before it touches A, C or the residual
+  cudaError_t e = launch_pdl(gemm_tc_kernel<A_MN, B_MN>, dim3(ctas), dim3(TC_THREADS), TC_SMEM, st, ma, mb, mc, kblocks, m_tiles,
+                             n_tiles, splits, b_is_weight, epi);
   g_launches.fetch_add(1, std::memory_order_relaxed);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return fail(I2T_ERR_CUDA, "gemm_tc launch failed: %s", cudaGetErrorString(e));
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return fail(I2T_ERR_CUDA, "gemm_tc launch failed: %s", cudaGetErrorString(e));
+  }
   return 1;
 }
 
@@ -772,7 +801,7 @@ static int launch_pair_layout(const CUtensorMap& ma, const CUtensorMap& mb, cons
 
 int gemm_tc_try(const void* A, const void* B, const float* bias, const void* residual, void* C, int64_t M, int64_t N,
                 int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int a_kmajor, int b_kmajor, int act, int accumulate,
-                int res_dtype, int c_dtype, cudaStream_t st) {
+                int res_dtype, int c_dtype, int flags, cudaStream_t st) {
   // leading dimensions are row pitches in elements: 16-byte multiples for TMA
   if (lda % 8 != 0 || ldb % 8 != 0 || !aligned16(A) || !aligned16(B)) return 0;
   if (M > 128 * 65535LL || N > 128LL * 0x7fffffff) return 0;
@@ -841,10 +870,14 @@ int gemm_tc_try(const void* A, const void* B, const float* bias, const void* res
       if (!accumulate && residual == nullptr)
         I2T_CUDA(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, st));
     }
-    if (a_kmajor && b_kmajor) return launch_tc<false, false>(ma, mb, mc, kb, epi, grid, splits, st);
-    if (a_kmajor && !b_kmajor) return launch_tc<false, true>(ma, mb, mc, kb, epi, grid, splits, st);
-    if (!a_kmajor && b_kmajor) return launch_tc<true, false>(ma, mb, mc, kb, epi, grid, splits, st);
-    return launch_tc<true, true>(ma, mb, mc, kb, epi, grid, splits, st);
+    // B is fetched ahead of the dependency wait only when the caller promises (I2T_GEMM_B_STABLE) that no preceding work in
+    // the stream writes it: the decode step's weights.  (Training cannot promise that: a bf16 weight shadow may have been
+    // refreshed by the kernel right before this one.)
+    const int b_is_weight = (flags & I2T_GEMM_B_STABLE) ? 1 : 0;
+    if (a_kmajor && b_kmajor) return launch_tc<false, false>(ma, mb, mc, kb, epi, grid, splits, b_is_weight, st);
+    if (a_kmajor && !b_kmajor) return launch_tc<false, true>(ma, mb, mc, kb, epi, grid, splits, b_is_weight, st);
+    if (!a_kmajor && b_kmajor) return launch_tc<true, false>(ma, mb, mc, kb, epi, grid, splits, b_is_weight, st);
+    return launch_tc<true, true>(ma, mb, mc, kb, epi, grid, splits, b_is_weight, st);
   }
 }
 

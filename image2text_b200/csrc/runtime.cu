@@ -4,6 +4,7 @@
 namespace i2t {
 
 std::atomic<int64_t> g_launches{0};
+std::atomic<int> g_pdl{1};
 
 char* err_buf() {
   static thread_local char buf[512] = {0};
@@ -34,4 +35,5 @@ extern "C" {
 int i2t_version(void) { return 100; }
 const char* i2t_last_error(void) { return i2t::err_buf(); }
 int64_t i2t_launch_count(void) { return i2t::g_launches.load(); }
+void i2t_set_pdl(int enabled) { i2t::g_pdl.store(enabled ? 1 : 0); }
 }

@@ -76,6 +76,7 @@ class DecodeEngine:
         self.qkv32 = torch.zeros((batch, 3 * C), **f32) if mode == "gemm" else None
         self.y16 = torch.zeros((batch, C), device=dev, dtype=self.cd) if mode == "gemm" else None
         self.h16 = torch.zeros((batch, self.F), device=dev, dtype=self.cd) if mode == "gemm" else None
+        self.xn = torch.zeros((batch, C), device=dev, dtype=self.cd) if mode == "gemm" else None
         # GEMM mode: rows pitched to 16 bytes so the LM-head tile leaves through TMA stores (V = 50257 floats per row would
         # force scalar, sector-splitting stores); the kernels / megakernel modes address logits with pitch V
         self.ldl = (V + 3) // 4 * 4 if mode == "gemm" else V
@@ -254,42 +255,49 @@ class DecodeEngine:
         call("i2t_dec_embed", ptr(self.ids), ptr(W[dp + "wte.weight"]), ptr(W[dp + "wpe.weight"]), ptr(self.x), pos, B, C,
              self.ids.shape[1], self.n_prompt, st)
 
-        def ln(key):
-            return ops.layernorm(self.x, W[key + ".weight"], W.get(key + ".bias"), 1e-5, out_dtype=cd)
+        ydt = ops.F32 if cd == torch.float32 else ops.BF16
 
-        def att_out():          # attention output as the next GEMM's A operand
-            if cd == torch.float32:
-                return self.y
-            self.y16.copy_(self.y)
-            return self.y16
+        def ln(key, zero=None):
+            """LayerNorm of the residual stream into self.xn (the next GEMM's A operand); `zero`: the fp32 buffer that GEMM
+            accumulates its split-K partial tiles into (zero-filled here instead of by a memset node, which would break the
+            programmatic launch chain)."""
+            call("i2t_dec_layernorm", ptr(self.x), ptr(W[key + ".weight"]), ptr(W.get(key + ".bias")), ptr(self.xn), B, C, 1e-5,
+                 ydt, ptr(zero), zero.numel() if zero is not None else 0, st)
+            return self.xn
 
+        def proj(a, wkey, bkey, out, rows=None, residual=None, accumulate=False):
+            """Projection over the batch; the weights are stable during generate(), so the kernel requests its first weight
+            tiles before the previous kernel has finished (b_stable)."""
+            w, b = W.c(wkey), W[bkey]
+            if rows is not None:
+                w, b = w[rows], b[rows]
+            return ops.gemm(a, w, bias=b, residual=residual, out=out, accumulate=accumulate, b_stable=True)
+
+        # attention writes its result in the compute dtype (the next GEMM's A operand); the self-attention call also rounds the
+        # new K / V row into the cache (no separate append / cast launches)
+        att = self.y if cd == torch.float32 else self.y16
         xi = 0
         for d in range(spec["n_layer"]):
             lp = f"{dp}h.{d}."
-            ops.gemm(ln(lp + "ln_1"), W.c(lp + "attn.c_attn.weight"), bias=W[lp + "attn.c_attn.bias"], out=self.qkv32)
-            call("i2t_dec_kv_append", ptr(self.qkv32), 3 * C, ptr(self.kcache[d]), ptr(self.vcache[d]), cbs, C, B, wd, pos, st)
-            call("i2t_dec_attn", ptr(self.qkv32), 3 * C, ptr(self.kcache[d]), ptr(self.vcache[d]), cbs, C, ptr(self.y), C, pos, 1,
-                 B, H, hs, wd, st)
-            ops.gemm(att_out(), W.c(lp + "attn.c_proj.weight"), bias=W[lp + "attn.c_proj.bias"], residual=self.x, out=self.x)
+            proj(ln(lp + "ln_1", self.qkv32), lp + "attn.c_attn.weight", lp + "attn.c_attn.bias", self.qkv32, accumulate=True)
+            qp = self.qkv32.data_ptr()
+            call("i2t_dec_attn_append", qp, 3 * C, ptr(self.kcache[d]), ptr(self.vcache[d]), cbs, C, ptr(att), C, pos, 1, B, H, hs,
+                 wd, qp + 4 * C, qp + 8 * C, 3 * C, wd, st)
+            proj(att, lp + "attn.c_proj.weight", lp + "attn.c_proj.bias", self.x, residual=self.x)
             if d in self.cross_layers:
                 kw, kb = lp + "cross_attn.in_proj_weight", lp + "cross_attn.in_proj_bias"
-                ops.gemm(ln(lp + "ln_3"), W.c(kw)[0:C], bias=W[kb][0:C], out=self.q)
+                proj(ln(lp + "ln_3", self.q), kw, kb, self.q, rows=slice(0, C), accumulate=True)
                 kv = self.xkv[xi]
                 es = kv.element_size()
-                call("i2t_dec_attn", ptr(self.q), C, kv.data_ptr(), kv.data_ptr() + C * es, self.S * 2 * C, 2 * C, ptr(self.y),
-                     C, None, self.S, B, H, hs, wd, st)
-                ops.gemm(att_out(), W.c(lp + "cross_attn.out_proj.weight"), bias=W[lp + "cross_attn.out_proj.bias"],
-                         residual=self.x, out=self.x)
+                call("i2t_dec_attn_append", ptr(self.q), C, kv.data_ptr(), kv.data_ptr() + C * es, self.S * 2 * C, 2 * C, ptr(att),
+                     C, None, self.S, B, H, hs, wd, None, None, 0, wd, st)
+                proj(att, lp + "cross_attn.out_proj.weight", lp + "cross_attn.out_proj.bias", self.x, residual=self.x)
                 xi += 1
-            if cd == torch.float32:
-                h = ops.gemm(ln(lp + "ln_2"), W.c(lp + "mlp.c_fc.weight"), bias=W[lp + "mlp.c_fc.bias"], act=ops.ACT_GELU_TANH,
-                             out_dtype=cd)
-            else:
-                # fp32 pre-activation (the few-tile GEMM splits K over the idle SMs), then GELU + cast in one small pass
-                ops.gemm(ln(lp + "ln_2"), W.c(lp + "mlp.c_fc.weight"), bias=W[lp + "mlp.c_fc.bias"], out=self.h)
-                call("i2t_act_fwd", ptr(self.h), ptr(self.h16), self.h.numel(), ops.ACT_GELU_TANH, ops.F32, ops.BF16, st)
-                h = self.h16
-            ops.gemm(h, W.c(lp + "mlp.c_proj.weight"), bias=W[lp + "mlp.c_proj.bias"], residual=self.x, out=self.x)
+            # fp32 pre-activation (the few-tile GEMM splits K over the idle SMs), then GELU + cast in one small pass
+            proj(ln(lp + "ln_2", self.h), lp + "mlp.c_fc.weight", lp + "mlp.c_fc.bias", self.h, accumulate=True)
+            hact = self.h if cd == torch.float32 else self.h16
+            call("i2t_dec_act", ptr(self.h), ptr(hact), self.h.numel(), ops.ACT_GELU_TANH, ydt, st)
+            proj(hact, lp + "mlp.c_proj.weight", lp + "mlp.c_proj.bias", self.x, residual=self.x)
         if sample:
             ops.gemm(ln(dp + "ln_f"), W.c("decoder.lm_head.weight"), out=self.logits)
             call("i2t_sample", ptr(self.logits), self.ldl, B, V, ptr(self.ids), self.ids.shape[1], pos, 1, 0, temperature,
@@ -373,6 +381,15 @@ class DecodeEngine:
             sig = self._mega["sig"] if self._mega is not None else None
             if sig is not None and sig[0] != W.c("decoder.transformer.h.0.attn.c_attn.weight").data_ptr():
                 self._mega, self.graphs = None, {}        # weights were re-materialised: rebuild tables and graphs
+        if self.mode == "gemm":
+            # every compute-dtype weight the step reads exists BEFORE the step is issued: the projections promise the kernels
+            # that nothing in front of them in the stream writes their weights (b_stable), and a captured step graph holds
+            # these addresses -- a refreshed shadow (optimiser step, load_state_dict) invalidates the graphs
+            W = m.weights()
+            wsig = tuple(W.c(k).data_ptr() for k in W.t if k.startswith("decoder.") and W.t[k].dim() == 2
+                         and not k.endswith(("wte.weight", "wpe.weight")))
+            if getattr(self, "_wsig", None) != wsig:
+                self._wsig, self.graphs = wsig, {}
         self.ids[:, :P].copy_(prompt_ids)
         self.pos.zero_()
         self.ticket.zero_()

@@ -97,7 +97,8 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, dx_dtype=torch.float3
 
 def gemm(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
          act: int = ACT_NONE, out: Optional[torch.Tensor] = None, out_dtype=torch.float32, a_kmajor: bool = True,
-         b_kmajor: bool = True, accumulate: bool = False, M=None, N=None, K=None, lda=None, ldb=None, ldc=None):
+         b_kmajor: bool = True, accumulate: bool = False, M=None, N=None, K=None, lda=None, ldb=None, ldc=None,
+         b_stable: bool = False):
     """C[M,N] = act(op(A) op(B) + bias) + residual.  Default: A (M,K) row-major, B (N,K) row-major (nn.Linear weight).
     a/b must be 2-D with a contiguous inner dimension (a row pitch is allowed)."""
     _need_cuda(a, b)
@@ -115,8 +116,9 @@ def gemm(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     ldc = (out.stride(0) if out.dim() == 2 else N) if ldc is None else ldc
     if residual is not None:
         assert residual.stride(-1) == 1 and (residual.stride(0) if residual.dim() == 2 else N) == ldc
-    call("i2t_gemm", ptr(a), ptr(b), ptr(bias), ptr(residual), ptr(out), M, N, K, lda, ldb, ldc, int(a_kmajor),
-         int(b_kmajor), act, int(accumulate), dt(a), dt(residual) if residual is not None else F32, dt(out), stream())
+    call("i2t_gemm_ex", ptr(a), ptr(b), ptr(bias), ptr(residual), ptr(out), M, N, K, lda, ldb, ldc, int(a_kmajor),
+         int(b_kmajor), act, int(accumulate), dt(a), dt(residual) if residual is not None else F32, dt(out), int(b_stable),
+         stream())
     return out
 
 

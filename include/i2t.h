@@ -72,6 +72,12 @@ int i2t_layernorm_bwd(const void* dy, const void* x, const float* gamma, const f
 int i2t_gemm(const void* A, const void* B, const float* bias, const void* residual, void* C, int64_t M, int64_t N,
              int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int a_kmajor, int b_kmajor, int act, int accumulate,
              int ab_dtype, int res_dtype, int c_dtype, void* stream);
+/* Same with flags.  I2T_GEMM_B_STABLE: no preceding work in the stream writes B (decode-time weights): the kernel, launched
+ * with programmatic stream serialization, requests its first B tiles before waiting for the previous kernel to finish. */
+#define I2T_GEMM_B_STABLE 1
+int i2t_gemm_ex(const void* A, const void* B, const float* bias, const void* residual, void* C, int64_t M, int64_t N,
+                int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int a_kmajor, int b_kmajor, int act, int accumulate,
+                int ab_dtype, int res_dtype, int c_dtype, int flags, void* stream);
 /* out[n] += sum_m X[m,n]   (bias gradients) */
 int i2t_colsum(const void* X, float* out, int64_t M, int64_t N, int64_t ldx, int x_dtype, void* stream);
 
@@ -169,6 +175,22 @@ int i2t_dec_linear(const float* x, const float* ln_gamma, const float* ln_beta, 
 int i2t_dec_attn(const float* q, int64_t q_ld, const void* kcache, const void* vcache, int64_t cache_batch_stride,
                  int64_t cache_row_stride, float* out, int64_t out_ld, const int32_t* len_ptr, int64_t len_add, int64_t B,
                  int64_t H, int64_t head_dim, int cache_dtype, void* stream);
+/* Same, with two fusions for the batched (GEMM-mode) decode step: (1) knew / vnew (optional, fp32, element (b,h,e) at
+ * ptr + b*new_ld + h*head_dim + e): the K / V row of the token being decoded, i.e. key len-1 -- rounded to the cache dtype, used
+ * from registers AND stored into the cache by this kernel (replaces i2t_dec_kv_append); (2) out_dtype = I2T_BF16 writes the
+ * result as bf16, ready to be the next GEMM's A operand (replaces a cast kernel). */
+int i2t_dec_attn_append(const float* q, int64_t q_ld, void* kcache, void* vcache, int64_t cache_batch_stride,
+                        int64_t cache_row_stride, void* out, int64_t out_ld, const int32_t* len_ptr, int64_t len_add, int64_t B,
+                        int64_t H, int64_t head_dim, int cache_dtype, const float* knew, const float* vnew, int64_t new_ld,
+                        int out_dtype, void* stream);
+/* LayerNorm of the (rows, cols) fp32 residual stream for the batched decode step (reference models/layers.py:357-358 on one
+ * token per sequence), launched with programmatic stream serialization: gamma / beta are fetched before the dependency wait.
+ * zero_ptr (optional, fp32, zero_count elements, multiple of 4): zero-filled after the wait -- the output buffer of the split-K
+ * projection that consumes this LayerNorm (call i2t_gemm on it with accumulate = 1). */
+int i2t_dec_layernorm(const float* x, const float* gamma, const float* beta, void* y, int64_t rows, int64_t cols, float eps,
+                      int y_dtype, float* zero_ptr, int64_t zero_count, void* stream);
+/* h = act(z), fp32 in, h_dtype out; PDL-aware variant of i2t_act_fwd for the batched decode step. */
+int i2t_dec_act(const float* z, void* h, int64_t n, int act, int h_dtype, void* stream);
 
 /* One whole decode step (every layer, LM head, sampler) as ONE cooperative launch: the same arithmetic as the
  * i2t_dec_* sequence, with the weights streamed through a shared-memory ring by a producer warp per CTA and ~1 us grid
@@ -213,6 +235,9 @@ int i2t_sample(float* logits, int64_t ldl, int64_t B, int64_t V, int64_t* ids, i
                int advance_pos, int64_t cur_len, float temperature, int64_t top_k, float nucleus_p, const int32_t* ngrams,
                int64_t n_ngrams, uint64_t seed, const uint64_t* seed_ptr, float* probs_out, int32_t* ticket, int write_token,
                void* stream);
+/* 1 (default): top_k = 1 without nucleus filter / probs_out takes the one-pass arg-max kernel (ties -> lowest id; the stored
+ * logits are banned in place but not divided by the temperature); 0: always the general sampler (A/B testing). */
+void i2t_set_sampler_greedy_fast_path(int enabled);
 
 /* ---- training-side memory-bound kernels ------------------------------------------------------------------------- */
 /* h = act(z) / dz = dh * act'(z): nn.GELU('tanh') models/layers.py:477,483; torchvision nn.GELU(); HF gelu_new.

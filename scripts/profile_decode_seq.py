@@ -35,3 +35,6 @@ t0 = evs[idx].time_range.start
 print(f"sequences {B}: last decode step, {len(evs) - idx} launches, {evs[-1].time_range.end - t0:.1f} us")
 for e in evs[idx: idx + n_show]:
     print(f"{e.time_range.start - t0:9.1f} us  +{e.time_range.end - e.time_range.start:7.2f} us  {e.name[:90]}")
+print("   ...")
+for e in evs[-5:]:
+    print(f"{e.time_range.start - t0:9.1f} us  +{e.time_range.end - e.time_range.start:7.2f} us  {e.name[:90]}")

@@ -457,6 +457,40 @@ def test_sampler_greedy_is_argmax_full_vocab():
     assert bool(((probs > 0).sum(-1) == 16).all())
 
 
+def test_sampler_greedy_fast_path_equals_general_sampler():
+    """top_k = 1 takes the one-pass arg-max kernel: same picks as the general sampler (A/B switch) and as the oracle's
+    ban + arg-max, with n-gram bans active, an unaligned row pitch, and the lowest id winning an exact tie."""
+    B, V = 37, 50257
+    logits = rnd(B, V, seed=44)
+    g = torch.Generator().manual_seed(45)
+    ids = torch.randint(0, 6, (B, 24), generator=g)              # tiny alphabet: every n-gram repeats -> many bans
+    logits[:, :6] += 6.0                                          # ... and the banned tokens would otherwise win
+    logits[3, 100] = logits[3, 20000] = 50.0                      # exact tie at the top
+    cur = 20
+    picks = {}
+    for fast in (1, 0):
+        lib().i2t_set_sampler_greedy_fast_path(fast)
+        try:
+            picks[fast], _ = _run_sampler(logits, ids, cur, 0.7, 1, (2, 3, 4, 5), want_probs=False)
+        finally:
+            lib().i2t_set_sampler_greedy_fast_path(1)
+    banned = O.apply_ngram_ban(ids[:, :cur], logits.clone(), (2, 3, 4, 5))
+    want = banned.argmax(-1)
+    assert torch.equal(picks[1], want) and picks[1][3] == 100
+    rows = [i for i in range(B) if i != 3]                         # the general sampler draws among exact ties
+    assert torch.equal(picks[0][rows], want[rows])
+    # pitched rows (GEMM-mode decode: 16-byte pitch) and a device-side position / ticket
+    pitched = torch.zeros(B, V + 3, device=DEV)
+    pitched[:, :V] = logits.to(DEV)
+    idd = ids.to(DEV).clone()
+    pos = torch.tensor([cur - 1], dtype=torch.int32, device=DEV)
+    ticket = torch.zeros(1, dtype=torch.int32, device=DEV)
+    ng = torch.tensor([2, 3, 4, 5], dtype=torch.int32, device=DEV)
+    call("i2t_sample", ptr(pitched), V + 3, B, V, ptr(idd), idd.shape[1], ptr(pos), 1, 0, 1.0, 1, 0.0, ptr(ng), 4, 1, None, None,
+         ptr(ticket), 1, stream())
+    assert torch.equal(idd[:, cur].cpu(), want) and int(pos.item()) == cur and int(ticket.item()) == 0
+
+
 def test_sampler_distribution_matches_topk_softmax():
     """top-k sampling must follow the reference's token distribution: chi-square over 20000 draws."""
     V, k, n = 1000, 8, 20000
