@@ -44,23 +44,36 @@ __global__ void __launch_bounds__(256) dropout_bwd_kernel(const TIN* __restrict_
   }
 }
 
-// x: (rows, nseg * seg) with row pitch ld; element (row, s*seg + c) *= keep(row, s) / (1-p); one Philox call per row
+// x: (rows, nseg * seg) with row pitch ld; element (row, s*seg + c) *= keep(row, s) / (1-p).  One warp per row: ONE Philox call
+// per row (the generator costs ~60 instructions; per 4 elements it was as expensive as the memory traffic), then 16-byte
+// vectors -- a lane's vector never straddles a segment (seg is a multiple of the vector width).
 template <typename T>
 __global__ void __launch_bounds__(256) token_dropout_kernel(T* __restrict__ x, int64_t rows, int64_t ld, int seg, int nseg,
                                                             DropArgs d) {
+  constexpr int VEC = 16 / (int)sizeof(T);
   const DropKey key = drop_key(d);
-  const int64_t per_row = (int64_t)seg * nseg / 4;
-  const int64_t total = rows * per_row;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = i / per_row;
-    const int c4 = (int)(i % per_row);
-    const int s = c4 * 4 / seg;
+  const int lane = threadIdx.x & 31;
+  const int nvec = seg * nseg / VEC;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps) {
     const Philox4 r = drop_elem4(d, key, (uint64_t)row);
-    const float m = philox_word(r, s) >= d.thr ? d.inv_keep : 0.f;
-    T* p = x + row * ld + (int64_t)c4 * 4;
-    float4 v = load4(p);
-    v.x *= m; v.y *= m; v.z *= m; v.w *= m;
-    store4(p, v);
+    float m[4];
+    m[0] = r.x >= d.thr ? d.inv_keep : 0.f;
+    m[1] = r.y >= d.thr ? d.inv_keep : 0.f;
+    m[2] = r.z >= d.thr ? d.inv_keep : 0.f;
+    m[3] = r.w >= d.thr ? d.inv_keep : 0.f;
+    T* xr = x + row * ld;
+    for (int v = lane; v < nvec; v += 32) {
+      const int sgm = v * VEC / seg;
+      const float mk = sgm == 0 ? m[0] : sgm == 1 ? m[1] : sgm == 2 ? m[2] : m[3];
+      T* p = xr + (int64_t)v * VEC;
+#pragma unroll
+      for (int h = 0; h < VEC / 4; ++h) {
+        float4 val = load4(p + 4 * h);
+        val.x *= mk; val.y *= mk; val.z *= mk; val.w *= mk;
+        store4(p + 4 * h, val);
+      }
+    }
   }
 }
 
@@ -114,12 +127,13 @@ extern "C" int i2t_dropout_bwd(const void* dy, void* g, int64_t n, float p, cons
 extern "C" int i2t_token_dropout(void* x, int64_t rows, int64_t ld, int64_t seg, int64_t nseg, float p, const void* rng_state,
                                  int64_t site, int dtype, void* stream) {
   I2T_REQUIRE(x && rng_state, "token_dropout: null pointer");
-  I2T_REQUIRE(rows > 0 && seg > 0 && seg % 4 == 0 && nseg >= 1 && nseg <= 4 && ld >= seg * nseg && ld % 4 == 0,
-              "token_dropout: bad sizes (segments of a multiple of 4 elements, at most 4 per row)");
+  I2T_REQUIRE(rows > 0 && seg > 0 && seg % 8 == 0 && nseg >= 1 && nseg <= 4 && ld >= seg * nseg && ld % 8 == 0 &&
+                  ((uintptr_t)x & 15u) == 0,
+              "token_dropout: bad sizes (16-byte aligned rows, segments of a multiple of 8 elements, at most 4 per row)");
   I2T_REQUIRE(p > 0.f && p < 1.f, "token_dropout: p must be in (0,1)");
   const DropArgs d = make_drop(p, rng_state, site);
   cudaStream_t st = (cudaStream_t)stream;
-  const unsigned grid = grid_for(rows * seg * nseg / 4);
+  const unsigned grid = grid_for(rows * 32);        // one warp per row
   if (dtype == I2T_F32)
     token_dropout_kernel<float><<<grid, 256, 0, st>>>((float*)x, rows, ld, (int)seg, (int)nseg, d);
   else if (dtype == I2T_BF16)
