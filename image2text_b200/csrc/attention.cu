@@ -189,6 +189,8 @@ attn_fwd_kernel(const TIN* __restrict__ q, const TIN* __restrict__ k, const TIN*
 template <typename T, int HS>
 __global__ void __launch_bounds__(128) attn_delta_kernel(const T* __restrict__ out, const T* __restrict__ dout,
                                                          float* __restrict__ delta, int H, int Tq, int64_t rows) {
+  pdl_launch_dependents();     // programmatic dependent launch: this grid may have started before its predecessor finished
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t r = (int64_t)blockIdx.x * 4 + warp;  // r = (b*Tq + i)*H + h
   if (r >= rows) return;
@@ -414,6 +416,8 @@ attn_bwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __res
 template <typename T, int HS>
 __global__ void attn_dq_scatter_kernel(const float* __restrict__ acc, T* __restrict__ dq, int H, int Tq, int64_t q_bs,
                                        int64_t q_rs, int64_t total) {
+  pdl_launch_dependents();     // programmatic dependent launch: this grid may have started before its predecessor finished
+  pdl_wait();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one float4 each
   if (i >= total) return;
   const int64_t e4 = i % (HS / 4), r = i / (HS / 4);
@@ -523,8 +527,8 @@ static int launch_attn_bwd(const void* q, const void* k, const void* v, const vo
   float* dq_acc = ws + (B * H * Tq + 3) / 4 * 4;      // keep the accumulator 16-byte aligned (float4 reads in the scatter)
   I2T_CUDA(cudaMemsetAsync(dq_acc, 0, (size_t)(B * H * Tq * HS) * sizeof(float), st));
   const int64_t rows = B * Tq * H;
-  attn_delta_kernel<T, HS><<<(unsigned)ceil_div(rows, 4), 128, 0, st>>>((const T*)out, (const T*)dout, delta, (int)H,
-                                                                        (int)Tq, rows);
+  I2T_CUDA(launch_pdl(attn_delta_kernel<T, HS>, dim3((unsigned)ceil_div(rows, 4)), dim3(128), 0, st, (const T*)out, (const T*)dout, delta,
+                      (int)H, (int)Tq, rows));
   I2T_LAUNCHED();
   if (sizeof(T) == 2 && g_attn_tc.load() != 0) {
     const int r = attn_bwd_tc(q, k, v, dout, lse, delta, dq_acc, dk, dv, B, H, Tq, Tk, HS, q_bs, q_rs, kv_bs, kv_rs, mode,
@@ -532,8 +536,8 @@ static int launch_attn_bwd(const void* q, const void* k, const void* v, const vo
     if (r < 0) return r;
     if (r == 1) {
       const int64_t total_tc = B * H * Tq * (HS / 4);
-      attn_dq_scatter_kernel<T, HS><<<(unsigned)ceil_div(total_tc, 256), 256, 0, st>>>(dq_acc, (T*)dq, (int)H, (int)Tq, q_bs,
-                                                                                       q_rs, total_tc);
+      I2T_CUDA(launch_pdl(attn_dq_scatter_kernel<T, HS>, dim3((unsigned)ceil_div(total_tc, 256)), dim3(256), 0, st, (const float*)dq_acc,
+                          (T*)dq, (int)H, (int)Tq, q_bs, q_rs, total_tc));
       I2T_LAUNCHED();
       return I2T_OK;
     }

@@ -11,6 +11,9 @@
 
 namespace i2t {
 
+// launch with programmatic stream serialization; a failed launch is reported by the cudaGetLastError() check that follows
+#define I2T_PDL_LAUNCH(kern, grid, block, smem, st, ...) (void)launch_pdl(kern, grid, block, smem, st, __VA_ARGS__)
+
 constexpr int ATC_BQ = 64, ATC_BK = 64, ATC_THREADS = 128;
 
 __device__ __forceinline__ bool atc_visible(int mode, int n_prompt, int qi, int kj) {
@@ -44,6 +47,8 @@ attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __r
                    __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int H, int Tq, int Tk, int64_t q_bs, int64_t q_rs,
                    int64_t kv_bs, int64_t kv_rs, int mode, int n_prompt, float scale_log2, DropArgs drop) {
   constexpr int PITCH = HS + 8;               // bf16 elements per shared-memory row (16 bytes of padding)
+  pdl_launch_dependents();     // programmatic dependent launch: this grid may have started before its predecessor finished
+  pdl_wait();
   constexpr int KS = HS / 16;                 // k-steps over the head dimension
   constexpr int NT_O = HS / 8;                // 8-wide output column tiles
   __shared__ __align__(16) __nv_bfloat16 Qs[ATC_BQ][PITCH];
@@ -206,6 +211,8 @@ attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __r
                    float* __restrict__ dq_acc, __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv, int H, int Tq,
                    int Tk, int64_t q_bs, int64_t q_rs, int64_t kv_bs, int64_t kv_rs, int mode, int n_prompt, float scale,
                    DropArgs drop) {
+  pdl_launch_dependents();     // programmatic dependent launch: this grid may have started before its predecessor finished
+  pdl_wait();
   constexpr int PITCH = HS + 8;
   constexpr int KS = HS / 16, NT_O = HS / 8;
   __shared__ __align__(16) __nv_bfloat16 Ks[ATC_BK][PITCH];
@@ -366,15 +373,19 @@ attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __r
           mma_bf16(adq[2 * np + 1], af, bk[2], bk[3]);
         }
       }
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int qi = q0 + w * 16 + g + half * 8;
-        if (qi >= Tq) continue;
-        float* dst = dq_acc + (((int64_t)b * H + h) * Tq + qi) * HS + tq * 2;
+      // 16-byte reductions (red.global.add.v4.f32): lanes (tq, tq^1) swap halves so that the even lane owns four adjacent
+      // columns of row g and the odd lane the same four columns of row g + 8 -- a quarter of the atomic operations of the
+      // scalar form (the L2 atomic rate, not the MMAs, bounded this kernel)
+      {
+        const bool odd = (tq & 1) != 0;
+        const int qi = q0 + w * 16 + g + (odd ? 8 : 0);
+        float* dst = dq_acc + (((int64_t)b * H + h) * Tq + qi) * HS + (tq & ~1) * 2;
 #pragma unroll
         for (int nt = 0; nt < NT_O; ++nt) {
-          atomicAdd(dst + nt * 8, adq[nt][half * 2]);
-          atomicAdd(dst + nt * 8 + 1, adq[nt][half * 2 + 1]);
+          const float sx = odd ? adq[nt][0] : adq[nt][2], sy = odd ? adq[nt][1] : adq[nt][3];
+          const float rx = __shfl_xor_sync(0xffffffffu, sx, 1), ry = __shfl_xor_sync(0xffffffffu, sy, 1);
+          const float4 v4 = odd ? make_float4(rx, ry, adq[nt][2], adq[nt][3]) : make_float4(adq[nt][0], adq[nt][1], rx, ry);
+          if (qi < Tq) atomicAdd(reinterpret_cast<float4*>(dst + nt * 8), v4);
         }
       }
     }
@@ -404,12 +415,12 @@ int attn_bwd_tc(const void* q, const void* k, const void* v, const void* dout, c
   dim3 grid((unsigned)ceil_div(Tk, ATC_BK), (unsigned)H, (unsigned)B);
   const float scale = 1.0f / sqrtf((float)head_dim);
   if (head_dim == 64)
-    attn_bwd_tc_kernel<64><<<grid, ATC_THREADS, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v,
+    I2T_PDL_LAUNCH(attn_bwd_tc_kernel<64>, grid, dim3(ATC_THREADS), 0, st, (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v,
                                                        (const __nv_bfloat16*)dout, lse, delta, dq_acc, (__nv_bfloat16*)dk,
                                                        (__nv_bfloat16*)dv, (int)H, (int)Tq, (int)Tk, q_bs, q_rs, kv_bs, kv_rs, mode,
                                                        (int)n_prompt, scale, drop);
   else if (head_dim == 32)
-    attn_bwd_tc_kernel<32><<<grid, ATC_THREADS, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v,
+    I2T_PDL_LAUNCH(attn_bwd_tc_kernel<32>, grid, dim3(ATC_THREADS), 0, st, (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v,
                                                        (const __nv_bfloat16*)dout, lse, delta, dq_acc, (__nv_bfloat16*)dk,
                                                        (__nv_bfloat16*)dv, (int)H, (int)Tq, (int)Tk, q_bs, q_rs, kv_bs, kv_rs, mode,
                                                        (int)n_prompt, scale, drop);
@@ -429,11 +440,11 @@ int attn_fwd_tc(const void* q, const void* k, const void* v, void* out, float* l
   dim3 grid((unsigned)ceil_div(Tq, ATC_BQ), (unsigned)H, (unsigned)B);
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)head_dim);
   if (head_dim == 64)
-    attn_fwd_tc_kernel<64><<<grid, ATC_THREADS, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v,
+    I2T_PDL_LAUNCH(attn_fwd_tc_kernel<64>, grid, dim3(ATC_THREADS), 0, st, (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v,
                                                        (__nv_bfloat16*)out, lse, (int)H, (int)Tq, (int)Tk, q_bs, q_rs, kv_bs, kv_rs,
                                                        mode, (int)n_prompt, scale_log2, drop);
   else if (head_dim == 32)
-    attn_fwd_tc_kernel<32><<<grid, ATC_THREADS, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v,
+    I2T_PDL_LAUNCH(attn_fwd_tc_kernel<32>, grid, dim3(ATC_THREADS), 0, st, (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v,
                                                        (__nv_bfloat16*)out, lse, (int)H, (int)Tq, (int)Tk, q_bs, q_rs, kv_bs, kv_rs,
                                                        mode, (int)n_prompt, scale_log2, drop);
   else

@@ -90,10 +90,12 @@ attn_fwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_launch_dependents();     // programmatic dependent launch: barrier init / TMEM allocation above overlap the previous kernel
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_slot;
+  pdl_wait();                  // q / k / v are produced by the previous kernels
 
   if (warp == 0) {
     if (lane == 0) {
@@ -267,8 +269,8 @@ int attn_fwd_tc5(const void* q, const void* k, const void* v, void* out, float* 
       if (e != cudaSuccess) return fail(I2T_ERR_CUDA, "cudaFuncSetAttribute(attn_fwd_tc5_kernel): %s", cudaGetErrorString(e));
       attr2 = true;
     }
-    attn_fwd_tc5_kernel<2><<<grid, A5_THREADS, SMEM, st>>>(mq, mk, mv, (__nv_bfloat16*)out, lse, (int)H, (int)Tq, (int)Tk, mode,
-                                                         (int)n_prompt, scale_log2, drop);
+    (void)launch_pdl(attn_fwd_tc5_kernel<2>, grid, dim3(A5_THREADS), (size_t)SMEM, st, mq, mk, mv, (__nv_bfloat16*)out, lse, (int)H, (int)Tq,
+                     (int)Tk, mode, (int)n_prompt, scale_log2, drop);
   } else {
     constexpr int SMEM = a5_smem(3);
     if (!attr3) {
@@ -276,8 +278,8 @@ int attn_fwd_tc5(const void* q, const void* k, const void* v, void* out, float* 
       if (e != cudaSuccess) return fail(I2T_ERR_CUDA, "cudaFuncSetAttribute(attn_fwd_tc5_kernel): %s", cudaGetErrorString(e));
       attr3 = true;
     }
-    attn_fwd_tc5_kernel<3><<<grid, A5_THREADS, SMEM, st>>>(mq, mk, mv, (__nv_bfloat16*)out, lse, (int)H, (int)Tq, (int)Tk, mode,
-                                                         (int)n_prompt, scale_log2, drop);
+    (void)launch_pdl(attn_fwd_tc5_kernel<3>, grid, dim3(A5_THREADS), (size_t)SMEM, st, mq, mk, mv, (__nv_bfloat16*)out, lse, (int)H, (int)Tq,
+                     (int)Tk, mode, (int)n_prompt, scale_log2, drop);
   }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();

@@ -14,6 +14,8 @@ namespace i2t {
 template <typename TY>
 __global__ void __launch_bounds__(256) dropout_add_kernel(const TY* __restrict__ y, const float* __restrict__ res,
                                                           float* __restrict__ out, int64_t n4, DropArgs d) {
+  pdl_launch_dependents();     // programmatic dependent launch: this grid may have started before its predecessor finished
+  pdl_wait();
   const DropKey key = drop_key(d);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     const Philox4 r = drop_elem4(d, key, (uint64_t)i);
@@ -32,6 +34,8 @@ __global__ void __launch_bounds__(256) dropout_add_kernel(const TY* __restrict__
 
 template <typename TIN, typename TG>
 __global__ void __launch_bounds__(256) dropout_bwd_kernel(const TIN* __restrict__ dy, TG* __restrict__ g, int64_t n4, DropArgs d) {
+  pdl_launch_dependents();     // programmatic dependent launch: this grid may have started before its predecessor finished
+  pdl_wait();
   const DropKey key = drop_key(d);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     const Philox4 r = drop_elem4(d, key, (uint64_t)i);
@@ -50,6 +54,8 @@ __global__ void __launch_bounds__(256) dropout_bwd_kernel(const TIN* __restrict_
 template <typename T>
 __global__ void __launch_bounds__(256) token_dropout_kernel(T* __restrict__ x, int64_t rows, int64_t ld, int seg, int nseg,
                                                             DropArgs d) {
+  pdl_launch_dependents();     // programmatic dependent launch: this grid may have started before its predecessor finished
+  pdl_wait();
   constexpr int VEC = 16 / (int)sizeof(T);
   const DropKey key = drop_key(d);
   const int lane = threadIdx.x & 31;
@@ -96,9 +102,10 @@ extern "C" int i2t_dropout_add_fwd(const void* y, const float* residual, float* 
   const DropArgs d = make_drop(p, rng_state, site);
   cudaStream_t st = (cudaStream_t)stream;
   if (y_dtype == I2T_F32)
-    dropout_add_kernel<float><<<grid_for(n / 4), 256, 0, st>>>((const float*)y, residual, out, n / 4, d);
+    I2T_CUDA(launch_pdl(dropout_add_kernel<float>, dim3(grid_for(n / 4)), dim3(256), 0, st, (const float*)y, residual, out, n / 4, d));
   else
-    dropout_add_kernel<__nv_bfloat16><<<grid_for(n / 4), 256, 0, st>>>((const __nv_bfloat16*)y, residual, out, n / 4, d);
+    I2T_CUDA(launch_pdl(dropout_add_kernel<__nv_bfloat16>, dim3(grid_for(n / 4)), dim3(256), 0, st, (const __nv_bfloat16*)y, residual, out,
+                        n / 4, d));
   I2T_LAUNCHED();
   return I2T_OK;
 }
@@ -113,11 +120,12 @@ extern "C" int i2t_dropout_bwd(const void* dy, void* g, int64_t n, float p, cons
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned grid = grid_for(n / 4);
   if (dy_dtype == I2T_F32 && g_dtype == I2T_F32)
-    dropout_bwd_kernel<float, float><<<grid, 256, 0, st>>>((const float*)dy, (float*)g, n / 4, d);
+    I2T_CUDA(launch_pdl(dropout_bwd_kernel<float, float>, dim3(grid), dim3(256), 0, st, (const float*)dy, (float*)g, n / 4, d));
   else if (dy_dtype == I2T_F32 && g_dtype == I2T_BF16)
-    dropout_bwd_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>((const float*)dy, (__nv_bfloat16*)g, n / 4, d);
+    I2T_CUDA(launch_pdl(dropout_bwd_kernel<float, __nv_bfloat16>, dim3(grid), dim3(256), 0, st, (const float*)dy, (__nv_bfloat16*)g, n / 4, d));
   else if (dy_dtype == I2T_BF16 && g_dtype == I2T_BF16)
-    dropout_bwd_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)dy, (__nv_bfloat16*)g, n / 4, d);
+    I2T_CUDA(launch_pdl(dropout_bwd_kernel<__nv_bfloat16, __nv_bfloat16>, dim3(grid), dim3(256), 0, st, (const __nv_bfloat16*)dy,
+                        (__nv_bfloat16*)g, n / 4, d));
   else
     return fail(I2T_ERR_INVALID, "dropout_bwd: dtype combination (%d,%d) not built", dy_dtype, g_dtype);
   I2T_LAUNCHED();
@@ -135,9 +143,9 @@ extern "C" int i2t_token_dropout(void* x, int64_t rows, int64_t ld, int64_t seg,
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned grid = grid_for(rows * 32);        // one warp per row
   if (dtype == I2T_F32)
-    token_dropout_kernel<float><<<grid, 256, 0, st>>>((float*)x, rows, ld, (int)seg, (int)nseg, d);
+    I2T_CUDA(launch_pdl(token_dropout_kernel<float>, dim3(grid), dim3(256), 0, st, (float*)x, rows, ld, (int)seg, (int)nseg, d));
   else if (dtype == I2T_BF16)
-    token_dropout_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((__nv_bfloat16*)x, rows, ld, (int)seg, (int)nseg, d);
+    I2T_CUDA(launch_pdl(token_dropout_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, st, (__nv_bfloat16*)x, rows, ld, (int)seg, (int)nseg, d));
   else
     return fail(I2T_ERR_INVALID, "token_dropout: bad dtype %d", dtype);
   I2T_LAUNCHED();

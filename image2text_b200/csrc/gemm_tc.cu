@@ -508,11 +508,13 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
+  pdl_launch_dependents();                     // barrier init / TMEM allocation above overlap the previous kernel's tail
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   cluster_sync_all();                          // the peer's barriers are initialised before anything remote happens
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_slot;
+  pdl_wait();                                  // operands, bias, residual and C belong to the previous kernels
 
   if (warp == 0) {
     if (lane == 0) {
@@ -774,13 +776,15 @@ static int launch_pair(const CUtensorMap& ma, const CUtensorMap& mb, const CUten
   cfg.blockDim = dim3(TC_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;     // the kernel waits (griddepcontrol) after its setup
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = g_pdl.load() ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma, mb, mc, kblocks, m_tiles, n_tiles, epi);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   if (e != cudaSuccess) {

@@ -11,6 +11,8 @@ __global__ void __launch_bounds__(128) ln_fwd_kernel(const TX* __restrict__ x, c
                                                      const float* __restrict__ beta, TY* __restrict__ y,
                                                      float* __restrict__ mean, float* __restrict__ rstd,
                                                      int64_t rows, int cols, int64_t xstride, float eps) {
+  pdl_launch_dependents();     // programmatic dependent launch: this grid may have started before its predecessor finished
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
   if (row >= rows) return;
@@ -74,6 +76,8 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(const TDY* __restrict__ dy,
                                                      float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                      int64_t rows, int cols) {
   extern __shared__ float red[];  // [4 warps][cols] reused for dgamma then dbeta
+  pdl_launch_dependents();     // programmatic dependent launch: this grid may have started before its predecessor finished
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = cols >> 2;
   float4 ag[MAXV], ab[MAXV];
@@ -141,11 +145,11 @@ static int launch_fwd(const void* x, const float* gamma, const float* beta, void
   const int warps = 4;
   dim3 grid((unsigned)ceil_div(rows, warps)), block(warps * 32);
   if (cols <= 1024) {
-    ln_fwd_kernel<TX, TY, 8><<<grid, block, 0, st>>>((const TX*)x, gamma, beta, (TY*)y, mean, rstd, rows, (int)cols,
-                                                     xstride, eps);
+    I2T_CUDA(launch_pdl(ln_fwd_kernel<TX, TY, 8>, grid, block, 0, st, (const TX*)x, gamma, beta, (TY*)y, mean, rstd, rows, (int)cols,
+                        xstride, eps));
   } else {
-    ln_fwd_kernel<TX, TY, 16><<<grid, block, 0, st>>>((const TX*)x, gamma, beta, (TY*)y, mean, rstd, rows, (int)cols,
-                                                      xstride, eps);
+    I2T_CUDA(launch_pdl(ln_fwd_kernel<TX, TY, 16>, grid, block, 0, st, (const TX*)x, gamma, beta, (TY*)y, mean, rstd, rows, (int)cols,
+                        xstride, eps));
   }
   I2T_LAUNCHED();
   return I2T_OK;
@@ -159,11 +163,11 @@ static int launch_bwd(const void* dy, const void* x, const float* gamma, const f
   if (ctas > cap) ctas = cap;
   const size_t smem = (size_t)4 * cols * sizeof(float);
   if (cols <= 1024) {
-    ln_bwd_kernel<TDY, TX, TDX, 8><<<(unsigned)ctas, 128, smem, st>>>((const TDY*)dy, (const TX*)x, gamma, mean, rstd,
-                                                                      (TDX*)dx, dgamma, dbeta, rows, (int)cols);
+    I2T_CUDA(launch_pdl(ln_bwd_kernel<TDY, TX, TDX, 8>, dim3((unsigned)ctas), dim3(128), smem, st, (const TDY*)dy, (const TX*)x, gamma,
+                        mean, rstd, (TDX*)dx, dgamma, dbeta, rows, (int)cols));
   } else {
-    ln_bwd_kernel<TDY, TX, TDX, 16><<<(unsigned)ctas, 128, smem, st>>>((const TDY*)dy, (const TX*)x, gamma, mean, rstd,
-                                                                       (TDX*)dx, dgamma, dbeta, rows, (int)cols);
+    I2T_CUDA(launch_pdl(ln_bwd_kernel<TDY, TX, TDX, 16>, dim3((unsigned)ctas), dim3(128), smem, st, (const TDY*)dy, (const TX*)x, gamma,
+                        mean, rstd, (TDX*)dx, dgamma, dbeta, rows, (int)cols));
   }
   I2T_LAUNCHED();
   return I2T_OK;

@@ -9,6 +9,8 @@ namespace i2t {
 
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) act_fwd_kernel(const TI* __restrict__ z, TO* __restrict__ h, int64_t n4, int act) {
+  pdl_launch_dependents();     // programmatic dependent launch: this grid may have started before its predecessor finished
+  pdl_wait();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 v = load4(z + i * 4);
     v.x = apply_act(v.x, act); v.y = apply_act(v.y, act); v.z = apply_act(v.z, act); v.w = apply_act(v.w, act);
@@ -19,6 +21,8 @@ __global__ void __launch_bounds__(256) act_fwd_kernel(const TI* __restrict__ z, 
 template <typename TZ, typename TG>
 __global__ void __launch_bounds__(256) act_bwd_kernel(const TZ* __restrict__ z, const TG* __restrict__ dh,
                                                       TG* __restrict__ dz, int64_t n4, int act) {
+  pdl_launch_dependents();     // programmatic dependent launch: this grid may have started before its predecessor finished
+  pdl_wait();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     const float4 v = load4(z + i * 4), g = load4(dh + i * 4);
     store4(dz + i * 4, make_float4(g.x * act_grad(v.x, act), g.y * act_grad(v.y, act), g.z * act_grad(v.z, act),
@@ -230,10 +234,12 @@ extern "C" int i2t_act_fwd(const void* z, void* h, int64_t n, int act, int z_dty
   if (n == 0) return I2T_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned g = grid_for(n / 4);
-  if (z_dtype == I2T_F32 && h_dtype == I2T_F32) act_fwd_kernel<float, float><<<g, 256, 0, st>>>((const float*)z, (float*)h, n / 4, act);
-  else if (z_dtype == I2T_F32) act_fwd_kernel<float, __nv_bfloat16><<<g, 256, 0, st>>>((const float*)z, (__nv_bfloat16*)h, n / 4, act);
-  else if (h_dtype == I2T_BF16) act_fwd_kernel<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)z, (__nv_bfloat16*)h, n / 4, act);
-  else act_fwd_kernel<__nv_bfloat16, float><<<g, 256, 0, st>>>((const __nv_bfloat16*)z, (float*)h, n / 4, act);
+  const dim3 gd(g), bd(256);
+  const int64_t n4 = n / 4;
+  if (z_dtype == I2T_F32 && h_dtype == I2T_F32) I2T_CUDA(launch_pdl(act_fwd_kernel<float, float>, gd, bd, 0, st, (const float*)z, (float*)h, n4, act));
+  else if (z_dtype == I2T_F32) I2T_CUDA(launch_pdl(act_fwd_kernel<float, __nv_bfloat16>, gd, bd, 0, st, (const float*)z, (__nv_bfloat16*)h, n4, act));
+  else if (h_dtype == I2T_BF16) I2T_CUDA(launch_pdl(act_fwd_kernel<__nv_bfloat16, __nv_bfloat16>, gd, bd, 0, st, (const __nv_bfloat16*)z, (__nv_bfloat16*)h, n4, act));
+  else I2T_CUDA(launch_pdl(act_fwd_kernel<__nv_bfloat16, float>, gd, bd, 0, st, (const __nv_bfloat16*)z, (float*)h, n4, act));
   I2T_LAUNCHED();
   return I2T_OK;
 }
@@ -244,8 +250,10 @@ extern "C" int i2t_act_bwd(const void* z, const void* dh, void* dz, int64_t n, i
   if (n == 0) return I2T_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned g = grid_for(n / 4);
-  if (z_dtype == I2T_F32 && g_dtype == I2T_F32) act_bwd_kernel<float, float><<<g, 256, 0, st>>>((const float*)z, (const float*)dh, (float*)dz, n / 4, act);
-  else if (z_dtype == I2T_BF16 && g_dtype == I2T_BF16) act_bwd_kernel<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)z, (const __nv_bfloat16*)dh, (__nv_bfloat16*)dz, n / 4, act);
+  const dim3 gd(g), bd(256);
+  const int64_t n4 = n / 4;
+  if (z_dtype == I2T_F32 && g_dtype == I2T_F32) I2T_CUDA(launch_pdl(act_bwd_kernel<float, float>, gd, bd, 0, st, (const float*)z, (const float*)dh, (float*)dz, n4, act));
+  else if (z_dtype == I2T_BF16 && g_dtype == I2T_BF16) I2T_CUDA(launch_pdl(act_bwd_kernel<__nv_bfloat16, __nv_bfloat16>, gd, bd, 0, st, (const __nv_bfloat16*)z, (const __nv_bfloat16*)dh, (__nv_bfloat16*)dz, n4, act));
   else return fail(I2T_ERR_INVALID, "act_bwd: dtype combination not built");
   I2T_LAUNCHED();
   return I2T_OK;
