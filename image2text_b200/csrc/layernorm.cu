@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(128) ln_fwd_kernel(const TX* __restrict__ x, c
 // sums of the columns it owns in registers, reduced across the CTA's warps in shared memory and
 // flushed with one atomicAdd per column per CTA.
 template <typename TDY, typename TX, typename TDX, int MAXV>
-__global__ void __launch_bounds__(128) ln_bwd_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x,
+__global__ void __launch_bounds__(128, MAXV <= 6 ? 4 : 1) ln_bwd_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x,
                                                      const float* __restrict__ gamma, const float* __restrict__ mean,
                                                      const float* __restrict__ rstd, TDX* __restrict__ dx,
                                                      float* __restrict__ dgamma, float* __restrict__ dbeta,
@@ -162,7 +162,10 @@ static int launch_bwd(const void* dy, const void* x, const float* gamma, const f
   const int64_t cap = (int64_t)num_sms() * 4;
   if (ctas > cap) ctas = cap;
   const size_t smem = (size_t)4 * cols * sizeof(float);
-  if (cols <= 1024) {
+  if (cols <= 768) {      // the model width: exactly 6 vectors per lane -> 128 registers, 4 CTAs per SM
+    I2T_CUDA(launch_pdl(ln_bwd_kernel<TDY, TX, TDX, 6>, dim3((unsigned)ctas), dim3(128), smem, st, (const TDY*)dy, (const TX*)x, gamma,
+                        mean, rstd, (TDX*)dx, dgamma, dbeta, rows, (int)cols));
+  } else if (cols <= 1024) {
     I2T_CUDA(launch_pdl(ln_bwd_kernel<TDY, TX, TDX, 8>, dim3((unsigned)ctas), dim3(128), smem, st, (const TDY*)dy, (const TX*)x, gamma,
                         mean, rstd, (TDX*)dx, dgamma, dbeta, rows, (int)cols));
   } else {

@@ -469,6 +469,11 @@ class HFDecodeEngine:
         self.y16 = torch.zeros((batch, C), device=dev, dtype=self.cd)
         self.ldl = (V + 3) // 4 * 4                      # 16-byte row pitch: TMA-store epilogue of the LM-head GEMM
         self.logits = torch.zeros((batch, self.ldl), **f32)[:, :V]
+        if self.cd == torch.bfloat16:                     # buffers of the PDL chain (_layers_chain)
+            F = self.F
+            self.xn = torch.zeros((batch, C), device=dev, dtype=self.cd)
+            self.h32 = torch.zeros((batch, F), **f32)
+            self.h16 = torch.zeros((batch, F), device=dev, dtype=self.cd)
         self.ngrams = torch.tensor(list(spec["no_repeat_n_grams"]) or [0], device=dev, dtype=torch.int32)
         self.n_ngrams = len(spec["no_repeat_n_grams"])
         self.graphs = {}
@@ -487,6 +492,9 @@ class HFDecodeEngine:
         dp = "decoder.backbone.transformer."
         cbs = self.cap * C
         es = self.kcache.element_size()
+
+        if cd == torch.bfloat16:
+            return self._layers_chain(slot_ptr, row_offset, len_add)
 
         def ln(key):
             return ops.layernorm(self.x, W[key + ".weight"], W.get(key + ".bias"), 1e-5, out_dtype=cd)
@@ -517,6 +525,46 @@ class HFDecodeEngine:
                 c1d(att_out(), lp + "crossattention.c_proj", residual=self.x, out=self.x)
             h = c1d(ln(lp + "ln_2"), lp + "mlp.c_fc", act=ops.ACT_GELU_TANH, out_dtype=cd)
             c1d(h, lp + "mlp.c_proj", residual=self.x, out=self.x)
+
+    def _layers_chain(self, slot_ptr: int, row_offset: int, len_add: int):
+        """bf16: the same position as a programmatic-dependent-launch chain (see DecodeEngine._gemm_step): LayerNorm zero-fills
+        the split-K output of the projection it feeds, self attention appends the new K / V row (cache row len - 1 = slot value
+        + row_offset in both step kinds) and writes bf16, GELU is a PDL-aware pass, every projection may request its Conv1D
+        weight tiles before its predecessor has finished."""
+        m, spec, B = self.model, self.spec, self.B
+        W = m.weights()
+        C, H = spec["n_embd"], spec["n_head"]
+        hs = C // H
+        st = stream()
+        dp = "decoder.backbone.transformer."
+        cbs = self.cap * C
+        assert row_offset + 1 == len_add
+
+        def ln(key, zero=None):
+            call("i2t_dec_layernorm", ptr(self.x), ptr(W[key + ".weight"]), ptr(W.get(key + ".bias")), ptr(self.xn), B, C, 1e-5,
+                 ops.BF16, ptr(zero), zero.numel() if zero is not None else 0, st)
+            return self.xn
+
+        def c1d(a, key, out, residual=None, accumulate=False):          # Conv1D: y = a @ W (in, out) + b
+            return ops.gemm(a, W.c(key + ".weight"), bias=W[key + ".bias"], b_kmajor=False, out=out, residual=residual,
+                            accumulate=accumulate, b_stable=True)
+
+        for i in range(spec["n_layer"]):
+            lp = f"{dp}h.{i}."
+            c1d(ln(lp + "ln_1", self.qkv32), lp + "attn.c_attn", self.qkv32, accumulate=True)
+            qp = self.qkv32.data_ptr()
+            call("i2t_dec_attn_append", qp, 3 * C, ptr(self.kcache[i]), ptr(self.vcache[i]), cbs, C, ptr(self.y16), C, slot_ptr,
+                 len_add, B, H, hs, ops.BF16, qp + 4 * C, qp + 8 * C, 3 * C, ops.BF16, st)
+            c1d(self.y16, lp + "attn.c_proj", self.x, residual=self.x)
+            if spec["use_cross_attn"]:
+                c1d(ln(lp + "ln_cross_attn", self.q), lp + "crossattention.q_attn", self.q, accumulate=True)
+                kv = self.xkv[i]
+                call("i2t_dec_attn_append", ptr(self.q), C, kv.data_ptr(), kv.data_ptr() + C * kv.element_size(), self.S * 2 * C,
+                     2 * C, ptr(self.y16), C, None, self.S, B, H, hs, ops.BF16, None, None, 0, ops.BF16, st)
+                c1d(self.y16, lp + "crossattention.c_proj", self.x, residual=self.x)
+            c1d(ln(lp + "ln_2", self.h32), lp + "mlp.c_fc", self.h32, accumulate=True)
+            call("i2t_dec_act", ptr(self.h32), ptr(self.h16), self.h32.numel(), ops.ACT_GELU_TANH, ops.BF16, st)
+            c1d(self.h16, lp + "mlp.c_proj", self.x, residual=self.x)
 
     def _prompt_step(self):
         W = self.model.weights()
@@ -579,6 +627,12 @@ class HFDecodeEngine:
             for i in range(spec["n_layer"]):
                 lp = f"decoder.backbone.transformer.h.{i}.crossattention.c_attn"
                 ops.gemm(e, W.c(lp + ".weight"), bias=W[lp + ".bias"], b_kmajor=False, out=self.xkv[i])
+        # compute-dtype weights exist before any step is issued (the chain's projections promise that nothing in front of them
+        # in the stream writes their weights); refreshed shadows invalidate the captured graphs, which hold their addresses
+        wsig = tuple(W.c(k).data_ptr() for k in W.t if k.startswith("decoder.") and W.t[k].dim() == 2
+                     and not k.endswith(("wte.weight", "wpe.weight")))
+        if getattr(self, "_wsig", None) != wsig:
+            self._wsig, self.graphs = wsig, {}
         self.ids.zero_()
         self.ids[:, :P].copy_(prompt_ids)
         self.pos.zero_()
