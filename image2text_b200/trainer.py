@@ -125,6 +125,7 @@ def train_loop(model_wrapper: ModelTrainerWrapper, optimizer, train_iter: Iterat
             _print(f"Epoch: {epoch} step {step + 1}/{num_steps} " + " ".join(f"{k}={float(v):.4f}" for k, v in metrics.items()))
     if last is not None:
         _print(f"Epoch: {epoch} " + " ".join(f"{k}={float(v):.4f}" for k, v in last.items()))
+        state["last_train_loss"] = float(last["train_loss_lm"])
     if reset_moco_after_k_epochs is not None and (epoch + 1) in reset_moco_after_k_epochs:
         model_wrapper.copy_momentum_params()
     if chckpt_fname is not None:
@@ -242,7 +243,7 @@ def main(args) -> dict:
     vocab = tokenizer.vocab_size
     train_iter = synthetic_batches(config.batch_size, size, vocab, tokenizer.eos_token_id, seed=args.seed + 1000 * rank)
     val_iter = synthetic_batches(config.batch_size, size, vocab, tokenizer.eos_token_id, seed=args.seed + 77 + 1000 * rank, pool=4)
-    state, history = {}, []
+    state, history, train_history = {}, [], []
     for epoch in range(args.epochs if args.epochs is not None else 10000):
         stop = train_loop(model_wrapper, optimizer, train_iter, epoch, config.num_steps if args.steps is None else args.steps,
                           accum=config.gradient_accumulation_steps, reducer=reducer,
@@ -250,6 +251,7 @@ def main(args) -> dict:
                           matchers=matchers, graph=bool(args.graph), log_every=args.log_every, state=state)
         if stop:
             break
+        train_history.append(state.get("last_train_loss"))
         if args.eval_captions:
             eval_model(model_wrapper, tokenizer, val_iter, epoch, config.ignore_index, max_new_tokens=args.eval_tokens,
                        seed=args.seed)
@@ -258,7 +260,7 @@ def main(args) -> dict:
         history.append(loss)
     if world > 1:
         torch.distributed.barrier()
-    return {"val_losses": history, "wrapper": model_wrapper}
+    return {"val_losses": history, "train_losses": train_history, "wrapper": model_wrapper}
 
 
 def parse_args(argv=None):
