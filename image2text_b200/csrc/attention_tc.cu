@@ -36,6 +36,11 @@ __device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], 
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ float atc_ex2(float x) {     // one MUFU op (exp2f() adds range fix-ups the softmax does not need)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -280,6 +285,12 @@ attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __r
     }
     __syncthreads();
 
+    bool tile_full = k0 + ATC_BK <= Tk && q0 + ATC_BQ <= Tq;
+    if (mode != I2T_MASK_NONE) {
+      tile_full = tile_full && (k0 + ATC_BK - 1 <= q0);                                   // every key <= every query
+      if (mode == I2T_MASK_PROMPT)
+        tile_full = tile_full && ((q0 + ATC_BQ <= n_prompt) || (q0 >= n_prompt && k0 >= n_prompt));
+    }
     // S^T = K Q^T and dP^T = V dO^T : rows = this warp's 16 keys, columns = the tile's 64 queries
     float s[8][4], dp[8][4];
 #pragma unroll
@@ -320,7 +331,10 @@ attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __r
         const int qi = q0 + ql;
         const float l = lse_s[ql];
         float p = 0.f;
-        if (kj < Tk && qi < Tq && l != -INFINITY && atc_visible(mode, n_prompt, qi, kj)) p = exp2f(s[nt][e] * scale_log2 - l * LOG2E);
+        // tile_full (uniform over the CTA): every (query, key) pair of this 64 x 64 tile is in range and visible -- the
+        // off-diagonal tiles of a causal mask -- so the per-element mask algebra is skipped
+        if (tile_full ? (l != -INFINITY) : (kj < Tk && qi < Tq && l != -INFINITY && atc_visible(mode, n_prompt, qi, kj)))
+          p = atc_ex2(fmaf(s[nt][e], scale_log2, -l * LOG2E));
         s[nt][e] = p * mk[e];
         dp[nt][e] = p * (dp[nt][e] * mk[e] - delta_s[ql]) * scale;
       }

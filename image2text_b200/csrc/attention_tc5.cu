@@ -33,6 +33,11 @@ __device__ __forceinline__ bool a5_visible(int mode, int n_prompt, int qi, int k
   if (mode == I2T_MASK_CAUSAL) return true;
   return qi < n_prompt ? true : kj >= n_prompt;
 }
+__device__ __forceinline__ float a5_ex2(float x) {      // one MUFU op; exp2f() adds range fix-ups the softmax does not need
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ uint32_t a5_pack(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -146,6 +151,14 @@ attn_fwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int r = wq * 32 + lane;                                   // query row of the tile = TMEM lane
     const int qi = q0 + r;
     const uint32_t trow = tmem_base + ((uint32_t)(wq * 32) << 16);
+    // The closed-form masks make the visible keys of a row ONE interval [lo, hi): a 32-key chunk is classified once
+    // (all visible / none / straddling) and only straddling chunks -- the diagonal -- pay per-element tests.  The softmax
+    // threads are instruction-bound (one row of up to 384 keys each), so this is what sets the kernel's latency.
+    int lo = 0, hi = Tk;
+    if (mode != I2T_MASK_NONE) {
+      hi = min(Tk, qi + 1);
+      if (mode == I2T_MASK_PROMPT && qi >= n_prompt) lo = n_prompt;
+    }
     // ---- pass A: masked row maximum over every key block ----
     float mx = -INFINITY;
     for (int j = 0; j < nb; ++j) {
@@ -155,15 +168,20 @@ attn_fwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       for (int c = 0; c < A5_BK / 32; ++c) {
         uint32_t v[32];
         tmem_ld32(trow + (uint32_t)(j * A5_BK + c * 32), v);
+        const int c0 = j * A5_BK + c * 32;
+        if (c0 >= lo && c0 + 32 <= hi) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int kj = j * A5_BK + c * 32 + i;
-          if (kj < Tk && a5_visible(mode, n_prompt, qi, kj)) mx = fmaxf(mx, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        } else if (c0 + 32 > lo && c0 < hi) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c0 + i >= lo && c0 + i < hi) mx = fmaxf(mx, __uint_as_float(v[i]));
         }
       }
     }
     const float m_use = mx == -INFINITY ? 0.f : mx;
-    // ---- pass B: P_j = exp2((S_j - m) * scale) as bf16 into the swizzled A-operand tile; row sum ----
+    const float m_scaled = m_use * scale_log2;
+    // ---- pass B: P_j = exp2(S_j * scale - m * scale) as bf16 into the swizzled A-operand tile; row sum ----
     float l = 0.f;
     for (int j = 0; j < nb; ++j) {
       if (j > 0) mbar_wait(&bar_pfree, (uint32_t)(j - 1) & 1u);    // the MMAs that read P_{j-1} have finished
@@ -172,12 +190,23 @@ attn_fwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         uint32_t v[32];
         tmem_ld32(trow + (uint32_t)(j * A5_BK + c * 32), v);
         float p[32];
+        const int c0 = j * A5_BK + c * 32;
+        if (c0 >= lo && c0 + 32 <= hi) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int kj = j * A5_BK + c * 32 + i;
-          const bool vis = kj < Tk && a5_visible(mode, n_prompt, qi, kj);
-          p[i] = vis ? exp2f((__uint_as_float(v[i]) - m_use) * scale_log2) : 0.f;
-          l += p[i];
+          for (int i = 0; i < 32; ++i) {
+            p[i] = a5_ex2(fmaf(__uint_as_float(v[i]), scale_log2, -m_scaled));
+            l += p[i];
+          }
+        } else if (c0 + 32 > lo && c0 < hi) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const bool vis = c0 + i >= lo && c0 + i < hi;
+            p[i] = vis ? a5_ex2(fmaf(__uint_as_float(v[i]), scale_log2, -m_scaled)) : 0.f;
+            l += p[i];
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) p[i] = 0.f;
         }
         if (drop.thr != 0u) {   // dropout on the probabilities (l keeps every key): 8 Philox calls per 32 keys
           const DropKey dkey = drop_key(drop);
