@@ -41,6 +41,16 @@ __device__ __forceinline__ float atc_ex2(float x) {     // one MUFU op (exp2f() 
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ void atc_cp_async16(void* dst, const void* src, bool valid) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src),
+               "r"(valid ? 16 : 0)
+               : "memory");
+}
+__device__ __forceinline__ void atc_cp_async4(void* dst, const void* src, bool valid) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src),
+               "r"(valid ? 4 : 0)
+               : "memory");
+}
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -220,12 +230,20 @@ attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __r
   pdl_wait();
   constexpr int PITCH = HS + 8;
   constexpr int KS = HS / 16, NT_O = HS / 8;
-  __shared__ __align__(16) __nv_bfloat16 Ks[ATC_BK][PITCH];
-  __shared__ __align__(16) __nv_bfloat16 Vs[ATC_BK][PITCH];
-  __shared__ __align__(16) __nv_bfloat16 Qs[ATC_BQ][PITCH];
-  __shared__ __align__(16) __nv_bfloat16 dOs[ATC_BQ][PITCH];
-  __shared__ __align__(16) __nv_bfloat16 dSs[ATC_BK][ATC_BQ + 8];     // dS^T: [key][query]
-  __shared__ float lse_s[ATC_BQ], delta_s[ATC_BQ];
+  // dynamic shared memory (56 KB at head_dim 64): K | V (dead after the fragment loads: becomes Q buffer 1) | Q buffer 0 |
+  // dO buffer 0 | dO buffer 1 | dS^T | lse, delta (2 buffers each).  Q / dO tiles are double buffered and filled with
+  // cp.async: the loads of query tile i+1 fly while tile i is in the MMAs (ncu on the single-buffered loop: long-scoreboard
+  // stalls 4.2 per issue at 8 warps / SM -- the kernel waited on its own synchronous tile loads)
+  extern __shared__ __align__(16) uint8_t atc_smem[];
+  typedef __nv_bfloat16 (*Tile)[PITCH];
+  constexpr int TILE_BYTES = ATC_BK * PITCH * 2;
+  Tile Ks = reinterpret_cast<Tile>(atc_smem);
+  Tile Vs = reinterpret_cast<Tile>(atc_smem + TILE_BYTES);
+  Tile Qb[2] = {reinterpret_cast<Tile>(atc_smem + 2 * TILE_BYTES), reinterpret_cast<Tile>(atc_smem + TILE_BYTES)};
+  Tile dOb[2] = {reinterpret_cast<Tile>(atc_smem + 3 * TILE_BYTES), reinterpret_cast<Tile>(atc_smem + 4 * TILE_BYTES)};
+  __nv_bfloat16 (*dSs)[ATC_BQ + 8] = reinterpret_cast<__nv_bfloat16 (*)[ATC_BQ + 8]>(atc_smem + 5 * TILE_BYTES);   // dS^T: [key][query]
+  float* lse_b = reinterpret_cast<float*>(atc_smem + 5 * TILE_BYTES + ATC_BK * (ATC_BQ + 8) * 2);                  // [2][64]
+  float* delta_b = lse_b + 2 * ATC_BQ;                                                                             // [2][64]
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
   const int g = lane >> 2, tq = lane & 3;
   const int mi = lane >> 3, r8 = lane & 7;
@@ -265,25 +283,35 @@ attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __r
 
   int qstart = 0;
   if (mode != I2T_MASK_NONE) qstart = (k0 / ATC_BQ) * ATC_BQ;       // queries before the key tile never see it
-  for (int q0 = qstart; q0 < Tq; q0 += ATC_BQ) {
-    __syncthreads();                                                  // previous tile's readers are done
+  // asynchronous fill of one (Q, dO, lse, delta) tile; rows past Tq are zero-filled (src-size 0)
+  auto issue_tile = [&](int q0, int buf) {
     for (int i = t; i < ATC_BQ * CH; i += ATC_THREADS) {
       const int r = i / CH, c = i % CH;
-      uint4 q4 = make_uint4(0u, 0u, 0u, 0u), d4 = q4;
-      if (q0 + r < Tq) {
-        q4 = *reinterpret_cast<const uint4*>(qb + (int64_t)(q0 + r) * q_rs + c * 8);
-        d4 = *reinterpret_cast<const uint4*>(dob + (int64_t)(q0 + r) * do_rs + c * 8);
-      }
-      *reinterpret_cast<uint4*>(&Qs[r][c * 8]) = q4;
-      *reinterpret_cast<uint4*>(&dOs[r][c * 8]) = d4;
+      const bool ok = q0 + r < Tq;
+      const int64_t row = ok ? q0 + r : 0;
+      atc_cp_async16(&Qb[buf][r][c * 8], qb + row * q_rs + c * 8, ok);
+      atc_cp_async16(&dOb[buf][r][c * 8], dob + row * do_rs + c * 8, ok);
     }
-    if (t < ATC_BQ) {
-      const bool ok = q0 + t < Tq;
-      const int64_t li = ((int64_t)b * H + h) * Tq + q0 + t;
-      lse_s[t] = ok ? lse[li] : -INFINITY;
-      delta_s[t] = ok ? delta[li] : 0.f;
+    {
+      const int r = t & (ATC_BQ - 1);
+      const bool ok = q0 + r < Tq;
+      const int64_t li = ((int64_t)b * H + h) * Tq + (ok ? q0 + r : 0);
+      if (t < ATC_BQ) atc_cp_async4(lse_b + buf * ATC_BQ + r, lse + li, ok);
+      else atc_cp_async4(delta_b + buf * ATC_BQ + r, delta + li, ok);
     }
-    __syncthreads();
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (qstart < Tq) issue_tile(qstart, 0);
+  int it = 0;
+  for (int q0 = qstart; q0 < Tq; q0 += ATC_BQ, ++it) {
+    const int buf = it & 1;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                   // tile `it` is visible; every warp has left iteration it-1 (and, for
+                                                       // it = 0, has loaded its V fragments: buffer 1 of Q aliases V)
+    if (q0 + ATC_BQ < Tq) issue_tile(q0 + ATC_BQ, buf ^ 1);
+    const Tile Qs = Qb[buf], dOs = dOb[buf];
+    const float* lse_s = lse_b + buf * ATC_BQ;
+    const float* delta_s = delta_b + buf * ATC_BQ;
 
     bool tile_full = k0 + ATC_BK <= Tk && q0 + ATC_BQ <= Tq;
     if (mode != I2T_MASK_NONE) {
@@ -428,16 +456,25 @@ int attn_bwd_tc(const void* q, const void* k, const void* v, const void* dout, c
   if (((uintptr_t)dk & 3u) != 0 || ((uintptr_t)dv & 3u) != 0) return 0;
   dim3 grid((unsigned)ceil_div(Tk, ATC_BK), (unsigned)H, (unsigned)B);
   const float scale = 1.0f / sqrtf((float)head_dim);
-  if (head_dim == 64)
-    I2T_PDL_LAUNCH(attn_bwd_tc_kernel<64>, grid, dim3(ATC_THREADS), 0, st, (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v,
-                                                       (const __nv_bfloat16*)dout, lse, delta, dq_acc, (__nv_bfloat16*)dk,
-                                                       (__nv_bfloat16*)dv, (int)H, (int)Tq, (int)Tk, q_bs, q_rs, kv_bs, kv_rs, mode,
-                                                       (int)n_prompt, scale, drop);
-  else if (head_dim == 32)
-    I2T_PDL_LAUNCH(attn_bwd_tc_kernel<32>, grid, dim3(ATC_THREADS), 0, st, (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v,
-                                                       (const __nv_bfloat16*)dout, lse, delta, dq_acc, (__nv_bfloat16*)dk,
-                                                       (__nv_bfloat16*)dv, (int)H, (int)Tq, (int)Tk, q_bs, q_rs, kv_bs, kv_rs, mode,
-                                                       (int)n_prompt, scale, drop);
+  const size_t smem = (size_t)5 * ATC_BK * (head_dim + 8) * 2 + (size_t)ATC_BK * (ATC_BQ + 8) * 2 + 4 * ATC_BQ * sizeof(float);
+  static bool attr64 = false, attr32 = false;
+  if (head_dim == 64) {
+    if (!attr64) {
+      I2T_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr64 = true;
+    }
+    I2T_PDL_LAUNCH(attn_bwd_tc_kernel<64>, grid, dim3(ATC_THREADS), smem, st, (const __nv_bfloat16*)q, (const __nv_bfloat16*)k,
+                   (const __nv_bfloat16*)v, (const __nv_bfloat16*)dout, lse, delta, dq_acc, (__nv_bfloat16*)dk, (__nv_bfloat16*)dv,
+                   (int)H, (int)Tq, (int)Tk, q_bs, q_rs, kv_bs, kv_rs, mode, (int)n_prompt, scale, drop);
+  } else if (head_dim == 32) {
+    if (!attr32) {
+      I2T_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr32 = true;
+    }
+    I2T_PDL_LAUNCH(attn_bwd_tc_kernel<32>, grid, dim3(ATC_THREADS), smem, st, (const __nv_bfloat16*)q, (const __nv_bfloat16*)k,
+                   (const __nv_bfloat16*)v, (const __nv_bfloat16*)dout, lse, delta, dq_acc, (__nv_bfloat16*)dk, (__nv_bfloat16*)dv,
+                   (int)H, (int)Tq, (int)Tk, q_bs, q_rs, kv_bs, kv_rs, mode, (int)n_prompt, scale, drop);
+  }
   else
     return 0;
   g_launches.fetch_add(1, std::memory_order_relaxed);

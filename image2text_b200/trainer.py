@@ -97,6 +97,7 @@ def train_loop(model_wrapper: ModelTrainerWrapper, optimizer, train_iter: Iterat
     stop = False
     num_steps = 100 if num_steps is None else num_steps
     last = None
+    loss_sum, n_done = None, 0
     for step in range(num_steps):
         try:
             images, labels = next(train_iter)
@@ -121,11 +122,14 @@ def train_loop(model_wrapper: ModelTrainerWrapper, optimizer, train_iter: Iterat
             optimizer.step()
             optimizer.zero_grad(set_to_none=False)
         last = metrics
+        lm = metrics["train_loss_lm"].detach().float()
+        loss_sum = lm.clone() if loss_sum is None else loss_sum + lm      # on the device: no per-step synchronisation
+        n_done += 1
         if log_every and (step + 1) % log_every == 0:
             _print(f"Epoch: {epoch} step {step + 1}/{num_steps} " + " ".join(f"{k}={float(v):.4f}" for k, v in metrics.items()))
     if last is not None:
         _print(f"Epoch: {epoch} " + " ".join(f"{k}={float(v):.4f}" for k, v in last.items()))
-        state["last_train_loss"] = float(last["train_loss_lm"])
+        state["last_train_loss"] = float(loss_sum) / n_done               # mean over the epoch
     if reset_moco_after_k_epochs is not None and (epoch + 1) in reset_moco_after_k_epochs:
         model_wrapper.copy_momentum_params()
     if chckpt_fname is not None:
@@ -224,7 +228,8 @@ def main(args) -> dict:
         tokenizer = types.SimpleNamespace(eos_token_id=50256, bos_token_id=50256, vocab_size=spec_probe_vocab,
                                           mask_token_id=50257 if config.trainer.mask_fraction > 0 else None)
     model_wrapper = ModelTrainerWrapper(config.model, tokenizer, config.trainer, config.ignore_index, device=device,
-                                        compute_dtype=cd, spec_overrides=getattr(args, "spec_overrides", None))
+                                        compute_dtype=cd, spec_overrides=getattr(args, "spec_overrides", None),
+                                        seed=getattr(args, "init_seed", None))
     if args.chkpt_file is not None and os.path.exists(args.chkpt_file) and not args.fresh:
         model_wrapper.model.load_partial_checkpoint(args.chkpt_file, map_location=device)     # resume (models/utils.py:31-36)
         model_wrapper.copy_momentum_params()
@@ -241,7 +246,8 @@ def main(args) -> dict:
     spec = model_wrapper.model.spec
     size = spec["vit_image"]
     vocab = tokenizer.vocab_size
-    train_iter = synthetic_batches(config.batch_size, size, vocab, tokenizer.eos_token_id, seed=args.seed + 1000 * rank)
+    train_iter = synthetic_batches(config.batch_size, size, vocab, tokenizer.eos_token_id, seed=args.seed + 1000 * rank,
+                                   pool=args.pool)
     val_iter = synthetic_batches(config.batch_size, size, vocab, tokenizer.eos_token_id, seed=args.seed + 77 + 1000 * rank, pool=4)
     state, history, train_history = {}, [], []
     for epoch in range(args.epochs if args.epochs is not None else 10000):
@@ -277,6 +283,8 @@ def parse_args(argv=None):
     ap.add_argument("--eval_tokens", type=int, default=32)
     ap.add_argument("--log_every", type=int, default=0)
     ap.add_argument("--seed", type=int, default=1234)
+    ap.add_argument("--init_seed", type=int, default=None, help="seed of the random initialisation (default: unseeded)")
+    ap.add_argument("--pool", type=int, default=8, help="number of distinct synthetic training batches that are cycled")
     args = ap.parse_args(argv)
     args.tokenizer = None
     return args

@@ -16,17 +16,18 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _config(tmp_path, **top):
     cfg = yaml.safe_load(open(os.path.join(ROOT, "configs", "tiny.yaml")))
-    cfg.update(dict(batch_size=4, gradient_accumulation_steps=2, num_steps=12, num_val_steps=3), **top)
-    cfg["optimizers"] = [dict(lr=3e-3, betas=[0.9, 0.95], target_modules=["decoder*.transformer.h.*.cross_attn.*",
+    cfg.update(dict(batch_size=4, gradient_accumulation_steps=2, num_steps=24, num_val_steps=3), **top)
+    cfg["optimizers"] = [dict(lr=1e-2, betas=[0.9, 0.95], target_modules=["decoder*.transformer.h.*.cross_attn.*",
                                                                           "decoder*.transformer.h.*.ln_3.*"]),
-                         dict(lr=1e-3, betas=[0.9, 0.95], target_modules=["decoder*.transformer.wpe.*", "encoder*.lsh_emb.*"])]
+                         dict(lr=1e-2, betas=[0.9, 0.95], target_modules=["decoder*.transformer.wpe.*", "encoder*.lsh_emb.*"])]
     path = str(tmp_path / "cfg.yaml")
     yaml.safe_dump(cfg, open(path, "w"))
     return path
 
 
 def _args(cfg, chk, **kw):
-    a = T.parse_args(["--config_file", cfg, "--chkpt_file", chk, "--synthetic", "--epochs", "3", "--eval_tokens", "8"])
+    a = T.parse_args(["--config_file", cfg, "--chkpt_file", chk, "--synthetic", "--epochs", "3", "--eval_tokens", "8", "--pool", "2",
+                      "--init_seed", "0"])
     a.spec_overrides = dict(vit_layers=2, vit_image=32)
     a.tokenizer = types.SimpleNamespace(eos_token_id=612, bos_token_id=612, vocab_size=613, mask_token_id=None)
     for k, v in kw.items():
@@ -41,7 +42,7 @@ def test_launcher_trains_checkpoints_and_resumes(tmp_path, graph):
     out = T.main(_args(cfg, chk, graph=graph))
     losses, tl = out["val_losses"], out["train_losses"]
     assert len(losses) == 3 and all(l == l and l < 7.0 for l in losses)  # finite, around ln(613) = 6.42 for random captions
-    assert len(tl) == 3 and tl[-1] < tl[0]                               # the optimised subset fits the cycled synthetic pool
+    assert len(tl) == 3 and tl[-1] < tl[0] - 0.05                        # epoch-mean loss: the optimised subset fits the 2-batch pool
     model = out["wrapper"].model
     on_disk = torch.load(chk)
     named = dict(model.named_parameters())
@@ -49,6 +50,9 @@ def test_launcher_trains_checkpoints_and_resumes(tmp_path, graph):
     assert sorted(on_disk) == sorted(want) and len(want) > 10
     for k, v in on_disk.items():
         assert torch.equal(v, named[k].detach().cpu()), k
-    # resume: a new run starts from the checkpointed subset (models/utils.py:31-36 semantics), not from scratch
+    # resume: a new run (same init seed) starts from the checkpointed subset (models/utils.py:31-36 semantics), not from scratch
     out2 = T.main(_args(cfg, chk, epochs=1, eval_captions=0, graph=0))
-    assert out2["train_losses"][0] < tl[0]
+    assert out2["train_losses"][0] < tl[0] - 0.05
+    fresh = T.main(_args(cfg, chk, epochs=0, eval_captions=0, graph=0, fresh=True))["wrapper"].model
+    resumed = T.main(_args(cfg, chk + ".none", epochs=0, eval_captions=0, graph=0))["wrapper"].model     # no file: plain init
+    assert all(torch.equal(a, b) for a, b in zip(fresh.state_dict().values(), resumed.state_dict().values()))
