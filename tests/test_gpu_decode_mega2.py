@@ -77,35 +77,3 @@ def test_mega2_tiny_prefill_small_batch_and_topk():
     assert not torch.equal(sampled, eng.generate(images, prompt, 20, 0.8, 5, seed=8))
     check_picks(m, images, sampled, 4, top_k=5)
 
-
-def test_batched_pdl_chain_teacher_forced():
-    """More than 8 sequences in bf16: the decode step is the programmatic-dependent-launch chain (split-K tensor-core
-    projections, LayerNorm that zero-fills their output, attention with the fused K/V append, one-pass greedy arg-max).
-    Same teacher-forced criterion; a prompt of 3 tokens exercises the prefill steps; a second call reuses the graph."""
-    m = build("nano", torch.bfloat16)
-    B = 24
-    images = synth_images(3, 224, seed=77).cuda().repeat_interleave(8, dim=0)
-    g = torch.Generator().manual_seed(9)
-    prompt = torch.cat([torch.full((B, 1), 50256), torch.randint(0, 50256, (B, 2), generator=g)], dim=1).cuda()
-    eng = DecodeEngine(m, B)
-    assert eng.mode == "gemm"
-    got = eng.generate(images, prompt, 40, 1.0, 1, seed=0)
-    assert got.shape == (B, 43) and torch.equal(got[:, :3], prompt)
-    check_picks(m, images, got, 3, top_k=1)
-    again = eng.generate(images, prompt, 40, 1.0, 1, seed=0)          # graph replay of the same step
-    check_picks(m, images, again, 3, top_k=1)
-    sampled = eng.generate(images, prompt, 24, 0.8, 5, seed=3)
-    assert torch.equal(sampled, eng.generate(images, prompt, 24, 0.8, 5, seed=3))
-    check_picks(m, images, sampled, 3, top_k=5)
-
-
-def test_hf_gpt2_pdl_chain_teacher_forced():
-    """HF GPT-2 layout decoder in bf16 (Conv1D weights as MN-major split-K operands, soft-prompt rows pushed through the
-    cache by the same chain): every greedy pick is an un-banned (near-)arg-max of the model's own full forward."""
-    m = build("gpt2", torch.bfloat16)
-    images = synth_images(4, 224, seed=33).cuda()
-    prompt = torch.tensor([[50256, 11, 257]] * 4, dtype=torch.long, device="cuda")
-    got = m.generate(images, prompt, max_new_tokens=20, temperature=1.0, top_k=1)
-    assert got.shape == (4, 23) and torch.equal(got[:, :3], prompt)
-    check_picks(m, images, got, 3, top_k=1)
-    check_picks(m, images, m.generate(images, prompt, max_new_tokens=20, temperature=1.0, top_k=1), 3, top_k=1)   # graph replays
