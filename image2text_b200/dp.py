@@ -47,6 +47,7 @@ class GradientAllReducer:
             self.buckets.append(cur)
         self.bucket_of = {id(p): bi for bi, b in enumerate(self.buckets) for p in b}
         self.flat: List[Optional[torch.Tensor]] = [None] * len(self.buckets)
+        self._flat_views: List[Optional[List[torch.Tensor]]] = [None] * len(self.buckets)
         self.pending = [0] * len(self.buckets)
         self.work = [None] * len(self.buckets)
         self.launched = [False] * len(self.buckets)
@@ -54,6 +55,8 @@ class GradientAllReducer:
         self.side_stream = None
         self.hooks = [p.register_post_accumulate_grad_hook(self._hook) for p in self.params]
         self.only_with_grad = only_with_grad
+        self._capturing = False
+        self._events: List[Optional["torch.cuda.Event"]] = [None] * len(self.buckets)     # per bucket, recorded INSIDE a graph
         self._reset()
 
     # -- public ------------------------------------------------------------------------------------------------
@@ -74,6 +77,43 @@ class GradientAllReducer:
         finally:
             self.sync_enabled = old
 
+    # -- CUDA-graphed micro-steps -----------------------------------------------------------------------------------
+    # A replayed micro-step runs no Python, so the hooks cannot launch anything during its backward.  Instead, while the step
+    # is CAPTURED the hooks record one EXTERNAL event per bucket at the point where the bucket's last gradient has been
+    # accumulated (an event-record node of the graph).  After launching the replay of a synchronising micro-step the host
+    # queues, per bucket, "wait for that event -> pack -> all-reduce" on the side stream: the exchange of a bucket starts as
+    # soon as the running graph passes its record node, i.e. it overlaps the rest of the backward, as in the eager path.
+    @contextlib.contextmanager
+    def capturing(self):
+        """Wrap the capture of a micro-step (forward + backward) so that the hooks record the per-bucket events."""
+        self._capturing = True
+        self._events = [None] * len(self.buckets)
+        self._reset()
+        try:
+            yield
+        finally:
+            self._capturing = False
+            self._reset()
+
+    def has_graph_events(self) -> bool:
+        return any(e is not None for e in self._events)
+
+    def exchange_after_replay(self):
+        """Call right after `graph.replay()` of the LAST micro-step of an optimiser step (then `finish()` as usual)."""
+        if self.world == 1:
+            return
+        dev = self.buckets[0][0].device
+        if self.side_stream is None:
+            self.side_stream = torch.cuda.Stream(device=dev)
+        for bi, ev in enumerate(self._events):
+            if ev is None or self.launched[bi]:
+                continue
+            self.side_stream.wait_event(ev)
+            with torch.cuda.stream(self.side_stream):
+                flat = self._pack(bi)
+                self.work[bi] = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            self.launched[bi] = True
+
     def finish(self):
         """Call after backward of the last micro-step, before optimizer.step()."""
         if self.world == 1:
@@ -93,13 +133,11 @@ class GradientAllReducer:
             for bi, bucket in enumerate(self.buckets):
                 if not self.launched[bi]:
                     continue
-                flat, off = self.flat[bi], 0
-                for p in bucket:
-                    n = p.numel()
-                    if p.grad is not None:
-                        p.grad.copy_(flat[off:off + n].view_as(p.grad))
-                        p.grad.mul_(inv)
-                    off += n
+                flat, views = self._views(bi)
+                flat.mul_(inv)                                      # mean over ranks: one launch per bucket
+                have = [(p.grad, v) for v, p in zip(views, bucket) if p.grad is not None]
+                if have:
+                    torch._foreach_copy_([g for g, _ in have], [v for _, v in have])
         self._reset()
 
     def remove(self):
@@ -114,29 +152,53 @@ class GradientAllReducer:
             self.launched[bi] = False
 
     def _hook(self, p: torch.nn.Parameter):
-        if not self.sync_enabled or self.world == 1:
+        if self.world == 1:
+            return
+        if self._capturing:
+            bi = self.bucket_of[id(p)]
+            self.pending[bi] -= 1
+            if self.pending[bi] == 0:
+                ev = torch.cuda.Event(external=True)
+                ev.record()                      # an event-record node of the graph being captured
+                self._events[bi] = ev
+            return
+        if not self.sync_enabled:
             return
         bi = self.bucket_of[id(p)]
         self.pending[bi] -= 1
         if self.pending[bi] == 0:
             self._launch(bi)
 
+    def _views(self, bi: int):
+        """Flat fp32 buffer of bucket `bi` and one view per parameter (created once)."""
+        if self.flat[bi] is None:
+            bucket = self.buckets[bi]
+            n = sum(p.numel() for p in bucket)
+            flat = torch.zeros(n, device=bucket[0].device, dtype=torch.float32)
+            views, off = [], 0
+            for p in bucket:
+                views.append(flat[off:off + p.numel()].view(p.shape))
+                off += p.numel()
+            self.flat[bi] = flat
+            self._flat_views[bi] = views
+        return self.flat[bi], self._flat_views[bi]
+
+    def _pack(self, bi: int) -> torch.Tensor:
+        """Gradients of bucket `bi` -> its flat fp32 buffer (on the current stream): one multi-tensor copy, not one launch
+        per parameter (a model that trains every weight has hundreds of them; the launches were most of the exposed time)."""
+        flat, views = self._views(bi)
+        with torch.no_grad():
+            have = [(v, p.grad) for v, p in zip(views, self.buckets[bi]) if p.grad is not None]
+            if len(have) != len(views):
+                flat.zero_()
+            if have:
+                torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
+        return flat
+
     def _launch(self, bi: int):
         bucket = self.buckets[bi]
         dev = bucket[0].device
-        n = sum(p.numel() for p in bucket)
-        if self.flat[bi] is None:
-            self.flat[bi] = torch.zeros(n, device=dev, dtype=torch.float32)
-        flat = self.flat[bi]
-        with torch.no_grad():
-            off = 0
-            for p in bucket:
-                m = p.numel()
-                if p.grad is not None:
-                    flat[off:off + m].copy_(p.grad.reshape(-1))
-                else:
-                    flat[off:off + m].zero_()
-                off += m
+        flat = self._pack(bi)
         if dev.type == "cuda":
             if self.side_stream is None:
                 self.side_stream = torch.cuda.Stream(device=dev)

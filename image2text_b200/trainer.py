@@ -111,7 +111,7 @@ def train_loop(model_wrapper: ModelTrainerWrapper, optimizer, train_iter: Iterat
         ctx = reducer.no_sync() if (reducer is not None and (not sync or graph)) else torch.enable_grad()
         with ctx:
             if graph:
-                loss = model_wrapper.train_step_graphed(images, labels, 1.0 / accum)
+                loss = model_wrapper.train_step_graphed(images, labels, 1.0 / accum, reducer=reducer, sync=sync)
                 metrics = {"train_loss_lm": loss}
             else:
                 loss, metrics = model_wrapper.train_step(images, labels)

@@ -76,7 +76,7 @@ class ModelTrainerWrapper(nn.Module):
     def val_step(self, images, labels):
         return self._step(images, labels, False)
 
-    def train_step_graphed(self, images, labels, loss_scale: float = 1.0):
+    def train_step_graphed(self, images, labels, loss_scale: float = 1.0, reducer=None, sync: bool = False):
         """train_step + backward of (loss * loss_scale) as ONE CUDA-graph replay (no counterpart in the reference, whose
         loop is `loss, _ = train_step(...); accelerator.backward(loss)`, training/utils.py:76-88).  A micro-step is ~1500
         kernel launches; issued one by one from Python they leave the GPU idle half of the time, so the fixed-shape
@@ -84,7 +84,10 @@ class ModelTrainerWrapper(nn.Module):
         up kernel attributes / TMA descriptors) and replayed from static input buffers.  Gradients ACCUMULATE into the
         existing .grad tensors exactly like the eager path (keep `zero_grad(set_to_none=False)`: the graph holds their
         addresses; parameters that received no gradient in the two eager calls are unused and stay untouched).  Returns the detached
-        loss (a static tensor that the next replay overwrites)."""
+        loss (a static tensor that the next replay overwrites).
+        Data parallel: pass the `GradientAllReducer` as `reducer` (always) and `sync=True` on the last micro-step of an
+        optimiser step: the captured graph carries one external event per gradient bucket, and the bucketed all-reduce of a
+        synchronising replay is queued behind those events -- it overlaps the rest of the backward (dp.py)."""
         key = (tuple(images.shape), images.dtype, tuple(labels.shape), float(loss_scale))
         st = getattr(self, "_graph_state", None)
         if st is None or st["key"] != key:
@@ -100,10 +103,12 @@ class ModelTrainerWrapper(nn.Module):
             g = torch.cuda.CUDAGraph()
             try:
                 self._grad_prescale = float(loss_scale)       # folded into dlogits by the loss kernel (no rescale pass)
-                with torch.cuda.graph(g):
-                    loss, _ = self._step(st["images"], st["labels"], True)
-                    (loss * loss_scale).backward()
-                    st["loss"] = loss.detach()
+                import contextlib
+                with (reducer.capturing() if reducer is not None else contextlib.nullcontext()):
+                    with torch.cuda.graph(g):
+                        loss, _ = self._step(st["images"], st["labels"], True)
+                        (loss * loss_scale).backward()
+                        st["loss"] = loss.detach()
             except Exception:
                 st["failed"] = True
                 torch.cuda.synchronize()
@@ -114,6 +119,8 @@ class ModelTrainerWrapper(nn.Module):
         st["images"].copy_(images)
         st["labels"].copy_(labels)
         st["graph"].replay()
+        if reducer is not None and sync:
+            reducer.exchange_after_replay()
         return st["loss"]
 
     def compute_lm_loss(self, lm_logits, labels, lm_logits_moco=None):

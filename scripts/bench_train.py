@@ -101,7 +101,7 @@ def main():
             ctx = red.no_sync() if (not last or args.graph) else torch.enable_grad()
             with ctx:
                 if args.graph:
-                    loss = w.train_step_graphed(images, labels, 1.0 / accum)
+                    loss = w.train_step_graphed(images, labels, 1.0 / accum, reducer=red, sync=last)
                 else:
                     loss, _ = w.train_step(images, labels)
                     (loss / accum).backward()

@@ -57,5 +57,36 @@ flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
     print(f"DP parity world={world}: buckets={nb} tensors={len(want)} worst rel err={worst:.2e} -> {'OK' if flag.item() == 1 else 'FAIL'}")
+
+
+def grads_graphed(shard_rank, micro=5):
+    """CUDA-graphed micro-steps (calls 1-2 eager, 3 captures, 3-5 replay): the exchange of the last replay is queued behind
+    the per-bucket events recorded inside the graph (GradientAllReducer.exchange_after_replay)."""
+    w = ModelTrainerWrapper(tc.model, tok, TrainerWrapperConfig(), -100, device=f"cuda:{local}", spec_overrides=over)
+    w.model.load_state_dict(synth_state_dict(w.model.spec, seed=0))
+    w.train()
+    red = GradientAllReducer(w.model.parameters(), bucket_mb=0.25)
+    images = synth_images(3, 32, seed=100 + shard_rank).cuda()
+    labels = synth_labels(3, 20, 613, seed=200 + shard_rank, min_len=3, max_len=14, eos=612).cuda()
+    for i in range(micro):
+        with red.no_sync():
+            w.train_step_graphed(images, labels, 1.0, reducer=red, sync=i == micro - 1)
+    n_ev = sum(e is not None for e in red._events)
+    red.finish()
+    red.remove()
+    return {n: p.grad.clone() for n, p in w.model.named_parameters() if p.grad is not None}, n_ev
+
+
+got_g, n_ev = grads_graphed(rank)
+worst_g = 0.0
+for k in want:
+    ref = 5.0 * want[k] / world
+    worst_g = max(worst_g, float((got_g[k] - ref).abs().max() / ref.abs().max().clamp_min(1e-20)))
+ok_g = worst_g < 1e-5 and set(got_g) == set(want) and n_ev > 0
+flag = torch.tensor([1.0 if ok_g else 0.0], device="cuda")
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print(f"DP parity (graphed micro-steps, exchange behind in-graph events) world={world}: bucket events={n_ev} "
+          f"worst rel err={worst_g:.2e} -> {'OK' if flag.item() == 1 else 'FAIL'}")
 dist.destroy_process_group()
 sys.exit(0 if flag.item() == 1 else 1)
