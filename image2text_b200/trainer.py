@@ -220,12 +220,10 @@ def main(args) -> dict:
     if config.precision not in ("no", "bf16"):
         raise NotImplementedError(f"precision {config.precision!r}: the B200 path computes in fp32 ('no') or bf16")
     cd = torch.bfloat16 if config.precision == "bf16" else torch.float32
-    spec_probe_vocab = None
     tokenizer = args.tokenizer
     if tokenizer is None:
         # the hub tokenizer is unreachable offline: GPT-2's special ids (reference trainer.py:116-126 adds missing ones)
-        spec_probe_vocab = 50257
-        tokenizer = types.SimpleNamespace(eos_token_id=50256, bos_token_id=50256, vocab_size=spec_probe_vocab,
+        tokenizer = types.SimpleNamespace(eos_token_id=50256, bos_token_id=50256, vocab_size=50257,
                                           mask_token_id=50257 if config.trainer.mask_fraction > 0 else None)
     model_wrapper = ModelTrainerWrapper(config.model, tokenizer, config.trainer, config.ignore_index, device=device,
                                         compute_dtype=cd, spec_overrides=getattr(args, "spec_overrides", None),

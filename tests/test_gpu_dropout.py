@@ -9,7 +9,6 @@ be compared with it; what is pinned instead:
 All calls go through the C ABI."""
 import types
 
-import numpy as np
 import pytest
 import torch
 
