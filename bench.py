@@ -98,6 +98,81 @@ def algorithmic_bytes_per_step(spec, batch, dtype_bytes, mean_len, greedy_fused=
     return w * dtype_bytes + small + kv_read + kv_write + xkv + logits, w * dtype_bytes
 
 
+def train_secondary(rank, world, local, batches=(8, 64), steps=3, warmup=3):
+    """The other half of BASELINE.json's metric (train img/s), measured live next to the headline: nano.yaml, bf16, the YAML's
+    dropout 0.1 and two AdamW parameter groups, gradient_accumulation_steps = 4, CUDA-graphed micro-steps, data parallel over
+    the ranks of this run (bucketed all-reduce behind in-graph events).  One optimiser step = 4 micro-batches per GPU; W >= 3
+    warm-up steps, CUDA events, max over ranks.  Returned as an extra object of the JSON line; it never replaces `value`."""
+    import fnmatch
+    import types
+    from image2text_b200 import load_training_config
+    from image2text_b200.config_schema import TrainerWrapperConfig
+    from image2text_b200.dp import GradientAllReducer
+    from image2text_b200.model_spec import synth_state_dict
+    from image2text_b200.optimizer import AdamW
+    from image2text_b200.synthetic import synth_images, synth_labels
+    from image2text_b200.wrapper import ModelTrainerWrapper
+    tc = load_training_config(os.path.join(ROOT, "configs", "nano.yaml"))
+    accum = tc.gradient_accumulation_steps
+    tok = types.SimpleNamespace(eos_token_id=50256, bos_token_id=50256, mask_token_id=None, vocab_size=50257)
+    out = {"metric": "train img/s (nano.yaml, bf16, dropout 0.1, AdamW on the YAML's parameter groups, accumulation %d, "
+                     "CUDA-graphed micro-steps, synthetic 224x224 images + random captions)" % accum, "unit": "img/s",
+           "gflop_per_img": 243.4}
+    for bs in batches:
+        w = ModelTrainerWrapper(tc.model, tok, TrainerWrapperConfig(), -100, device=f"cuda:{local}", compute_dtype=torch.bfloat16)
+        w.model.load_state_dict(synth_state_dict(w.model.spec, seed=0))
+        w.model.set_dropout_seed(1234 + rank)
+        w.train()
+        groups, chosen = [], set()
+        for oc in tc.optimizers:          # reference trainer.py:145-172
+            ps = [p for n, p in w.named_parameters() if n.split(".", 1)[0] != "model_m" and
+                  (oc.target_modules is None or any(fnmatch.fnmatch(n.split(".", 1)[-1], pat) for pat in oc.target_modules))]
+            groups.append(dict(params=ps, lr=oc.lr, weight_decay=oc.weight_decay, betas=oc.betas))
+            chosen.update(id(p) for p in ps)
+        for _, p in w.model.named_parameters():
+            if id(p) not in chosen:
+                p.requires_grad_(False)   # never stepped by the reference either (SURVEY Q5): skip their weight gradients
+        opt = AdamW(groups)
+        red = GradientAllReducer([p for g in groups for p in g["params"]])
+        red.broadcast_parameters(w.model)
+        images = synth_images(bs, 224, seed=1234 + rank).cuda()
+        labels = synth_labels(bs, 256, seed=1234 + rank).cuda()
+
+        def one_step():
+            for micro in range(accum):
+                with red.no_sync():
+                    loss = w.train_step_graphed(images, labels, 1.0 / accum, reducer=red, sync=micro == accum - 1)
+            red.finish()
+            opt.step()
+            opt.zero_grad(set_to_none=False)
+            return loss
+
+        for _ in range(max(warmup, 3)):
+            one_step()
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss = one_step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        imgs = bs * accum * steps * world
+        out[f"batch_{bs}_per_gpu"] = {"value": round(imgs / (ms / 1e3), 1), "ms_per_step": round(ms / steps, 2),
+                                      "model_tflops": round(imgs * 243.4 / (ms / 1e3) / 1e3, 1), "loss": round(float(loss), 4)}
+        red.remove()
+        del w, opt, red, images, labels
+        torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args):
     from image2text_b200 import VisionEncoderDecoder, load_training_config
     from image2text_b200._lib import call, launch_count
@@ -254,6 +329,14 @@ def run_ours(args):
         "roofline": roofline,
         "clocks": sampler.summary(),
     }
+    if not args.no_train:
+        # every rank takes part (data parallel); a failure here must not cost the headline line
+        del model
+        torch.cuda.empty_cache()
+        try:
+            line["train"] = train_secondary(rank, world, local)
+        except Exception as e:  # noqa: BLE001
+            line["train"] = {"error": repr(e)[:300]}
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(sample_tokens=NEW_TOKENS)
@@ -322,6 +405,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default=os.environ.get("I2T_BENCH_DTYPE", "bf16"), choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the secondary train img/s measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
