@@ -352,6 +352,11 @@ def cpu_generate_tok_s(new_tokens: int, steps: int = 1, warmup: int = 0):
     from image2text_b200.model_spec import spec_from_config, synth_state_dict
     from image2text_b200.synthetic import synth_images
     from oracle import i2t_oracle as O
+    # all host cores: torchrun exports OMP_NUM_THREADS=1 to its workers, which would time a single-threaded CPU
+    try:
+        torch.set_num_threads(max(torch.get_num_threads(), len(os.sched_getaffinity(0))))
+    except (AttributeError, OSError):
+        torch.set_num_threads(max(torch.get_num_threads(), os.cpu_count() or 1))
     tc = load_training_config(os.path.join(ROOT, "configs", "nano.yaml"))
     spec = spec_from_config(tc.model)
     sd = synth_state_dict(spec, seed=0)
