@@ -189,7 +189,8 @@ int i2t_dec_attn_append(const float* q, int64_t q_ld, void* kcache, void* vcache
  * projection that consumes this LayerNorm (call i2t_gemm on it with accumulate = 1). */
 int i2t_dec_layernorm(const float* x, const float* gamma, const float* beta, void* y, int64_t rows, int64_t cols, float eps,
                       int y_dtype, float* zero_ptr, int64_t zero_count, void* stream);
-/* h = act(z), fp32 in, h_dtype out; PDL-aware variant of i2t_act_fwd for the batched decode step. */
+/* h = act(z), fp32 in, h_dtype out (nn.GELU(approximate='tanh'), reference models/layers.py:477,483, applied to the one-token
+ * MLP pre-activation); PDL-aware variant of i2t_act_fwd for the batched decode step. */
 int i2t_dec_act(const float* z, void* h, int64_t n, int act, int h_dtype, void* stream);
 
 /* One whole decode step (every layer, LM head, sampler) as ONE cooperative launch: the same arithmetic as the
