@@ -127,12 +127,7 @@ __device__ __forceinline__ int sample_row_smem(float* __restrict__ sv, SampleScr
       uint32_t* hist = S.ghist[w & (SAMP_HGROUPS - 1)];
       for (int i = t; i < V; i += nthreads) {
         const uint32_t key = float_key(sv[i]);
-        // warp-aggregated histogram: logits share their top bits, so nearly every lane hits the same bin and a plain
-        // shared-memory atomic would serialise 32 ways (it dominated the sampler: ~26 us of a 32 us row)
-        const bool in = (key & mask) == prefix;
-        const uint32_t bin = in ? ((key >> shift) & 255u) : 256u;
-        const unsigned peers = __match_any_sync(__activemask(), bin);
-        if (in && lane == __ffs(peers) - 1) atomicAdd(&hist[bin], (uint32_t)__popc(peers));
+        if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
       }
       samp_sync(nthreads);
       if (t < 256) {
