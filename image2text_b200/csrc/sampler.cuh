@@ -137,15 +137,34 @@ __device__ __forceinline__ int sample_row_smem(float* __restrict__ sv, SampleScr
         S.ghist[0][t] = tot;
       }
       samp_sync(nthreads);
-      if (t == 0) {
-        uint32_t left = S.kleft;
-        int bin = 255;
-        for (; bin > 0; --bin) {
-          if (S.ghist[0][bin] >= left) break;
-          left -= S.ghist[0][bin];
+      if (w == 0) {
+        // which of the 256 bins holds the kleft-th largest key: warp 0 does the top-down scan in parallel (lane l owns bins
+        // 8l .. 8l+7, a shuffle suffix-sum gives the count above them); a serial scan by one thread cost ~4 us per pass
+        uint32_t hb[8], own = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          hb[i] = S.ghist[0][8 * lane + i];
+          own += hb[i];
         }
-        S.kleft = left;
-        S.prefix = prefix | ((uint32_t)bin << shift);
+        uint32_t suf = own;                                   // keys in this lane's bins and every higher bin
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t up = __shfl_down_sync(0xffffffffu, suf, o);
+          if (lane + o < 32) suf += up;
+        }
+        const uint32_t above = suf - own, left = S.kleft;
+        const bool mine = (above < left && left <= suf) || (lane == 0 && left > suf);      // second term: cannot happen (k <= count)
+        __syncwarp();
+        if (mine) {
+          uint32_t l2 = left - above;
+          int bsel = 7;
+          for (; bsel > 0; --bsel) {
+            if (hb[bsel] >= l2) break;
+            l2 -= hb[bsel];
+          }
+          S.kleft = l2;
+          S.prefix = prefix | ((uint32_t)(8 * lane + bsel) << shift);
+        }
       }
       samp_sync(nthreads);
     }
