@@ -128,6 +128,7 @@ class VisionEncoderDecoder(nn.Module):
     # ------------------------------------------------------------------ parameters ----------------------------
     def __setstate__(self, state):
         super().__setstate__(state)            # copy.deepcopy / pickle: re-point the sub-objects at THIS model
+        self.__dict__["_tensor_cache"] = None
         self.encoder._bind(self)
         self.decoder._bind(self)
 
@@ -139,9 +140,27 @@ class VisionEncoderDecoder(nn.Module):
         return self
 
     def _tensors(self) -> Dict[str, torch.Tensor]:
-        d = dict(self.named_parameters(remove_duplicate=False))
-        d.update(dict(self.named_buffers()))
-        return d
+        """name -> Parameter / buffer.  Memoised: walking the 432-tensor module tree costs ~0.3 ms of host time, which every
+        forward() and generate() call used to pay (twice) while the GPU sat idle.  The Parameter objects are stable under
+        optimiser steps, load_state_dict (in-place copies) and .to(); the cache is dropped wherever they could be replaced."""
+        c = self.__dict__.get("_tensor_cache")
+        if c is None:
+            c = dict(self.named_parameters(remove_duplicate=False))
+            c.update(dict(self.named_buffers()))
+            self.__dict__["_tensor_cache"] = c
+        return c
+
+    def _apply(self, fn, *args, **kwargs):
+        self.__dict__["_tensor_cache"] = None
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self.__dict__["_tensor_cache"] = None
+        return super().load_state_dict(*args, **kwargs)
+
+    def register_parameter(self, name, param):
+        self.__dict__["_tensor_cache"] = None
+        return super().register_parameter(name, param)
 
     def _lsh_tables(self, pre: str):
         """Device pointer tables for the LSH tail kernel (slot-major, then resolution)."""
