@@ -242,20 +242,24 @@ def run_ours(args):
     ms_e2e = timed(step_e2e, args.steps)
     reps = 40
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if eng.mode == "mega2":
-        # the decode kernel alone: ONE launch = the whole 64-token loop (cache length grows 1..64 inside it)
+    if eng.mode in ("mega2", "mega3"):
+        # the decode kernel alone: ONE launch = the whole 64-token loop (cache length grows 1..64 inside it); mega3: the
+        # poison fills of the exchange buffers / new cache rows (~25 MB of memset per launch) are inside the timed region
         reps = 10
         eng.generate(images, prompt, NEW_TOKENS, 1.0, 1, seed=0)
         torch.cuda.synchronize()
         e0.record()
         for _ in range(reps):
             eng.pos.zero_()
-            eng._mega2_run(0, NEW_TOKENS, 1.0, 1)
+            if eng.mode == "mega3":
+                eng._mega3_run(0, NEW_TOKENS, 1.0, 1, 1)
+            else:
+                eng._mega2_run(0, NEW_TOKENS, 1.0, 1)
         e1.record()
         torch.cuda.synchronize()
         step_ms = e0.elapsed_time(e1) / (reps * NEW_TOKENS)
         mean_len = (NEW_TOKENS + 1) / 2
-        kernel_desc = "decode_mega2_kernel: one cooperative launch = %d decode steps; per-step figures" % NEW_TOKENS
+        kernel_desc = "decode_%s_kernel: one cooperative launch = %d decode steps; per-step figures" % (eng.mode, NEW_TOKENS)
     else:
         # decode step alone: replay the captured step graph (positions keep advancing inside the cache window)
         g = next(iter(eng.graphs.values()))
@@ -291,14 +295,21 @@ def run_ours(args):
     value = tokens * args.steps / (ms / 1e3)
     e2e = tokens * args.steps / (ms_e2e / 1e3)
     esz = 2 if cd == torch.bfloat16 else 4
-    step_bytes, weight_bytes = algorithmic_bytes_per_step(spec, CAPTIONS, esz, mean_len=mean_len, greedy_fused=eng.mode == "mega2")
+    step_bytes, weight_bytes = algorithmic_bytes_per_step(spec, CAPTIONS, esz, mean_len=mean_len, greedy_fused=eng.mode in ("mega2", "mega3"))
     peak, peak_src = read_peaks()
     achieved = step_bytes / (step_ms / 1e3) / 1e9
     lm_bytes = V * C * esz + CAPTIONS * V * 4
     lm = {"name": "dec_linear_kernel (LM head 50257x768 as a stand-alone launch; not on the mega2 path)",
           "algorithmic_bytes": int(lm_bytes), "us": round(lm_ms * 1e3, 2), "achieved": round(lm_bytes / (lm_ms / 1e3) / 1e9, 1),
           "frac": round(lm_bytes / (lm_ms / 1e3) / 1e9 / peak, 4)}
-    if eng.mode == "mega2":
+    if eng.mode == "mega3":
+        roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                    "traffic": None, "peak_source": peak_src, "kernel": kernel_desc,
+                    "algorithmic_bytes_per_launch": int(step_bytes * NEW_TOKENS), "us_per_launch": round(step_ms * 1e3 * NEW_TOKENS, 1),
+                    "algorithmic_bytes_per_step": int(step_bytes), "us_per_step": round(step_ms * 1e3, 2),
+                    "note": "dataflow megakernel: no grid barriers, poison-tagged exchange buffers, packed per-CTA weight streams "
+                            "prefetched through a shared-memory ring (DESIGN.md section 8)"}
+    elif eng.mode == "mega2":
         # the dominant (only) decode kernel: one launch = NEW_TOKENS steps.  traffic: dram__bytes_read.sum + dram__bytes_write.sum
         # of this kernel for this workload from the committed ncu --set full capture (profiles/r01_ncu_full_decode_mega2_bf16_raw.csv)
         roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),

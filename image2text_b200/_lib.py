@@ -50,6 +50,12 @@ SIGNATURES = {
     "i2t_decode_mega": (c_int, [P, P, P, L, L, L, L, L, L, L, I, P, L, P, P, P, P, P, P, F, L, P, L, P, P, L, P, P]),
     "i2t_decode_mega2_max_keys": (c_int, []),
     "i2t_decode_mega2": (c_int, [P, P, P, L, P, L, L, L, L, L, L, L, L, L, L, P, L, P, P, P, P, P, P, P, F, L, P, L, P, L, L, P, P]),
+    "i2t_decode_mega3_max_keys": (c_int, []),
+    "i2t_decode_mega3_grid": (c_int, []),
+    "i2t_decode_mega3_tile_bytes": (c_int64, [L]),
+    "i2t_decode_mega3_pack": (c_int, [P, L, L, P, P, P]),
+    "i2t_decode_mega3": (c_int, [P, P, P, L, L, L, L, L, L, L, L, L, L, P, L, P, P, L, P, P, P, P, P, L, F, L, P, L, P, L, L,
+                                 P, L, P]),
     "i2t_act_fwd": (c_int, [P, P, L, I, I, I, P]),
     "i2t_act_bwd": (c_int, [P, P, P, L, I, I, I, P]),
     "i2t_embed_bwd": (c_int, [P, P, P, L, L, L, L, L, P]),
@@ -67,6 +73,7 @@ SIGNATURES = {
     "i2t_adamw_multi": (c_int, [P, P, P, P, L, D, D, D, D, D, L, D, P]),
     "i2t_snradam_multi": (c_int, [P, P, P, P, L, D, D, D, D, D, L, D, P]),
     "i2t_ema_multi": (c_int, [P, P, P, P, L, D, P]),
+    "i2t_cast_bf16_multi": (c_int, [P, P, P, P, L, P]),
 }
 
 _lib = None

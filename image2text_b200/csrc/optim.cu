@@ -4,7 +4,8 @@
 // update (reference training/wrapper.py:53-60) reads p_m,p and writes p_m (12 B per parameter, in place instead of the
 // reference's allocate-and-rebind).
 //
-// Layout: `table` is a device array of n_tensors x 4 pointers [p, g, m, v] (EMA: [p_m, p, -, -]); work is cut into
+// Layout: `table` is a device array of n_tensors x 4 pointers [p, g, m, v] (EMA: [p_m, p, bf16 shadow of p_m or 0, -];
+// cast: [src fp32, dst bf16, -, -]); work is cut into
 // fixed-size chunks, chunk c covers elements [chunk_off[c], chunk_off[c] + chunk_len[c]) of tensor chunk_tensor[c].
 #include "common.cuh"
 
@@ -113,7 +114,10 @@ ema_multi_kernel(const int64_t* __restrict__ table, const int32_t* __restrict__ 
   chunk_range(chunk_tensor, chunk_off, chunk_len, ti, off, len);
   float* pm = reinterpret_cast<float*>(table[ti * 4 + 0]) + off;
   const float* p = reinterpret_cast<const float*>(table[ti * 4 + 1]) + off;
-  const bool vec = ((reinterpret_cast<uintptr_t>(pm) | reinterpret_cast<uintptr_t>(p)) & 15u) == 0;
+  // optional compute-dtype shadow of the teacher weight, refreshed in the same pass (bf16 forward passes read it)
+  __nv_bfloat16* sh = table[ti * 4 + 2] != 0 ? reinterpret_cast<__nv_bfloat16*>(table[ti * 4 + 2]) + off : nullptr;
+  const bool vec = ((reinterpret_cast<uintptr_t>(pm) | reinterpret_cast<uintptr_t>(p)) & 15u) == 0 &&
+                   (reinterpret_cast<uintptr_t>(sh) & 7u) == 0;
   if (vec) {
     const int n4 = len >> 2;
     for (int i = threadIdx.x; i < n4; i += OPT_THREADS) {
@@ -122,10 +126,36 @@ ema_multi_kernel(const int64_t* __restrict__ table, const int32_t* __restrict__ 
       A.x = A.x * momentum + Bv.x * om; A.y = A.y * momentum + Bv.y * om;
       A.z = A.z * momentum + Bv.z * om; A.w = A.w * momentum + Bv.w * om;
       store4(pm + i * 4, A);
+      if (sh != nullptr) store4(sh + i * 4, A);
     }
-    for (int i = (n4 << 2) + threadIdx.x; i < len; i += OPT_THREADS) pm[i] = pm[i] * momentum + p[i] * om;
+    for (int i = (n4 << 2) + threadIdx.x; i < len; i += OPT_THREADS) {
+      pm[i] = pm[i] * momentum + p[i] * om;
+      if (sh != nullptr) sh[i] = __float2bfloat16_rn(pm[i]);
+    }
   } else {
-    for (int i = threadIdx.x; i < len; i += OPT_THREADS) pm[i] = pm[i] * momentum + p[i] * om;
+    for (int i = threadIdx.x; i < len; i += OPT_THREADS) {
+      pm[i] = pm[i] * momentum + p[i] * om;
+      if (sh != nullptr) sh[i] = __float2bfloat16_rn(pm[i]);
+    }
+  }
+}
+
+// dst (bf16) = src (fp32) over a tensor list: refreshes the compute-dtype shadows of the parameters an optimiser step wrote
+__global__ void __launch_bounds__(OPT_THREADS)
+cast_bf16_multi_kernel(const int64_t* __restrict__ table, const int32_t* __restrict__ chunk_tensor,
+                       const int64_t* __restrict__ chunk_off, const int32_t* __restrict__ chunk_len) {
+  int ti, len;
+  int64_t off;
+  chunk_range(chunk_tensor, chunk_off, chunk_len, ti, off, len);
+  const float* src = reinterpret_cast<const float*>(table[ti * 4 + 0]) + off;
+  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(table[ti * 4 + 1]) + off;
+  const bool vec = (reinterpret_cast<uintptr_t>(src) & 15u) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7u) == 0;
+  if (vec) {
+    const int n4 = len >> 2;
+    for (int i = threadIdx.x; i < n4; i += OPT_THREADS) store4(dst + i * 4, load4(src + i * 4));
+    for (int i = (n4 << 2) + threadIdx.x; i < len; i += OPT_THREADS) dst[i] = __float2bfloat16_rn(src[i]);
+  } else {
+    for (int i = threadIdx.x; i < len; i += OPT_THREADS) dst[i] = __float2bfloat16_rn(src[i]);
   }
 }
 
@@ -178,6 +208,15 @@ extern "C" int i2t_ema_multi(const int64_t* table, const int32_t* chunk_tensor, 
   if (n_chunks == 0) return I2T_OK;
   ema_multi_kernel<<<(unsigned)n_chunks, OPT_THREADS, 0, (cudaStream_t)stream>>>(table, chunk_tensor, chunk_off, chunk_len,
                                                                                (float)momentum, (float)(1.0 - momentum));
+  I2T_LAUNCHED();
+  return I2T_OK;
+}
+
+extern "C" int i2t_cast_bf16_multi(const int64_t* table, const int32_t* chunk_tensor, const int64_t* chunk_off,
+                                   const int32_t* chunk_len, int64_t n_chunks, void* stream) {
+  I2T_REQUIRE(table && chunk_tensor && chunk_off && chunk_len && n_chunks >= 0, "cast_bf16_multi: bad arguments");
+  if (n_chunks == 0) return I2T_OK;
+  cast_bf16_multi_kernel<<<(unsigned)n_chunks, OPT_THREADS, 0, (cudaStream_t)stream>>>(table, chunk_tensor, chunk_off, chunk_len);
   I2T_LAUNCHED();
   return I2T_OK;
 }

@@ -6,8 +6,11 @@ What this engine does per new token: every decoder weight is touched exactly onc
 K/V rows are appended in place, the sampler runs on the device and advances the position counter -- one CUDA-graph
 replay per token, no host round trip.  Two executions of the same arithmetic:
 
-  mode "mega2"   (default for bf16, B <= 8): ONE cooperative launch per generate() call -- the token loop, every layer,
-                 the LM head with the n-gram ban + arg-max fused (greedy) or the sampler (csrc/decode_mega2.cu);
+  mode "mega3"   (default for bf16, B <= 8): ONE cooperative launch per generate() call and NO grid barriers: activations
+                 cross CTAs through poison-tagged exchange buffers (a consumer polls the data itself), the weights are
+                 re-packed into one contiguous stream per CTA and prefetched by a producer warp through a shared-memory
+                 ring, several stages ahead (csrc/decode_mega3.cu);
+  mode "mega2"   : ONE cooperative launch per generate() call, 81 grid barriers per step (csrc/decode_mega2.cu; round 1);
   mode "mega"    : ONE cooperative launch per step (csrc/decode_mega.cu), fp32 or bf16;
   mode "kernels" : ~81 launches per step (csrc/decode.cu + sampler.cu), up to 16 sequences / wider models and as the
                    cross-check of the megakernel;
@@ -27,6 +30,7 @@ import torch
 
 from . import ops
 from ._lib import I2TError, call, launch_count
+from ._lib import lib as _lib
 from .model_spec import layer_has_cross_attn
 from .ops import ptr, stream
 
@@ -45,15 +49,16 @@ class DecodeEngine:
         self.n_prompt = spec["n_cls"] if spec["use_soft_prompting"] else 0
         self.Tmax = spec["block_size"] - self.n_prompt
         # measured on B200 (profiles/r01_*): the megakernel wins in bf16, the separate kernels win in fp32
-        mode = mode or os.environ.get("I2T_DECODE", "mega2" if self.cd == torch.bfloat16 else "kernels")
+        mode = mode or os.environ.get("I2T_DECODE", "mega3" if self.cd == torch.bfloat16 else "kernels")
         if batch > 8 or max(C, self.F) > 3072 or C > 1024:
             mode = "kernels"
         # bf16, more sequences than the megakernel's 8: split-K tensor-core GEMMs over the batch beat the per-stage FMA
         # kernels from 9 sequences on (16 sequences: 24.4k vs 11.4k tok/s); fp32 keeps the exact-FMA kernels up to 16
         if (batch >= int(os.environ.get("I2T_DECODE_GEMM_MIN", "9")) and self.cd == torch.bfloat16) or batch > 16:
             mode = "gemm"           # projections as tensor-core GEMMs over the batch
-        if mode == "mega2" and (self.cd != torch.bfloat16 or C > 768 or C % 64 or self.F % 64 or self.F > 3072
-                                or max(self.Tmax, spec["n_cls"]) > 256 or batch * spec["n_head"] > 132):
+        if mode in ("mega2", "mega3") and (self.cd != torch.bfloat16 or C > 768 or C % 64 or self.F % 64 or self.F > 3072
+                                           or max(self.Tmax, spec["n_cls"]) > 256 or batch * spec["n_head"] > 132
+                                           or C // spec["n_head"] not in (32, 64)):
             mode = "mega" if self.cd == torch.bfloat16 else "kernels"
         self.mode = mode
         self.ids = torch.zeros((batch, self.Tmax + 1), device=dev, dtype=torch.int64)
@@ -88,6 +93,7 @@ class DecodeEngine:
         self.launches_per_step = None
         self.replays_last = 0
         self._mega = None
+        self._mega3 = None
         self._enc_graph = None
         self.nucleus_p = None       # top-p filter (kernels mode only: the sampler kernel implements it)
         self.graph_launches = 0     # kernels executed through graph replays (they bypass the library's launch counter)
@@ -181,6 +187,157 @@ class DecodeEngine:
              ptr(self.y), ptr(self.logits), ptr(self.bar), ptr(self.err), ptr(self.keys), temperature,
              int(top_k) if top_k is not None else 0, ptr(self.ngrams), self.n_ngrams, ptr(self.seed_dev),
              max(spec["n_embd"], self.F), max(self.Tmax, self.S), ptr(self.trace), stream())
+
+    # ------------------------------------------------------------------ megakernel v3: dataflow + packed weight streams ----
+    def _mega3_tables(self):
+        """Tables, exchange buffers and the packed per-CTA weight streams of decode_mega3.cu.  Rebuilt (and the weights
+        re-packed) when the model's weight generation changes."""
+        W = self.model.weights()
+        spec, C, F, V, B8 = self.spec, self.spec["n_embd"], self.F, self.spec["vocab_size"], 8
+        dev = self.dev
+        lib = _lib()
+        G = int(lib.i2t_decode_mega3_grid())
+        dp = "decoder.transformer."
+        lin, att, sched, wsrc = [], [], [], []
+        loads = [0] * G                      # bytes of packed weights per CTA so far (tile -> CTA balancing)
+        cursor = [0]                         # exchange-buffer bump allocator (bytes within one generation)
+
+        def P(t):
+            return 0 if t is None else t.data_ptr()
+
+        def xalloc(nbytes):
+            off = cursor[0]
+            cursor[0] = (off + nbytes + 255) // 256 * 256
+            return off
+
+        def balance(total, tile_bytes):
+            """rotation r (tile u -> CTA (u + r) % G) that keeps the most loaded CTA lowest"""
+            base, rem = divmod(total, G)
+            best, best_r = None, 0
+            for r in range(G):
+                worst = 0
+                for c in range(G):
+                    cnt = base + (1 if (c - r) % G < rem else 0)
+                    worst = max(worst, loads[c] + cnt * tile_bytes)
+                if best is None or worst < best:
+                    best, best_r = worst, r
+            for c in range(G):
+                loads[c] += (base + (1 if (c - best_r) % G < rem else 0)) * tile_bytes
+            return best_r
+
+        FL_LM, FL_IN16, FL_OUT16, FL_PUB = 1, 2, 4, 8
+
+        class X(int):
+            """byte offset inside one generation of the exchange buffers (resolved to an address below)"""
+
+        def add_lin(wkey, bkey, ln, inp, out, residual, N, K, act=0, mode=0, kc=None, vc=None, in_mode=0, rows=None, ldo=None,
+                    wpe=None, flags=0, pub=0):
+            w = W.c(wkey)
+            b = W.get(bkey) if bkey else None
+            if rows is not None:
+                w = w[rows]
+                b = b[rows] if b is not None else None
+            g = W[ln + ".weight"] if ln else None
+            be = W.get(ln + ".bias") if ln else None
+            tb = int(lib.i2t_decode_mega3_tile_bytes(K))
+            rot = balance((N + 15) // 16, tb)
+            lin.append([0, P(b), P(g), P(be), inp, out, residual, N, K, act, mode, P(kc), P(vc), in_mode, P(wpe),
+                        ldo if ldo is not None else N, self.Tmax * C, flags, rot, pub, 0, 0, 0, 0])
+            wsrc.append((w, N, K, tb, rot))
+            sched.append([0, len(lin) - 1, 0, 0])
+
+        def add_att(k_ptr, v_ptr, bs, rs, len_mode, len_const, q_off, y_off):
+            att.append([k_ptr, v_ptr, bs, rs, len_mode, len_const, q_off, y_off, (len(att) * 53) % G, 0, 0, 0])
+            sched.append([1, len(att) - 1, 0, 0])
+
+        x32, x16 = B8 * C * 4, B8 * C * 2
+        xnew = lambda nbytes: X(xalloc(nbytes))
+        x_prev = xnew(x32)                   # the embedding, published by the CTA that owns tile 0 of the first op
+        xi = 0
+        for d in range(spec["n_layer"]):
+            lp = f"{dp}h.{d}."
+            q_d, y_d, x1 = xnew(x32), xnew(x16), xnew(x32)
+            if d == 0:
+                add_lin(lp + "attn.c_attn.weight", lp + "attn.c_attn.bias", lp + "ln_1", P(W[dp + "wte.weight"]), q_d, 0,
+                        3 * C, C, mode=1, kc=self.kcache[d], vc=self.vcache[d], in_mode=1, ldo=C, wpe=W[dp + "wpe.weight"],
+                        flags=FL_PUB, pub=x_prev)
+            else:
+                add_lin(lp + "attn.c_attn.weight", lp + "attn.c_attn.bias", lp + "ln_1", x_prev, q_d, 0, 3 * C, C, mode=1,
+                        kc=self.kcache[d], vc=self.vcache[d], ldo=C)
+            add_att(self.kcache[d].data_ptr(), self.vcache[d].data_ptr(), self.Tmax * C, C, 0, 0, q_d, y_d)
+            add_lin(lp + "attn.c_proj.weight", lp + "attn.c_proj.bias", None, y_d, x1, x_prev, C, C, flags=FL_IN16)
+            if d in self.cross_layers:
+                kw, kb = lp + "cross_attn.in_proj_weight", lp + "cross_attn.in_proj_bias"
+                q2, y2, x2 = xnew(x32), xnew(x16), xnew(x32)
+                add_lin(kw, kb, lp + "ln_3", x1, q2, 0, C, C, rows=slice(0, C))
+                kv = self.xkv[xi]
+                add_att(kv.data_ptr(), kv.data_ptr() + C * kv.element_size(), self.S * 2 * C, 2 * C, 1, self.S, q2, y2)
+                add_lin(lp + "cross_attn.out_proj.weight", lp + "cross_attn.out_proj.bias", None, y2, x2, x1, C, C, flags=FL_IN16)
+                x1 = x2
+                xi += 1
+            h_d, x3 = xnew(B8 * F * 2), xnew(x32)
+            add_lin(lp + "mlp.c_fc.weight", lp + "mlp.c_fc.bias", lp + "ln_2", x1, h_d, 0, F, C, act=ops.ACT_GELU_TANH,
+                    flags=FL_OUT16)
+            add_lin(lp + "mlp.c_proj.weight", lp + "mlp.c_proj.bias", None, h_d, x3, x1, C, F, flags=FL_IN16)
+            x_prev = x3
+        add_lin("decoder.lm_head.weight", None, dp + "ln_f", x_prev, 0, 0, V, C, flags=FL_LM)
+        sched.append([2, 0, 0, 0])
+        # exchange buffers: 3 generations, poisoned before every launch
+        gen_stride = (cursor[0] + 4095) // 4096 * 4096
+        exch = torch.empty(3 * gen_stride, device=dev, dtype=torch.uint8)
+        base = exch.data_ptr()
+        lin = [[base + int(v) if isinstance(v, X) else int(v) for v in row] for row in lin]
+        att = [[base + int(v) if isinstance(v, X) else int(v) for v in row] for row in att]
+        # per-CTA weight streams: ops in schedule order, a CTA's tiles of an op in ascending order
+        offs = [0] * G
+        tile_offs = []
+        for (w, N, K, tb, rot) in wsrc:
+            total = (N + 15) // 16
+            to = [0] * total
+            for u in range(total):
+                c = (u + rot) % G
+                to[u] = offs[c]
+                offs[c] += tb
+            tile_offs.append(to)
+        stride = (max(offs) + 255) // 256 * 256
+        wpack = torch.empty(G * stride, device=dev, dtype=torch.uint8)
+        cta_base = torch.arange(G, dtype=torch.int64, device=dev) * stride
+        st = stream()
+        keep = []
+        for (w, N, K, tb, rot), to in zip(wsrc, tile_offs):
+            tt = torch.tensor([((u + rot) % G) * stride + o for u, o in enumerate(to)], dtype=torch.int64, device=dev)
+            wc = w if w.is_contiguous() else w.contiguous()
+            keep.append((tt, wc))
+            call("i2t_decode_mega3_pack", ptr(wc), N, K, ptr(wpack), ptr(tt), st)
+        torch.cuda.current_stream().synchronize()          # the temporaries of the pack calls may go now
+        kpad = max((K - 1) // 768 * 768 + ((K - 1) % 768 + 256) // 256 * 256 for (_, _, K, _, _) in wsrc)
+        t64 = lambda rows: torch.tensor(rows, dtype=torch.int64, device=dev).contiguous()
+        return dict(lin=t64(lin), att=t64(att), sched=torch.tensor(sched, dtype=torch.int32, device=dev).contiguous(),
+                    n_ops=len(lin), exch=exch, gen_stride=gen_stride, wpack=wpack, cta_base=cta_base, grid=G,
+                    ctakeys=torch.zeros(3 * G * 8, device=dev, dtype=torch.int64), max_k=kpad,
+                    packed_bytes=int(sum(offs)), sig=self.model.weight_generation())
+
+    def _mega3_run(self, n_prefill: int, n_sample: int, temperature: float, top_k: Optional[int], P: int):
+        """n_prefill prompt steps + n_sample sampled steps in ONE launch (decode_mega3.cu)."""
+        if self._mega3 is None or self._mega3["sig"] != self.model.weight_generation():
+            self._mega3 = None               # release the old streams before packing new ones
+            self._mega3 = self._mega3_tables()
+        T = self._mega3
+        spec = self.spec
+        steps = n_prefill + n_sample
+        # poison: exchange buffers, the cache rows this launch appends, the ids the sampler has not produced yet
+        T["exch"].fill_(0xFF)
+        T["ctakeys"].zero_()
+        self.kcache.view(torch.int16)[:, :, :steps].fill_(-1)
+        self.vcache.view(torch.int16)[:, :, :steps].fill_(-1)
+        self.ids[:, P:].fill_(-1)
+        self.err.zero_()
+        call("i2t_decode_mega3", ptr(T["lin"]), ptr(T["att"]), ptr(T["sched"]), T["sched"].shape[0], T["n_ops"],
+             T["att"].shape[0], n_prefill, n_sample, self.B, spec["n_embd"], spec["n_head"], spec["vocab_size"], self.n_prompt,
+             ptr(self.ids), self.ids.shape[1], ptr(self.pos), ptr(self.logits), self.logits.stride(0), ptr(self.bar), ptr(self.err),
+             ptr(T["ctakeys"]), ptr(T["wpack"]), ptr(T["cta_base"]), T["gen_stride"], temperature,
+             int(top_k) if top_k is not None else 0, ptr(self.ngrams), self.n_ngrams, ptr(self.seed_dev), T["max_k"],
+             max(self.Tmax, self.S), ptr(self.trace), int(os.environ.get("I2T_TRACE_CTA", "0")), stream())
 
     # ------------------------------------------------------------------ one step, separate kernels -------------
     def _kernel_step(self, sample: bool, temperature: float, top_k: Optional[int]):
@@ -375,6 +532,7 @@ class DecodeEngine:
         self.nucleus_p = nucleus_p
         P = prompt_ids.shape[1]
         assert prompt_ids.shape[0] == B and P + max_new_tokens <= self.Tmax + 1
+        m.sync_compute_weights()       # captured graphs / tables hold the bf16 copies' addresses: refresh them in place
         self._encode(images)
         if self.mode in ("mega", "mega2"):
             W = m.weights()
@@ -394,6 +552,17 @@ class DecodeEngine:
         self.pos.zero_()
         self.ticket.zero_()
         self.seed_dev.fill_(int(seed) & 0x7FFFFFFFFFFFFFFF)
+        if self.mode == "mega3":
+            n0 = launch_count()
+            self._mega3_run(P - 1, max_new_tokens, temperature, top_k, P)
+            self.launches_per_step = launch_count() - n0
+            self.replays_last = 0
+            out = self.ids[:, :P + max_new_tokens].clone()
+            err = int(self.err.item())
+            if err != 0:
+                raise I2TError(f"decode megakernel v3 reported an internal error (code {err}: 2 = a dataflow wait timed out, "
+                               f"3 = weight ring wait timed out, 5 = more than 128 banned tokens for one sequence)")
+            return out
         if self.mode == "mega2":
             n0 = launch_count()
             self._mega2_run(P - 1, max_new_tokens, temperature, top_k)

@@ -65,8 +65,11 @@ class GradientAllReducer:
         if self.world == 1:
             return
         with torch.no_grad():
-            for t in list(module.parameters()) + list(module.buffers()):
+            ts = list(module.parameters()) + list(module.buffers())
+            for t in ts:
                 dist.broadcast(t.data, src=src, group=self.group)
+            torch.autograd.graph.increment_version(ts)      # `.data` writes are invisible to the version counters the
+            # bf16 weight copies are keyed on (VisionEncoderDecoder.weights)
 
     @contextlib.contextmanager
     def no_sync(self):

@@ -7,7 +7,12 @@
 ``ema_update`` -- the momentum-distillation teacher update (training/wrapper.py:53-60), in place, one launch.
 
 State layout matches the originals (``exp_avg`` / ``exp_avg_sq`` / step counter per parameter) so ``state_dict()``
-round-trips.  Only parameters that received a gradient are stepped, like the originals.
+round-trips.  Only parameters whose ``.grad`` is not None are stepped, like the originals (a training loop that keeps
+``zero_grad(set_to_none=False)`` for CUDA-graph replays therefore also steps parameters whose gradient is all zero).
+
+The kernels write parameters through raw pointers, which PyTorch cannot see: every step bumps the tensors' version
+counters (``torch.autograd.graph.increment_version``) and refreshes, IN PLACE, the bf16 copies the bf16 forward / decode
+paths read (``refresh_shadows``) -- their addresses stay valid for captured CUDA graphs.
 """
 from __future__ import annotations
 
@@ -20,6 +25,34 @@ from ._lib import call
 from .ops import ptr, stream
 
 CHUNK = 1 << 16        # elements per CTA: ~1.8 MB of HBM traffic for AdamW
+
+
+def shadow_of(p: torch.Tensor):
+    """the compute-dtype (bf16) copy of a parameter that VisionEncoderDecoder.weights().c() created, or None"""
+    sh = getattr(p, "_i2t_shadow", None)
+    if sh is None or sh.device != p.device or sh.shape != p.shape:
+        return None
+    return sh
+
+
+class _ShadowRefresher:
+    """bf16 copies of a parameter list <- their fp32 masters, one launch (i2t_cast_bf16_multi)."""
+
+    def __init__(self):
+        self._table = None
+
+    @torch.no_grad()
+    def __call__(self, params: List[torch.Tensor]):
+        ps = [p for p in params if shadow_of(p) is not None]
+        if not ps:
+            return
+        if self._table is None:
+            self._table = _PointerTable()
+        cols = [ps, [shadow_of(p) for p in ps], [None] * len(ps), [None] * len(ps)]
+        table, ct, co, cl, n = self._table.get(cols, ps[0].device)
+        call("i2t_cast_bf16_multi", ptr(table), ptr(ct), ptr(co), ptr(cl), n, stream())
+        for p in ps:
+            p._i2t_shadow_version = p._version
 
 
 class _PointerTable:
@@ -64,6 +97,7 @@ class _FusedAdamBase(Optimizer):
         super().__init__(params, dict(lr=lr, betas=betas, weight_decay=weight_decay, eps=eps))
         self.grad_scale = grad_scale
         self._tables: Dict[int, _PointerTable] = {}
+        self._refresh = _ShadowRefresher()
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -71,6 +105,7 @@ class _FusedAdamBase(Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
+        stepped: List[torch.Tensor] = []
         for gi, group in enumerate(self.param_groups):
             # parameters are bucketed by their own step count (all equal unless some got no gradient earlier)
             by_step: Dict[int, List[torch.Tensor]] = {}
@@ -94,6 +129,10 @@ class _FusedAdamBase(Optimizer):
                 table, ct, co, cl, n = tab.get(cols, ps[0].device)
                 call(self.KERNEL, ptr(table), ptr(ct), ptr(co), ptr(cl), n, float(group["lr"]), float(b1), float(b2),
                      float(group["eps"]), float(group["weight_decay"]), int(step), float(self.grad_scale), stream())
+                stepped.extend(ps)
+        if stepped:
+            torch.autograd.graph.increment_version(stepped)     # the kernels wrote them behind PyTorch's back
+            self._refresh(stepped)
         return loss
 
 
@@ -116,6 +155,11 @@ class EmaUpdater:
     def __call__(self, params_m: List[torch.Tensor], params: List[torch.Tensor], momentum: float):
         if not params_m:
             return
-        cols = [list(params_m), list(params), [None] * len(params), [None] * len(params)]
+        # column 2: the teacher weight's bf16 copy (if the bf16 forward created one) is rewritten in the same pass
+        cols = [list(params_m), list(params), [shadow_of(p) for p in params_m], [None] * len(params)]
         table, ct, co, cl, n = self._table.get(cols, params_m[0].device)
         call("i2t_ema_multi", ptr(table), ptr(ct), ptr(co), ptr(cl), n, float(momentum), stream())
+        torch.autograd.graph.increment_version(list(params_m))
+        for p in params_m:
+            if getattr(p, "_i2t_shadow", None) is not None:
+                p._i2t_shadow_version = p._version

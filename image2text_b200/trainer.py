@@ -241,6 +241,9 @@ def main(args) -> dict:
     reducer = GradientAllReducer([p for g in groups for p in g["params"]]) if world > 1 else None
     if reducer is not None:
         reducer.broadcast_parameters(model_wrapper.model)
+        # the teacher must start from rank 0's student on every rank too (accelerate's DDP wrapper broadcasts the whole
+        # ModelTrainerWrapper, model_m included: reference trainer.py:173-174)
+        model_wrapper.copy_momentum_params()
     spec = model_wrapper.model.spec
     size = spec["vit_image"]
     vocab = tokenizer.vocab_size

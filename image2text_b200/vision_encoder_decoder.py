@@ -117,7 +117,6 @@ class VisionEncoderDecoder(nn.Module):
         self.use_cross_attn = config.use_cross_attn
         self.use_soft_prompting = config.use_soft_prompting
         self.processor = tuple(spec["no_repeat_n_grams"])   # consumed on the device by the sampler kernel
-        self._shadow: Dict[str, tuple] = {}
         self._ptr_tables = None
         self._decode_engines = {}
         self._rng = None               # device int64[2] {seed, step offset} of the training-mode dropout masks
@@ -197,9 +196,35 @@ class VisionEncoderDecoder(nn.Module):
         return ops.DropCtx(self._rng.clone())
 
     def weights(self):
-        """key -> tensor accessor; `.c(key)` returns the tensor in the compute dtype (bf16 shadows are cached and
-        refreshed when the fp32 master changes version, i.e. after an optimiser step or load_state_dict)."""
+        """key -> tensor accessor; `.c(key)` returns the tensor in the compute dtype.  bf16 copies live on the Parameter
+        object (`_i2t_shadow`) and are refreshed IN PLACE when the fp32 master's version counter moved (load_state_dict,
+        torch ops) -- the fused optimiser / EMA kernels refresh them themselves (optimizer.py) -- so their addresses stay
+        valid for captured CUDA graphs and decode tables."""
         return _Weights(self)
+
+    @torch.no_grad()
+    def sync_compute_weights(self):
+        """Refresh every stale bf16 copy now (a CUDA-graph replay runs no Python, so nothing would do it lazily)."""
+        if self.compute_dtype == torch.float32:
+            return
+        stale = [w for w in self._tensors().values()
+                 if getattr(w, "_i2t_shadow", None) is not None and w._i2t_shadow_version != w._version]
+        seen = set()
+        for w in stale:
+            if id(w) in seen:
+                continue
+            seen.add(id(w))
+            w._i2t_shadow.copy_(w.detach())
+            w._i2t_shadow_version = w._version
+
+    def weight_generation(self):
+        """Changes whenever a decoder weight changed (version counters; the fused optimiser bumps them)."""
+        c = self.__dict__.get("_wgen_tensors")
+        t = self._tensors()
+        if c is None or c[0] is not t:
+            c = (t, [w for k, w in t.items() if k.startswith("decoder.") and w.dim() == 2])
+            self.__dict__["_wgen_tensors"] = c
+        return tuple(w._version for w in c[1]) + tuple(w.data_ptr() for w in c[1][:1])
 
     # ------------------------------------------------------------------ forward -------------------------------
     def forward(self, images: Optional[torch.Tensor], ids: torch.Tensor, attn_msk: Optional[torch.Tensor] = None,
@@ -300,9 +325,12 @@ class _Weights:
         w = self.t[key]
         cd = self.m.compute_dtype
         if cd != torch.float32:
-            ent = self.m._shadow.get(key)
-            if ent is None or ent[0] != w._version or ent[1].data_ptr() == 0:
-                ent = (w._version, w.detach().to(cd).contiguous())
-                self.m._shadow[key] = ent
-            w = ent[1]
+            sh = getattr(w, "_i2t_shadow", None)
+            if sh is None or sh.dtype != cd or sh.device != w.device or sh.shape != w.shape:
+                sh = w.detach().to(cd).contiguous()
+                w._i2t_shadow, w._i2t_shadow_version = sh, w._version
+            elif w._i2t_shadow_version != w._version:
+                sh.copy_(w.detach())                   # in place: captured graphs / decode tables keep the address
+                w._i2t_shadow_version = w._version
+            w = sh
         return w if rows is None else w[rows]

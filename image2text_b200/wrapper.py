@@ -118,6 +118,9 @@ class ModelTrainerWrapper(nn.Module):
             st["graph"] = g
         st["images"].copy_(images)
         st["labels"].copy_(labels)
+        self.model.sync_compute_weights()          # a replay runs no Python: stale bf16 copies (load_state_dict) go now
+        if self.model_m is not None:
+            self.model_m.sync_compute_weights()
         st["graph"].replay()
         if reducer is not None and sync:
             reducer.exchange_after_replay()

@@ -225,6 +225,31 @@ int i2t_decode_mega2(const int64_t* lin, const int64_t* att, const int32_t* sche
                      uint64_t* keys, float temperature, int64_t top_k, const int32_t* ngrams, int64_t n_ngrams,
                      const uint64_t* seed_ptr, int64_t max_k, int64_t max_len, int64_t* trace, void* stream);
 
+/* Whole generate() loop as ONE cooperative launch WITHOUT grid barriers, bf16 weights (decode_mega3.cu; the default for
+ * up to 8 sequences).  Activations cross CTAs through exchange buffers the caller pre-fills with 0xFF bytes (NaN poison):
+ * a producer stores its result, a consumer polls the words it needs until none is poison (3 generations per buffer,
+ * `gen_stride` bytes apart; the writer of step t re-poisons generation t + 1).  Weights are read from `wpack`: one
+ * contiguous stream per CTA (start offsets cta_base[grid]) in consumption order and mma fragment layout, written by
+ * i2t_decode_mega3_pack (one call per linear op: W = bf16 [N][K] row major, tile_off[tile] = byte offset of the tile's
+ * chunks; a tile = 16 rows, i2t_decode_mega3_tile_bytes(K) bytes; tile u of an op belongs to CTA (u + rot) % grid with
+ * grid = i2t_decode_mega3_grid(), a CTA's tiles in ascending order, ops in schedule order).  A producer warp streams them
+ * through a shared-memory ring with cp.async.bulk, several stages ahead of the arithmetic.
+ * Tables: lin[op][24], att[a][12], sched[s][4] as documented at the top of decode_mega3.cu.  The caller also fills the
+ * cache rows [*pos, *pos + steps) of every layer with 0xFF bytes, ids beyond the prompt with -1 and ctakeys
+ * (uint64[3 * grid * 8]) with 0.  error_flag: 2 = a wait timed out, 3 = ring wait timed out, 5 = too many banned tokens.
+ * Replaces models/vision_encoder_decoder.py:144-180 (the per-token loop, which re-runs the whole prefix). */
+int i2t_decode_mega3_max_keys(void);
+int i2t_decode_mega3_grid(void);
+int64_t i2t_decode_mega3_tile_bytes(int64_t K);
+int i2t_decode_mega3_pack(const void* W, int64_t N, int64_t K, void* dst, const int64_t* tile_off, void* stream);
+int i2t_decode_mega3(const int64_t* lin, const int64_t* att, const int32_t* sched, int64_t n_sched, int64_t n_ops,
+                     int64_t n_att, int64_t n_prefill, int64_t n_sample, int64_t B, int64_t C, int64_t H, int64_t V,
+                     int64_t n_prompt, int64_t* ids, int64_t ids_ld, int32_t* pos, float* logits, int64_t ldl,
+                     uint32_t* bar, int32_t* error_flag, uint64_t* ctakeys, const void* wpack, const int64_t* cta_base,
+                     int64_t gen_stride, float temperature, int64_t top_k, const int32_t* ngrams, int64_t n_ngrams,
+                     const uint64_t* seed_ptr, int64_t max_k, int64_t max_len, int64_t* trace, int64_t trace_cta,
+                     void* stream);
+
 /* ---- sampler: models/vision_encoder_decoder.py:152-180 + transformers NoRepeatNGramLogitsProcessor ----------------
  * logits (B,ldl) fp32 are modified in place (/temperature, banned -> -inf).  Tokens ids[b, 0..cur_len) are the history
  * (cur_len = *pos_ptr + 1 when pos_ptr != NULL, else the cur_len argument); the draw is written to ids[b, cur_len] when
@@ -309,9 +334,14 @@ int i2t_adamw_multi(const int64_t* table, const int32_t* chunk_tensor, const int
 int i2t_snradam_multi(const int64_t* table, const int32_t* chunk_tensor, const int64_t* chunk_off,
                       const int32_t* chunk_len, int64_t n_chunks, double lr, double beta1, double beta2, double eps,
                       double weight_decay, int64_t step, double grad_scale, void* stream);
-/* momentum-distillation teacher: p_m = p_m*momentum + p*(1-momentum), training/wrapper.py:53-60; table = {p_m, p, 0, 0} */
+/* momentum-distillation teacher: p_m = p_m*momentum + p*(1-momentum), training/wrapper.py:53-60; table = {p_m, p, s, 0}
+ * with s = the bf16 copy of p_m the bf16 forward reads (refreshed in the same pass) or 0 */
 int i2t_ema_multi(const int64_t* table, const int32_t* chunk_tensor, const int64_t* chunk_off, const int32_t* chunk_len,
                   int64_t n_chunks, double momentum, void* stream);
+/* dst (bf16) = src (fp32) over a tensor list, table = {src, dst, 0, 0}: refreshes the bf16 copies of the weights an
+ * optimiser step wrote (the reference's autocast re-casts fp32 masters on every use, training/utils.py:96) */
+int i2t_cast_bf16_multi(const int64_t* table, const int32_t* chunk_tensor, const int64_t* chunk_off, const int32_t* chunk_len,
+                        int64_t n_chunks, void* stream);
 
 #ifdef __cplusplus
 }
