@@ -51,11 +51,12 @@ SIGNATURES = {
     "i2t_decode_mega2_max_keys": (c_int, []),
     "i2t_decode_mega2": (c_int, [P, P, P, L, P, L, L, L, L, L, L, L, L, L, L, P, L, P, P, P, P, P, P, P, F, L, P, L, P, L, L, P, P]),
     "i2t_decode_mega3_max_keys": (c_int, []),
+    "i2t_set_decode_poll_sleep": (None, [I]),
     "i2t_decode_mega3_grid": (c_int, []),
     "i2t_decode_mega3_tile_bytes": (c_int64, [L]),
-    "i2t_decode_mega3_pack": (c_int, [P, L, L, P, P, P]),
-    "i2t_decode_mega3": (c_int, [P, P, P, L, L, L, L, L, L, L, L, L, L, P, L, P, P, L, P, P, P, P, P, L, F, L, P, L, P, L, L,
-                                 P, L, P]),
+    "i2t_decode_mega3_pack": (c_int, [P, L, L, L, P, P, P]),
+    "i2t_decode_mega3": (c_int, [P, P, P, P, L, L, L, L, L, L, L, L, L, L, L, P, L, P, P, L, P, P, P, P, P, L, F, L, P, L, P, L,
+                                 L, P, L, P]),
     "i2t_act_fwd": (c_int, [P, P, L, I, I, I, P]),
     "i2t_act_bwd": (c_int, [P, P, P, L, I, I, I, P]),
     "i2t_embed_bwd": (c_int, [P, P, P, L, L, L, L, L, P]),
@@ -104,6 +105,8 @@ def lib() -> ctypes.CDLL:
             handle.i2t_set_gemm_split_k(int(os.environ["I2T_GEMM_SPLITK"]))
         if os.environ.get("I2T_GEMM_PAIR") is not None:
             handle.i2t_set_gemm_cta_pair(int(os.environ["I2T_GEMM_PAIR"]))
+        if os.environ.get("I2T_POLL_SLEEP") is not None:
+            handle.i2t_set_decode_poll_sleep(int(os.environ["I2T_POLL_SLEEP"]))
         if os.environ.get("I2T_TC_ATTN") is not None:
             handle.i2t_set_tensor_core_attention(int(os.environ["I2T_TC_ATTN"]))
         _lib = handle

@@ -25,10 +25,14 @@
 //   6 residual (generation 0) or 0 | 7 N | 8 K | 9 activation | 10 mode (1 = packed q|k|v: q -> output, k / v -> cache row
 //   `pos`) | 11 k cache | 12 v cache | 13 in_mode (1 = token embedding wte[tok] + wpe[n_prompt + pos]) | 14 wpe | 15 output
 //   row pitch | 16 cache batch stride | 17 flags (1 LM head, 2 input is bf16, 4 output is bf16, 8 publish the embedding)
-//   18 rot (tile u belongs to CTA (u + rot) % grid) | 19 where the embedding is published (generation 0) | 20-23 unused
+//   18 rot (tile u belongs to CTA (u + rot) % grid) | 19 where the embedding is published (generation 0) | 20 input row
+//   pitch in elements (0 = K: lets a K-split op read a column range of a wider buffer) | 21-23 unused
+// cmb[c][8] (combine: out = bias + residual + sum of n partial buffers, the second half of a K-split projection) =
+//   0 n partials | 1 first partial f32 (generation 0) | 2 bytes between partials | 3 bias f32* | 4 residual (generation 0)
+//   5 output (generation 0) | 6 N (row length) | 7 rot
 // att[a][12] = 0 K | 1 V | 2 batch stride | 3 row stride | 4 len mode (0: pos + 1 keys, the last one appended this step;
 //   1: constant) | 5 constant length | 6 q f32 (generation 0) | 7 y bf16 out (generation 0) | 8 rot | 9-11 unused
-// sched[s][4] = {kind (0 linear, 1 attention, 2 sample), index, 0, 0}; LM-head ops and the sample entry are skipped in
+// sched[s][4] = {kind (0 linear, 1 attention, 2 sample, 3 combine), index, 0, 0}; LM-head ops and the sample entry are skipped in
 // prefill steps.
 #include "common.cuh"
 #include "sampler.cuh"
@@ -49,20 +53,22 @@ constexpr int M3_SLOT_BYTES = M3_NB * M3_BLOCK_BYTES;        // 24 KB
 constexpr int M3_MAX_SLOTS = 8;
 constexpr int M3_LIN_FIELDS = 24;
 constexpr int M3_ATT_FIELDS = 12;
+constexpr int M3_CMB_FIELDS = 8;
 constexpr int M3_MAX_BANNED = 128;            // per sequence
 constexpr int M3_MAX_KEYS = M3_CTHREADS;      // attention: one key per thread
 constexpr int M3_GENS = 3;
 constexpr int M3_RED_T = 160;                 // floats per partial tile: [8 batch][20] (16 rows + 4 pad: conflict-free STS)
 constexpr int M3_NVX = 6;                     // 16-byte vectors per lane and staging pass
-constexpr int M3_TRACE = 4;                   // stamps per stage
+constexpr int M3_TRACE = 8;                   // stamps per stage
 
 struct M3Args {
   const int64_t* lin;
   const int64_t* att;
+  const int64_t* cmb;
   const int32_t* sched;
-  int n_sched, n_ops, n_att;
+  int n_sched, n_ops, n_att, n_cmb;
   int n_prefill, n_sample;
-  int B, C, H, V, n_prompt, max_k, nslots;
+  int B, C, H, V, n_prompt, max_k, max_len, nslots;
   int64_t* ids;
   int64_t ids_ld;
   int32_t* pos;
@@ -79,11 +85,13 @@ struct M3Args {
   const int32_t* ngrams;
   int n_ngrams;
   const uint64_t* seed_ptr;
+  int sleep_ns;                  // back-off between unsuccessful polls (0 = spin)
   long long* trace;              // optional [n_sched][4] clock64 stamps of CTA `trace_cta` for the LAST sampled step
   int trace_cta;
 };
 
 struct M3AttScratch {
+  uint4 kfresh[8];                                 // the K row appended this step (polled by warp 7, read by thread `pos`)
   float att_q[64];
   float att_p[M3_MAX_KEYS];
   float att_red[M3_CWARPS];
@@ -91,9 +99,9 @@ struct M3AttScratch {
 };
 struct __align__(16) M3Fixed {
   union {                                          // a CTA runs one stage at a time:
-    float red[2][M3_CWARPS][2 * M3_RED_T];         //   linear: per-warp partial tiles (a pair), double buffered (20 KB);
-    M3AttScratch att;                              //   attention: query, probabilities, partial outputs;
-  };                                               //   sampler: SampleScratch
+    float red[M3_CWARPS][2 * M3_RED_T];            //   linear: per-warp partial tiles of a pair (10 KB);
+    M3AttScratch att;                              //   attention: query, probabilities, partial outputs
+  };
   uint64_t full[M3_MAX_SLOTS], empty[M3_MAX_SLOTS];
   int banned[M3_B][M3_MAX_BANNED];
   int nbanned[M3_B];
@@ -102,21 +110,47 @@ struct __align__(16) M3Fixed {
   unsigned long long best[M3_CWARPS][2];
 };
 
-// Dynamic shared memory: [ring | M3Fixed | xs (aliased by the V rows of an attention stage) | lin | att | sched]
+// Dynamic shared memory: [ring | M3Fixed | work | lin | att | cmb | sched | (sampler scratch, sampling mode only)].
+// `work` is used by one stage at a time: a linear stage keeps the staged activation rows (bf16, 8 x xpitch) and its LayerNorm
+// gamma / beta there, an attention stage the V rows of its (batch, head).
 extern __shared__ __align__(128) uint8_t m3_smem[];
 __host__ __device__ inline size_t m3_align16(size_t x) { return (x + 15) & ~(size_t)15; }
 struct M3Sm {
   int xpitch;                         // bf16 elements between the staged activation rows
-  uint32_t fixed_off, xs_off, lin_off, att_off, sched_off;
+  uint32_t fixed_off, xs_off, ln_off, lin_off, att_off, cmb_off, sched_off, samp_off, total;
 };
+__host__ __device__ inline M3Sm m3_layout(int nslots, int max_k, int max_len, int hs, int n_ops, int n_att, int n_cmb, int n_sched,
+                                          bool sampling) {
+  M3Sm S;
+  S.xpitch = max_k + 32;              // bytes = 2 * max_k + 64 = 64 (mod 128): conflict-free LDS.128 of the B fragments
+  uint32_t off = (uint32_t)nslots * 24576u;
+  S.fixed_off = off; off += (uint32_t)m3_align16(sizeof(M3Fixed));
+  S.xs_off = off;
+  const uint32_t xs = (uint32_t)m3_align16((size_t)8 * S.xpitch * 2);
+  S.ln_off = off + xs;
+  const uint32_t lin_work = xs + 2u * 768u * 4u, att_work = (uint32_t)m3_align16((size_t)max_len * hs * 2);
+  off += lin_work > att_work ? lin_work : att_work;
+  S.lin_off = off; off += (uint32_t)m3_align16((size_t)n_ops * 24 * 8);
+  S.att_off = off; off += (uint32_t)m3_align16((size_t)n_att * 12 * 8);
+  S.cmb_off = off; off += (uint32_t)m3_align16((size_t)n_cmb * 8 * 8);
+  S.sched_off = off; off += (uint32_t)m3_align16((size_t)n_sched * 16);
+  S.samp_off = off;
+  if (sampling) off += (uint32_t)m3_align16(sizeof(SampleScratch));
+  S.total = off;
+  return S;
+}
 __device__ __forceinline__ uint4* m3_ring(int slot) { return reinterpret_cast<uint4*>(m3_smem + (size_t)slot * M3_SLOT_BYTES); }
 __device__ __forceinline__ M3Fixed* m3_f(const M3Sm& S) { return reinterpret_cast<M3Fixed*>(m3_smem + S.fixed_off); }
 __device__ __forceinline__ __nv_bfloat16* m3_xs(const M3Sm& S) { return reinterpret_cast<__nv_bfloat16*>(m3_smem + S.xs_off); }
+__device__ __forceinline__ float* m3_ln(const M3Sm& S) { return reinterpret_cast<float*>(m3_smem + S.ln_off); }   // gamma[768] | beta[768]
 __device__ __forceinline__ const int64_t* m3_lin(const M3Sm& S, int op) {
   return reinterpret_cast<const int64_t*>(m3_smem + S.lin_off) + (size_t)op * M3_LIN_FIELDS;
 }
 __device__ __forceinline__ const int64_t* m3_att(const M3Sm& S, int ai) {
   return reinterpret_cast<const int64_t*>(m3_smem + S.att_off) + (size_t)ai * M3_ATT_FIELDS;
+}
+__device__ __forceinline__ const int64_t* m3_cmb(const M3Sm& S, int ci) {
+  return reinterpret_cast<const int64_t*>(m3_smem + S.cmb_off) + (size_t)ci * M3_CMB_FIELDS;
 }
 __device__ __forceinline__ const int32_t* m3_sched(const M3Sm& S) { return reinterpret_cast<const int32_t*>(m3_smem + S.sched_off); }
 
@@ -163,6 +197,22 @@ __device__ __forceinline__ unsigned long long m3_ld8(const void* p) {
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
+// stores another CTA polls for: issued as strong gpu-scope stores (never parked in a write-combining buffer)
+__device__ __forceinline__ void m3_st16(void* p, uint4 v) {
+  asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void m3_st8(void* p, uint2 v) {
+  asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ void m3_st8(void* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void m3_st2(void* p, unsigned short v) {
+  asm volatile("st.relaxed.gpu.global.u16 [%0], %1;" ::"l"(p), "h"(v) : "memory");
+}
+__device__ __forceinline__ uint4 m3_f4_bits(float4 v) {
+  return make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
+}
 __device__ __forceinline__ bool m3_ok32(uint4 v) {   // no fp32 poison word
   return v.x != 0xFFFFFFFFu && v.y != 0xFFFFFFFFu && v.z != 0xFFFFFFFFu && v.w != 0xFFFFFFFFu;
 }
@@ -174,7 +224,7 @@ __device__ __forceinline__ bool m3_ok16(uint4 v) {   // no bf16 poison half-word
 __device__ __forceinline__ bool m3_giveup(uint32_t& spins, int32_t* error_flag) {
   ++spins;
   if (spins == 1u || (spins & 255u) == 0u) {
-    if (*reinterpret_cast<volatile int32_t*>(error_flag) != 0) return true;
+    if (m3_ld4(error_flag) != 0u) return true;
     if (spins > (1u << 22)) {
       atomicExch(error_flag, 2);
       return true;
@@ -283,7 +333,7 @@ __device__ __forceinline__ uint32_t m3_pack(float lo, float hi) {
 // per warp and round instead of the whole row), then the row is re-read; LayerNorm on registers.  bf16 input (attention
 // output, MLP hidden): passes of 6 vectors per lane, copied as they are.
 __device__ __forceinline__ void m3_stage_x(const M3Args& a, const int64_t* d, const M3Sm& S, int gen, int pos, int u0, int warp,
-                                           int lane) {
+                                           int lane, long long* trace) {
   const int K = (int)d[8];
   const int flags = (int)d[17];
   const int in_mode = (int)d[13];
@@ -292,30 +342,38 @@ __device__ __forceinline__ void m3_stage_x(const M3Args& a, const int64_t* d, co
   const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
   if (warp >= a.B) {                         // unused batch rows: zeros
     for (int k = lane * 8; k < kpad; k += 256) *reinterpret_cast<uint4*>(xr + k) = zero4;
+    if ((flags & 2) == 0 && d[2] != 0) {     // (the LayerNorm path has one CTA barrier: keep the count equal)
+      m3_cp_wait0();
+      m3_csync();
+    }
     return;
   }
   for (int k = K + lane * 8; k < kpad; k += 256) *reinterpret_cast<uint4*>(xr + k) = zero4;     // (K % 8 == 0)
   if ((flags & 2) != 0) {                    // bf16 exchange buffer, no LayerNorm
-    const uint8_t* src = m3_gen<const uint8_t>(d[4], a.gen_stride, gen) + (int64_t)warp * K * 2;
+    const uint8_t* src = m3_gen<const uint8_t>(d[4], a.gen_stride, gen) + (int64_t)warp * (d[20] != 0 ? d[20] : (int64_t)K) * 2;
     const int nvec = K / 8;
     for (int v0 = 0; v0 < nvec; v0 += 32 * M3_NVX) {
       uint4 v[M3_NVX];
       uint32_t spins = 0;
+      if (v0 + lane < nvec) {
+        while (!m3_ok16(m3_ld16(src + (size_t)(v0 + lane) * 16))) {
+          if (m3_giveup(spins, a.error_flag)) break;
+          if (a.sleep_ns > 0) __nanosleep(a.sleep_ns);
+        }
+      }
       while (true) {
         int bad = -1;
 #pragma unroll
         for (int i = M3_NVX - 1; i >= 0; --i) {
-          const int vi = v0 + lane + 32 * i;
-          if (vi < nvec) {
-            v[i] = m3_ld16(src + (size_t)vi * 16);
-            if (!m3_ok16(v[i])) bad = vi;
-          }
+          const int vi = min(v0 + lane + 32 * i, nvec - 1);      // (clamped: every element is defined, the array stays in registers)
+          v[i] = m3_ld16(src + (size_t)vi * 16);
+          if (!m3_ok16(v[i])) bad = vi;
         }
         if (__all_sync(0xffffffffu, bad < 0)) break;
         bool quit = false;
         while (bad >= 0 && !m3_ok16(m3_ld16(src + (size_t)bad * 16))) {
           if (m3_giveup(spins, a.error_flag)) { quit = true; break; }
-          __nanosleep(20);
+          if (a.sleep_ns > 0) __nanosleep(a.sleep_ns);
         }
         if (__any_sync(0xffffffffu, quit)) break;
       }
@@ -336,60 +394,56 @@ __device__ __forceinline__ void m3_stage_x(const M3Args& a, const int64_t* d, co
     const float* wpe = reinterpret_cast<const float*>(d[14]) + (int64_t)(a.n_prompt + pos) * K;
 #pragma unroll
     for (int i = 0; i < M3_NVX; ++i) {
-      const int k = (lane + 32 * i) * 4;
-      if (k < K) {
-        const float4 te = __ldcg(reinterpret_cast<const float4*>(wte + k));
-        const float4 pe = __ldcg(reinterpret_cast<const float4*>(wpe + k));
-        v[i] = make_float4(te.x + pe.x, te.y + pe.y, te.z + pe.z, te.w + pe.w);
-      }
+      const int k = min((lane + 32 * i) * 4, K - 4);
+      const float4 te = __ldcg(reinterpret_cast<const float4*>(wte + k));
+      const float4 pe = __ldcg(reinterpret_cast<const float4*>(wpe + k));
+      v[i] = make_float4(te.x + pe.x, te.y + pe.y, te.z + pe.z, te.w + pe.w);
     }
     if ((flags & 8) != 0 && u0 == 0) {       // the CTA that owns tile 0 publishes the embedding as the residual stream
       float* xo = m3_gen<float>(d[19], a.gen_stride, gen) + (int64_t)warp * K;
       float* xp = m3_gen<float>(d[19], a.gen_stride, (gen + 1) % M3_GENS) + (int64_t)warp * K;
-      const float4 poison = make_float4(__uint_as_float(0xFFFFFFFFu), __uint_as_float(0xFFFFFFFFu), __uint_as_float(0xFFFFFFFFu),
-                                        __uint_as_float(0xFFFFFFFFu));
 #pragma unroll
       for (int i = 0; i < M3_NVX; ++i) {
         const int k = (lane + 32 * i) * 4;
         if (k < K) {
-          store4(xp + k, poison);
-          store4(xo + k, v[i]);
+          m3_st16(xp + k, make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu));
+          m3_st16(xo + k, m3_f4_bits(v[i]));
         }
       }
     }
   } else {
     const float* src = m3_gen<const float>(d[4], a.gen_stride, gen) + (int64_t)warp * K;
     uint32_t spins = 0;
+    // consumers are usually early: poll ONE vector per lane (512 B per warp and round) before reading the whole row
+    if (lane * 4 < K) {
+      while (!m3_ok32(m3_ld16(src + lane * 4))) {
+        if (m3_giveup(spins, a.error_flag)) break;
+        if (a.sleep_ns > 0) __nanosleep(a.sleep_ns);
+      }
+    }
     while (true) {
       int bad = -1;
 #pragma unroll
       for (int i = M3_NVX - 1; i >= 0; --i) {
-        const int k = (lane + 32 * i) * 4;
-        if (k < K) {
-          const uint4 r = m3_ld16(src + k);
-          v[i] = make_float4(__uint_as_float(r.x), __uint_as_float(r.y), __uint_as_float(r.z), __uint_as_float(r.w));
-          if (!m3_ok32(r)) bad = k;
-        }
+        const int k = min((lane + 32 * i) * 4, K - 4);
+        const uint4 r = m3_ld16(src + k);
+        v[i] = make_float4(__uint_as_float(r.x), __uint_as_float(r.y), __uint_as_float(r.z), __uint_as_float(r.w));
+        if (!m3_ok32(r)) bad = k;
       }
       if (__all_sync(0xffffffffu, bad < 0)) break;
       bool quit = false;
       while (bad >= 0 && !m3_ok32(m3_ld16(src + bad))) {
         if (m3_giveup(spins, a.error_flag)) { quit = true; break; }
-        __nanosleep(20);
+        if (a.sleep_ns > 0) __nanosleep(a.sleep_ns);
       }
       if (__any_sync(0xffffffffu, quit)) break;
     }
+    if (trace != nullptr) { trace[6] = clock64(); trace[7] = (long long)spins; }
   }
   if (ln_g != nullptr) {
-    // LayerNorm parameters: L2 hits, requested now so that they land while the row statistics are reduced (holding them
-    // across the polling loop above costs 48 registers and spilled)
-    float4 gam[M3_NVX], bet[M3_NVX];
-#pragma unroll
-    for (int i = 0; i < M3_NVX; ++i) {
-      const int k = min((lane + 32 * i) * 4, K - 4);          // (clamped: every element defined, no predicated loads)
-      gam[i] = __ldg(reinterpret_cast<const float4*>(ln_g + k));
-      bet[i] = __ldg(reinterpret_cast<const float4*>((ln_b != nullptr ? ln_b : ln_g) + k));
-    }
+    // LayerNorm parameters: requested with cp.async by the whole CTA before the polling started (m3_linear)
+    m3_cp_wait0();
+    m3_csync();
     const float has_b = ln_b != nullptr ? 1.f : 0.f;
     // one pass: sums of (x - s) and (x - s)^2 with s = the row's first element (no cancellation for rows with a large mean)
     const float sh = __shfl_sync(0xffffffffu, v[0].x, 0);
@@ -412,8 +466,10 @@ __device__ __forceinline__ void m3_stage_x(const M3Args& a, const int64_t* d, co
 #pragma unroll
     for (int i = 0; i < M3_NVX; ++i)
       if ((lane + 32 * i) * 4 < K) {
-        v[i].x = fmaf((v[i].x - mu) * rs, gam[i].x, has_b * bet[i].x); v[i].y = fmaf((v[i].y - mu) * rs, gam[i].y, has_b * bet[i].y);
-        v[i].z = fmaf((v[i].z - mu) * rs, gam[i].z, has_b * bet[i].z); v[i].w = fmaf((v[i].w - mu) * rs, gam[i].w, has_b * bet[i].w);
+        const float4 gm = *reinterpret_cast<const float4*>(m3_ln(S) + (lane + 32 * i) * 4);
+        const float4 bt = *reinterpret_cast<const float4*>(m3_ln(S) + M3_KC + (lane + 32 * i) * 4);
+        v[i].x = fmaf((v[i].x - mu) * rs, gm.x, has_b * bt.x); v[i].y = fmaf((v[i].y - mu) * rs, gm.y, has_b * bt.y);
+        v[i].z = fmaf((v[i].z - mu) * rs, gm.z, has_b * bt.z); v[i].w = fmaf((v[i].w - mu) * rs, gm.w, has_b * bt.w);
       }
   }
 #pragma unroll
@@ -424,9 +480,8 @@ __device__ __forceinline__ void m3_stage_x(const M3Args& a, const int64_t* d, co
 }
 
 // ---- banned next tokens of every sequence (transformers NoRepeatNGramLogitsProcessor) from the in-kernel history ----
-__device__ __noinline__ void m3_banned(const M3Sm& S, int B, const int32_t* ngrams, int n_ngrams, int32_t* error_flag, int cur_len,
+__device__ __noinline__ void m3_banned(M3Fixed* f, int B, const int32_t* ngrams, int n_ngrams, int32_t* error_flag, int cur_len,
                                        int tid) {
-  M3Fixed* f = m3_f(S);
   if (tid < M3_B) f->nbanned[tid] = 0;
   m3_csync();
   for (int g = 0; g < n_ngrams; ++g) {
@@ -479,8 +534,17 @@ __device__ __forceinline__ void m3_linear(const M3Args& a, int op, const M3Sm& S
   float best_v = -INFINITY;
   int best_n = 0x7fffffff;
   if (u0 < total) {
-    if (argmax) m3_banned(S, a.B, a.ngrams, a.n_ngrams, a.error_flag, pos + 1, tid);
-    m3_stage_x(a, d, S, gen, pos, u0, warp, lane);
+    if (argmax) m3_banned(f, a.B, a.ngrams, a.n_ngrams, a.error_flag, pos + 1, tid);
+    if (d[2] != 0) {                           // LayerNorm gamma / beta -> shared memory, in flight while the inputs are polled
+      const float* ln_g = reinterpret_cast<const float*>(d[2]);
+      const float* ln_b = reinterpret_cast<const float*>(d[3]);
+      for (int k = tid * 4; k < K; k += M3_CTHREADS * 4) {
+        m3_cp_async16(m3_ln(S) + k, ln_g + k);
+        m3_cp_async16(m3_ln(S) + M3_KC + k, (ln_b != nullptr ? ln_b : ln_g) + k);
+      }
+      m3_cp_commit();
+    }
+    m3_stage_x(a, d, S, gen, pos, u0, warp, lane, trace);
     m3_csync();                                // xs visible
     if (trace != nullptr) trace[1] = clock64();
     const float* bias = reinterpret_cast<const float*>(d[1]);
@@ -522,6 +586,7 @@ __device__ __forceinline__ void m3_linear(const M3Args& a, int op, const M3Sm& S
           m3_mbar_wait(&f->full[s1], R.phase, a.error_flag);
           R.advance(a.nslots);
         }
+        if (trace != nullptr && pidx == 0 && kc == 0) trace[3] = clock64();
         const uint4* w0p = m3_ring(s0) + tid;
         const uint4* w1p = m3_ring(s1) + tid;
         const __nv_bfloat16* xk = xp + kc * M3_KC + warp * M3_BLK;
@@ -545,8 +610,10 @@ __device__ __forceinline__ void m3_linear(const M3Args& a, int op, const M3Sm& S
           if (two) m3_mbar_arrive(&f->empty[s1]);
         }
       }
+      if (trace != nullptr && pidx == 0) trace[4] = clock64() + (long long)(acc[0][0] == 123.f);
       // acc: D[g][2qd], D[g][2qd+1], D[g+8][2qd], D[g+8][2qd+1]  ->  red[tile][batch][row]
-      float* red = &f->red[pidx & 1][warp][0];
+      if (pidx > 0) m3_csync();                          // the previous pair's epilogue is done with the partial tiles
+      float* red = &f->red[warp][0];
       red[(2 * qd) * 20 + g] = acc[0][0];
       red[(2 * qd + 1) * 20 + g] = acc[0][1];
       red[(2 * qd) * 20 + g + 8] = acc[0][2];
@@ -558,8 +625,9 @@ __device__ __forceinline__ void m3_linear(const M3Args& a, int op, const M3Sm& S
         red[M3_RED_T + (2 * qd + 1) * 20 + g + 8] = acc[1][3];
       }
       m3_csync();
+      if (trace != nullptr && pidx == 0) trace[5] = clock64();
       if (e_on) {
-        const float* rp = &f->red[pidx & 1][0][et * M3_RED_T + eb * 20 + 4 * rg];
+        const float* rp = &f->red[0][et * M3_RED_T + eb * 20 + 4 * rg];
         float4 v = *reinterpret_cast<const float4*>(rp);
 #pragma unroll
         for (int i = 1; i < M3_CWARPS; ++i) {
@@ -596,17 +664,15 @@ __device__ __forceinline__ void m3_linear(const M3Args& a, int op, const M3Sm& S
         } else if (mode == 1 && n0 >= a.C) {   // k / v rows of the packed q|k|v output: appended at `pos` (poisoned by the host)
           const int seg = n0 / a.C, nl = nq - seg * a.C;
           __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(seg == 1 ? d[11] : d[12]);
-          *reinterpret_cast<uint2*>(base + (int64_t)eb * cache_bs + (int64_t)pos * a.C + nl) =
-              make_uint2(m3_pack(v.x, v.y), m3_pack(v.z, v.w));
+          m3_st8(base + (int64_t)eb * cache_bs + (int64_t)pos * a.C + nl, make_uint2(m3_pack(v.x, v.y), m3_pack(v.z, v.w)));
         } else if (out_bf16) {
           const int64_t off = ((int64_t)eb * ldo + nq) * 2;
-          *reinterpret_cast<uint2*>(m3_gen<uint8_t>(d[5], a.gen_stride, gen1) + off) = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
-          *reinterpret_cast<uint2*>(m3_gen<uint8_t>(d[5], a.gen_stride, gen) + off) = make_uint2(m3_pack(v.x, v.y), m3_pack(v.z, v.w));
+          m3_st8(m3_gen<uint8_t>(d[5], a.gen_stride, gen1) + off, make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu));
+          m3_st8(m3_gen<uint8_t>(d[5], a.gen_stride, gen) + off, make_uint2(m3_pack(v.x, v.y), m3_pack(v.z, v.w)));
         } else {
           const int64_t off = ((int64_t)eb * ldo + nq) * 4;
-          *reinterpret_cast<uint4*>(m3_gen<uint8_t>(d[5], a.gen_stride, gen1) + off) =
-              make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-          *reinterpret_cast<float4*>(m3_gen<uint8_t>(d[5], a.gen_stride, gen) + off) = v;
+          m3_st16(m3_gen<uint8_t>(d[5], a.gen_stride, gen1) + off, make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu));
+          m3_st16(m3_gen<uint8_t>(d[5], a.gen_stride, gen) + off, m3_f4_bits(v));
         }
       }
     }
@@ -627,8 +693,8 @@ __device__ __forceinline__ void m3_linear(const M3Args& a, int op, const M3Sm& S
       unsigned long long k = ka > kb ? ka : kb;
       if (k == 0ull) k = 1ull;                          // "nothing from this CTA": still not the poison value
       const int64_t o = (int64_t)blockIdx.x * M3_B + tid;
-      a.ctakeys[(int64_t)((keyslot + 1) % M3_GENS) * G * M3_B + o] = 0ull;
-      a.ctakeys[(int64_t)keyslot * G * M3_B + o] = k;
+      m3_st8(a.ctakeys + (int64_t)((keyslot + 1) % M3_GENS) * G * M3_B + o, 0ull);
+      m3_st8(a.ctakeys + (int64_t)keyslot * G * M3_B + o, k);
     }
   }
 }
@@ -671,27 +737,26 @@ __device__ __forceinline__ void m3_attention(const M3Args& a, int ai, const M3Sm
     }
     f->att.att_q[tid] = __bfloat162float(__float2bfloat16_rn(__uint_as_float(r))) * scale;      // autocast: SDPA sees a bf16 query
   }
-  if (fresh) {
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      kr[i] = m3_ld16(reinterpret_cast<const uint4*>(kp) + i);
-      while (!m3_ok16(kr[i])) {
-        if (m3_giveup(spins, a.error_flag)) break;
-        kr[i] = m3_ld16(reinterpret_cast<const uint4*>(kp) + i);
-      }
+  if (self && warp == M3_CWARPS - 1 && lane < 2 * NV) {
+    // the K / V row the QKV stage of THIS step appends: 2 * NV vectors polled in parallel by the last warp
+    const bool isv = lane >= NV;
+    const int i = isv ? lane - NV : lane;
+    const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(isv ? d[1] : d[0]) + b * d[2] +
+                                                      (int64_t)pos * d[3] + h * HS) + i;
+    uint4 vv = m3_ld16(src);
+    while (!m3_ok16(vv)) {
+      if (m3_giveup(spins, a.error_flag)) break;
+      vv = m3_ld16(src);
     }
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      uint4 vv = m3_ld16(reinterpret_cast<const uint4*>(vp) + i);
-      while (!m3_ok16(vv)) {
-        if (m3_giveup(spins, a.error_flag)) break;
-        vv = m3_ld16(reinterpret_cast<const uint4*>(vp) + i);
-      }
-      vs[(size_t)tid * NV + i] = vv;
-    }
+    if (isv) vs[(size_t)pos * NV + i] = vv;
+    else f->att.kfresh[i] = vv;
   }
   m3_cp_wait0();
-  m3_csync();                                // q and every V row visible
+  m3_csync();                                // q and every K / V row visible
+  if (fresh) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) kr[i] = f->att.kfresh[i];
+  }
   float s = -INFINITY;
   if (on) {
     float acc = 0.f;
@@ -737,21 +802,62 @@ __device__ __forceinline__ void m3_attention(const M3Args& a, int ai, const M3Sm
 #pragma unroll
     for (int i = 0; i < M3_CWARPS; ++i) { tot += f->att.att_red[i]; ov += f->att.att_o[i][tid]; }
     const int64_t off = (int64_t)b * a.C + h * HS + tid;
-    m3_gen<__nv_bfloat16>(d[7], a.gen_stride, (gen + 1) % M3_GENS)[off] = __ushort_as_bfloat16((unsigned short)0xFFFFu);
-    m3_gen<__nv_bfloat16>(d[7], a.gen_stride, gen)[off] = __float2bfloat16_rn(tot > 0.f ? ov / tot : 0.f);
+    m3_st2(m3_gen<__nv_bfloat16>(d[7], a.gen_stride, (gen + 1) % M3_GENS) + off, (unsigned short)0xFFFFu);
+    m3_st2(m3_gen<__nv_bfloat16>(d[7], a.gen_stride, gen) + off, __bfloat16_as_ushort(__float2bfloat16_rn(tot > 0.f ? ov / tot : 0.f)));
+  }
+}
+
+// ---- combine: the second half of a K-split projection.  out[b][n] = bias[n] + residual[b][n] + sum_j partial_j[b][n];
+//      a unit = 256 float4 outputs (one per thread); every operand is polled (5 loads in flight), fixed summation order ----
+__device__ __forceinline__ void m3_combine(const M3Args& a, int ci, const M3Sm& S, int gen, int tid) {
+  const int64_t* d = m3_cmb(S, ci);
+  const int N = (int)d[6];
+  const int nvec_row = N / 4, total = (M3_B * nvec_row + M3_CTHREADS - 1) / M3_CTHREADS;
+  const int G = (int)gridDim.x;
+  const int np = (int)d[0];
+  for (int u = m3_first_unit((int)d[7]); u < total; u += G) {
+    const int vi = u * M3_CTHREADS + tid;
+    const int b = vi / nvec_row, n = (vi - b * nvec_row) * 4;
+    if (b >= a.B) continue;
+    const int64_t off = ((int64_t)b * N + n) * 4;
+    const uint8_t* p0 = m3_gen<const uint8_t>(d[1], a.gen_stride, gen) + off;
+    const uint8_t* rp = m3_gen<const uint8_t>(d[4], a.gen_stride, gen) + off;
+    float4 acc = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(d[3]) + n));
+    uint4 r = m3_ld16(rp);
+    uint4 pv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j < np) pv[j] = m3_ld16(p0 + (int64_t)j * d[2]);
+    uint32_t spins = 0;
+    while (!m3_ok32(r)) {
+      if (m3_giveup(spins, a.error_flag)) break;
+      r = m3_ld16(rp);
+    }
+    acc.x += __uint_as_float(r.x); acc.y += __uint_as_float(r.y); acc.z += __uint_as_float(r.z); acc.w += __uint_as_float(r.w);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j < np) {
+        while (!m3_ok32(pv[j])) {
+          if (m3_giveup(spins, a.error_flag)) break;
+          pv[j] = m3_ld16(p0 + (int64_t)j * d[2]);
+        }
+        acc.x += __uint_as_float(pv[j].x); acc.y += __uint_as_float(pv[j].y);
+        acc.z += __uint_as_float(pv[j].z); acc.w += __uint_as_float(pv[j].w);
+      }
+    m3_st16(m3_gen<uint8_t>(d[5], a.gen_stride, (gen + 1) % M3_GENS) + off, make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu));
+    m3_st16(m3_gen<uint8_t>(d[5], a.gen_stride, gen) + off, m3_f4_bits(acc));
   }
 }
 
 // general sampler on B CTAs, vocabulary row processed in place (global / L2).  Not inlined: its register needs (double
 // precision prefix sums) and code size must not shape the hot loop.
-__device__ __noinline__ void m3_sample_stage(const M3Sm& S, float* logits, int64_t ldl, int V, int B, int64_t* ids, int64_t ids_ld,
+__device__ __noinline__ void m3_sample_stage(SampleScratch* scratch, float* logits, int64_t ldl, int V, int B, int64_t* ids, int64_t ids_ld,
                                              float temperature, int top_k, const int32_t* ngrams, int n_ngrams,
                                              const uint64_t* seed_ptr, int pos, int tid) {
   if ((int)blockIdx.x >= B) return;
   const int b = blockIdx.x;
   float* row = logits + (int64_t)b * ldl;
-  SampleScratch& samp = *reinterpret_cast<SampleScratch*>(&m3_f(S)->red[0][0][0]);
-  static_assert(sizeof(SampleScratch) <= sizeof(((M3Fixed*)nullptr)->red), "sampler scratch must fit the partial-tile buffers");
+  SampleScratch& samp = *scratch;
   const int choice = sample_row_smem(row, samp, row, V, ids + (int64_t)b * ids_ld, pos + 1, temperature, top_k, ngrams,
                                      n_ngrams, *seed_ptr, b, nullptr, tid, M3_CTHREADS);
   if (tid == 0) {
@@ -772,14 +878,21 @@ __device__ __forceinline__ void m3_tokens(const M3Args& a, const M3Sm& S, int po
     if (from_keys) {                 // greedy: max over the per-CTA keys of the previous step's LM head
       unsigned long long best = 0ull;
       const unsigned long long* kp = a.ctakeys + (int64_t)keyslot * G * M3_B + warp;
-      for (int c = lane; c < G; c += 32) {
-        unsigned long long k = m3_ld8(kp + (int64_t)c * M3_B);
-        while (k == 0ull) {
+      unsigned long long kk[8];                       // grid <= 256 CTAs: up to 8 keys per lane, all requested before any is checked
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = lane + 32 * j;
+        kk[j] = c < G ? m3_ld8(kp + (int64_t)c * M3_B) : 1ull;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = lane + 32 * j;
+        while (kk[j] == 0ull) {
           if (m3_giveup(spins, a.error_flag)) break;
-          __nanosleep(20);
-          k = m3_ld8(kp + (int64_t)c * M3_B);
+          if (a.sleep_ns > 0) __nanosleep(a.sleep_ns);
+          kk[j] = m3_ld8(kp + (int64_t)c * M3_B);
         }
-        best = k > best ? k : best;
+        best = kk[j] > best ? kk[j] : best;
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -793,7 +906,7 @@ __device__ __forceinline__ void m3_tokens(const M3Args& a, const M3Sm& S, int po
       long long t = (long long)m3_ld8(ip);
       while (poll_ids && t < 0) {
         if (m3_giveup(spins, a.error_flag)) break;
-        __nanosleep(20);
+        if (a.sleep_ns > 0) __nanosleep(a.sleep_ns);
         t = (long long)m3_ld8(ip);
       }
       tok = (int)(t < 0 ? 0 : t);
@@ -811,18 +924,13 @@ template <int HS>
 __global__ void __launch_bounds__(M3_THREADS, 1) decode_mega3_kernel(M3Args a) {
   const int tid = threadIdx.x;
   // ---- lay out dynamic shared memory, copy the tables, arm the ring ----
-  M3Sm S;
+  const M3Sm S = m3_layout(a.nslots, a.max_k, a.max_len, HS, a.n_ops, a.n_att, a.n_cmb, a.n_sched, a.top_k != 1);
   {
-    S.xpitch = a.max_k + 32;                 // bytes = 2 * max_k + 64 = 64 (mod 128): conflict-free LDS.128 of the B fragments
-    uint32_t off = (uint32_t)a.nslots * M3_SLOT_BYTES;
-    S.fixed_off = off; off += (uint32_t)m3_align16(sizeof(M3Fixed));
-    S.xs_off = off; off += (uint32_t)m3_align16((size_t)M3_B * S.xpitch * 2);
-    S.lin_off = off; off += (uint32_t)m3_align16((size_t)a.n_ops * M3_LIN_FIELDS * 8);
-    S.att_off = off; off += (uint32_t)m3_align16((size_t)a.n_att * M3_ATT_FIELDS * 8);
-    S.sched_off = off;
     int64_t* lin = reinterpret_cast<int64_t*>(m3_smem + S.lin_off);
     int64_t* att = reinterpret_cast<int64_t*>(m3_smem + S.att_off);
     int32_t* sc = reinterpret_cast<int32_t*>(m3_smem + S.sched_off);
+    int64_t* cmb = reinterpret_cast<int64_t*>(m3_smem + S.cmb_off);
+    for (int i = tid; i < a.n_cmb * M3_CMB_FIELDS; i += M3_THREADS) cmb[i] = a.cmb[i];
     for (int i = tid; i < a.n_ops * M3_LIN_FIELDS; i += M3_THREADS) lin[i] = a.lin[i];
     for (int i = tid; i < a.n_att * M3_ATT_FIELDS; i += M3_THREADS) att[i] = a.att[i];
     for (int i = tid; i < a.n_sched * 4; i += M3_THREADS) sc[i] = a.sched[i];
@@ -871,9 +979,11 @@ __global__ void __launch_bounds__(M3_THREADS, 1) decode_mega3_kernel(M3Args a) {
         m3_linear(a, idx, S, R, gen, pos, sstep >= 0 ? sstep % M3_GENS : 0, tid, trace);
       } else if (kind == 1) {
         m3_attention<HS>(a, idx, S, gen, pos, tid);
+      } else if (kind == 3) {
+        m3_combine(a, idx, S, gen, tid);
       } else if (kind == 2 && sampling && !greedy) {
         m3_grid_sync(a.bar, epoch, a.error_flag, tid);          // every logit of this step is in L2
-        m3_sample_stage(S, a.logits, a.ldl, a.V, a.B, a.ids, a.ids_ld, a.temperature, a.top_k, a.ngrams, a.n_ngrams, a.seed_ptr,
+        m3_sample_stage(reinterpret_cast<SampleScratch*>(m3_smem + S.samp_off), a.logits, a.ldl, a.V, a.B, a.ids, a.ids_ld, a.temperature, a.top_k, a.ngrams, a.n_ngrams, a.seed_ptr,
                         pos, tid);
       }
       if (trace_step) trace[2] = clock64();
@@ -891,7 +1001,7 @@ __global__ void __launch_bounds__(M3_THREADS, 1) decode_mega3_kernel(M3Args a) {
 // grid.x = tiles of 16 rows; a tile's chunks are contiguous at tile_off[tile]; within a chunk the 16-byte vector
 // (2 * i + half) * 256 + t holds row tile * 16 + g + 8 * half, k = chunk * 768 + (warp + 8 * i) * 32 + qd * 8 .. + 8
 // (t = warp * 32 + lane, g = lane / 4, qd = lane % 4) -- exactly what consumer thread t feeds to its two MMAs.
-__global__ void __launch_bounds__(M3_CTHREADS) decode_mega3_pack_kernel(const __nv_bfloat16* __restrict__ W, int N, int K,
+__global__ void __launch_bounds__(M3_CTHREADS) decode_mega3_pack_kernel(const __nv_bfloat16* __restrict__ W, int N, int K, int64_t ldw,
                                                                         uint8_t* __restrict__ dst, const int64_t* __restrict__ tile_off) {
   const int tile = blockIdx.x, t = threadIdx.x;
   const int lane = t & 31, warp = t >> 5, g = lane >> 2, qd = lane & 3;
@@ -906,7 +1016,7 @@ __global__ void __launch_bounds__(M3_CTHREADS) decode_mega3_pack_kernel(const __
       for (int half = 0; half < 2; ++half) {
         const int row = tile * M3_ROWS + g + 8 * half;
         uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (row < N && k < K) v = *reinterpret_cast<const uint4*>(W + (size_t)row * K + k);
+        if (row < N && k < K) v = *reinterpret_cast<const uint4*>(W + (size_t)row * ldw + k);
         out[(2 * i + half) * M3_CTHREADS + t] = v;
       }
     }
@@ -914,15 +1024,12 @@ __global__ void __launch_bounds__(M3_CTHREADS) decode_mega3_pack_kernel(const __
   }
 }
 
-static size_t m3_smem_bytes(int nslots, int64_t max_k, int64_t n_ops, int64_t n_att, int64_t n_sched) {
-  return (size_t)nslots * M3_SLOT_BYTES + m3_align16(sizeof(M3Fixed)) + m3_align16((size_t)M3_B * (max_k + 32) * 2) +
-         m3_align16((size_t)n_ops * M3_LIN_FIELDS * 8) + m3_align16((size_t)n_att * M3_ATT_FIELDS * 8) +
-         m3_align16((size_t)n_sched * 16);
-}
-
 }  // namespace i2t
 
 using namespace i2t;
+
+static std::atomic<int> g_m3_sleep_ns{0};
+extern "C" void i2t_set_decode_poll_sleep(int ns) { g_m3_sleep_ns.store(ns < 0 ? 0 : ns); }
 
 extern "C" int i2t_decode_mega3_max_keys(void) { return M3_MAX_KEYS; }
 
@@ -939,12 +1046,13 @@ extern "C" int64_t i2t_decode_mega3_tile_bytes(int64_t K) {
 // number of CTAs the decode kernel runs (= SMs): the host lays the weight streams out for exactly this grid
 extern "C" int i2t_decode_mega3_grid(void) { return num_sms(); }
 
-extern "C" int i2t_decode_mega3_pack(const void* W, int64_t N, int64_t K, void* dst, const int64_t* tile_off, void* stream) {
+extern "C" int i2t_decode_mega3_pack(const void* W, int64_t N, int64_t K, int64_t ldw, void* dst, const int64_t* tile_off,
+                                     void* stream) {
   I2T_REQUIRE(W && dst && tile_off, "decode_mega3_pack: null pointer");
-  I2T_REQUIRE(N > 0 && K > 0 && K % 8 == 0, "decode_mega3_pack: K must be a positive multiple of 8");
+  I2T_REQUIRE(N > 0 && K > 0 && K % 8 == 0 && ldw >= K && ldw % 8 == 0, "decode_mega3_pack: K and the row pitch must be positive multiples of 8");
   I2T_REQUIRE(aligned16(W) && aligned16(dst), "decode_mega3_pack: pointers must be 16-byte aligned");
   const int tiles = (int)((N + M3_ROWS - 1) / M3_ROWS);
-  decode_mega3_pack_kernel<<<tiles, M3_CTHREADS, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(W), (int)N, (int)K,
+  decode_mega3_pack_kernel<<<tiles, M3_CTHREADS, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(W), (int)N, (int)K, ldw,
                                                                             reinterpret_cast<uint8_t*>(dst), tile_off);
   I2T_LAUNCHED();
   return I2T_OK;
@@ -953,14 +1061,14 @@ extern "C" int i2t_decode_mega3_pack(const void* W, int64_t N, int64_t K, void* 
 // Runs n_prefill prompt steps (no LM head) followed by n_sample sampled steps, starting at the device-side position *pos.
 // The caller poisons the exchange buffers (0xFF bytes), the cache rows [pos, pos + steps) (0xFF bytes) and ids beyond the
 // prompt (-1), zeroes ctakeys, and packs the weights (i2t_decode_mega3_pack) with the tile -> CTA map `rot` of the tables.
-extern "C" int i2t_decode_mega3(const int64_t* lin, const int64_t* att, const int32_t* sched, int64_t n_sched, int64_t n_ops,
-                                int64_t n_att, int64_t n_prefill, int64_t n_sample, int64_t B, int64_t C, int64_t H, int64_t V,
+extern "C" int i2t_decode_mega3(const int64_t* lin, const int64_t* att, const int64_t* cmb, const int32_t* sched, int64_t n_sched,
+                                int64_t n_ops, int64_t n_att, int64_t n_cmb, int64_t n_prefill, int64_t n_sample, int64_t B, int64_t C, int64_t H, int64_t V,
                                 int64_t n_prompt, int64_t* ids, int64_t ids_ld, int32_t* pos, float* logits, int64_t ldl,
                                 uint32_t* bar, int32_t* error_flag, uint64_t* ctakeys, const void* wpack, const int64_t* cta_base,
                                 int64_t gen_stride, float temperature, int64_t top_k, const int32_t* ngrams, int64_t n_ngrams,
                                 const uint64_t* seed_ptr, int64_t max_k, int64_t max_len, int64_t* trace, int64_t trace_cta,
                                 void* stream) {
-  I2T_REQUIRE(lin && att && sched && ids && pos && logits && bar && error_flag && ctakeys && wpack && cta_base && seed_ptr,
+  I2T_REQUIRE(lin && att && cmb && sched && ids && pos && logits && bar && error_flag && ctakeys && wpack && cta_base && seed_ptr,
               "decode_mega3: null pointer");
   I2T_REQUIRE(B > 0 && B <= M3_B, "decode_mega3: batch %lld outside 1..8", (long long)B);
   I2T_REQUIRE(H > 0 && C % H == 0 && (C / H == 64 || C / H == 32), "decode_mega3: head_dim must be 32 or 64");
@@ -968,29 +1076,33 @@ extern "C" int i2t_decode_mega3(const int64_t* lin, const int64_t* att, const in
   I2T_REQUIRE(max_k % 256 == 0 && max_k >= C, "decode_mega3: max_k must be the padded widest input (multiple of 256)");
   I2T_REQUIRE(max_len <= M3_MAX_KEYS, "decode_mega3: %lld cached positions exceed the one-key-per-thread limit %d",
               (long long)max_len, M3_MAX_KEYS);
-  I2T_REQUIRE(max_len * (C / H) * 2 <= M3_B * (max_k + 32) * 2, "decode_mega3: V rows of %lld keys do not fit the staging buffer",
-              (long long)max_len);
   I2T_REQUIRE(temperature > 0.f && n_prefill >= 0 && n_sample >= 0 && n_prefill + n_sample > 0, "decode_mega3: bad step counts / temperature");
   I2T_REQUIRE(gen_stride % 16 == 0, "decode_mega3: generation stride must be a multiple of 16 bytes");
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = num_sms();
-  I2T_REQUIRE(B * H <= grid, "decode_mega3: %lld (batch, head) pairs exceed the %d CTAs", (long long)(B * H), grid);
+  I2T_REQUIRE(B * H <= grid && grid <= 256, "decode_mega3: %lld (batch, head) pairs exceed the %d CTAs (or more than 256 SMs)",
+              (long long)(B * H), grid);
+  const bool sampling = top_k != 1;
   int nslots = 0;
   for (int n = M3_MAX_SLOTS; n >= 3; --n)
-    if (m3_smem_bytes(n, max_k, n_ops, n_att, n_sched) <= 227 * 1024) { nslots = n; break; }
+    if (m3_layout(n, (int)max_k, (int)max_len, (int)(C / H), (int)n_ops, (int)n_att, (int)n_cmb, (int)n_sched, sampling).total <= 227 * 1024) {
+      nslots = n;
+      break;
+    }
   I2T_REQUIRE(nslots >= 3, "decode_mega3: tables + activations leave no room for a 3-slot weight ring");
-  const size_t smem = m3_smem_bytes(nslots, max_k, n_ops, n_att, n_sched);
+  const size_t smem = m3_layout(nslots, (int)max_k, (int)max_len, (int)(C / H), (int)n_ops, (int)n_att, (int)n_cmb, (int)n_sched, sampling).total;
   M3Args a;
-  a.lin = lin; a.att = att; a.sched = reinterpret_cast<const int32_t*>(sched);
-  a.n_sched = (int)n_sched; a.n_ops = (int)n_ops; a.n_att = (int)n_att;
+  a.lin = lin; a.att = att; a.cmb = cmb; a.sched = reinterpret_cast<const int32_t*>(sched);
+  a.n_sched = (int)n_sched; a.n_ops = (int)n_ops; a.n_att = (int)n_att; a.n_cmb = (int)n_cmb;
   a.n_prefill = (int)n_prefill; a.n_sample = (int)n_sample;
-  a.B = (int)B; a.C = (int)C; a.H = (int)H; a.V = (int)V; a.n_prompt = (int)n_prompt; a.max_k = (int)max_k; a.nslots = nslots;
+  a.B = (int)B; a.C = (int)C; a.H = (int)H; a.V = (int)V; a.n_prompt = (int)n_prompt; a.max_k = (int)max_k; a.max_len = (int)max_len; a.nslots = nslots;
   a.ids = ids; a.ids_ld = ids_ld; a.pos = pos; a.logits = logits; a.ldl = ldl; a.bar = bar; a.error_flag = error_flag;
   a.ctakeys = reinterpret_cast<unsigned long long*>(ctakeys);
   a.wpack = reinterpret_cast<const uint8_t*>(wpack); a.cta_base = cta_base; a.gen_stride = gen_stride;
   a.temperature = temperature; a.top_k = (int)(top_k > 0 ? top_k : 0);
   a.ngrams = ngrams; a.n_ngrams = (int)n_ngrams; a.seed_ptr = seed_ptr;
   a.trace = reinterpret_cast<long long*>(trace); a.trace_cta = (int)trace_cta;
+  a.sleep_ns = g_m3_sleep_ns.load();
   const void* kern = (C / H == 64) ? (const void*)decode_mega3_kernel<64> : (const void*)decode_mega3_kernel<32>;
   I2T_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;

@@ -198,7 +198,7 @@ class DecodeEngine:
         lib = _lib()
         G = int(lib.i2t_decode_mega3_grid())
         dp = "decoder.transformer."
-        lin, att, sched, wsrc = [], [], [], []
+        lin, att, cmb, sched, wsrc = [], [], [], [], []
         loads = [0] * G                      # bytes of packed weights per CTA so far (tile -> CTA balancing)
         cursor = [0]                         # exchange-buffer bump allocator (bytes within one generation)
 
@@ -231,20 +231,26 @@ class DecodeEngine:
             """byte offset inside one generation of the exchange buffers (resolved to an address below)"""
 
         def add_lin(wkey, bkey, ln, inp, out, residual, N, K, act=0, mode=0, kc=None, vc=None, in_mode=0, rows=None, ldo=None,
-                    wpe=None, flags=0, pub=0):
+                    wpe=None, flags=0, pub=0, cols=None, in_ld=0):
             w = W.c(wkey)
             b = W.get(bkey) if bkey else None
             if rows is not None:
                 w = w[rows]
                 b = b[rows] if b is not None else None
+            if cols is not None:             # K-split: this op contracts a column range of the weight (and of its input)
+                w = w[:, cols]
             g = W[ln + ".weight"] if ln else None
             be = W.get(ln + ".bias") if ln else None
             tb = int(lib.i2t_decode_mega3_tile_bytes(K))
             rot = balance((N + 15) // 16, tb)
             lin.append([0, P(b), P(g), P(be), inp, out, residual, N, K, act, mode, P(kc), P(vc), in_mode, P(wpe),
-                        ldo if ldo is not None else N, self.Tmax * C, flags, rot, pub, 0, 0, 0, 0])
+                        ldo if ldo is not None else N, self.Tmax * C, flags, rot, pub, in_ld, 0, 0, 0])
             wsrc.append((w, N, K, tb, rot))
             sched.append([0, len(lin) - 1, 0, 0])
+
+        def add_cmb(n_parts, p0, pstride, bias, residual, out, N):
+            cmb.append([n_parts, p0, pstride, P(bias), residual, out, N, (len(cmb) * 29 + 7) % G])
+            sched.append([3, len(cmb) - 1, 0, 0])
 
         def add_att(k_ptr, v_ptr, bs, rs, len_mode, len_const, q_off, y_off):
             att.append([k_ptr, v_ptr, bs, rs, len_mode, len_const, q_off, y_off, (len(att) * 53) % G, 0, 0, 0])
@@ -278,7 +284,20 @@ class DecodeEngine:
             h_d, x3 = xnew(B8 * F * 2), xnew(x32)
             add_lin(lp + "mlp.c_fc.weight", lp + "mlp.c_fc.bias", lp + "ln_2", x1, h_d, 0, F, C, act=ops.ACT_GELU_TANH,
                     flags=FL_OUT16)
-            add_lin(lp + "mlp.c_proj.weight", lp + "mlp.c_proj.bias", None, h_d, x3, x1, C, F, flags=FL_IN16)
+            if F > 768 and F % 768 == 0 and F // 768 <= 8:
+                # K-split down projection: F / 768 independent single-chunk ops (192 units instead of 48 four-chunk tiles: every
+                # SM takes part, a unit stages 12 KB of the hidden row instead of 48 KB) writing fp32 partial rows, then a
+                # light combine stage adds them (fixed order), the bias and the residual
+                nk = F // 768
+                parts = [xnew(x32) for _ in range(nk)]
+                pstride = int(parts[1]) - int(parts[0])
+                assert all(int(parts[j]) - int(parts[0]) == j * pstride for j in range(nk))
+                for j in range(nk):
+                    add_lin(lp + "mlp.c_proj.weight", None, None, X(int(h_d) + j * 768 * 2), parts[j], 0, C, 768, flags=FL_IN16,
+                            cols=slice(j * 768, (j + 1) * 768), in_ld=F)
+                add_cmb(nk, parts[0], pstride, W[lp + "mlp.c_proj.bias"], x1, x3, C)
+            else:
+                add_lin(lp + "mlp.c_proj.weight", lp + "mlp.c_proj.bias", None, h_d, x3, x1, C, F, flags=FL_IN16)
             x_prev = x3
         add_lin("decoder.lm_head.weight", None, dp + "ln_f", x_prev, 0, 0, V, C, flags=FL_LM)
         sched.append([2, 0, 0, 0])
@@ -288,6 +307,7 @@ class DecodeEngine:
         base = exch.data_ptr()
         lin = [[base + int(v) if isinstance(v, X) else int(v) for v in row] for row in lin]
         att = [[base + int(v) if isinstance(v, X) else int(v) for v in row] for row in att]
+        cmb = [[base + int(v) if isinstance(v, X) else int(v) for v in row] for row in cmb] or [[0] * 8]
         # per-CTA weight streams: ops in schedule order, a CTA's tiles of an op in ascending order
         offs = [0] * G
         tile_offs = []
@@ -306,14 +326,14 @@ class DecodeEngine:
         keep = []
         for (w, N, K, tb, rot), to in zip(wsrc, tile_offs):
             tt = torch.tensor([((u + rot) % G) * stride + o for u, o in enumerate(to)], dtype=torch.int64, device=dev)
-            wc = w if w.is_contiguous() else w.contiguous()
-            keep.append((tt, wc))
-            call("i2t_decode_mega3_pack", ptr(wc), N, K, ptr(wpack), ptr(tt), st)
+            assert w.stride(1) == 1
+            keep.append((tt, w))
+            call("i2t_decode_mega3_pack", ptr(w), N, K, w.stride(0), ptr(wpack), ptr(tt), st)
         torch.cuda.current_stream().synchronize()          # the temporaries of the pack calls may go now
         kpad = max((K - 1) // 768 * 768 + ((K - 1) % 768 + 256) // 256 * 256 for (_, _, K, _, _) in wsrc)
         t64 = lambda rows: torch.tensor(rows, dtype=torch.int64, device=dev).contiguous()
-        return dict(lin=t64(lin), att=t64(att), sched=torch.tensor(sched, dtype=torch.int32, device=dev).contiguous(),
-                    n_ops=len(lin), exch=exch, gen_stride=gen_stride, wpack=wpack, cta_base=cta_base, grid=G,
+        return dict(lin=t64(lin), att=t64(att), cmb=t64(cmb), n_cmb=len(cmb),
+                    sched=torch.tensor(sched, dtype=torch.int32, device=dev).contiguous(), n_ops=len(lin), exch=exch, gen_stride=gen_stride, wpack=wpack, cta_base=cta_base, grid=G,
                     ctakeys=torch.zeros(3 * G * 8, device=dev, dtype=torch.int64), max_k=kpad,
                     packed_bytes=int(sum(offs)), sig=self.model.weight_generation())
 
@@ -332,8 +352,8 @@ class DecodeEngine:
         self.vcache.view(torch.int16)[:, :, :steps].fill_(-1)
         self.ids[:, P:].fill_(-1)
         self.err.zero_()
-        call("i2t_decode_mega3", ptr(T["lin"]), ptr(T["att"]), ptr(T["sched"]), T["sched"].shape[0], T["n_ops"],
-             T["att"].shape[0], n_prefill, n_sample, self.B, spec["n_embd"], spec["n_head"], spec["vocab_size"], self.n_prompt,
+        call("i2t_decode_mega3", ptr(T["lin"]), ptr(T["att"]), ptr(T["cmb"]), ptr(T["sched"]), T["sched"].shape[0], T["n_ops"],
+             T["att"].shape[0], T["n_cmb"], n_prefill, n_sample, self.B, spec["n_embd"], spec["n_head"], spec["vocab_size"], self.n_prompt,
              ptr(self.ids), self.ids.shape[1], ptr(self.pos), ptr(self.logits), self.logits.stride(0), ptr(self.bar), ptr(self.err),
              ptr(T["ctakeys"]), ptr(T["wpack"]), ptr(T["cta_base"]), T["gen_stride"], temperature,
              int(top_k) if top_k is not None else 0, ptr(self.ngrams), self.n_ngrams, ptr(self.seed_dev), T["max_k"],

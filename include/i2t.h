@@ -230,20 +230,23 @@ int i2t_decode_mega2(const int64_t* lin, const int64_t* att, const int32_t* sche
  * a producer stores its result, a consumer polls the words it needs until none is poison (3 generations per buffer,
  * `gen_stride` bytes apart; the writer of step t re-poisons generation t + 1).  Weights are read from `wpack`: one
  * contiguous stream per CTA (start offsets cta_base[grid]) in consumption order and mma fragment layout, written by
- * i2t_decode_mega3_pack (one call per linear op: W = bf16 [N][K] row major, tile_off[tile] = byte offset of the tile's
+ * i2t_decode_mega3_pack (one call per linear op: W = bf16 [N][K], rows ldw elements apart, tile_off[tile] = byte offset of the tile's
  * chunks; a tile = 16 rows, i2t_decode_mega3_tile_bytes(K) bytes; tile u of an op belongs to CTA (u + rot) % grid with
  * grid = i2t_decode_mega3_grid(), a CTA's tiles in ascending order, ops in schedule order).  A producer warp streams them
  * through a shared-memory ring with cp.async.bulk, several stages ahead of the arithmetic.
- * Tables: lin[op][24], att[a][12], sched[s][4] as documented at the top of decode_mega3.cu.  The caller also fills the
+ * Tables: lin[op][24], att[a][12], cmb[c][8] (combine stages of K-split projections), sched[s][4] as documented at the top
+ * of decode_mega3.cu.  The caller also fills the
  * cache rows [*pos, *pos + steps) of every layer with 0xFF bytes, ids beyond the prompt with -1 and ctakeys
  * (uint64[3 * grid * 8]) with 0.  error_flag: 2 = a wait timed out, 3 = ring wait timed out, 5 = too many banned tokens.
  * Replaces models/vision_encoder_decoder.py:144-180 (the per-token loop, which re-runs the whole prefix). */
 int i2t_decode_mega3_max_keys(void);
+/* back-off (ns) between unsuccessful polls of an exchange buffer; 0 (default) = spin */
+void i2t_set_decode_poll_sleep(int ns);
 int i2t_decode_mega3_grid(void);
 int64_t i2t_decode_mega3_tile_bytes(int64_t K);
-int i2t_decode_mega3_pack(const void* W, int64_t N, int64_t K, void* dst, const int64_t* tile_off, void* stream);
-int i2t_decode_mega3(const int64_t* lin, const int64_t* att, const int32_t* sched, int64_t n_sched, int64_t n_ops,
-                     int64_t n_att, int64_t n_prefill, int64_t n_sample, int64_t B, int64_t C, int64_t H, int64_t V,
+int i2t_decode_mega3_pack(const void* W, int64_t N, int64_t K, int64_t ldw, void* dst, const int64_t* tile_off, void* stream);
+int i2t_decode_mega3(const int64_t* lin, const int64_t* att, const int64_t* cmb, const int32_t* sched, int64_t n_sched,
+                     int64_t n_ops, int64_t n_att, int64_t n_cmb, int64_t n_prefill, int64_t n_sample, int64_t B, int64_t C, int64_t H, int64_t V,
                      int64_t n_prompt, int64_t* ids, int64_t ids_ld, int32_t* pos, float* logits, int64_t ldl,
                      uint32_t* bar, int32_t* error_flag, uint64_t* ctakeys, const void* wpack, const int64_t* cta_base,
                      int64_t gen_stride, float temperature, int64_t top_k, const int32_t* ngrams, int64_t n_ngrams,

@@ -45,10 +45,10 @@ n_sched = sched.shape[0]
 mhz = 1965.0
 for cta in ctas:
     os.environ["I2T_TRACE_CTA"] = str(cta)
-    eng.trace = torch.zeros(n_sched * 4, dtype=torch.int64, device="cuda")
+    eng.trace = torch.zeros(n_sched * 8, dtype=torch.int64, device="cuda")
     eng.generate(images, prompt, 32, 1.0, 1, seed=0)      # stamps of the LAST step (cache length 32)
     torch.cuda.synchronize()
-    tr = eng.trace.view(n_sched, 4).cpu()
+    tr = eng.trace.view(n_sched, 8).cpu()
     t0 = int(tr[0, 0])
     tot = {}
     rows = []
@@ -70,11 +70,17 @@ for cta in ctas:
             a[1] += 1
             a[2] += wait
             a[3] += work
-        rows.append((s, name, took, (b - t0) / mhz, wait, work))
+        fine = ""
+        if kind == 0 and st > 0:
+            polled, spins, wr, mm, cs = int(tr[s, 6]), int(tr[s, 7]), int(tr[s, 3]), int(tr[s, 4]), int(tr[s, 5])
+            fine = "  poll %5.2f (%4d spins) ln+stage %5.2f | weights %5.2f mma %5.2f sync %5.2f epilogue+rest %5.2f" % (
+                ((polled - b) / mhz if polled > 0 else 0.0), spins, ((st - polled) / mhz if polled > 0 else (st - b) / mhz),
+                (wr - st) / mhz, (mm - wr) / mhz, (cs - mm) / mhz, (dn - cs) / mhz)
+        rows.append((s, name, took, (b - t0) / mhz, wait, work, fine))
     last = int(tr[n_sched - 2, 2])
     print(f"--- CTA {cta}: step (first stage entry -> LM head done) {(last - t0) / mhz:.1f} us")
-    for s, name, took, at, wait, work in rows[:14] + rows[-3:]:
-        print(f"  stage {s:3d} {name:22s} {'run ' if took else 'skip'} at {at:7.2f} us  wait {wait:6.2f}  work {work:6.2f}")
+    for s, name, took, at, wait, work, fine in rows[:20] + rows[-3:]:
+        print(f"  stage {s:3d} {name:22s} {'run ' if took else 'skip'} at {at:7.2f} us  wait {wait:6.2f}  work {work:6.2f}{fine}")
     for k, (n, nt, w, c) in tot.items():
         if nt:
             print(f"  {k:22s} x{n:3d} (took part in {nt:3d})  wait {w / nt:6.2f}  work {c / nt:6.2f}  sum {w + c:8.1f} us")
