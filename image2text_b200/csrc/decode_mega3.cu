@@ -54,7 +54,7 @@ constexpr int M3_MAX_SLOTS = 8;
 constexpr int M3_LIN_FIELDS = 24;
 constexpr int M3_ATT_FIELDS = 12;
 constexpr int M3_CMB_FIELDS = 8;
-constexpr int M3_MAX_BANNED = 128;            // per sequence
+constexpr int M3_MAX_LM_ROWS = 1024;          // vocabulary rows one CTA can own in the LM head (64 tiles)
 constexpr int M3_MAX_KEYS = M3_CTHREADS;      // attention: one key per thread
 constexpr int M3_GENS = 3;
 constexpr int M3_RED_T = 160;                 // floats per partial tile: [8 batch][20] (16 rows + 4 pad: conflict-free STS)
@@ -103,8 +103,7 @@ struct __align__(16) M3Fixed {
     M3AttScratch att;                              //   attention: query, probabilities, partial outputs
   };
   uint64_t full[M3_MAX_SLOTS], empty[M3_MAX_SLOTS];
-  int banned[M3_B][M3_MAX_BANNED];
-  int nbanned[M3_B];
+  uint32_t banmask[M3_MAX_LM_ROWS / 4];          // no-repeat-n-gram ban: one byte per LM-head row this CTA owns, bit b = sequence b
   int hist[M3_B][M3_MAX_KEYS + 8];               // token history of every sequence (n-gram ban)
   int tok[M3_B];                                  // the tokens this step embeds
   unsigned long long best[M3_CWARPS][2];
@@ -480,9 +479,10 @@ __device__ __forceinline__ void m3_stage_x(const M3Args& a, const int64_t* d, co
 }
 
 // ---- banned next tokens of every sequence (transformers NoRepeatNGramLogitsProcessor) from the in-kernel history ----
-__device__ __noinline__ void m3_banned(M3Fixed* f, int B, const int32_t* ngrams, int n_ngrams, int32_t* error_flag, int cur_len,
-                                       int tid) {
-  if (tid < M3_B) f->nbanned[tid] = 0;
+// The result is a bitmap over the vocabulary rows THIS CTA owns in the LM head (tiles u0, u0 + G, ...: local row =
+// 16 * (u - u0) / G + token % 16), so the epilogue tests 4 rows with one shared-memory word instead of scanning a list.
+__device__ __noinline__ void m3_banned(M3Fixed* f, int B, const int32_t* ngrams, int n_ngrams, int cur_len, int tid, int u0, int G) {
+  for (int i = tid; i < M3_MAX_LM_ROWS / 4; i += M3_CTHREADS) f->banmask[i] = 0u;
   m3_csync();
   for (int g = 0; g < n_ngrams; ++g) {
     const int n = ngrams[g];
@@ -495,9 +495,12 @@ __device__ __noinline__ void m3_banned(M3Fixed* f, int B, const int32_t* ngrams,
       bool same = true;
       for (int j = 0; j < n - 1; ++j) same = same && (idr[i + j] == idr[tail + j]);
       if (same) {
-        const int slot = atomicAdd(&f->nbanned[b], 1);
-        if (slot < M3_MAX_BANNED) f->banned[b][slot] = idr[i + n - 1];
-        else atomicExch(error_flag, 5);
+        const int tok = idr[i + n - 1];
+        const int du = (tok >> 4) - u0;
+        if (du >= 0 && du % G == 0) {
+          const int r = (du / G) * M3_ROWS + (tok & 15);
+          atomicOr(&f->banmask[r >> 2], (1u << b) << (8 * (r & 3)));
+        }
       }
     }
   }
@@ -534,7 +537,7 @@ __device__ __forceinline__ void m3_linear(const M3Args& a, int op, const M3Sm& S
   float best_v = -INFINITY;
   int best_n = 0x7fffffff;
   if (u0 < total) {
-    if (argmax) m3_banned(f, a.B, a.ngrams, a.n_ngrams, a.error_flag, pos + 1, tid);
+    if (argmax) m3_banned(f, a.B, a.ngrams, a.n_ngrams, pos + 1, tid, u0, G);
     if (d[2] != 0) {                           // LayerNorm gamma / beta -> shared memory, in flight while the inputs are polled
       const float* ln_g = reinterpret_cast<const float*>(d[2]);
       const float* ln_b = reinterpret_cast<const float*>(d[3]);
@@ -559,6 +562,7 @@ __device__ __forceinline__ void m3_linear(const M3Args& a, int op, const M3Sm& S
     const bool pairs = nkc == 1;
     const int ustep = pairs ? 2 * G : G;
     int pidx = 0;
+    long long wait_cycles = 0;
 #pragma unroll 1
     for (int u = u0; u < total; u += ustep, ++pidx) {
       const bool two = pairs && u + G < total;
@@ -579,6 +583,7 @@ __device__ __forceinline__ void m3_linear(const M3Args& a, int op, const M3Sm& S
       for (int kc = 0; kc < nkc; ++kc) {
         const int nbc = m3_chunk_nb(K, kc);
         const int s0 = R.slot;
+        const long long tw0 = trace != nullptr ? clock64() : 0;
         m3_mbar_wait(&f->full[s0], R.phase, a.error_flag);
         R.advance(a.nslots);
         const int s1 = R.slot;
@@ -586,7 +591,11 @@ __device__ __forceinline__ void m3_linear(const M3Args& a, int op, const M3Sm& S
           m3_mbar_wait(&f->full[s1], R.phase, a.error_flag);
           R.advance(a.nslots);
         }
-        if (trace != nullptr && pidx == 0 && kc == 0) trace[3] = clock64();
+        if (trace != nullptr) {
+          const long long tw1 = clock64();
+          if (pidx == 0 && kc == 0) trace[3] = tw1;
+          else wait_cycles += tw1 - tw0;                // time parked on the weight ring after the first tile (LM head)
+        }
         const uint4* w0p = m3_ring(s0) + tid;
         const uint4* w1p = m3_ring(s1) + tid;
         const __nv_bfloat16* xk = xp + kc * M3_KC + warp * M3_BLK;
@@ -648,12 +657,11 @@ __device__ __forceinline__ void m3_linear(const M3Args& a, int op, const M3Sm& S
         if (lm_head) {
           const float vv[4] = {v.x, v.y, v.z, v.w};
           if (argmax) {
-            const int nb = min(f->nbanned[eb], M3_MAX_BANNED);
+            const uint32_t bw = f->banmask[(2 * pidx + et) * 4 + rg] >> eb;      // byte j = row nq + j, bit 0 = this sequence
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const int n = nq + j;
-              bool ban = n >= N;
-              for (int i = 0; i < nb; ++i) ban = ban || (f->banned[eb][i] == n);
+              const bool ban = n >= N || ((bw >> (8 * j)) & 1u) != 0u;
               if (!ban && (vv[j] > best_v || best_n == 0x7fffffff)) { best_v = vv[j]; best_n = n; }
             }
           } else {
@@ -676,6 +684,7 @@ __device__ __forceinline__ void m3_linear(const M3Args& a, int op, const M3Sm& S
         }
       }
     }
+    if (trace != nullptr && lm_head) trace[7] = wait_cycles;
   }
   if (argmax) {
     // CTA-level arg-max per sequence: the 4 row groups of a warp, then the two tiles (warps w, w + 4), then this CTA's key
@@ -1080,6 +1089,8 @@ extern "C" int i2t_decode_mega3(const int64_t* lin, const int64_t* att, const in
   I2T_REQUIRE(gen_stride % 16 == 0, "decode_mega3: generation stride must be a multiple of 16 bytes");
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = num_sms();
+  I2T_REQUIRE(((V + M3_ROWS - 1) / M3_ROWS + grid - 1) / grid * M3_ROWS <= M3_MAX_LM_ROWS,
+              "decode_mega3: vocabulary %lld gives a CTA more than %d LM-head rows", (long long)V, M3_MAX_LM_ROWS);
   I2T_REQUIRE(B * H <= grid && grid <= 256, "decode_mega3: %lld (batch, head) pairs exceed the %d CTAs (or more than 256 SMs)",
               (long long)(B * H), grid);
   const bool sampling = top_k != 1;

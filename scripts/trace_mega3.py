@@ -73,6 +73,8 @@ for cta in ctas:
         fine = ""
         if kind == 0 and st > 0:
             polled, spins, wr, mm, cs = int(tr[s, 6]), int(tr[s, 7]), int(tr[s, 3]), int(tr[s, 4]), int(tr[s, 5])
+            if int(lin[idx, 17]) & 1:
+                print("  LM head: %.2f us of the stage parked on the weight ring after the first tile" % (spins / mhz))
             fine = "  poll %5.2f (%4d spins) ln+stage %5.2f | weights %5.2f mma %5.2f sync %5.2f epilogue+rest %5.2f" % (
                 ((polled - b) / mhz if polled > 0 else 0.0), spins, ((st - polled) / mhz if polled > 0 else (st - b) / mhz),
                 (wr - st) / mhz, (mm - wr) / mhz, (cs - mm) / mhz, (dn - cs) / mhz)
