@@ -977,7 +977,9 @@ __global__ void __launch_bounds__(M3_THREADS, 1) decode_mega3_kernel(M3Args a) {
     const int gen = step % M3_GENS;
     const bool trace_step = a.trace != nullptr && step == n_steps - 1 && (int)blockIdx.x == a.trace_cta && tid == 0;
     // token source: the previous sampled step's arg-max keys (greedy) or the ids row the sampler CTAs publish, else the prompt
+    if (trace_step) a.trace[(a.n_sched - 1) * M3_TRACE + 3] = clock64();       // (the sample entry's slot: step begin / tokens known)
     m3_tokens(a, S, pos, greedy && sstep > 0, (sstep + M3_GENS - 1) % M3_GENS, !greedy && sstep > 0, tid);
+    if (trace_step) a.trace[(a.n_sched - 1) * M3_TRACE + 4] = clock64();
 #pragma unroll 1
     for (int s = 0; s < a.n_sched; ++s) {
       const int kind = sched[s * 4], idx = sched[s * 4 + 1];
@@ -1037,6 +1039,27 @@ __global__ void __launch_bounds__(M3_CTHREADS) decode_mega3_pack_kernel(const __
 
 using namespace i2t;
 
+// ---- everything a launch needs poisoned / zeroed, in ONE launch (six torch fills cost ~60 us of host time per generate) ----
+__global__ void __launch_bounds__(256) decode_mega3_prepare_kernel(uint4* exch, int64_t exch_vecs, uint8_t* kcache, uint8_t* vcache,
+                                                                   int64_t n_rows, int64_t row_pitch, int64_t row_off, int64_t fill_vecs,
+                                                                   int64_t* ids, int64_t ids_ld, int B, int P, int ids_cols,
+                                                                   unsigned long long* ctakeys, int n_keys, int32_t* err) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  const uint4 ff = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+  for (int64_t i = tid; i < exch_vecs; i += nth) exch[i] = ff;
+  for (int64_t i = tid; i < n_rows * fill_vecs; i += nth) {          // cache rows [pos0, pos0 + steps) of every (layer, sequence)
+    const int64_t r = i / fill_vecs, c = i - r * fill_vecs;
+    reinterpret_cast<uint4*>(kcache + r * row_pitch + row_off)[c] = ff;
+    reinterpret_cast<uint4*>(vcache + r * row_pitch + row_off)[c] = ff;
+  }
+  for (int64_t i = tid; i < (int64_t)B * (ids_cols - P); i += nth) {
+    const int64_t b = i / (ids_cols - P), c = i - b * (ids_cols - P);
+    ids[b * ids_ld + P + c] = -1;
+  }
+  for (int64_t i = tid; i < n_keys; i += nth) ctakeys[i] = 0ull;
+  if (tid == 0) *err = 0;
+}
+
 static std::atomic<int> g_m3_sleep_ns{0};
 extern "C" void i2t_set_decode_poll_sleep(int ns) { g_m3_sleep_ns.store(ns < 0 ? 0 : ns); }
 
@@ -1063,6 +1086,23 @@ extern "C" int i2t_decode_mega3_pack(const void* W, int64_t N, int64_t K, int64_
   const int tiles = (int)((N + M3_ROWS - 1) / M3_ROWS);
   decode_mega3_pack_kernel<<<tiles, M3_CTHREADS, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(W), (int)N, (int)K, ldw,
                                                                             reinterpret_cast<uint8_t*>(dst), tile_off);
+  I2T_LAUNCHED();
+  return I2T_OK;
+}
+
+// Poisons what i2t_decode_mega3 expects poisoned: exch (exch_bytes of 0xFF), rows [pos0, pos0 + steps) of the two caches
+// (n_rows = layers x sequences rows of row_pitch bytes, a position = pos_bytes bytes), ids[:, P:] = -1, ctakeys = 0, *err = 0.
+extern "C" int i2t_decode_mega3_prepare(void* exch, int64_t exch_bytes, void* kcache, void* vcache, int64_t n_rows, int64_t row_pitch,
+                                        int64_t pos_bytes, int64_t pos0, int64_t steps, int64_t* ids, int64_t ids_ld, int64_t B,
+                                        int64_t P, int64_t ids_cols, uint64_t* ctakeys, int64_t n_keys, int32_t* err, void* stream) {
+  I2T_REQUIRE(exch && kcache && vcache && ids && ctakeys && err, "decode_mega3_prepare: null pointer");
+  I2T_REQUIRE(exch_bytes % 16 == 0 && pos_bytes % 16 == 0 && row_pitch % 16 == 0 && aligned16(exch) && aligned16(kcache) && aligned16(vcache),
+              "decode_mega3_prepare: buffers must be 16-byte granular");
+  I2T_REQUIRE(P >= 0 && P <= ids_cols && steps >= 0 && (pos0 + steps) * pos_bytes <= row_pitch, "decode_mega3_prepare: bad ranges");
+  decode_mega3_prepare_kernel<<<num_sms() * 4, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<uint4*>(exch), exch_bytes / 16, reinterpret_cast<uint8_t*>(kcache), reinterpret_cast<uint8_t*>(vcache), n_rows,
+      row_pitch, pos0 * pos_bytes, steps * pos_bytes / 16, ids, ids_ld, (int)B, (int)P, (int)ids_cols,
+      reinterpret_cast<unsigned long long*>(ctakeys), (int)n_keys, err);
   I2T_LAUNCHED();
   return I2T_OK;
 }

@@ -345,13 +345,12 @@ class DecodeEngine:
         T = self._mega3
         spec = self.spec
         steps = n_prefill + n_sample
-        # poison: exchange buffers, the cache rows this launch appends, the ids the sampler has not produced yet
-        T["exch"].fill_(0xFF)
-        T["ctakeys"].zero_()
-        self.kcache.view(torch.int16)[:, :, :steps].fill_(-1)
-        self.vcache.view(torch.int16)[:, :, :steps].fill_(-1)
-        self.ids[:, P:].fill_(-1)
-        self.err.zero_()
+        # poison (one launch): exchange buffers, the cache rows this launch appends, the ids the sampler has not produced yet
+        C, L = spec["n_embd"], spec["n_layer"]
+        es = self.kcache.element_size()
+        call("i2t_decode_mega3_prepare", ptr(T["exch"]), T["exch"].numel(), ptr(self.kcache), ptr(self.vcache), L * self.B,
+             self.Tmax * C * es, C * es, 0, steps, ptr(self.ids), self.ids.shape[1], self.B, P, self.ids.shape[1],
+             ptr(T["ctakeys"]), T["ctakeys"].numel(), ptr(self.err), stream())
         call("i2t_decode_mega3", ptr(T["lin"]), ptr(T["att"]), ptr(T["cmb"]), ptr(T["sched"]), T["sched"].shape[0], T["n_ops"],
              T["att"].shape[0], T["n_cmb"], n_prefill, n_sample, self.B, spec["n_embd"], spec["n_head"], spec["vocab_size"], self.n_prompt,
              ptr(self.ids), self.ids.shape[1], ptr(self.pos), ptr(self.logits), self.logits.stride(0), ptr(self.bar), ptr(self.err),

@@ -245,6 +245,11 @@ void i2t_set_decode_poll_sleep(int ns);
 int i2t_decode_mega3_grid(void);
 int64_t i2t_decode_mega3_tile_bytes(int64_t K);
 int i2t_decode_mega3_pack(const void* W, int64_t N, int64_t K, int64_t ldw, void* dst, const int64_t* tile_off, void* stream);
+/* one launch that poisons / zeroes everything i2t_decode_mega3 expects: exch (0xFF), cache rows [pos0, pos0 + steps) of
+ * n_rows = layers x sequences rows (row_pitch bytes each, pos_bytes per position), ids[:, P:ids_cols] = -1, ctakeys, *err */
+int i2t_decode_mega3_prepare(void* exch, int64_t exch_bytes, void* kcache, void* vcache, int64_t n_rows, int64_t row_pitch,
+                             int64_t pos_bytes, int64_t pos0, int64_t steps, int64_t* ids, int64_t ids_ld, int64_t B, int64_t P,
+                             int64_t ids_cols, uint64_t* ctakeys, int64_t n_keys, int32_t* err, void* stream);
 int i2t_decode_mega3(const int64_t* lin, const int64_t* att, const int64_t* cmb, const int32_t* sched, int64_t n_sched,
                      int64_t n_ops, int64_t n_att, int64_t n_cmb, int64_t n_prefill, int64_t n_sample, int64_t B, int64_t C, int64_t H, int64_t V,
                      int64_t n_prompt, int64_t* ids, int64_t ids_ld, int32_t* pos, float* logits, int64_t ldl,

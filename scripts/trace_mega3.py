@@ -39,6 +39,22 @@ for _ in range(5):
     ts.append(e0.elapsed_time(e1) * 1e3 / 64)
 print("decode loop, CUDA events: %.1f us per step (best of 5; all: %s)" % (min(ts), " ".join("%.1f" % t for t in ts)))
 
+def loop_us(n):
+    best = 1e30
+    for _ in range(3):
+        eng.pos.zero_()
+        e0.record()
+        eng._mega3_run(0, n, 1.0, 1, 1)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) * 1e3)
+    return best
+
+
+t64, t128 = loop_us(64), loop_us(128)
+print("one launch of 64 steps %.0f us, of 128 steps %.0f us -> %.1f us per additional step, %.0f us of per-launch overhead "
+      "(poison fills, cooperative launch, table copy, first-step effects)" % (t64, t128, (t128 - t64) / 64, t64 - (t128 - t64)))
+
 sched = T["sched"].cpu()
 lin = T["lin"].cpu()
 n_sched = sched.shape[0]
@@ -79,6 +95,8 @@ for cta in ctas:
                 ((polled - b) / mhz if polled > 0 else 0.0), spins, ((st - polled) / mhz if polled > 0 else (st - b) / mhz),
                 (wr - st) / mhz, (mm - wr) / mhz, (cs - mm) / mhz, (dn - cs) / mhz)
         rows.append((s, name, took, (b - t0) / mhz, wait, work, fine))
+    print("  step begin -> tokens known: %.2f us (waiting for every CTA's LM-head keys of the previous step)" %
+          ((int(tr[n_sched - 1, 4]) - int(tr[n_sched - 1, 3])) / mhz))
     last = int(tr[n_sched - 2, 2])
     print(f"--- CTA {cta}: step (first stage entry -> LM head done) {(last - t0) / mhz:.1f} us")
     for s, name, took, at, wait, work, fine in rows[:20] + rows[-3:]:

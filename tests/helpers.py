@@ -25,6 +25,33 @@ def spec_and_weights(name: str, seed: int = 0):
     return _CACHE[key]
 
 
+def check_picks_vs_oracle(name, m, images, got, n_prompt_tokens, top_k, tol_frac=2e-2):
+    """Teacher-forced parity of a bf16 decode against the fp32 CPU ORACLE (oracle/i2t_oracle.py, pinned to the unmodified
+    reference by tests/golden): oracle logits over got[:, :-1]; every pick must be un-banned (no-repeat-n-gram rule) and within
+    tol_frac * max|logit| (BASELINE.json's bf16 tolerance) of the oracle's k-th best un-banned logit.  The oracle is given the
+    encoder output the model under test computed: the LSH tail is an integer hash of the ViT feature, so a bf16 feature may land
+    in a neighbouring bucket (the bf16 ViT trunk itself is pinned by test_gpu_model.py).  Returns (worst gap, logit scale)."""
+    from oracle import i2t_oracle as O
+    _, spec, sd = spec_and_weights(name)
+    with torch.no_grad():
+        enc = m.encoder(images).float().cpu()
+        _, logits, _ = O.ved_forward(sd, spec, None, got[:, :-1].cpu(), encoder_output=enc, normalize_grads=False)
+    logits = logits.float()[..., :spec["vocab_size"]]
+    got = got.cpu()
+    scale = float(logits.abs().max())
+    worst = 0.0
+    for t in range(n_prompt_tokens - 1, got.shape[1] - 1):
+        row = logits[:, t]
+        allowed = O.apply_ngram_ban(got[:, :t + 1], row.clone(), spec["no_repeat_n_grams"])
+        pick = got[:, t + 1:t + 2]
+        assert bool(torch.isfinite(allowed.gather(1, pick)).all()), f"banned token picked at position {t + 1}"
+        kth = torch.topk(allowed, top_k, dim=-1).values[:, -1:]
+        gap = (kth - row.gather(1, pick)).clamp_min(0)
+        worst = max(worst, float(gap.max()))
+        assert float(gap.max()) <= tol_frac * scale, (t, float(gap.max()), scale)
+    return worst, scale
+
+
 def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     """max |a-b| / max |b|  (the '1e-4 relative' of BASELINE.json is read as relative to the tensor scale)."""
     a, b = a.double(), b.double()

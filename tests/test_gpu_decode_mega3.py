@@ -17,31 +17,8 @@ pytestmark = pytest.mark.gpu
 
 from image2text_b200.decode_engine import DecodeEngine  # noqa: E402
 from image2text_b200.synthetic import synth_images  # noqa: E402
-from oracle import i2t_oracle as O  # noqa: E402
-from tests.helpers import spec_and_weights  # noqa: E402
+from tests.helpers import check_picks_vs_oracle, spec_and_weights  # noqa: E402,F401
 from tests.test_gpu_model import build  # noqa: E402
-
-
-def check_picks_vs_oracle(name, m, images, got, n_prompt_tokens, top_k, tol_frac=2e-2):
-    """Teacher-forced: oracle logits (fp32, CPU) over got[:, :-1]; returns (worst gap, logit scale)."""
-    _, spec, sd = spec_and_weights(name)
-    with torch.no_grad():
-        enc = m.encoder(images).float().cpu()
-        _, logits, _ = O.ved_forward(sd, spec, None, got[:, :-1].cpu(), encoder_output=enc, normalize_grads=False)
-    logits = logits.float()
-    got = got.cpu()
-    scale = float(logits.abs().max())
-    worst = 0.0
-    for t in range(n_prompt_tokens - 1, got.shape[1] - 1):
-        row = logits[:, t]
-        allowed = O.apply_ngram_ban(got[:, :t + 1], row.clone(), spec["no_repeat_n_grams"])
-        pick = got[:, t + 1:t + 2]
-        assert bool(torch.isfinite(allowed.gather(1, pick)).all()), f"banned token picked at position {t + 1}"
-        kth = torch.topk(allowed, top_k, dim=-1).values[:, -1:]
-        gap = (kth - row.gather(1, pick)).clamp_min(0)
-        worst = max(worst, float(gap.max()))
-        assert float(gap.max()) <= tol_frac * scale, (t, float(gap.max()), scale)
-    return worst, scale
 
 
 def test_mega3_is_the_default_bf16_engine():

@@ -146,6 +146,36 @@ def test_nano_bf16_logits_within_2e_2(golden):
     assert got.shape == (8, 9)
 
 
+def test_bf16_vit_trunk_matches_oracle():
+    """The bf16 ViT-B/16 trunk (tcgen05 GEMMs, bf16 flash attention, fp32 residual stream and LayerNorm) against the fp32 oracle
+    trunk on the same images: 2e-2 of the feature scale (BASELINE.json's bf16 tolerance), full 12 layers at 224 x 224."""
+    from image2text_b200 import functional as Fn
+    m = build("nano", torch.bfloat16)
+    _, spec, sd = spec_and_weights("nano")
+    images = synth_images(2, 224, seed=21)
+    with torch.no_grad():
+        got = Fn.vit_trunk(m.weights(), m.spec, images.cuda(), torch.bfloat16, "encoder.model.").float().cpu()
+        want = O.vit_trunk(sd, spec, images)
+    assert got.shape == want.shape
+    assert rel_err(got, want) < 2e-2, rel_err(got, want)
+
+
+def test_nano_bf16_full_logits_within_2e_2_of_oracle():
+    """Every logit (all 50257 columns, every position) of the bf16 forward against the fp32 oracle on the same encoder output."""
+    m = build("nano", torch.bfloat16)
+    _, spec, sd = spec_and_weights("nano")
+    images = synth_images(2, 224, seed=21).cuda()
+    ids = torch.randint(0, 50256, (2, 24), generator=torch.Generator().manual_seed(3))
+    with torch.no_grad():
+        out = m(images=images, ids=ids.cuda())
+        _, want, hidden = O.ved_forward(sd, spec, None, ids, encoder_output=out.encoder_output.float().cpu(), normalize_grads=False)
+    got = out.logits.float().cpu()[..., :spec["vocab_size"]]
+    want = want[..., :spec["vocab_size"]]
+    assert got.shape == want.shape
+    assert float((got - want).abs().max()) < 2e-2 * float(want.abs().max())
+    assert rel_err(out.hidden_state.float().cpu(), hidden) < 2e-2
+
+
 def test_tiny_nucleus_sampling_stays_in_reference_support():
     """generate(nucleus_p=...) (reference models/vision_encoder_decoder.py:160-175): every sampled token must have non-zero
     probability under the reference's top-k + top-p distribution given the same prefix; same seed -> same draw."""

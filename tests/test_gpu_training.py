@@ -180,3 +180,57 @@ def test_graphed_micro_step_accumulates_the_same_gradients():
         assert rel_err(pg[k].grad.cpu(), p.grad.cpu()) < 2e-5, k
         checked += 1
     assert checked > 20
+
+
+@pytest.mark.parametrize("graphed", [False, True])
+def test_bf16_training_sees_the_updated_weights(graphed):
+    """The fused optimiser / EMA kernels write fp32 masters through raw pointers; the bf16 copies every bf16 GEMM and the decode
+    engines read must follow (refreshed IN PLACE: CUDA graphs and decode tables hold their addresses).  On ONE fixed batch the
+    loss must fall over optimiser steps, every bf16 copy must equal its master rounded to bf16, and the teacher's copies must
+    follow the EMA (they used to stay at the initial weights)."""
+    tc, spec, sd = spec_and_weights("tiny")
+    tok = types.SimpleNamespace(eos_token_id=612, bos_token_id=612, mask_token_id=None, vocab_size=spec["vocab_size"])
+    w = ModelTrainerWrapper(tc.model, tok, TrainerWrapperConfig(moco_momentum=0.9, moco_alpha=0.4), -100, device="cuda",
+                            compute_dtype=torch.bfloat16, spec_overrides=SPEC_OVERRIDES["tiny"])
+    w.model.load_state_dict(sd)
+    w.copy_momentum_params()
+    w.train()
+    opt = AdamW([dict(params=[p for p in w.model.parameters() if p.requires_grad], lr=3e-3, betas=(0.9, 0.95), weight_decay=0.0)])
+    images = synth_images(4, 32, seed=11).cuda()
+    labels = synth_labels(4, 20, spec["vocab_size"], seed=12, min_len=3, max_len=14, eos=612).cuda()
+    addr0 = {k: v._i2t_shadow.data_ptr() for k, v in w.model._tensors().items() if getattr(v, "_i2t_shadow", None) is not None}
+    losses = []
+    for step in range(12):
+        if graphed:
+            loss = w.train_step_graphed(images, labels, 1.0)
+        else:
+            loss, _ = w.train_step(images, labels)
+            loss.backward()
+        losses.append(float(loss))
+        opt.step()
+        opt.zero_grad(set_to_none=False)
+        if step == 0:
+            addr0 = {k: v._i2t_shadow.data_ptr() for k, v in w.model._tensors().items() if getattr(v, "_i2t_shadow", None) is not None}
+    assert losses[-1] < losses[0] - 0.5, losses
+    for mdl in (w.model, w.model_m):
+        n = 0
+        for k, v in mdl._tensors().items():
+            sh = getattr(v, "_i2t_shadow", None)
+            if sh is not None:
+                assert torch.equal(sh, v.detach().to(torch.bfloat16)), k
+                n += 1
+        assert n > 20
+    for k, a in addr0.items():                    # refreshed in place: same addresses as after the first step
+        assert w.model._tensors()[k]._i2t_shadow.data_ptr() == a, k
+    # the teacher moved away from its initial copy of the student (EMA) and its bf16 copies moved with it
+    k = "decoder.transformer.h.0.mlp.c_fc.weight"
+    assert not torch.equal(w.model_m._tensors()[k].detach().cpu(), sd[k])
+    # generate() after training uses the trained weights (tables are rebuilt / copies refreshed)
+    w.eval()
+    prompt = torch.full((4, 1), 612, dtype=torch.long, device="cuda")
+    a = w.model.generate(images, prompt, max_new_tokens=8, top_k=1)
+    fresh = ModelTrainerWrapper(tc.model, tok, TrainerWrapperConfig(), -100, device="cuda", compute_dtype=torch.bfloat16,
+                                spec_overrides=SPEC_OVERRIDES["tiny"]).model
+    fresh.load_state_dict(w.model.state_dict())
+    fresh.eval()
+    assert torch.equal(a, fresh.generate(images, prompt, max_new_tokens=8, top_k=1))
