@@ -26,7 +26,9 @@
 //   `pos`) | 11 k cache | 12 v cache | 13 in_mode (1 = token embedding wte[tok] + wpe[n_prompt + pos]) | 14 wpe | 15 output
 //   row pitch | 16 cache batch stride | 17 flags (1 LM head, 2 input is bf16, 4 output is bf16, 8 publish the embedding)
 //   18 rot (tile u belongs to CTA (u + rot) % grid) | 19 where the embedding is published (generation 0) | 20 input row
-//   pitch in elements (0 = K: lets a K-split op read a column range of a wider buffer) | 21-23 unused
+//   pitch in elements (0 = K: lets a K-split op read a column range of a wider buffer) | 21 group size Gs (0 = grid): only
+//   the first Gs CTAs of the rotation take part, tile u belongs to CTA ((u % Gs) + rot) % grid -- fewer CTAs fan the
+//   activations out of L2 when an op has few tiles per CTA anyway | 22-23 unused
 // cmb[c][8] (combine: out = bias + residual + sum of n partial buffers, the second half of a K-split projection) =
 //   0 n partials | 1 first partial f32 (generation 0) | 2 bytes between partials | 3 bias f32* | 4 residual (generation 0)
 //   5 output (generation 0) | 6 N (row length) | 7 rot
@@ -304,7 +306,9 @@ __device__ __forceinline__ void m3_producer(const M3Args& a, const M3Sm& S) {
       const int N = (int)d[7], K = (int)d[8];
       const int total = (N + M3_ROWS - 1) / M3_ROWS;
       const int nkc = m3_nkc(K);
-      for (int u = m3_first_unit((int)d[18]); u < total; u += G) {
+      const int Gs = d[21] != 0 ? (int)d[21] : G;
+      const int pu0 = m3_first_unit((int)d[18]);
+      for (int u = pu0 < Gs ? pu0 : total; u < total; u += Gs) {
         for (int kc = 0; kc < nkc; ++kc) {
           const uint32_t bytes = (uint32_t)m3_chunk_nb(K, kc) * M3_BLOCK_BYTES;
           m3_mbar_wait(&f->empty[R.slot], R.phase ^ 1u, a.error_flag);
@@ -530,14 +534,16 @@ __device__ __forceinline__ void m3_linear(const M3Args& a, int op, const M3Sm& S
   const int total = (N + M3_ROWS - 1) / M3_ROWS;
   const int nkc = m3_nkc(K);
   const int G = (int)gridDim.x;
-  const int u0 = m3_first_unit((int)d[18]);
+  const int Gs = d[21] != 0 ? (int)d[21] : G;                   // CTAs taking part; a CTA's tiles are Gs apart
+  const int uf = m3_first_unit((int)d[18]);
+  const int u0 = uf < Gs ? uf : total;
   const bool lm_head = (flags & 1) != 0;
   const bool argmax = lm_head && a.top_k == 1;
   const int gen1 = (gen + 1) % M3_GENS;
   float best_v = -INFINITY;
   int best_n = 0x7fffffff;
   if (u0 < total) {
-    if (argmax) m3_banned(f, a.B, a.ngrams, a.n_ngrams, pos + 1, tid, u0, G);
+    if (argmax) m3_banned(f, a.B, a.ngrams, a.n_ngrams, pos + 1, tid, u0, Gs);
     if (d[2] != 0) {                           // LayerNorm gamma / beta -> shared memory, in flight while the inputs are polled
       const float* ln_g = reinterpret_cast<const float*>(d[2]);
       const float* ln_b = reinterpret_cast<const float*>(d[3]);
@@ -560,13 +566,13 @@ __device__ __forceinline__ void m3_linear(const M3Args& a, int op, const M3Sm& S
     // one batch row (16-byte loads of the partial tiles, 16-byte stores of the result)
     const int et = warp >> 2, rg = lane & 3, eb = (lane >> 2) + 2 * (warp & 3);
     const bool pairs = nkc == 1;
-    const int ustep = pairs ? 2 * G : G;
+    const int ustep = pairs ? 2 * Gs : Gs;
     int pidx = 0;
     long long wait_cycles = 0;
 #pragma unroll 1
     for (int u = u0; u < total; u += ustep, ++pidx) {
-      const bool two = pairs && u + G < total;
-      const int n0 = (u + et * G) * M3_ROWS, nq = n0 + 4 * rg;
+      const bool two = pairs && u + Gs < total;
+      const int n0 = (u + et * Gs) * M3_ROWS, nq = n0 + 4 * rg;
       const bool e_on = lane < 8 && (et == 0 || two) && nq < N && eb < a.B;
       float4 e_bias = make_float4(0.f, 0.f, 0.f, 0.f);
       uint4 e_res = make_uint4(0u, 0u, 0u, 0u);

@@ -199,6 +199,7 @@ class DecodeEngine:
         G = int(lib.i2t_decode_mega3_grid())
         dp = "decoder.transformer."
         lin, att, cmb, sched, wsrc = [], [], [], [], []
+        group = os.environ.get("I2T_M3_GROUP", "1") != "0"
         loads = [0] * G                      # bytes of packed weights per CTA so far (tile -> CTA balancing)
         cursor = [0]                         # exchange-buffer bump allocator (bytes within one generation)
 
@@ -210,19 +211,16 @@ class DecodeEngine:
             cursor[0] = (off + nbytes + 255) // 256 * 256
             return off
 
-        def balance(total, tile_bytes):
-            """rotation r (tile u -> CTA (u + r) % G) that keeps the most loaded CTA lowest"""
-            base, rem = divmod(total, G)
+        def balance(total, tile_bytes, gs):
+            """rotation r (tile u -> CTA ((u % gs) + r) % G) that keeps the most loaded CTA lowest"""
+            cnt = [(total - j + gs - 1) // gs if j < min(gs, total) else 0 for j in range(G)]     # tiles of participant j
             best, best_r = None, 0
             for r in range(G):
-                worst = 0
-                for c in range(G):
-                    cnt = base + (1 if (c - r) % G < rem else 0)
-                    worst = max(worst, loads[c] + cnt * tile_bytes)
+                worst = max(loads[(j + r) % G] + cnt[j] * tile_bytes for j in range(G))
                 if best is None or worst < best:
                     best, best_r = worst, r
-            for c in range(G):
-                loads[c] += (base + (1 if (c - best_r) % G < rem else 0)) * tile_bytes
+            for j in range(G):
+                loads[(j + best_r) % G] += cnt[j] * tile_bytes
             return best_r
 
         FL_LM, FL_IN16, FL_OUT16, FL_PUB = 1, 2, 4, 8
@@ -242,10 +240,16 @@ class DecodeEngine:
             g = W[ln + ".weight"] if ln else None
             be = W.get(ln + ".bias") if ln else None
             tb = int(lib.i2t_decode_mega3_tile_bytes(K))
-            rot = balance((N + 15) // 16, tb)
+            total = (N + 15) // 16
+            # few tiles per CTA anyway: let half as many CTAs take two tiles each (one pass over a pair) -- half as many SMs pull
+            # the activations out of L2 at the same instant (the fan-out is L2-bandwidth bound: 24 KB x the CTAs taking part)
+            gs = G
+            if group and K <= 768 and G // 2 < total <= 2 * G:
+                gs = (total + 1) // 2
+            rot = balance(total, tb, gs)
             lin.append([0, P(b), P(g), P(be), inp, out, residual, N, K, act, mode, P(kc), P(vc), in_mode, P(wpe),
-                        ldo if ldo is not None else N, self.Tmax * C, flags, rot, pub, in_ld, 0, 0, 0])
-            wsrc.append((w, N, K, tb, rot))
+                        ldo if ldo is not None else N, self.Tmax * C, flags, rot, pub, in_ld, gs if gs != G else 0, 0, 0])
+            wsrc.append((w, N, K, tb, rot, gs))
             sched.append([0, len(lin) - 1, 0, 0])
 
         def add_cmb(n_parts, p0, pstride, bias, residual, out, N):
@@ -311,11 +315,11 @@ class DecodeEngine:
         # per-CTA weight streams: ops in schedule order, a CTA's tiles of an op in ascending order
         offs = [0] * G
         tile_offs = []
-        for (w, N, K, tb, rot) in wsrc:
+        for (w, N, K, tb, rot, gs) in wsrc:
             total = (N + 15) // 16
             to = [0] * total
             for u in range(total):
-                c = (u + rot) % G
+                c = ((u % gs) + rot) % G
                 to[u] = offs[c]
                 offs[c] += tb
             tile_offs.append(to)
@@ -324,13 +328,13 @@ class DecodeEngine:
         cta_base = torch.arange(G, dtype=torch.int64, device=dev) * stride
         st = stream()
         keep = []
-        for (w, N, K, tb, rot), to in zip(wsrc, tile_offs):
-            tt = torch.tensor([((u + rot) % G) * stride + o for u, o in enumerate(to)], dtype=torch.int64, device=dev)
+        for (w, N, K, tb, rot, gs), to in zip(wsrc, tile_offs):
+            tt = torch.tensor([(((u % gs) + rot) % G) * stride + o for u, o in enumerate(to)], dtype=torch.int64, device=dev)
             assert w.stride(1) == 1
             keep.append((tt, w))
             call("i2t_decode_mega3_pack", ptr(w), N, K, w.stride(0), ptr(wpack), ptr(tt), st)
         torch.cuda.current_stream().synchronize()          # the temporaries of the pack calls may go now
-        kpad = max((K - 1) // 768 * 768 + ((K - 1) % 768 + 256) // 256 * 256 for (_, _, K, _, _) in wsrc)
+        kpad = max((K - 1) // 768 * 768 + ((K - 1) % 768 + 256) // 256 * 256 for (_, _, K, _, _, _) in wsrc)
         t64 = lambda rows: torch.tensor(rows, dtype=torch.int64, device=dev).contiguous()
         return dict(lin=t64(lin), att=t64(att), cmb=t64(cmb), n_cmb=len(cmb),
                     sched=torch.tensor(sched, dtype=torch.int32, device=dev).contiguous(), n_ops=len(lin), exch=exch, gen_stride=gen_stride, wpack=wpack, cta_base=cta_base, grid=G,
@@ -512,11 +516,11 @@ class DecodeEngine:
         key = (tuple(images.shape), images.dtype, W.c("decoder.transformer.h.0.attn.c_attn.weight").data_ptr())
 
         def run(img):
-            enc = Fn.encoder_forward(W, self.spec, img, self.cd, train_trunk=False)
+            enc = self.model.encode(img)
             self._prefill_cross(enc)
 
         st = self._enc_graph
-        if os.environ.get("I2T_ENCODER_GRAPH", "1") == "0" or (st is not None and st.get("failed")):
+        if os.environ.get("I2T_ENCODER_GRAPH", "1") == "0" or (st is not None and st.get("failed")) or self.spec.get("injected_encoder"):
             return run(images)
         if st is None or st["key"] != key:
             self._enc_graph = dict(key=key, calls=1, graph=None, static=None)
@@ -807,7 +811,7 @@ class HFDecodeEngine:
         P = prompt_ids.shape[1]
         assert prompt_ids.shape[0] == B and self.n_prompt + P + max_new_tokens <= self.cap + 1
         self.nucleus_p = nucleus_p
-        enc = Fn.encoder_forward(W, spec, images, self.cd, train_trunk=False)
+        enc = m.encode(images)
         self.enc.copy_(enc)
         if spec["use_cross_attn"]:
             e = self.enc.reshape(B * self.S, C)

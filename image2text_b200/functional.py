@@ -176,19 +176,31 @@ def encoder_forward(W, spec, images: torch.Tensor, cd: torch.dtype, train_trunk:
 # ------------------------------------------------------------------------------------------------------------
 # decoder: reference models/vision_encoder_decoder.py:84-134 + models/decoder.py:214-256 + models/layers.py:565-614
 # ------------------------------------------------------------------------------------------------------------
-def hf_gpt2_forward(W, spec, ids: torch.Tensor, encoder_output: torch.Tensor, cd: torch.dtype, drop=None):
+def _given_embeds(inputs_embeds, limit):
+    """(ids stand-in, prompt rows, T): every row of the decoder input comes from the caller's inputs_embeds (+ wpe)."""
+    T = min(inputs_embeds.shape[1], limit)
+    rows = inputs_embeds[:, :T].contiguous().float()
+    return torch.zeros((rows.shape[0], 1), dtype=torch.long, device=rows.device), rows, T
+
+
+def hf_gpt2_forward(W, spec, ids: torch.Tensor, encoder_output: torch.Tensor, cd: torch.dtype, drop=None, inputs_embeds=None):
     """transformers GPT2LMHeadModel with add_cross_attention=True exactly as the reference drives it
     (models/decoder.py:335-361: attention_mask=None -> plain causal over prompt + text; every block has
     ln_cross_attn + crossattention {q_attn, c_attn -> [k|v], c_proj}); Conv1D weights stay (in, out)."""
     from .autograd_ops import conv1d
     C, H = spec["n_embd"], spec["n_head"]
-    B, S = ids.shape
-    n_prompt = spec["n_cls"] if spec["use_soft_prompting"] else 0
-    T = min(n_prompt + S, 1024)
     dp = "decoder.backbone.transformer."
-    prompt = encoder_output.contiguous().float() if n_prompt else None
     pd = spec.get("dropout", 0.0)              # GPT2Config embd_pdrop = attn_pdrop = resid_pdrop (training mode only)
-    x = EmbedFn.apply(ids.contiguous(), prompt, W[dp + "wte.weight"], W[dp + "wpe.weight"], T, n_prompt, _site(drop, pd))
+    if inputs_embeds is not None:              # HuggingfaceDecoder.forward(inputs_embeds=...), models/decoder.py:335-361
+        ids, rows, T = _given_embeds(inputs_embeds, 1024)
+        B, n_prompt = rows.shape[0], 0
+        x = EmbedFn.apply(ids, rows, W[dp + "wte.weight"], W[dp + "wpe.weight"], T, T, _site(drop, pd))
+    else:
+        B, S = ids.shape
+        n_prompt = spec["n_cls"] if spec["use_soft_prompting"] else 0
+        T = min(n_prompt + S, 1024)
+        prompt = encoder_output.contiguous().float() if n_prompt else None
+        x = EmbedFn.apply(ids.contiguous(), prompt, W[dp + "wte.weight"], W[dp + "wpe.weight"], T, n_prompt, _site(drop, pd))
     cross = spec["use_cross_attn"]
     S_enc = encoder_output.shape[1]
     enc_c = None
@@ -223,20 +235,25 @@ def hf_gpt2_forward(W, spec, ids: torch.Tensor, encoder_output: torch.Tensor, cd
 
 
 def decoder_forward(W, spec, ids: torch.Tensor, encoder_output: torch.Tensor, cd: torch.dtype, training: bool = False,
-                    drop=None):
+                    drop=None, inputs_embeds=None):
     """`drop` (ops.DropCtx) switches the training-mode dropouts on: transformer.drop (models/decoder.py:236-243), the
     per-token q/k/v masks + SDPA dropout_p + resid_dropout of models/layers.py:454-469, nn.MultiheadAttention's dropout
     (:537-542) and _MLP.dropout (:485).  Site order = call order below (the oracle's mask provider counts the same way)."""
     if spec["decoder"] == "hf_gpt2":
-        return hf_gpt2_forward(W, spec, ids, encoder_output, cd, drop)
+        return hf_gpt2_forward(W, spec, ids, encoder_output, cd, drop, inputs_embeds=inputs_embeds)
     C, H, blk = spec["n_embd"], spec["n_head"], spec["block_size"]
-    B, S = ids.shape
-    n_prompt = spec["n_cls"] if spec["use_soft_prompting"] else 0
-    T = min(n_prompt + S, blk)
     dp = "decoder.transformer."
-    prompt = encoder_output.contiguous().float() if n_prompt else None
     pd, pa = spec.get("dropout", 0.0), spec.get("attn_dropout", 0.0)
-    x = EmbedFn.apply(ids.contiguous(), prompt, W[dp + "wte.weight"], W[dp + "wpe.weight"], T, n_prompt, _site(drop, pd))
+    if inputs_embeds is not None:              # TransformerDecoder.forward(inputs_embeds=...), models/decoder.py:231-243
+        ids, rows, T = _given_embeds(inputs_embeds, blk)
+        B, n_prompt = rows.shape[0], 0
+        x = EmbedFn.apply(ids, rows, W[dp + "wte.weight"], W[dp + "wpe.weight"], T, T, _site(drop, pd))
+    else:
+        B, S = ids.shape
+        n_prompt = spec["n_cls"] if spec["use_soft_prompting"] else 0
+        T = min(n_prompt + S, blk)
+        prompt = encoder_output.contiguous().float() if n_prompt else None
+        x = EmbedFn.apply(ids.contiguous(), prompt, W[dp + "wte.weight"], W[dp + "wpe.weight"], T, n_prompt, _site(drop, pd))
     if n_prompt:
         mask_mode = ops.MASK_PROMPT
     else:

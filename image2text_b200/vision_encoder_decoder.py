@@ -68,14 +68,19 @@ class _Side(ParamTree):
             return Fn.encoder_forward(W, self._spec, images, m.compute_dtype,
                                       train_trunk=m.training and self._spec["refine_base_model"])
         idx = kwargs.get("idx", args[0] if args else None)
+        embeds = kwargs.get("inputs_embeds", args[1] if len(args) > 1 else None)
         cross = kwargs.get("cross_attn_embeds", args[2] if len(args) > 2 else None)
-        if kwargs.get("inputs_embeds", args[1] if len(args) > 1 else None) is not None or idx is None:
-            raise NotImplementedError("Decoder.forward(inputs_embeds=...) is composed inside VisionEncoderDecoder.forward here "
-                                      "(soft prompt + text rows are embedded by one kernel); pass idx")
-        # stand-alone decoder call: no soft prompt rows, cross attention iff embeddings are given (attn_msk: no-op, D9)
+        if embeds is None and idx is None:
+            raise ValueError("Decoder.forward needs idx or inputs_embeds")
+        # stand-alone decoder call (reference models/decoder.py:214-256): rows are wte[idx] or the given inputs_embeds, + wpe;
+        # no soft-prompt semantics, cross attention iff embeddings are given; the blocks' own causal mask applies (a caller's
+        # additive attn_msk is not: the only caller in the reference passes the closed forms of Appendix C, which
+        # VisionEncoderDecoder.forward composes itself)
         spec = dict(self._spec, use_soft_prompting=False, use_cross_attn=cross is not None)
-        enc = cross if cross is not None else torch.zeros((idx.shape[0], 1, spec["n_embd"]), device=idx.device)
-        logits, hidden = Fn.decoder_forward(W, spec, idx, enc, m.compute_dtype, training=m.training, drop=m._drop_ctx())
+        lead = embeds if embeds is not None else idx
+        enc = cross if cross is not None else torch.zeros((lead.shape[0], 1, spec["n_embd"]), device=lead.device)
+        logits, hidden = Fn.decoder_forward(W, spec, idx, enc, m.compute_dtype, training=m.training, drop=m._drop_ctx(),
+                                            inputs_embeds=embeds)
         return logits[..., :spec["vocab_size"]], hidden
 
     def get_inputs_embeds(self, idx):
@@ -92,27 +97,40 @@ class VisionEncoderDecoder(nn.Module):
     def __init__(self, config: VisionEncoderDecoderConfig, encoder=None, decoder=None, spec_overrides: Optional[dict] = None,
                  device="cuda", compute_dtype: torch.dtype = torch.float32, seed: Optional[int] = None):
         super().__init__()
-        if encoder is not None or decoder is not None:
-            raise NotImplementedError("constructor injection of foreign encoder/decoder modules is not supported: the "
-                                      "B200 path owns both halves (their kernels share buffers)")
+        if decoder is not None:
+            raise NotImplementedError("constructor injection of a foreign DECODER is not supported: the decoder is the B200 "
+                                      "hot path (its kernels own the weight layout and the KV cache); inject an encoder instead")
         if not (config.use_cross_attn or config.use_soft_prompting):
             raise ValueError("Misconfigured!!! Need to either use cross attn or soft prompting or both")
         self.config = config
         self.spec = spec_from_config(config, **(spec_overrides or {}))
+        if encoder is not None:
+            # reference models/vision_encoder_decoder.py:19-37: a caller-supplied Encoder (any nn.Module with `num_outputs`,
+            # `output_embed_dim` and forward(images) -> (B, num_outputs, output_embed_dim)) replaces Encoder.from_config; it
+            # runs as the torch module it is and feeds `encoder_output` to the B200 decoder path
+            self.spec = dict(self.spec, n_cls=int(encoder.num_outputs), n_embd_out_vit=int(encoder.output_embed_dim),
+                             injected_encoder=True)
         spec = self.spec
         if spec["decoder"] == "transformer" and spec["use_soft_prompting"] and not spec["is_causal"]:
             raise NotImplementedError("non-causal decoder blocks with a soft prompt are a 'next' row (SURVEY.md 8f-1)")
         if spec["decoder"] == "transformer" and spec["use_cross_attn"] != spec["is_cross_attn"]:
             raise ValueError("use_cross_attn must match decoder transformer_config.is_cross_attn")
         self.compute_dtype = compute_dtype
-        self.encoder = _Side("encoder", spec)
         self.decoder = _Side("decoder", spec)
-        self.encoder._bind(self)
         self.decoder._bind(self)
         gen = None
         if seed is not None:
             gen = torch.Generator(device="cpu").manual_seed(seed)
-        build_param_tree(self, state_schema(spec), spec, TIED_KEYS, torch.device(device), gen)
+        schema = state_schema(spec)
+        if encoder is None:
+            self.encoder = _Side("encoder", spec)
+            self.encoder._bind(self)
+        else:
+            schema = type(schema)((k, v) for k, v in schema.items() if not k.startswith("encoder"))
+            if spec["n_embd_out_vit"] != spec["n_embd"]:            # the reference bridges with a Linear (:33-37)
+                encoder = nn.Sequential(encoder, nn.Linear(spec["n_embd_out_vit"], spec["n_embd"]))
+            self.encoder = encoder.to(torch.device(device))
+        build_param_tree(self, schema, spec, TIED_KEYS, torch.device(device), gen)
         self.space_for_prompt = spec["n_cls"] if config.use_soft_prompting else 0
         self.use_cross_attn = config.use_cross_attn
         self.use_soft_prompting = config.use_soft_prompting
@@ -128,8 +146,17 @@ class VisionEncoderDecoder(nn.Module):
     def __setstate__(self, state):
         super().__setstate__(state)            # copy.deepcopy / pickle: re-point the sub-objects at THIS model
         self.__dict__["_tensor_cache"] = None
-        self.encoder._bind(self)
+        if isinstance(self.encoder, _Side):
+            self.encoder._bind(self)
         self.decoder._bind(self)
+
+    def encode(self, images: torch.Tensor) -> torch.Tensor:
+        """images -> (B, n_cls, n_embd) fp32 encoder output: the B200 ViT path, or the injected torch encoder."""
+        from . import functional as Fn
+        if self.spec.get("injected_encoder"):
+            return self.encoder(images).float()
+        return Fn.encoder_forward(self.weights(), self.spec, images, self.compute_dtype,
+                                  train_trunk=self.training and self.spec["refine_base_model"])
 
     def load_partial_checkpoint(self, path: str, map_location=None):
         """reference models/utils.py:31-36: state_dict().update(torch.load(path)); load_state_dict."""
@@ -232,8 +259,7 @@ class VisionEncoderDecoder(nn.Module):
         from . import functional as Fn
         W = self.weights()
         if encoder_output is None:
-            encoder_output = Fn.encoder_forward(W, self.spec, images, self.compute_dtype,
-                                                train_trunk=self.training and self.spec["refine_base_model"])
+            encoder_output = self.encode(images)
         # attn_msk: accepted and ignored -- it has no effect in the reference either (D9)
         logits, hidden = Fn.decoder_forward(W, self.spec, ids, encoder_output, self.compute_dtype, training=self.training,
                                             drop=self._drop_ctx())
@@ -286,7 +312,7 @@ class VisionEncoderDecoder(nn.Module):
         from ._lib import call
         spec = self.spec
         W = self.weights()
-        enc = Fn.encoder_forward(W, spec, images, self.compute_dtype, train_trunk=False)
+        enc = self.encode(images)
         B, P = prompt_ids.shape
         V = spec["vocab_size"]
         blk = spec["block_size"] - self.space_for_prompt

@@ -279,3 +279,62 @@ def test_beam_search_matches_reference_golden(golden):
                                            consolidation_temperature=0.7)(images, prompt)
     assert ids.shape == (2, 3, 8) and scores.shape == (2, 3) and bool(torch.isfinite(scores).all())
     assert bool((ids[:, :, 0] == eos).all())
+
+
+def test_decoder_forward_accepts_inputs_embeds():
+    """reference models/decoder.py:214-256: Decoder.forward(inputs_embeds=E) == Decoder.forward(idx) when E = wte[idx]; with
+    arbitrary rows it matches the oracle's stand-alone decoder."""
+    m = build("tiny")
+    _, spec, sd = spec_and_weights("tiny")
+    ids = torch.randint(0, spec["vocab_size"], (3, 12), generator=torch.Generator().manual_seed(4))
+    enc = torch.randn(3, spec["n_cls"], spec["n_embd"], generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        a_logits, a_hidden = m.decoder(idx=ids.cuda(), cross_attn_embeds=enc.cuda())
+        emb = m.decoder.get_inputs_embeds(ids.cuda())
+        b_logits, b_hidden = m.decoder(inputs_embeds=emb, cross_attn_embeds=enc.cuda())
+        assert torch.equal(a_logits, b_logits) and torch.equal(a_hidden, b_hidden)
+        rows = torch.randn(3, 12, spec["n_embd"], generator=torch.Generator().manual_seed(6))
+        c_logits, c_hidden = m.decoder(inputs_embeds=rows.cuda(), cross_attn_embeds=enc.cuda())
+        ospec = dict(spec, use_soft_prompting=False)
+        causal = torch.zeros(1, 1, 12, 12).masked_fill(~torch.ones(12, 12, dtype=torch.bool).tril(), float("-inf"))
+        want_logits, want_hidden = O.transformer_decoder_forward(sd, ospec, inputs_embeds=rows, cross_attn_embeds=enc, attn_msk=causal,
+                                                                 prefix="decoder.", normalize_grads=False)
+    assert rel_err(c_hidden.cpu(), want_hidden) < 1e-4
+    assert rel_err(c_logits.float().cpu()[..., :spec["vocab_size"]], want_logits[..., :spec["vocab_size"]]) < 1e-4
+
+
+def test_constructor_injection_of_a_torch_encoder():
+    """reference models/vision_encoder_decoder.py:19-37: VisionEncoderDecoder(config, encoder=E) uses the caller's encoder
+    (num_outputs summary tokens of output_embed_dim, bridged to n_embd with a Linear when the widths differ)."""
+    import torch.nn as nn
+    from image2text_b200 import VisionEncoderDecoder as VED
+    tc, spec, sd = spec_and_weights("tiny")
+
+    class TinyEncoder(nn.Module):
+        num_outputs, output_embed_dim = 4, 96
+
+        def __init__(self):
+            super().__init__()
+            self.proj = nn.Linear(3 * 32 * 32, 4 * 96)
+
+        def forward(self, images):
+            return self.proj(images.flatten(1)).view(-1, 4, 96)
+
+    torch.manual_seed(0)
+    m = VED(tc.model, encoder=TinyEncoder(), spec_overrides=SPEC_OVERRIDES["tiny"], device="cuda")
+    assert m.space_for_prompt == 4 and isinstance(m.encoder, nn.Sequential)          # 96 != 128: bridged like the reference
+    m.load_state_dict({**{k: v for k, v in sd.items() if k.startswith("decoder.")}, **{k: v for k, v in m.state_dict().items()
+                                                                                        if k.startswith("encoder.")}})
+    m.eval()
+    images = synth_images(3, 32, seed=11).cuda()
+    ids = torch.randint(0, spec["vocab_size"] - 1, (3, 10), generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        out = m(images=images, ids=ids.cuda())
+        enc = m.encoder(images)
+        _, want, _ = O.ved_forward(sd, spec, None, ids, encoder_output=enc.float().cpu(), normalize_grads=False)
+    assert torch.equal(out.encoder_output, enc.float())
+    assert rel_err(out.logits.cpu(), want) < 1e-4
+    got = m.generate(images, torch.full((3, 1), spec["vocab_size"] - 1, dtype=torch.long, device="cuda"), max_new_tokens=8, top_k=1)
+    assert got.shape == (3, 9)
+    with pytest.raises(NotImplementedError):
+        VED(tc.model, decoder=nn.Identity(), spec_overrides=SPEC_OVERRIDES["tiny"], device="cuda")
