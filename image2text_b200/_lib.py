@@ -54,10 +54,10 @@ SIGNATURES = {
     "i2t_set_decode_poll_sleep": (None, [I]),
     "i2t_decode_mega3_grid": (c_int, []),
     "i2t_decode_mega3_tile_bytes": (c_int64, [L]),
-    "i2t_decode_mega3_pack": (c_int, [P, L, L, L, P, P, P]),
+    "i2t_decode_mega3_pack": (c_int, [P, L, L, L, P, P, L, P]),
     "i2t_decode_mega3_prepare": (c_int, [P, L, P, P, L, L, L, L, L, P, L, L, L, L, P, L, P, P]),
     "i2t_decode_mega3": (c_int, [P, P, P, P, L, L, L, L, L, L, L, L, L, L, L, P, L, P, P, L, P, P, P, P, P, L, F, L, P, L, P, L,
-                                 L, P, L, P]),
+                                 L, P, L, L, P]),
     "i2t_act_fwd": (c_int, [P, P, L, I, I, I, P]),
     "i2t_act_bwd": (c_int, [P, P, P, L, I, I, I, P]),
     "i2t_embed_bwd": (c_int, [P, P, P, L, L, L, L, L, P]),

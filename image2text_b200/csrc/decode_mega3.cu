@@ -28,7 +28,7 @@
 //   18 rot (tile u belongs to CTA (u + rot) % grid) | 19 where the embedding is published (generation 0) | 20 input row
 //   pitch in elements (0 = K: lets a K-split op read a column range of a wider buffer) | 21 group size Gs (0 = grid): only
 //   the first Gs CTAs of the rotation take part, tile u belongs to CTA ((u % Gs) + rot) % grid -- fewer CTAs fan the
-//   activations out of L2 when an op has few tiles per CTA anyway | 22-23 unused
+//   activations out of L2 when an op has few tiles per CTA anyway | 22 1 = tcgen05 stage (weights packed as UMMA atoms) | 23 unused
 // cmb[c][8] (combine: out = bias + residual + sum of n partial buffers, the second half of a K-split projection) =
 //   0 n partials | 1 first partial f32 (generation 0) | 2 bytes between partials | 3 bias f32* | 4 residual (generation 0)
 //   5 output (generation 0) | 6 N (row length) | 7 rot
@@ -44,7 +44,8 @@ namespace i2t {
 
 constexpr int M3_CWARPS = 8;                  // consumer warps
 constexpr int M3_CTHREADS = M3_CWARPS * 32;
-constexpr int M3_THREADS = M3_CTHREADS + 32;  // + the weight-stream producer warp
+constexpr int M3_THREADS = M3_CTHREADS + 64;  // + the weight-stream producer warp + the tcgen05 issuer warp
+constexpr int M3_TBUFS = 2;                   // TMEM tile buffers (tcgen05 path): 4 partial accumulators x 16 columns each
 constexpr int M3_B = 8;                       // batch rows = MMA N
 constexpr int M3_ROWS = 16;                   // weight rows per tile = MMA M
 constexpr int M3_BLK = 32;                    // k elements per block (one 16-byte vector per thread and row)
@@ -88,6 +89,7 @@ struct M3Args {
   int n_ngrams;
   const uint64_t* seed_ptr;
   int sleep_ns;                  // back-off between unsuccessful polls (0 = spin)
+  int tc;                        // 1: linear stages on tcgen05 (weights packed in the 128B-swizzled K-major UMMA layout)
   long long* trace;              // optional [n_sched][4] clock64 stamps of CTA `trace_cta` for the LAST sampled step
   int trace_cta;
 };
@@ -105,6 +107,9 @@ struct __align__(16) M3Fixed {
     M3AttScratch att;                              //   attention: query, probabilities, partial outputs
   };
   uint64_t full[M3_MAX_SLOTS], empty[M3_MAX_SLOTS];
+  uint64_t tfull[M3_TBUFS], tempty[M3_TBUFS];    // tcgen05 path: accumulator buffer complete / drained
+  uint64_t xsempty;                              // tcgen05 path: every MMA of the stage has read the staged activations
+  uint32_t tmem_base, pad_;
   uint32_t banmask[M3_MAX_LM_ROWS / 4];          // no-repeat-n-gram ban: one byte per LM-head row this CTA owns, bit b = sequence b
   int hist[M3_B][M3_MAX_KEYS + 8];               // token history of every sequence (n-gram ban)
   int tok[M3_B];                                  // the tokens this step embeds
@@ -126,8 +131,10 @@ __host__ __device__ inline M3Sm m3_layout(int nslots, int max_k, int max_len, in
   S.xpitch = max_k + 32;              // bytes = 2 * max_k + 64 = 64 (mod 128): conflict-free LDS.128 of the B fragments
   uint32_t off = (uint32_t)nslots * 24576u;
   S.fixed_off = off; off += (uint32_t)m3_align16(sizeof(M3Fixed));
+  off = (off + 1023u) & ~1023u;      // the tcgen05 path reads the activations as 128B-swizzled atoms (1024-byte aligned)
   S.xs_off = off;
-  const uint32_t xs = (uint32_t)m3_align16((size_t)8 * S.xpitch * 2);
+  const uint32_t xs_plain = (uint32_t)m3_align16((size_t)8 * S.xpitch * 2), xs_tc = (uint32_t)(max_k / 64 + 1) * 1024u;
+  const uint32_t xs = xs_plain > xs_tc ? xs_plain : xs_tc;
   S.ln_off = off + xs;
   const uint32_t lin_work = xs + 2u * 768u * 4u, att_work = (uint32_t)m3_align16((size_t)max_len * hs * 2);
   off += lin_work > att_work ? lin_work : att_work;
@@ -143,6 +150,13 @@ __host__ __device__ inline M3Sm m3_layout(int nslots, int max_k, int max_len, in
 __device__ __forceinline__ uint4* m3_ring(int slot) { return reinterpret_cast<uint4*>(m3_smem + (size_t)slot * M3_SLOT_BYTES); }
 __device__ __forceinline__ M3Fixed* m3_f(const M3Sm& S) { return reinterpret_cast<M3Fixed*>(m3_smem + S.fixed_off); }
 __device__ __forceinline__ __nv_bfloat16* m3_xs(const M3Sm& S) { return reinterpret_cast<__nv_bfloat16*>(m3_smem + S.xs_off); }
+// where the 8 (4) consecutive k of batch row `row` starting at k live: plain rows (mma.sync path) or the K-major,
+// 128B-swizzled atoms the tcgen05 path reads as its B operand ([k / 64][row][16-byte chunk ((k % 64) / 8) ^ row])
+__device__ __forceinline__ __nv_bfloat16* m3_xaddr(const M3Sm& S, bool tc, int row, int k) {
+  __nv_bfloat16* xs = m3_xs(S);
+  if (!tc) return xs + row * S.xpitch + k;
+  return xs + (k >> 6) * 512 + row * 64 + ((((k >> 3) & 7) ^ row) << 3) + (k & 7);
+}
 __device__ __forceinline__ float* m3_ln(const M3Sm& S) { return reinterpret_cast<float*>(m3_smem + S.ln_off); }   // gamma[768] | beta[768]
 __device__ __forceinline__ const int64_t* m3_lin(const M3Sm& S, int op) {
   return reinterpret_cast<const int64_t*>(m3_smem + S.lin_off) + (size_t)op * M3_LIN_FIELDS;
@@ -207,6 +221,9 @@ __device__ __forceinline__ void m3_st8(void* p, uint2 v) {
 }
 __device__ __forceinline__ void m3_st8(void* p, unsigned long long v) {
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void m3_st4(void* p, uint32_t v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void m3_st2(void* p, unsigned short v) {
   asm volatile("st.relaxed.gpu.global.u16 [%0], %1;" ::"l"(p), "h"(v) : "memory");
@@ -273,9 +290,10 @@ __device__ __forceinline__ int m3_kpad(int K) {                       // staged 
   const int last = m3_nkc(K) - 1;
   return last * M3_KC + m3_chunk_nb(K, last) * M3_BLK * M3_CWARPS;
 }
-__device__ __forceinline__ int m3_first_unit(int rot) {
+__device__ __forceinline__ int m3_first_unit(int rot) {          // (blockIdx - rot) mod grid, rot in [0, grid): no division
   const int G = (int)gridDim.x;
-  return (int)((blockIdx.x + (unsigned)(G - rot)) % (unsigned)G);
+  const int t = (int)blockIdx.x + G - rot;
+  return t >= G ? t - G : t;
 }
 
 struct M3Ring {
@@ -336,22 +354,21 @@ __device__ __forceinline__ uint32_t m3_pack(float lo, float hi) {
 // per warp and round instead of the whole row), then the row is re-read; LayerNorm on registers.  bf16 input (attention
 // output, MLP hidden): passes of 6 vectors per lane, copied as they are.
 __device__ __forceinline__ void m3_stage_x(const M3Args& a, const int64_t* d, const M3Sm& S, int gen, int pos, int u0, int warp,
-                                           int lane, long long* trace) {
+                                           int lane, long long* trace, const bool tc = false) {
   const int K = (int)d[8];
   const int flags = (int)d[17];
   const int in_mode = (int)d[13];
   const int kpad = m3_kpad(K);
-  __nv_bfloat16* xr = m3_xs(S) + warp * S.xpitch;
   const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
   if (warp >= a.B) {                         // unused batch rows: zeros
-    for (int k = lane * 8; k < kpad; k += 256) *reinterpret_cast<uint4*>(xr + k) = zero4;
+    for (int k = lane * 8; k < kpad; k += 256) *reinterpret_cast<uint4*>(m3_xaddr(S, tc, warp, k)) = zero4;
     if ((flags & 2) == 0 && d[2] != 0) {     // (the LayerNorm path has one CTA barrier: keep the count equal)
       m3_cp_wait0();
       m3_csync();
     }
     return;
   }
-  for (int k = K + lane * 8; k < kpad; k += 256) *reinterpret_cast<uint4*>(xr + k) = zero4;     // (K % 8 == 0)
+  for (int k = K + lane * 8; k < kpad; k += 256) *reinterpret_cast<uint4*>(m3_xaddr(S, tc, warp, k)) = zero4;     // (K % 8 == 0)
   if ((flags & 2) != 0) {                    // bf16 exchange buffer, no LayerNorm
     const uint8_t* src = m3_gen<const uint8_t>(d[4], a.gen_stride, gen) + (int64_t)warp * (d[20] != 0 ? d[20] : (int64_t)K) * 2;
     const int nvec = K / 8;
@@ -383,7 +400,7 @@ __device__ __forceinline__ void m3_stage_x(const M3Args& a, const int64_t* d, co
 #pragma unroll
       for (int i = 0; i < M3_NVX; ++i) {
         const int vi = v0 + lane + 32 * i;
-        if (vi < nvec) *reinterpret_cast<uint4*>(xr + vi * 8) = v[i];
+        if (vi < nvec) *reinterpret_cast<uint4*>(m3_xaddr(S, tc, warp, vi * 8)) = v[i];
       }
     }
     return;
@@ -478,7 +495,7 @@ __device__ __forceinline__ void m3_stage_x(const M3Args& a, const int64_t* d, co
 #pragma unroll
   for (int i = 0; i < M3_NVX; ++i) {
     const int k = (lane + 32 * i) * 4;
-    if (k < K) *reinterpret_cast<uint2*>(xr + k) = make_uint2(m3_pack(v[i].x, v[i].y), m3_pack(v[i].z, v[i].w));
+    if (k < K) *reinterpret_cast<uint2*>(m3_xaddr(S, tc, warp, k)) = make_uint2(m3_pack(v[i].x, v[i].y), m3_pack(v[i].z, v[i].w));
   }
 }
 
@@ -525,7 +542,7 @@ __device__ __forceinline__ float m3_act(float x, int act) {
 
 // ---- one linear stage ----
 __device__ __forceinline__ void m3_linear(const M3Args& a, int op, const M3Sm& S, M3Ring& R, int gen, int pos, int keyslot,
-                                          int tid, long long* trace) {
+                                          int tid, long long* trace, uint32_t xcount = 0) {
   const int lane = tid & 31, warp = tid >> 5;
   M3Fixed* f = m3_f(S);
   const int64_t* d = m3_lin(S, op);
@@ -553,6 +570,7 @@ __device__ __forceinline__ void m3_linear(const M3Args& a, int op, const M3Sm& S
       }
       m3_cp_commit();
     }
+    if (a.tc) m3_mbar_wait(&f->xsempty, (xcount & 1u) ^ 1u, a.error_flag);   // a tcgen05 stage may still be reading the rows
     m3_stage_x(a, d, S, gen, pos, u0, warp, lane, trace);
     m3_csync();                                // xs visible
     if (trace != nullptr) trace[1] = clock64();
@@ -584,7 +602,9 @@ __device__ __forceinline__ void m3_linear(const M3Args& a, int op, const M3Sm& S
           e_res = m3_ld16(resp);
         }
       }
+      int rs0 = 0, rs1 = 0;
       float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      // (three independent accumulator chains per tile were measured: no gain in the MMA phase, 12 bytes of spills, +20 us / step)
 #pragma unroll 1
       for (int kc = 0; kc < nkc; ++kc) {
         const int nbc = m3_chunk_nb(K, kc);
@@ -619,11 +639,13 @@ __device__ __forceinline__ void m3_linear(const M3Args& a, int op, const M3Sm& S
             }
           }
         }
-        __syncwarp();
-        if (lane == 0) {                               // this warp is done with the slot(s): hand them back to the producer
+        // hand the slot(s) back to the producer once all 8 warps are done with them: warps 0..3 arrive (the barrier counts 4)
+        if (nkc > 1) m3_csync();                       // (single-chunk tiles: the barrier in front of the epilogue does it)
+        if (nkc > 1 && lane == 0 && warp < 4) {
           m3_mbar_arrive(&f->empty[s0]);
           if (two) m3_mbar_arrive(&f->empty[s1]);
         }
+        rs0 = s0; rs1 = s1;
       }
       if (trace != nullptr && pidx == 0) trace[4] = clock64() + (long long)(acc[0][0] == 123.f);
       // acc: D[g][2qd], D[g][2qd+1], D[g+8][2qd], D[g+8][2qd+1]  ->  red[tile][batch][row]
@@ -640,6 +662,10 @@ __device__ __forceinline__ void m3_linear(const M3Args& a, int op, const M3Sm& S
         red[M3_RED_T + (2 * qd + 1) * 20 + g + 8] = acc[1][3];
       }
       m3_csync();
+      if (nkc == 1 && lane == 0 && warp < 4) {         // every warp has read the slot(s): 4 arrivals free them
+        m3_mbar_arrive(&f->empty[rs0]);
+        if (two) m3_mbar_arrive(&f->empty[rs1]);
+      }
       if (trace != nullptr && pidx == 0) trace[5] = clock64();
       if (e_on) {
         const float* rp = &f->red[0][et * M3_RED_T + eb * 20 + 4 * rg];
@@ -676,7 +702,7 @@ __device__ __forceinline__ void m3_linear(const M3Args& a, int op, const M3Sm& S
               if (nq + j < N) a.logits[(int64_t)eb * a.ldl + nq + j] = vv[j];
           }
         } else if (mode == 1 && n0 >= a.C) {   // k / v rows of the packed q|k|v output: appended at `pos` (poisoned by the host)
-          const int seg = n0 / a.C, nl = nq - seg * a.C;
+          const int seg = n0 >= 2 * a.C ? 2 : 1, nl = nq - seg * a.C;
           __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(seg == 1 ? d[11] : d[12]);
           m3_st8(base + (int64_t)eb * cache_bs + (int64_t)pos * a.C + nl, make_uint2(m3_pack(v.x, v.y), m3_pack(v.z, v.w)));
         } else if (out_bf16) {
@@ -714,10 +740,202 @@ __device__ __forceinline__ void m3_linear(const M3Args& a, int op, const M3Sm& S
   }
 }
 
+
+// =====================================================================================================================
+// tcgen05 path of a linear stage.  The weights of a tile (16 rows) sit in a ring slot as K-major, 128B-swizzled atoms
+// ([k / 64][row][128 B]); the staged activations likewise ([k / 64][batch row][128 B]).  A single tcgen05.mma M128 N16 K16
+// takes ~4-8 tensor-core cycles but tens of issue cycles, so FOUR consumer warps (1, 2, 3, 5) each issue the MMAs of every
+// fourth 64-wide K block into their own TMEM accumulator (4 partials x 16 columns per tile, 2 tiles in flight); rows
+// 16..127 of the A operand and columns 8..15 of the B operand read whatever follows in shared memory -- their results land
+// in TMEM lanes / columns nobody reads.  tcgen05.commit hands the ring slot back to the weight producer and wakes the
+// epilogue warps 0 and 4 (the warps that may read TMEM lanes 0..31): lane r owns row r of the tile, warp 0 the sequences
+// 0..3, warp 4 the sequences 4..7; they add the four partials in a fixed order.  No partial tiles through shared memory.
+// =====================================================================================================================
+struct M3Tc {
+  uint32_t tcount;      // tiles this CTA has pushed through TMEM so far (buffer = tcount % 2)
+  uint32_t xcount;      // tcgen05 linear stages this CTA took part in so far (parity of xsempty)
+};
+constexpr int M3_TC_ISSUERS = 4;
+constexpr uint32_t M3_TC_COLS = 128;          // 2 tile buffers x 4 partial accumulators x 16 columns
+
+__device__ __forceinline__ void m3_tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ bool m3_elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0u;
+}
+
+__device__ __forceinline__ void m3_linear_tc(const M3Args& a, int op, const M3Sm& S, M3Ring& R, M3Tc& T, int gen, int pos, int keyslot,
+                                             int tid, long long* trace) {
+  const int lane = tid & 31, warp = tid >> 5;
+  M3Fixed* f = m3_f(S);
+  const int64_t* d = m3_lin(S, op);
+  const int N = (int)d[7], K = (int)d[8];
+  const int flags = (int)d[17];
+  const int total = (N + M3_ROWS - 1) / M3_ROWS;
+  const int nkc = m3_nkc(K);
+  const int G = (int)gridDim.x;
+  const int Gs = d[21] != 0 ? (int)d[21] : G;
+  const int uf = m3_first_unit((int)d[18]);
+  const int u0 = uf < Gs ? uf : total;
+  const int gen1 = (gen + 1) % M3_GENS;
+  if (u0 >= total) return;
+  if (d[2] != 0) {                           // LayerNorm gamma / beta -> shared memory, in flight while the inputs are polled
+    const float* ln_g = reinterpret_cast<const float*>(d[2]);
+    const float* ln_b = reinterpret_cast<const float*>(d[3]);
+    for (int k = tid * 4; k < K; k += M3_CTHREADS * 4) {
+      m3_cp_async16(m3_ln(S) + k, ln_g + k);
+      m3_cp_async16(m3_ln(S) + M3_KC + k, (ln_b != nullptr ? ln_b : ln_g) + k);
+    }
+    m3_cp_commit();
+  }
+  m3_mbar_wait(&f->xsempty, (T.xcount & 1u) ^ 1u, a.error_flag);   // the MMAs of the previous stage are done with the rows
+  m3_stage_x(a, d, S, gen, pos, u0, warp, lane, trace, true);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the tensor core
+  m3_csync();
+  ++T.xcount;
+  if (trace != nullptr) trace[1] = clock64();
+  // roles: issuer q (warps 1, 2, 3, 5) takes the K blocks q, q + 4, ...; warps 0 / 4 the epilogue of sequences 0..3 / 4..7
+  const int q = warp == 5 ? 3 : warp - 1;
+  const bool issuer = warp == 1 || warp == 2 || warp == 3 || warp == 5;
+  const bool epi = (warp & 3) == 0;
+  const uint32_t tmem_base = f->tmem_base;
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);   // f32 += bf16 x bf16, N 16, M 128
+  const uint32_t xs_addr = smem_u32(m3_xs(S));
+  const float* bias = reinterpret_cast<const float*>(d[1]);
+  const int act = (int)d[9], mode = (int)d[10];
+  const int64_t ldo = d[15], cache_bs = d[16];
+  const bool out_bf16 = (flags & 4) != 0;
+  const bool has_res = mode == 0 && d[6] != 0;
+  const int b0 = (warp >> 2) * 4;                                  // first sequence of this epilogue warp
+  int ti = 0;
+#pragma unroll 1
+  for (int u = u0; u < total; u += Gs, ++ti) {
+    const uint32_t tc = T.tcount + (uint32_t)ti, buf = tc & 1u;
+    if (issuer) {
+      m3_mbar_wait(&f->tempty[buf], ((tc >> 1) & 1u) ^ 1u, a.error_flag);       // both epilogue warps have drained this buffer
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    const int n = u * M3_ROWS + lane;
+    const bool on = epi && lane < M3_ROWS && n < N;
+    float e_bias = 0.f;
+    uint32_t e_res[4] = {0u, 0u, 0u, 0u};
+    const float* resp = nullptr;
+    if (on) {                                        // epilogue operands do not depend on the MMAs: request them now
+      if (bias != nullptr) e_bias = __ldg(bias + n);
+      if (has_res) {
+        resp = m3_gen<const float>(d[6], a.gen_stride, gen) + (int64_t)b0 * ldo + n;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) e_res[j] = b0 + j < a.B ? m3_ld4(resp + (int64_t)j * ldo) : 0u;
+      }
+    }
+    uint32_t accf = 0u;
+#pragma unroll 1
+    for (int kc = 0; kc < nkc; ++kc) {
+      const int npq = m3_chunk_nb(K, kc);                          // 64-wide K blocks per issuer in this chunk (1..3)
+      const int slot = R.slot;
+      if (issuer) {
+        m3_mbar_wait(&f->full[slot], R.phase, a.error_flag);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (m3_elect_one()) {
+          const uint32_t tmem_d = tmem_base + buf * 64u + (uint32_t)q * 16u;
+          const uint64_t adesc = umma_desc_sw128(smem_u32(m3_ring(slot))) + (uint64_t)(q * (2048 >> 4));
+          const uint64_t bdesc = umma_desc_sw128(xs_addr + (uint32_t)kc * (M3_KC / 64) * 1024u) + (uint64_t)(q * (1024 >> 4));
+#pragma unroll
+          for (int i = 0; i < M3_NB; ++i) {
+            if (i < npq) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {                         // 16 values of K = 32 bytes inside the 128-byte swizzle span
+                umma_bf16(tmem_d, adesc + (uint64_t)(i * 4 * (2048 >> 4) + 2 * j), bdesc + (uint64_t)(i * 4 * (1024 >> 4) + 2 * j),
+                          idesc, (accf | (uint32_t)(i | j)) != 0u ? 1u : 0u);
+              }
+            }
+          }
+          umma_commit(&f->empty[slot]);                             // one of 4 arrivals: the slot goes back to the weight producer
+        }
+        __syncwarp();
+        accf = 1u;
+      }
+      R.advance(a.nslots);
+    }
+    if (issuer) {
+      if (m3_elect_one()) umma_commit(&f->tfull[buf]);              // one of 4 arrivals: the partial accumulators are complete
+      __syncwarp();
+    }
+    if (epi) {
+      m3_mbar_wait(&f->tfull[buf], (tc >> 1) & 1u, a.error_flag);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      uint32_t r0[4], r1[4], r2[4], r3[4];
+      const uint32_t taddr = tmem_base + buf * 64u + (uint32_t)b0;   // lane r of the warp = TMEM lane r = row r of the tile
+      m3_tmem_ld4(taddr, r0);
+      m3_tmem_ld4(taddr + 16u, r1);
+      m3_tmem_ld4(taddr + 32u, r2);
+      m3_tmem_ld4(taddr + 48u, r3);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) m3_mbar_arrive(&f->tempty[buf]);
+      if (trace != nullptr && ti == 0) trace[5] = clock64();
+      if (on) {
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          v[j] = m3_act(((__uint_as_float(r0[j]) + __uint_as_float(r1[j])) + (__uint_as_float(r2[j]) + __uint_as_float(r3[j]))) + e_bias, act);
+        if (has_res) {
+          uint32_t spins = 0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (b0 + j < a.B) {
+              while (e_res[j] == 0xFFFFFFFFu) {
+                if (m3_giveup(spins, a.error_flag)) break;
+                e_res[j] = m3_ld4(resp + (int64_t)j * ldo);
+              }
+              v[j] += __uint_as_float(e_res[j]);
+            }
+        }
+        if (mode == 1 && n >= a.C) {           // k / v rows of the packed q|k|v output: appended at `pos` (poisoned by the host)
+          const int seg = n >= 2 * a.C ? 2 : 1, nl = n - seg * a.C;
+          __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(seg == 1 ? d[11] : d[12]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (b0 + j < a.B)
+              m3_st2(base + (int64_t)(b0 + j) * cache_bs + (int64_t)pos * a.C + nl, __bfloat16_as_ushort(__float2bfloat16_rn(v[j])));
+        } else if (out_bf16) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (b0 + j < a.B) {
+              const int64_t off = ((int64_t)(b0 + j) * ldo + n) * 2;
+              m3_st2(m3_gen<uint8_t>(d[5], a.gen_stride, gen1) + off, (unsigned short)0xFFFFu);
+              m3_st2(m3_gen<uint8_t>(d[5], a.gen_stride, gen) + off, __bfloat16_as_ushort(__float2bfloat16_rn(v[j])));
+            }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (b0 + j < a.B) {
+              const int64_t off = ((int64_t)(b0 + j) * ldo + n) * 4;
+              m3_st4(m3_gen<uint8_t>(d[5], a.gen_stride, gen1) + off, 0xFFFFFFFFu);
+              m3_st4(m3_gen<uint8_t>(d[5], a.gen_stride, gen) + off, __float_as_uint(v[j]));
+            }
+        }
+      }
+    }
+  }
+  if (issuer) {
+    if (m3_elect_one()) umma_commit(&f->xsempty);                   // one of 4 arrivals: every MMA of the stage has read the rows
+    __syncwarp();
+  }
+  T.tcount += (uint32_t)ti;
+}
+
 // ---- single-query attention for one (batch, head) per CTA: one key per thread for q.k (K row in registers),
 //      V rows staged in shared memory (aliasing the idle activation rows) for P.V ----
 template <int HS>
-__device__ __forceinline__ void m3_attention(const M3Args& a, int ai, const M3Sm& S, int gen, int pos, int tid) {
+__device__ __forceinline__ void m3_attention(const M3Args& a, int ai, const M3Sm& S, int gen, int pos, int tid, uint32_t xcount = 0) {
   constexpr int NV = HS / 8, DPL = HS / 32;          // 16-byte vectors per row; dims per lane in P.V
   const int lane = tid & 31, warp = tid >> 5;
   M3Fixed* f = m3_f(S);
@@ -730,6 +948,7 @@ __device__ __forceinline__ void m3_attention(const M3Args& a, int ai, const M3Sm
   const int b = unit / a.H, h = unit - b * a.H;
   const bool on = tid < len;
   const bool fresh = self && tid == pos;             // the row the QKV stage of THIS step appends
+  if (a.tc) m3_mbar_wait(&f->xsempty, (xcount & 1u) ^ 1u, a.error_flag);   // the V rows alias the rows the tensor core may still read
   uint4 kr[NV];
   uint4* vs = reinterpret_cast<uint4*>(m3_xs(S));
   const __nv_bfloat16* kp = reinterpret_cast<const __nv_bfloat16*>(d[0]) + b * d[2] + (int64_t)tid * d[3] + h * HS;
@@ -832,7 +1051,12 @@ __device__ __forceinline__ void m3_combine(const M3Args& a, int ci, const M3Sm& 
   const int np = (int)d[0];
   for (int u = m3_first_unit((int)d[7]); u < total; u += G) {
     const int vi = u * M3_CTHREADS + tid;
-    const int b = vi / nvec_row, n = (vi - b * nvec_row) * 4;
+    int b = 0, rem = vi;
+#pragma unroll
+    for (int j = 0; j < M3_B; ++j)
+      if (rem >= nvec_row) { rem -= nvec_row; ++b; }
+    const int n = rem * 4;
+    if (rem >= nvec_row) continue;
     if (b >= a.B) continue;
     const int64_t off = ((int64_t)b * N + n) * 4;
     const uint8_t* p0 = m3_gen<const uint8_t>(d[1], a.gen_stride, gen) + off;
@@ -935,8 +1159,12 @@ __device__ __forceinline__ void m3_tokens(const M3Args& a, const M3Sm& S, int po
   m3_csync();
 }
 
-template <int HS>
-__global__ void __launch_bounds__(M3_THREADS, 1) decode_mega3_kernel(M3Args a) {
+template <int HS, bool TC>
+__global__ void __launch_bounds__(M3_THREADS, 1) decode_mega3_kernel(M3Args a_in) {
+  // TC = false: no tcgen05 code in the kernel at all (the default; the experimental tcgen05 instantiation costs the hot loop
+  // registers and instruction-cache footprint: 281 -> 292 us per step when both paths shared one kernel)
+  M3Args a = a_in;
+  a.tc = TC ? 1 : 0;
   const int tid = threadIdx.x;
   // ---- lay out dynamic shared memory, copy the tables, arm the ring ----
   const M3Sm S = m3_layout(a.nslots, a.max_k, a.max_len, HS, a.n_ops, a.n_att, a.n_cmb, a.n_sched, a.top_k != 1);
@@ -955,21 +1183,40 @@ __global__ void __launch_bounds__(M3_THREADS, 1) decode_mega3_kernel(M3Args a) {
   if (tid == 0) {
     for (int i = 0; i < a.nslots; ++i) {
       mbar_init(&f->full[i], 1);
-      mbar_init(&f->empty[i], M3_CWARPS);
+      mbar_init(&f->empty[i], 4);            // 4 arrivals free a slot: the 4 issuing warps' tcgen05.commit, or warps 0..3 (mma.sync path)
     }
+    for (int i = 0; i < M3_TBUFS; ++i) {
+      mbar_init(&f->tfull[i], M3_TC_ISSUERS);
+      mbar_init(&f->tempty[i], 2);
+    }
+    mbar_init(&f->xsempty, M3_TC_ISSUERS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
+  if (TC && (tid >> 5) == M3_CWARPS + 1) {   // warp 9 owns the tensor memory: 4 accumulator buffers of 16 columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&f->tmem_base)), "r"(M3_TC_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   // token history before the first position this launch processes
   for (int w = tid; w < pos0 * a.B; w += M3_THREADS) {
     const int b = w / pos0, i = w - b * pos0;
     f->hist[b][i] = (int)a.ids[(int64_t)b * a.ids_ld + i];
   }
   __syncthreads();
-  if (tid >= M3_CTHREADS) {                  // the producer warp: one thread streams the weights, then the warp retires
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (tid >= M3_CTHREADS + 32) {             // warp 9: one thread issues every tcgen05.mma; the warp frees the tensor memory at the end
+    if (!TC) return;
+    asm volatile("bar.sync 3, %0;" ::"n"(M3_CTHREADS + 32) : "memory");      // every epilogue has read its accumulators
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(f->tmem_base), "r"(M3_TC_COLS) : "memory");
+    return;
+  }
+  if (tid >= M3_CTHREADS) {                  // warp 8: one thread streams the weights, then the warp retires
     if (tid == M3_CTHREADS) m3_producer(a, S);
     return;
   }
+  M3Tc T{0u, 0u};
   const int32_t* sched = m3_sched(S);
   M3Ring R{0, 0u};
   unsigned int epoch = 0;
@@ -993,9 +1240,10 @@ __global__ void __launch_bounds__(M3_THREADS, 1) decode_mega3_kernel(M3Args a) {
       if (trace_step) trace[0] = clock64();
       if (kind == 0) {
         if (!sampling && ((int)m3_lin(S, idx)[17] & 1) != 0) continue;
-        m3_linear(a, idx, S, R, gen, pos, sstep >= 0 ? sstep % M3_GENS : 0, tid, trace);
+        if (TC && m3_lin(S, idx)[22] != 0) m3_linear_tc(a, idx, S, R, T, gen, pos, sstep >= 0 ? sstep % M3_GENS : 0, tid, trace);
+        else m3_linear(a, idx, S, R, gen, pos, sstep >= 0 ? sstep % M3_GENS : 0, tid, trace, T.xcount);
       } else if (kind == 1) {
-        m3_attention<HS>(a, idx, S, gen, pos, tid);
+        m3_attention<HS>(a, idx, S, gen, pos, tid, T.xcount);
       } else if (kind == 3) {
         m3_combine(a, idx, S, gen, tid);
       } else if (kind == 2 && sampling && !greedy) {
@@ -1012,6 +1260,10 @@ __global__ void __launch_bounds__(M3_THREADS, 1) decode_mega3_kernel(M3Args a) {
     if (a.n_sample > 0) m3_tokens(a, S, pos_end, greedy, (a.n_sample - 1) % M3_GENS, !greedy, tid);
     if (tid == 0) *a.pos = pos_end;
   }
+  if (TC) {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    asm volatile("bar.sync 3, %0;" ::"n"(M3_CTHREADS + 32) : "memory");
+  }
 }
 
 // ---- weight re-pack: one op's [N][K] bf16 matrix into the per-CTA streams (fragment order, zero padded) ----
@@ -1019,11 +1271,30 @@ __global__ void __launch_bounds__(M3_THREADS, 1) decode_mega3_kernel(M3Args a) {
 // (2 * i + half) * 256 + t holds row tile * 16 + g + 8 * half, k = chunk * 768 + (warp + 8 * i) * 32 + qd * 8 .. + 8
 // (t = warp * 32 + lane, g = lane / 4, qd = lane % 4) -- exactly what consumer thread t feeds to its two MMAs.
 __global__ void __launch_bounds__(M3_CTHREADS) decode_mega3_pack_kernel(const __nv_bfloat16* __restrict__ W, int N, int K, int64_t ldw,
-                                                                        uint8_t* __restrict__ dst, const int64_t* __restrict__ tile_off) {
+                                                                        uint8_t* __restrict__ dst, const int64_t* __restrict__ tile_off,
+                                                                        int tc_layout) {
   const int tile = blockIdx.x, t = threadIdx.x;
   const int lane = t & 31, warp = t >> 5, g = lane >> 2, qd = lane & 3;
   uint4* out = reinterpret_cast<uint4*>(dst + tile_off[tile]);
   const int nkc = (K + M3_KC - 1) / M3_KC;
+  if (tc_layout) {
+    // tcgen05 path: a chunk = [k / 64][row 0..15][128 bytes], the 16-byte chunk c of a row stored at c ^ (row % 8)
+    // (the canonical K-major SWIZZLE_128B atom the UMMA shared-memory descriptor of tc_common.cuh describes)
+    for (int kc = 0; kc < nkc; ++kc) {
+      const int span = min(M3_KC, K - kc * M3_KC);
+      const int nbc = ((span + M3_BLK - 1) / M3_BLK + M3_CWARPS - 1) / M3_CWARPS;
+      const int nvec = nbc * 4 * 128;                               // 16-byte vectors of the chunk
+      for (int v = t; v < nvec; v += M3_CTHREADS) {
+        const int kb = v >> 7, row = (v >> 3) & 15, c = v & 7;
+        const int grow = tile * M3_ROWS + row, k = kc * M3_KC + kb * 64 + c * 8;
+        uint4 val = make_uint4(0u, 0u, 0u, 0u);
+        if (grow < N && k < K) val = *reinterpret_cast<const uint4*>(W + (size_t)grow * ldw + k);
+        out[kb * 128 + row * 8 + (c ^ (row & 7))] = val;
+      }
+      out += nvec;
+    }
+    return;
+  }
   for (int kc = 0; kc < nkc; ++kc) {
     const int span = min(M3_KC, K - kc * M3_KC);
     const int nbc = ((span + M3_BLK - 1) / M3_BLK + M3_CWARPS - 1) / M3_CWARPS;
@@ -1085,13 +1356,13 @@ extern "C" int64_t i2t_decode_mega3_tile_bytes(int64_t K) {
 extern "C" int i2t_decode_mega3_grid(void) { return num_sms(); }
 
 extern "C" int i2t_decode_mega3_pack(const void* W, int64_t N, int64_t K, int64_t ldw, void* dst, const int64_t* tile_off,
-                                     void* stream) {
+                                     int64_t tc_layout, void* stream) {
   I2T_REQUIRE(W && dst && tile_off, "decode_mega3_pack: null pointer");
   I2T_REQUIRE(N > 0 && K > 0 && K % 8 == 0 && ldw >= K && ldw % 8 == 0, "decode_mega3_pack: K and the row pitch must be positive multiples of 8");
   I2T_REQUIRE(aligned16(W) && aligned16(dst), "decode_mega3_pack: pointers must be 16-byte aligned");
   const int tiles = (int)((N + M3_ROWS - 1) / M3_ROWS);
   decode_mega3_pack_kernel<<<tiles, M3_CTHREADS, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(W), (int)N, (int)K, ldw,
-                                                                            reinterpret_cast<uint8_t*>(dst), tile_off);
+                                                                            reinterpret_cast<uint8_t*>(dst), tile_off, (int)tc_layout);
   I2T_LAUNCHED();
   return I2T_OK;
 }
@@ -1122,7 +1393,7 @@ extern "C" int i2t_decode_mega3(const int64_t* lin, const int64_t* att, const in
                                 uint32_t* bar, int32_t* error_flag, uint64_t* ctakeys, const void* wpack, const int64_t* cta_base,
                                 int64_t gen_stride, float temperature, int64_t top_k, const int32_t* ngrams, int64_t n_ngrams,
                                 const uint64_t* seed_ptr, int64_t max_k, int64_t max_len, int64_t* trace, int64_t trace_cta,
-                                void* stream) {
+                                int64_t tc, void* stream) {
   I2T_REQUIRE(lin && att && cmb && sched && ids && pos && logits && bar && error_flag && ctakeys && wpack && cta_base && seed_ptr,
               "decode_mega3: null pointer");
   I2T_REQUIRE(B > 0 && B <= M3_B, "decode_mega3: batch %lld outside 1..8", (long long)B);
@@ -1160,7 +1431,9 @@ extern "C" int i2t_decode_mega3(const int64_t* lin, const int64_t* att, const in
   a.ngrams = ngrams; a.n_ngrams = (int)n_ngrams; a.seed_ptr = seed_ptr;
   a.trace = reinterpret_cast<long long*>(trace); a.trace_cta = (int)trace_cta;
   a.sleep_ns = g_m3_sleep_ns.load();
-  const void* kern = (C / H == 64) ? (const void*)decode_mega3_kernel<64> : (const void*)decode_mega3_kernel<32>;
+  a.tc = tc != 0 ? 1 : 0;
+  const void* kern = tc != 0 ? ((C / H == 64) ? (const void*)decode_mega3_kernel<64, true> : (const void*)decode_mega3_kernel<32, true>)
+                             : ((C / H == 64) ? (const void*)decode_mega3_kernel<64, false> : (const void*)decode_mega3_kernel<32, false>);
   I2T_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   I2T_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, M3_THREADS, smem));

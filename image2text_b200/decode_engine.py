@@ -199,7 +199,13 @@ class DecodeEngine:
         G = int(lib.i2t_decode_mega3_grid())
         dp = "decoder.transformer."
         lin, att, cmb, sched, wsrc = [], [], [], [], []
-        group = os.environ.get("I2T_M3_GROUP", "1") != "0"
+        # measured (gpurun r2k): halving the CTAs that take part in the 144 / 192-tile stages (two tiles each) makes the step
+        # SLOWER (297 vs 281 us): the per-CTA instruction latency, not the L2 fan-out, paces a stage.  Off by default.
+        group = os.environ.get("I2T_M3_GROUP", "0") != "0"
+        # I2T_M3_TC=1: the layer projections on tcgen05 (UMMA atoms in the ring, accumulators in TMEM, 4 issuing warps).  Correct
+        # (same oracle parity), but an M128 SS-MMA fetches 128 A rows from shared memory for a tile of 16: 373 vs 281 us per
+        # step (gpurun r2m / r2n) -- experimental, off by default
+        tc = 1 if os.environ.get("I2T_M3_TC", "0") == "1" else 0
         loads = [0] * G                      # bytes of packed weights per CTA so far (tile -> CTA balancing)
         cursor = [0]                         # exchange-buffer bump allocator (bytes within one generation)
 
@@ -241,6 +247,9 @@ class DecodeEngine:
             be = W.get(ln + ".bias") if ln else None
             tb = int(lib.i2t_decode_mega3_tile_bytes(K))
             total = (N + 15) // 16
+            # the layer projections run on tcgen05 (accumulators in TMEM); the LM head streams 21 tiles per CTA and is HBM-bound
+            # on the mma.sync path already (5.8 TB/s), where the issue rate of tiny N = 16 MMAs would pace it
+            tc_op = 1 if (tc and not (flags & FL_LM)) else 0
             # few tiles per CTA anyway: let half as many CTAs take two tiles each (one pass over a pair) -- half as many SMs pull
             # the activations out of L2 at the same instant (the fan-out is L2-bandwidth bound: 24 KB x the CTAs taking part)
             gs = G
@@ -248,8 +257,8 @@ class DecodeEngine:
                 gs = (total + 1) // 2
             rot = balance(total, tb, gs)
             lin.append([0, P(b), P(g), P(be), inp, out, residual, N, K, act, mode, P(kc), P(vc), in_mode, P(wpe),
-                        ldo if ldo is not None else N, self.Tmax * C, flags, rot, pub, in_ld, gs if gs != G else 0, 0, 0])
-            wsrc.append((w, N, K, tb, rot, gs))
+                        ldo if ldo is not None else N, self.Tmax * C, flags, rot, pub, in_ld, gs if gs != G else 0, tc_op, 0])
+            wsrc.append((w, N, K, tb, rot, gs, tc_op))
             sched.append([0, len(lin) - 1, 0, 0])
 
         def add_cmb(n_parts, p0, pstride, bias, residual, out, N):
@@ -315,7 +324,7 @@ class DecodeEngine:
         # per-CTA weight streams: ops in schedule order, a CTA's tiles of an op in ascending order
         offs = [0] * G
         tile_offs = []
-        for (w, N, K, tb, rot, gs) in wsrc:
+        for (w, N, K, tb, rot, gs, tc_op) in wsrc:
             total = (N + 15) // 16
             to = [0] * total
             for u in range(total):
@@ -328,18 +337,18 @@ class DecodeEngine:
         cta_base = torch.arange(G, dtype=torch.int64, device=dev) * stride
         st = stream()
         keep = []
-        for (w, N, K, tb, rot, gs), to in zip(wsrc, tile_offs):
+        for (w, N, K, tb, rot, gs, tc_op), to in zip(wsrc, tile_offs):
             tt = torch.tensor([(((u % gs) + rot) % G) * stride + o for u, o in enumerate(to)], dtype=torch.int64, device=dev)
             assert w.stride(1) == 1
             keep.append((tt, w))
-            call("i2t_decode_mega3_pack", ptr(w), N, K, w.stride(0), ptr(wpack), ptr(tt), st)
+            call("i2t_decode_mega3_pack", ptr(w), N, K, w.stride(0), ptr(wpack), ptr(tt), tc_op, st)
         torch.cuda.current_stream().synchronize()          # the temporaries of the pack calls may go now
-        kpad = max((K - 1) // 768 * 768 + ((K - 1) % 768 + 256) // 256 * 256 for (_, _, K, _, _, _) in wsrc)
+        kpad = max((K - 1) // 768 * 768 + ((K - 1) % 768 + 256) // 256 * 256 for (_, _, K, _, _, _, _) in wsrc)
         t64 = lambda rows: torch.tensor(rows, dtype=torch.int64, device=dev).contiguous()
         return dict(lin=t64(lin), att=t64(att), cmb=t64(cmb), n_cmb=len(cmb),
                     sched=torch.tensor(sched, dtype=torch.int32, device=dev).contiguous(), n_ops=len(lin), exch=exch, gen_stride=gen_stride, wpack=wpack, cta_base=cta_base, grid=G,
                     ctakeys=torch.zeros(3 * G * 8, device=dev, dtype=torch.int64), max_k=kpad,
-                    packed_bytes=int(sum(offs)), sig=self.model.weight_generation())
+                    packed_bytes=int(sum(offs)), sig=self.model.weight_generation(), tc=tc)
 
     def _mega3_run(self, n_prefill: int, n_sample: int, temperature: float, top_k: Optional[int], P: int):
         """n_prefill prompt steps + n_sample sampled steps in ONE launch (decode_mega3.cu)."""
@@ -360,7 +369,7 @@ class DecodeEngine:
              ptr(self.ids), self.ids.shape[1], ptr(self.pos), ptr(self.logits), self.logits.stride(0), ptr(self.bar), ptr(self.err),
              ptr(T["ctakeys"]), ptr(T["wpack"]), ptr(T["cta_base"]), T["gen_stride"], temperature,
              int(top_k) if top_k is not None else 0, ptr(self.ngrams), self.n_ngrams, ptr(self.seed_dev), T["max_k"],
-             max(self.Tmax, self.S), ptr(self.trace), int(os.environ.get("I2T_TRACE_CTA", "0")), stream())
+             max(self.Tmax, self.S), ptr(self.trace), int(os.environ.get("I2T_TRACE_CTA", "0")), T["tc"], stream())
 
     # ------------------------------------------------------------------ one step, separate kernels -------------
     def _kernel_step(self, sample: bool, temperature: float, top_k: Optional[int]):

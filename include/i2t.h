@@ -233,7 +233,10 @@ int i2t_decode_mega2(const int64_t* lin, const int64_t* att, const int32_t* sche
  * i2t_decode_mega3_pack (one call per linear op: W = bf16 [N][K], rows ldw elements apart, tile_off[tile] = byte offset of the tile's
  * chunks; a tile = 16 rows, i2t_decode_mega3_tile_bytes(K) bytes; tile u of an op belongs to CTA (u + rot) % grid with
  * grid = i2t_decode_mega3_grid(), a CTA's tiles in ascending order, ops in schedule order).  A producer warp streams them
- * through a shared-memory ring with cp.async.bulk, several stages ahead of the arithmetic.
+ * through a shared-memory ring with cp.async.bulk, several stages ahead of the arithmetic.  tc (and tc_layout of the pack
+ * call) = 1: the linear stages run on tcgen05 -- a tile's weights are packed as K-major 128B-swizzled UMMA atoms, one thread
+ * issues tcgen05.mma M128 N16 K16 over the tile's whole K, accumulators live in TMEM, tcgen05.commit frees the ring slot;
+ * 0: mma.sync tiles with K split over 8 warps.
  * Tables: lin[op][24], att[a][12], cmb[c][8] (combine stages of K-split projections), sched[s][4] as documented at the top
  * of decode_mega3.cu.  The caller also fills the
  * cache rows [*pos, *pos + steps) of every layer with 0xFF bytes, ids beyond the prompt with -1 and ctakeys
@@ -244,7 +247,8 @@ int i2t_decode_mega3_max_keys(void);
 void i2t_set_decode_poll_sleep(int ns);
 int i2t_decode_mega3_grid(void);
 int64_t i2t_decode_mega3_tile_bytes(int64_t K);
-int i2t_decode_mega3_pack(const void* W, int64_t N, int64_t K, int64_t ldw, void* dst, const int64_t* tile_off, void* stream);
+int i2t_decode_mega3_pack(const void* W, int64_t N, int64_t K, int64_t ldw, void* dst, const int64_t* tile_off, int64_t tc_layout,
+                          void* stream);
 /* one launch that poisons / zeroes everything i2t_decode_mega3 expects: exch (0xFF), cache rows [pos0, pos0 + steps) of
  * n_rows = layers x sequences rows (row_pitch bytes each, pos_bytes per position), ids[:, P:ids_cols] = -1, ctakeys, *err */
 int i2t_decode_mega3_prepare(void* exch, int64_t exch_bytes, void* kcache, void* vcache, int64_t n_rows, int64_t row_pitch,
@@ -256,7 +260,7 @@ int i2t_decode_mega3(const int64_t* lin, const int64_t* att, const int64_t* cmb,
                      uint32_t* bar, int32_t* error_flag, uint64_t* ctakeys, const void* wpack, const int64_t* cta_base,
                      int64_t gen_stride, float temperature, int64_t top_k, const int32_t* ngrams, int64_t n_ngrams,
                      const uint64_t* seed_ptr, int64_t max_k, int64_t max_len, int64_t* trace, int64_t trace_cta,
-                     void* stream);
+                     int64_t tc, void* stream);
 
 /* ---- sampler: models/vision_encoder_decoder.py:152-180 + transformers NoRepeatNGramLogitsProcessor ----------------
  * logits (B,ldl) fp32 are modified in place (/temperature, banned -> -inf).  Tokens ids[b, 0..cur_len) are the history

@@ -113,3 +113,20 @@ def test_mega3_repacks_after_a_weight_update():
         with torch.no_grad():
             w.copy_(saved)
     assert torch.equal(before, eng.generate(images, prompt, 16, 1.0, 1, seed=0))
+
+
+def test_mega3_tcgen05_linear_stages_match_oracle(monkeypatch):
+    """The experimental tcgen05 instantiation (I2T_M3_TC=1): layer projections as tcgen05.mma M128 N16 K16 over weights packed as
+    128B-swizzled UMMA atoms, accumulators in TMEM, four issuing warps -- same oracle parity as the default mma.sync tiles."""
+    monkeypatch.setenv("I2T_M3_TC", "1")
+    for name, B, size, P in (("tiny", 3, 32, 2), ("nano", 8, 224, 1)):
+        m = build(name, torch.bfloat16)
+        images = synth_images(B, size, seed=11).cuda()
+        eos = m.spec["vocab_size"] - 1
+        g = torch.Generator().manual_seed(5)
+        prompt = torch.cat([torch.full((B, 1), eos), torch.randint(0, eos, (B, P - 1), generator=g)], dim=1).cuda()
+        eng = DecodeEngine(m, B, mode="mega3")
+        got = eng.generate(images, prompt, 20, 1.0, 1, seed=0)
+        assert eng._mega3["tc"] == 1
+        assert torch.equal(got, eng.generate(images, prompt, 20, 1.0, 1, seed=0))
+        check_picks_vs_oracle(name, m, images, got, P, top_k=1)
