@@ -168,6 +168,7 @@ def train_secondary(rank, world, local, steps=3, warmup=3, only=None):
                     p.requires_grad_(False)   # never stepped by the reference either: skip their weight gradients
             opt = AdamW(groups)
             red = GradientAllReducer([p for g in groups for p in g["params"]])
+            red.attach_optimizer(opt)
             red.broadcast_parameters(w.model)
             w.copy_momentum_params()
             images = synth_images(bs, 224, seed=1234 + rank).cuda()

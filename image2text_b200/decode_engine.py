@@ -203,7 +203,7 @@ class DecodeEngine:
         # SLOWER (297 vs 281 us): the per-CTA instruction latency, not the L2 fan-out, paces a stage.  Off by default.
         group = os.environ.get("I2T_M3_GROUP", "0") != "0"
         # I2T_M3_TC=1: the layer projections on tcgen05 (UMMA atoms in the ring, accumulators in TMEM, 4 issuing warps).  Correct
-        # (same oracle parity), but an M128 SS-MMA fetches 128 A rows from shared memory for a tile of 16: 373 vs 281 us per
+        # (same parity tests pass), but an M128 SS-MMA fetches 128 A rows from shared memory for a tile of 16: 373 vs 281 us per
         # step (gpurun r2m / r2n) -- experimental, off by default
         tc = 1 if os.environ.get("I2T_M3_TC", "0") == "1" else 0
         loads = [0] * G                      # bytes of packed weights per CTA so far (tile -> CTA balancing)

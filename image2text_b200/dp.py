@@ -5,11 +5,15 @@ The reference wraps the trainer in accelerate's DDP (trainer.py:173-174) but the
 and replicas drift.  This module does the exchange the reference intends: the MEAN over ranks of the
 per-rank gradients (each rank's loss is already normalised by its local batch, training/wrapper.py:96).
 
-Mechanics: parameters that need a gradient are packed, in reverse registration order (the order backward produces
-them), into flat fp32 buckets of ~``bucket_mb``; ``register_post_accumulate_grad_hook`` counts arrivals; when a bucket is
-complete its gradients are copied into the flat buffer and an asynchronous ``all_reduce`` is launched on a side stream
-that waits only on that point of the compute stream -- the remaining backward kernels keep running.  ``finish()`` joins
-the side stream, scales by 1/world and scatters the averaged values back into ``.grad``.  With
+Mechanics: parameters that need a gradient are grouped, in reverse registration order (the order backward produces
+them), into flat fp32 buckets of ~``bucket_mb``, and every ``.grad`` IS a view of its bucket (created up front, so autograd
+accumulates straight into the buffer NCCL reduces: no pack before and no scatter after the exchange.  The view is bound
+the first time a gradient arrives -- a parameter that never receives one keeps ``.grad is None`` and is not stepped, like
+in the reference; a ``.grad`` that was replaced behind our back, ``zero_grad(set_to_none=True)``, is re-bound the same way).  ``register_post_accumulate_grad_hook``
+counts arrivals; when a bucket is complete an asynchronous ``all_reduce`` is launched on a side stream that waits only on
+that point of the compute stream -- the remaining backward kernels keep running.  ``finish()`` joins the side stream; the
+1/world of the mean is folded into the fused optimiser's ``grad_scale`` (``attach_optimizer``) or, without one, applied
+with one ``mul_`` per bucket.  With
 ``gradient_accumulation_steps`` > 1 call ``no_sync()`` on the non-final micro-steps.  Collectives: NCCL over
 NVLink/NVSwitch on GPUs, gloo on CPU (tests).  Nothing here touches the data path of generation (captions shard by
 image, no collective).
@@ -57,7 +61,17 @@ class GradientAllReducer:
         self.only_with_grad = only_with_grad
         self._capturing = False
         self._events: List[Optional["torch.cuda.Event"]] = [None] * len(self.buckets)     # per bucket, recorded INSIDE a graph
+        self._scale_in_optimizer = False
         self._reset()
+        self._slot = {id(p): (bi, i) for bi, b in enumerate(self.buckets) for i, p in enumerate(b)}
+
+    def attach_optimizer(self, optimizer):
+        """Fold the 1/world of the gradient mean into a fused optimiser's `grad_scale` (image2text_b200.optimizer): the kernel
+        multiplies the gradient on the fly, so finish() has nothing left to do but wait for the collectives."""
+        if self.world > 1 and hasattr(optimizer, "grad_scale"):
+            optimizer.grad_scale = float(optimizer.grad_scale) / self.world
+            self._scale_in_optimizer = True
+        return optimizer
 
     # -- public ------------------------------------------------------------------------------------------------
     def broadcast_parameters(self, module: torch.nn.Module, src: int = 0):
@@ -137,8 +151,10 @@ class GradientAllReducer:
                 if not self.launched[bi]:
                     continue
                 flat, views = self._views(bi)
-                flat.mul_(inv)                                      # mean over ranks: one launch per bucket
-                have = [(p.grad, v) for v, p in zip(views, bucket) if p.grad is not None]
+                if not self._scale_in_optimizer:
+                    flat.mul_(inv)                                  # mean over ranks: one launch per bucket
+                # gradients that are not views of the bucket (replaced by zero_grad(set_to_none=True) ...): scatter back
+                have = [(p.grad, v) for v, p in zip(views, bucket) if p.grad is not None and p.grad.data_ptr() != v.data_ptr()]
                 if have:
                     torch._foreach_copy_([g for g, _ in have], [v for _, v in have])
         self._reset()
@@ -157,6 +173,12 @@ class GradientAllReducer:
     def _hook(self, p: torch.nn.Parameter):
         if self.world == 1:
             return
+        bi0, i0 = self._slot[id(p)]
+        v = self._views(bi0)[1][i0]
+        if p.grad is not None and p.grad.data_ptr() != v.data_ptr():      # first gradient (or a replaced one): move it into the bucket
+            with torch.no_grad():
+                v.copy_(p.grad)
+            p.grad = v
         if self._capturing:
             bi = self.bucket_of[id(p)]
             self.pending[bi] -= 1
@@ -191,11 +213,12 @@ class GradientAllReducer:
         per parameter (a model that trains every weight has hundreds of them; the launches were most of the exposed time)."""
         flat, views = self._views(bi)
         with torch.no_grad():
-            have = [(v, p.grad) for v, p in zip(views, self.buckets[bi]) if p.grad is not None]
-            if len(have) != len(views):
-                flat.zero_()
-            if have:
-                torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
+            stray = [(v, p.grad) for v, p in zip(views, self.buckets[bi]) if p.grad is not None and p.grad.data_ptr() != v.data_ptr()]
+            gone = [v for v, p in zip(views, self.buckets[bi]) if p.grad is None]
+            if gone:
+                torch._foreach_zero_(gone)
+            if stray:                           # the normal case has nothing to copy: .grad already lives in the bucket
+                torch._foreach_copy_([v for v, _ in stray], [g for _, g in stray])
         return flat
 
     def _launch(self, bi: int):

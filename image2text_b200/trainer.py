@@ -240,6 +240,7 @@ def main(args) -> dict:
     optimizer = (SNRAdam if config.use_snr_optim else AdamW)(groups)
     reducer = GradientAllReducer([p for g in groups for p in g["params"]]) if world > 1 else None
     if reducer is not None:
+        reducer.attach_optimizer(optimizer)                 # the 1/world of the gradient mean rides on the fused step's grad_scale
         reducer.broadcast_parameters(model_wrapper.model)
         # the teacher must start from rank 0's student on every rank too (accelerate's DDP wrapper broadcasts the whole
         # ModelTrainerWrapper, model_m included: reference trainer.py:173-174)

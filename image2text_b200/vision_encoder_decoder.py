@@ -116,13 +116,11 @@ class VisionEncoderDecoder(nn.Module):
         if spec["decoder"] == "transformer" and spec["use_cross_attn"] != spec["is_cross_attn"]:
             raise ValueError("use_cross_attn must match decoder transformer_config.is_cross_attn")
         self.compute_dtype = compute_dtype
-        self.decoder = _Side("decoder", spec)
-        self.decoder._bind(self)
         gen = None
         if seed is not None:
             gen = torch.Generator(device="cpu").manual_seed(seed)
         schema = state_schema(spec)
-        if encoder is None:
+        if encoder is None:                     # (the encoder registers first: state_dict / named_parameters order of the reference)
             self.encoder = _Side("encoder", spec)
             self.encoder._bind(self)
         else:
@@ -130,6 +128,8 @@ class VisionEncoderDecoder(nn.Module):
             if spec["n_embd_out_vit"] != spec["n_embd"]:            # the reference bridges with a Linear (:33-37)
                 encoder = nn.Sequential(encoder, nn.Linear(spec["n_embd_out_vit"], spec["n_embd"]))
             self.encoder = encoder.to(torch.device(device))
+        self.decoder = _Side("decoder", spec)
+        self.decoder._bind(self)
         build_param_tree(self, schema, spec, TIED_KEYS, torch.device(device), gen)
         self.space_for_prompt = spec["n_cls"] if config.use_soft_prompting else 0
         self.use_cross_attn = config.use_cross_attn

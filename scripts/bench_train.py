@@ -87,7 +87,9 @@ def main():
             p.requires_grad_(False)
     opt = AdamW(groups)
     red = GradientAllReducer([p for g in groups for p in g["params"]])
+    red.attach_optimizer(opt)
     red.broadcast_parameters(w.model)
+    w.copy_momentum_params()
     images = synth_images(bs, 224, seed=1234 + rank).cuda()
     labels = synth_labels(bs, 256, seed=1234 + rank).cuda()
 
