@@ -46,15 +46,11 @@ __global__ void __launch_bounds__(GREEDY_THREADS)
 sample_greedy_kernel(float* __restrict__ logits, int64_t ldl, int V, int64_t* __restrict__ ids, int64_t ids_ld,
                      const int32_t* pos_ptr_c, int32_t* pos_ptr_adv, int cur_len_const, const int32_t* __restrict__ ngrams,
                      int n_ngrams, int32_t* __restrict__ ticket, int write_token) {
-  __shared__ int banned[SAMP_MAX_BANNED];
-  __shared__ int nbanned;
   __shared__ unsigned long long best[GREEDY_THREADS / 32];
   const int t = threadIdx.x, b = blockIdx.x, lane = t & 31, w = t >> 5;
   const int cur_len = pos_ptr_c != nullptr ? (*pos_ptr_c + 1) : cur_len_const;
   float* row = logits + (int64_t)b * ldl;
   const int64_t* idr = ids + (int64_t)b * ids_ld;
-  if (t == 0) nbanned = 0;
-  __syncthreads();
   for (int g = 0; g < n_ngrams; ++g) {               // generation/logits_process.py:1012-1076, as in sample_row_smem
     const int n = ngrams[g];
     if (n <= 0 || cur_len + 1 < n) continue;
@@ -62,17 +58,11 @@ sample_greedy_kernel(float* __restrict__ logits, int64_t ldl, int V, int64_t* __
     for (int i = t; i <= cur_len - n; i += GREEDY_THREADS) {
       bool same = true;
       for (int j = 0; j < n - 1; ++j) same = same && (__ldcg(idr + i + j) == __ldcg(idr + tail + j));
-      if (same) {
-        const int slot = atomicAdd(&nbanned, 1);
-        if (slot < SAMP_MAX_BANNED) banned[slot] = (int)__ldcg(idr + i + n - 1);
+      if (same) {                                     // banned straight in the row: no list, so no cap on how many
+        const int tok = (int)__ldcg(idr + i + n - 1);
+        if (tok >= 0 && tok < V) row[tok] = -INFINITY;
       }
     }
-  }
-  __syncthreads();
-  const int nb = min(nbanned, SAMP_MAX_BANNED);
-  for (int i = t; i < nb; i += GREEDY_THREADS) {
-    const int tok = banned[i];
-    if (tok >= 0 && tok < V) row[tok] = -INFINITY;
   }
   __syncthreads();                                    // the -inf stores are visible to this CTA's loads below
   // packed key: order-preserving float bits in the high word, ~index in the low word -> max = largest logit, lowest index

@@ -81,7 +81,10 @@ __device__ __forceinline__ int sample_row_smem(float* __restrict__ sv, SampleScr
   const int lane = t & 31, w = t >> 5;
   if (t == 0) { S.nbanned = 0; S.choice = 0x7fffffff; S.fallback = 0x7fffffff; }
   samp_sync(nthreads);
-  // ---- banned tokens (generation/logits_process.py:1012-1076) ----
+  // ---- one pass over global memory: logits / temperature (a true division, like the reference) ----
+  for (int i = t; i < V; i += nthreads) sv[i] = __ldcg(row + i) / temperature;
+  samp_sync(nthreads);
+  // ---- banned tokens (generation/logits_process.py:1012-1076): -inf straight into the resident row -- no list, no cap ----
   for (int g = 0; g < n_ngrams; ++g) {
     const int n = ngrams[g];
     if (n <= 0 || cur_len + 1 < n) continue;
@@ -90,20 +93,16 @@ __device__ __forceinline__ int sample_row_smem(float* __restrict__ sv, SampleScr
       bool same = true;
       for (int j = 0; j < n - 1; ++j) same = same && (__ldcg(idr + i + j) == __ldcg(idr + tail + j));
       if (same) {
-        const int slot = atomicAdd(&S.nbanned, 1);
-        if (slot < SAMP_MAX_BANNED) S.banned[slot] = (int)__ldcg(idr + i + n - 1);
+        const int tok = (int)__ldcg(idr + i + n - 1);
+        if (tok >= 0 && tok < V) {
+          sv[tok] = -INFINITY;
+          S.nbanned = 1;                           // (benign race: every writer stores 1)
+        }
       }
     }
   }
-  // ---- one pass over global memory: logits / temperature (a true division, like the reference) ----
-  for (int i = t; i < V; i += nthreads) sv[i] = __ldcg(row + i) / temperature;
   samp_sync(nthreads);
-  const int nb = min(S.nbanned, SAMP_MAX_BANNED);
-  for (int i = t; i < nb; i += nthreads) {
-    const int tok = S.banned[i];
-    if (tok >= 0 && tok < V) sv[tok] = -INFINITY;
-  }
-  samp_sync(nthreads);
+  const int nb = S.nbanned;
   if (temperature != 1.0f || nb > 0) {             // documented in-place contract: scaled / banned logits
     for (int i = t; i < V; i += nthreads) row[i] = sv[i];
   }

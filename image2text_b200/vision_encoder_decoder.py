@@ -271,15 +271,23 @@ class VisionEncoderDecoder(nn.Module):
     @torch.no_grad()
     def generate(self, images, prompt_ids, max_new_tokens=128, temperature=1.0, top_k=None, nucleus_p=None,
                  seed: Optional[int] = None) -> torch.LongTensor:
-        """reference models/vision_encoder_decoder.py:136-182, with a KV cache, an on-device sampler and one CUDA graph
-        per step shape.  Returns (B, prompt + max_new_tokens) int64 including the prompt."""
+        """reference models/vision_encoder_decoder.py:136-182, with a KV cache, an on-device sampler and one launch (<= 8
+        sequences, bf16) or one CUDA graph per step shape.  Returns (B, prompt + max_new_tokens) int64 including the prompt.
+        Determinism: fp32 greedy ids are bit-exact and run-to-run identical (fixed summation order); bf16 with <= 8 sequences
+        (the dataflow megakernel) is run-to-run identical too; bf16 with MORE than 8 sequences adds split-K partial tiles
+        with fp32 atomics, so greedy ids may differ between runs at near-ties -- `image2text_b200._lib.lib().
+        i2t_set_gemm_split_k(0)` (or I2T_GEMM_SPLITK=0) selects the fixed-order projections at ~20 % lower tok/s."""
         from .decode_engine import DecodeEngine
         blk = self.spec["block_size"] - self.space_for_prompt
         assert max_new_tokens <= blk - prompt_ids.size(-1)
         if seed is None:
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())   # torch's RNG seeds the device Philox stream
-        if nucleus_p is not None and not (0.0 < float(nucleus_p) < 1.0):
-            nucleus_p = None
+        if nucleus_p is not None and float(nucleus_p) <= 0.0:
+            # the reference keeps the sorted tokens whose cumulative probability is <= max(p, p_max): p <= 0 leaves only the
+            # most probable one (vision_encoder_decoder.py:160-172) -- the greedy pick after the ban / top-k filter
+            top_k, nucleus_p = 1, None
+        if nucleus_p is not None and float(nucleus_p) >= 1.0:
+            nucleus_p = None                   # keeps everything: plain sampling
         if self.spec["decoder"] != "transformer":
             if os.environ.get("I2T_HF_DECODE", "cached") == "cacheless":
                 return self._generate_cacheless(images, prompt_ids, max_new_tokens, float(temperature), top_k, nucleus_p, seed)

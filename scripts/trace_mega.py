@@ -55,6 +55,8 @@ print("stage kind idx   N     K   | stage_x  compute  barrier  total (us)")
 for s in range(n_sched):
     kind, idx = int(sched[s, 0]), int(sched[s, 1])
     b, st, cp, sy = [int(v) for v in tr[s][:4]]
+    if min(b, st, cp, sy) <= 0 or not (b <= st <= cp <= sy):
+        continue            # CTA 0 owns no unit of this stage: some of its clock64 stamps were never written
     if W == 8 and kind == 0 and int(tr[s][1]) > b:
         N, K = int(lin[idx, 7]), int(lin[idx, 8])
         ld, arr, pf, mma = [int(v) for v in tr[s][4:8]]
