@@ -363,3 +363,41 @@ class Conv1DFn(torch.autograd.Function):
 
 def conv1d(x2d, w, w_c, bias=None, residual=None, act=ops.ACT_NONE, out_dtype=torch.float32, drop=None):
     return Conv1DFn.apply(x2d, w, w_c, bias, residual, act, out_dtype, drop)
+
+
+class PeerLookupFn(torch.autograd.Function):
+    """Everything of PeerLookup.forward (reference models/layers.py:73-109) that is not a dense projection: the two top-k
+    selections, the top-k of their sums, softmax, expert gather, the dot with the key projection, GELU and the weighted sum
+    of the output experts (csrc/peer.cu).  ql, qr: (M, H, U); key: (M, H, D); emb_in (E, D); emb_out (E, O) -> (M, O)."""
+
+    @staticmethod
+    def forward(ctx, ql, qr, key, emb_in, emb_out, topk):
+        M, H, U = ql.shape
+        D, O = key.shape[-1], emb_out.shape[1]
+        ql, qr, key = ql.contiguous().float(), qr.contiguous().float(), key.contiguous().float()
+        dev = ql.device
+        out = torch.empty((M, O), device=dev, dtype=torch.float32)
+        i32 = dict(device=dev, dtype=torch.int32)
+        f32 = dict(device=dev, dtype=torch.float32)
+        idx, lpos, rpos = (torch.empty((M, H, topk), **i32) for _ in range(3))
+        score, dot = (torch.empty((M, H, topk), **f32) for _ in range(2))
+        call("i2t_peer_lookup_fwd", ptr(ql), ptr(qr), ptr(key), ptr(emb_in), ptr(emb_out), ptr(out), ptr(idx), ptr(score), ptr(dot),
+             ptr(lpos), ptr(rpos), M, H, U, topk, D, O, stream())
+        ctx.save_for_backward(key, emb_in, emb_out, idx, score, dot, lpos, rpos)
+        ctx.dims = (M, H, U, topk, D, O)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        key, emb_in, emb_out, idx, score, dot, lpos, rpos = ctx.saved_tensors
+        M, H, U, K, D, O = ctx.dims
+        dout = dout.contiguous().float()
+        dev = dout.device
+        dql = torch.empty((M, H, U), device=dev, dtype=torch.float32)
+        dqr = torch.empty_like(dql)
+        dkey = torch.empty((M, H, D), device=dev, dtype=torch.float32)
+        demb_in = torch.zeros_like(emb_in)
+        demb_out = torch.zeros_like(emb_out)
+        call("i2t_peer_lookup_bwd", ptr(dout), ptr(key), ptr(emb_in), ptr(emb_out), ptr(idx), ptr(score), ptr(dot), ptr(lpos),
+             ptr(rpos), ptr(dql), ptr(dqr), ptr(dkey), ptr(demb_in), ptr(demb_out), M, H, U, K, D, O, stream())
+        return dql, dqr, dkey, demb_in, demb_out, None

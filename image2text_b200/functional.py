@@ -150,6 +150,33 @@ def posbias_tail(W, spec, feat: torch.Tensor, cd: torch.dtype, pre: str) -> torc
     return L2NormFn.apply(torch.stack(outs, dim=1))
 
 
+def peer_tail(W, spec, feat: torch.Tensor, pre: str) -> torch.Tensor:
+    """reference models/encoder.py:114-115 + models/layers.py:73-109: per-slot projection of the ViT feature
+    (einsum 'bd,des->bse' with peer_proj_wt (768, 768, n_cls): its memory layout is a (in, out) matrix with out = (e, s), i.e. the
+    Conv1D GEMM), then PeerLookup: four dense projections (fp32 GEMMs: the expert selection is discrete, see csrc/peer.cu) and the
+    fused selection / gather / weighting kernel."""
+    from .autograd_ops import PeerLookupFn, conv1d
+    B, d = feat.shape
+    S, nh, qd, K = spec["n_cls"], spec["peer_nhead"], spec["peer_query_dim"], spec["peer_topk"]
+    f32 = torch.float32
+    feat = feat.float()
+    pw = W[pre + "peer_proj_wt"]
+    inp = conv1d(feat, pw.view(d, d * S), pw.view(d, d * S), None, None, ops.ACT_NONE, f32)        # (B, (e, s))
+    inp = inp.view(B, d, S).transpose(1, 2).contiguous().view(B * S, d)                            # (B * S, e)
+
+    def lin(key, x):
+        w = W[pre + "peer." + key + ".weight"]
+        return linear(x, w, w, None, None, ops.ACT_NONE, f32)
+
+    q = lin("query_linear", inp).view(B * S * nh, qd)
+    keyp = lin("key_linear", inp).view(B * S, nh, d)
+    residual = lin("residual", inp)
+    ql = lin("query_left.linear", q).view(B * S, nh, -1)
+    qr = lin("query_right.linear", q).view(B * S, nh, -1)
+    out = PeerLookupFn.apply(ql, qr, keyp, W[pre + "peer.emb_in.weight"], W[pre + "peer.emb_out.weight"], K)
+    return (out + residual).view(B, S, -1)
+
+
 def encoder_forward(W, spec, images: torch.Tensor, cd: torch.dtype, train_trunk: bool = False) -> torch.Tensor:
     bridged = "encoder.1.weight" in W
     pre = "encoder.0." if bridged else "encoder."
@@ -164,6 +191,8 @@ def encoder_forward(W, spec, images: torch.Tensor, cd: torch.dtype, train_trunk:
                 for r in range(len(spec["lsh_num_bins"]))]
         out = _LshTailFn.apply(feat, tables, spec["lsh_num_bins"], spec["n_cls"], spec["lsh_num_proj"],
                                spec["n_embd_out_vit"], *embs)
+    elif spec["tail"] == "peer":
+        out = peer_tail(W, spec, feat, pre)
     else:
         out = posbias_tail(W, spec, feat, cd, pre + "proj.models.")
     if bridged:

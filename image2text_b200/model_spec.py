@@ -34,8 +34,6 @@ def spec_from_config(cfg: VisionEncoderDecoderConfig, **overrides) -> dict:
     if not isinstance(enc, PretrainedViTConfig):
         raise NotImplementedError("VisionTransformerEncoder (reference models/encoder.py:130-195) is a "
                                   "'next' row (SURVEY.md 8f-1); only PretrainedViT is built")
-    if enc.peer_config is not None:
-        raise NotImplementedError("PEER tail (reference models/layers.py:21-109) is a 'next' row (SURVEY.md 8f-2)")
     if enc.lora_spec is not None or dec.lora_spec is not None:
         raise NotImplementedError("LoRA needs peft, which is not part of the hot path (SURVEY.md section 2)")
     spec = dict(
@@ -46,7 +44,12 @@ def spec_from_config(cfg: VisionEncoderDecoderConfig, **overrides) -> dict:
         use_cross_attn=cfg.use_cross_attn, use_soft_prompting=cfg.use_soft_prompting,
         no_repeat_n_grams=tuple(cfg.no_repeat_n_grams),
     )
-    if enc.lsh_config is not None:
+    if enc.peer_config is not None:            # PretrainedViT: PEER wins over LSH (reference models/encoder.py:64-66)
+        pc = enc.peer_config
+        spec.update(tail="peer", lsh_num_bins=(), lsh_num_proj=0, peer_units_sqrt=pc.num_units_sqrt, peer_topk=pc.topk,
+                    peer_nhead=pc.nhead, peer_query_dim=pc.query_dim or 768 // 2,
+                    refine_base_model=bool(enc.refine_base_model))
+    elif enc.lsh_config is not None:
         if enc.lsh_config.learnable:
             raise NotImplementedError("learnable LSH tail (reference models/layers.py:156-191) is not on the hot path")
         spec.update(tail="lsh", lsh_num_bins=tuple(enc.lsh_config.num_bins), lsh_num_proj=enc.lsh_config.num_proj)
@@ -94,7 +97,7 @@ def state_schema(spec: dict) -> "OrderedDict[str, Tuple[Tuple[int, ...], torch.d
     seq = (spec["vit_image"] // p) ** 2 + 1
     bridged = spec["n_embd_out_vit"] != spec["n_embd"]
     e = "encoder.0." if bridged else "encoder."
-    out[e + "peer_proj_wt"] = ((1,), f32)
+    out[e + "peer_proj_wt"] = ((d, d, spec["n_cls"]) if spec["tail"] == "peer" else (1,), f32)
     out[e + "model.class_token"] = ((1, 1, d), f32)
     out[e + "model.conv_proj.weight"] = ((d, 3, p, p), f32)
     out[e + "model.conv_proj.bias"] = ((d,), f32)
@@ -116,7 +119,16 @@ def state_schema(spec: dict) -> "OrderedDict[str, Tuple[Tuple[int, ...], torch.d
     out[e + "model.encoder.ln.weight"] = ((d,), f32)
     out[e + "model.encoder.ln.bias"] = ((d,), f32)
     eo = spec["n_embd_out_vit"]
-    if spec["tail"] == "lsh":
+    if spec["tail"] == "peer":                 # reference models/layers.py:36-71 (registration order of PeerLookup.__init__)
+        nh, qd, nq = spec["peer_nhead"], spec["peer_query_dim"], spec["peer_units_sqrt"]
+        out[e + "peer.residual.weight"] = ((eo, d), f32)
+        out[e + "peer.query_linear.weight"] = ((qd * nh, d), f32)
+        out[e + "peer.key_linear.weight"] = ((d * nh, d), f32)
+        out[e + "peer.query_left.linear.weight"] = ((nq, qd), f32)
+        out[e + "peer.query_right.linear.weight"] = ((nq, qd), f32)
+        out[e + "peer.emb_in.weight"] = ((nq * nq, d), f32)
+        out[e + "peer.emb_out.weight"] = ((nq * nq, eo), f32)
+    elif spec["tail"] == "lsh":
         for s in range(spec["n_cls"]):
             for r, nb in enumerate(spec["lsh_num_bins"]):
                 kp = f"{e}lsh_emb.{s}.emb.{r}."
@@ -213,7 +225,9 @@ def synth_state_dict(spec: dict, seed: int = 0) -> Dict[str, torch.Tensor]:
         g = _gen(key, seed)
         leaf = key.rsplit(".", 1)[-1]
         if key.endswith("peer_proj_wt"):
-            t = torch.zeros(shape)
+            t = torch.zeros(shape) if len(shape) == 1 else torch.randn(shape, generator=g) / (shape[0] ** 0.5)
+        elif ".peer." in key:                    # O(1) scores / activations so that the top-k choice and the softmax are not degenerate
+            t = torch.randn(shape, generator=g) * (0.5 if ".emb_" in key else 1.0 / (shape[-1] ** 0.5))
         elif leaf == "projection_mat":
             t = torch.nn.functional.normalize(torch.randn(shape, generator=g), p=2.0, dim=0)
         elif leaf == "grid":

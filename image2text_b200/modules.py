@@ -33,7 +33,9 @@ class ParamTree(nn.Module):
             node.register_buffer(leaf, tensor, persistent=True)
             return None
         if param is None:
-            param = nn.Parameter(tensor, requires_grad=not any(dotted.endswith(k) for k in FROZEN_KEYS))
+            # (peer_proj_wt is a frozen (1,) dummy unless the PEER tail is configured: reference models/encoder.py:86-95)
+            frozen = any(dotted.endswith(k) for k in FROZEN_KEYS) and tensor.numel() == 1
+            param = nn.Parameter(tensor, requires_grad=not frozen)
         node.register_parameter(leaf, param)
         return param
 
@@ -44,7 +46,9 @@ def reference_like_init(key: str, shape, dtype, spec: dict, gen: Optional[torch.
     torchvision ViT defaults, nn.EmbeddingBag N(0,1), unit-column LSH projections (models/layers.py:119-134)."""
     leaf = key.rsplit(".", 1)[-1]
     if key.endswith("peer_proj_wt"):
-        return torch.zeros(shape)
+        return torch.zeros(shape) if len(shape) == 1 else torch.randn(shape, generator=gen) / math.sqrt(shape[0])
+    if ".peer." in key:                        # nn.Embedding N(0, 1); nn.Linear ~ U(+-1/sqrt(in)) (same scale, not the same stream)
+        return torch.randn(shape, generator=gen) * (1.0 if ".emb_" in key else 1.0 / math.sqrt(3 * shape[-1]))
     if leaf == "projection_mat":
         return torch.nn.functional.normalize(torch.randn(shape, generator=gen), p=2.0, dim=0)
     if leaf == "grid":

@@ -113,6 +113,21 @@ int i2t_lsh_tail(const float* feat, const void* const* proj, const void* const* 
                  const int32_t* num_bins, float* out, int32_t* bucket_out, int64_t B, int64_t D, int64_t n_cls,
                  int64_t n_res, int64_t n_proj, int64_t E, void* stream);
 
+/* ---- PEER tail core: models/layers.py:73-109 minus its dense projections (i2t_gemm) ---------------------------- */
+/* ql / qr (M,H,U) fp32: scores of the left / right query units (query . W_left/right); key (M,H,D): key projection;
+ * emb_in (E,D), emb_out (E,O).  Per (row, head): top-K of ql and qr, top-K of their K x K sums, softmax, expert id =
+ * left * K + right (:93-96, literally), w_k = softmax_k * gelu_tanh(emb_in[id_k] . key); out (M,O) = sum_{h,k} w_k emb_out[id_k]
+ * (the residual projection is added by the caller).  s_* (M,H,K) are saved for the backward pass.  M = batch * n_cls. */
+int i2t_peer_lookup_fwd(const float* ql, const float* qr, const float* key, const float* emb_in, const float* emb_out, float* out,
+                        int32_t* s_idx, float* s_score, float* s_dot, int32_t* s_lpos, int32_t* s_rpos, int64_t M, int64_t H,
+                        int64_t U, int64_t K, int64_t D, int64_t O, void* stream);
+/* Backward: dql, dqr (M,H,U) and dkey (M,H,D) are written; demb_in (E,D) / demb_out (E,O) are ACCUMULATED (zero them first;
+ * dense like the reference's nn.Embedding gradients). */
+int i2t_peer_lookup_bwd(const float* dout, const float* key, const float* emb_in, const float* emb_out, const int32_t* s_idx,
+                        const float* s_score, const float* s_dot, const int32_t* s_lpos, const int32_t* s_rpos, float* dql,
+                        float* dqr, float* dkey, float* demb_in, float* demb_out, int64_t M, int64_t H, int64_t U, int64_t K,
+                        int64_t D, int64_t O, void* stream);
+
 /* ---- decoder input: models/vision_encoder_decoder.py:84-88 + models/decoder.py:234-243 ----------------- */
 /* x[b,t,:] = (t < n_prompt ? prompt[b,t,:] : wte[ids[b,t-n_prompt],:]) + wpe[t,:],  t < T */
 int i2t_embed_fwd(const int64_t* ids, const float* prompt, const float* wte, const float* wpe, float* x, int64_t B,

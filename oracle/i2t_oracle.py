@@ -180,6 +180,33 @@ def posbias_tail(sd: Dict[str, Tensor], spec: dict, feat: Tensor, prefix: str = 
     return F.normalize(torch.stack(outs, dim=1), p=2.0, dim=-1)
 
 
+def peer_lookup(sd: Dict[str, Tensor], spec: dict, inp: Tensor, prefix: str = "encoder.peer.") -> Tensor:
+    """models/layers.py:73-109 (PeerLookup.forward) with the query units of :21-34.  inp (B, S, 768) -> (B, S, out).
+    Literal restatement, including `left * topk + right` at :93-96 (the expert id is NOT left * sqrt(num_units) + right:
+    only the first topk * sqrt(num_units) rows of the two tables are ever addressed)."""
+    nh, qd, topk = spec["peer_nhead"], spec["peer_query_dim"], spec["peer_topk"]
+    bs, seq, fin = inp.shape
+    x = F.linear(inp, sd[prefix + "query_linear.weight"]).view(bs, seq, nh, qd)
+    inp_proj = F.linear(inp, sd[prefix + "key_linear.weight"]).view(bs, seq, nh, fin)
+    residual = F.linear(inp, sd[prefix + "residual.weight"])
+    left = torch.topk(F.linear(x, sd[prefix + "query_left.linear.weight"]), k=topk, dim=-1)
+    right = torch.topk(F.linear(x, sd[prefix + "query_right.linear.weight"]), k=topk, dim=-1)
+    cross = (left.values.unsqueeze(-1) + right.values.unsqueeze(-2)).view(bs, seq, nh, topk * topk)
+    y = torch.topk(cross, k=topk, dim=-1)
+    scores = F.softmax(y.values, dim=-1)
+    li = left.indices.gather(-1, y.indices // topk)
+    ri = right.indices.gather(-1, y.indices % topk)
+    final = li * topk + ri                                              # (B, S, H, K)
+    in_dot = torch.einsum("bshkd,bshd->bshk", sd[prefix + "emb_in.weight"][final], inp_proj)
+    weight = scores * gelu_tanh(in_dot)
+    return torch.einsum("bshk,bshkd->bsd", weight, sd[prefix + "emb_out.weight"][final]) + residual
+
+
+def peer_tail(sd: Dict[str, Tensor], spec: dict, feat: Tensor, pre: str = "encoder.") -> Tensor:
+    """models/encoder.py:114-115: per-slot projection of the ViT feature, then the expert lookup."""
+    return peer_lookup(sd, spec, torch.einsum("bd,des->bse", feat, sd[pre + "peer_proj_wt"]), prefix=pre + "peer.")
+
+
 def encoder_forward(sd: Dict[str, Tensor], spec: dict, images: Tensor) -> Tensor:
     """models/encoder.py:108-119, plus the bridging Linear of models/vision_encoder_decoder.py:33-37
     (state-dict keys then move under ``encoder.0.`` / ``encoder.1.``)."""
@@ -190,6 +217,8 @@ def encoder_forward(sd: Dict[str, Tensor], spec: dict, images: Tensor) -> Tensor
         out = lsh_tail(sd, spec, feat, prefix=pre + "lsh_emb.")
     elif spec["tail"] == "posbias":
         out = posbias_tail(sd, spec, feat, prefix=pre + "proj.models.")
+    elif spec["tail"] == "peer":
+        out = peer_tail(sd, spec, feat, pre=pre)
     else:
         raise ValueError(spec["tail"])
     if bridged:

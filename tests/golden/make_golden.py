@@ -262,6 +262,43 @@ def case_beam(ref, out):
     restore_vit_patch(ref)
 
 
+def case_peer(ref, out):
+    """SURVEY.md 8f-2 (the gpu/nano.yaml variant): PretrainedViT + PEER tail + bridging Linear + cross-attention-only decoder,
+    small dims (configs/tiny_peer.yaml): forward, greedy ids and one training step (loss + gradients of the PEER parameters)."""
+    small_vit_patch(ref, layers=2, image=32)
+    over = dict(vit_layers=2, vit_image=32)
+    tc, mdl, spec, sd, model = build(ref, "tiny_peer", over)
+    model.eval()
+    B, S = 3, 20
+    images = synth_images(B, 32, seed=11)
+    labels = synth_labels(B, S, spec["vocab_size"], seed=12, min_len=3, max_len=14, eos=spec["vocab_size"] - 1)
+    ids = torch.where(labels != -100, labels, torch.full_like(labels, spec["vocab_size"] - 1))
+    with torch.no_grad():
+        o = model(images=images, ids=ids, attn_msk=None)
+    res = dict(labels=labels.numpy(), enc=f32(o.encoder_output), logits=f32(o.logits), hidden=f32(o.hidden_state))
+    prompt = torch.full((B, 1), spec["vocab_size"] - 1, dtype=torch.long)
+    res["greedy"] = model.generate(images, prompt, max_new_tokens=16, top_k=1).numpy()
+    tok = ref_harness.fake_tokenizer(vocab_size=spec["vocab_size"], eos=spec["vocab_size"] - 1, bos=spec["vocab_size"] - 1)
+    cfg = ref.CM.VisionEncoderDecoderConfig.model_validate(mdl)
+    wrapper = ref.TW.ModelTrainerWrapper(cfg, tok, ref.CT.TrainerWrapperConfig(), -100)
+    wrapper.model.load_state_dict(sd, strict=True)
+    wrapper.train()
+    loss, _ = wrapper.train_step(images, labels)
+    loss.backward()
+    res["train_loss"] = f32(loss)
+    named = dict(wrapper.model.named_parameters())
+    for k, p in named.items():
+        if p.grad is not None and ("peer" in k or k == "encoder.1.weight"):
+            res[f"gnorm::{k}"] = f32(p.grad.norm())
+    for k in ("encoder.0.peer.query_left.linear.weight", "encoder.0.peer.query_linear.weight", "encoder.0.peer.residual.weight",
+              "encoder.0.peer.emb_out.weight", "encoder.0.peer.emb_in.weight", "encoder.1.weight"):
+        res[f"grad::{k}"] = f32(named[k].grad)
+    res["grad_head::encoder.0.peer.key_linear.weight"] = f32(named["encoder.0.peer.key_linear.weight"].grad[:64])
+    res["grad_head::encoder.0.peer_proj_wt"] = f32(named["encoder.0.peer_proj_wt"].grad[:32, :32])
+    out["tiny_peer"] = res
+    restore_vit_patch(ref)
+
+
 def main():
     torch.manual_seed(0)
     ref = ref_harness.load_reference()

@@ -13,7 +13,8 @@ _CACHE = {}
 # the reference-made goldens were produced with every dropout at 0 (tests/golden/make_golden.py: zero_dropout / .eval()),
 # so the parity models switch the YAML's p = 0.1 off; the dropout tests switch it back on explicitly
 NO_DROPOUT = dict(dropout=0.0, attn_dropout=0.0)
-SPEC_OVERRIDES = {"tiny": dict(vit_layers=2, vit_image=32), "nano": dict(NO_DROPOUT), "gpt2": dict(NO_DROPOUT)}
+SPEC_OVERRIDES = {"tiny": dict(vit_layers=2, vit_image=32), "tiny_peer": dict(vit_layers=2, vit_image=32),
+                  "nano": dict(NO_DROPOUT), "gpt2": dict(NO_DROPOUT)}
 
 
 def spec_and_weights(name: str, seed: int = 0):

@@ -185,3 +185,44 @@ def test_gpt2_hf_layout_forward_and_greedy(golden):
     prompt = torch.full((2, 1), 50256, dtype=torch.long)
     got = O.generate(sd, spec, images, prompt, 12, top_k=1)
     assert np.array_equal(got.numpy(), g["greedy"])
+
+
+def test_peer_tail_variant_forward_greedy_and_grads(golden):
+    """SURVEY.md 8f-2 (gpu/nano.yaml variant): PEER tail + bridging Linear + cross-attention-only decoder (configs/tiny_peer.yaml)
+    against the reference-made fixture: encoder output, logits, greedy ids, train-step loss and the PEER gradients."""
+    g = golden("tiny_peer")
+    _, spec, sd0 = spec_and_weights("tiny_peer")
+    assert spec["tail"] == "peer" and not spec["use_soft_prompting"]
+    images = synth_images(3, 32, seed=11)
+    labels = T(g["labels"])
+    eos = spec["vocab_size"] - 1
+    ids = torch.where(labels != -100, labels, torch.full_like(labels, eos))
+    with torch.no_grad():
+        enc, logits, hidden = O.ved_forward(sd0, spec, images, ids)
+    assert rel_err(enc, T(g["enc"])) < TOL
+    assert rel_err(logits, T(g["logits"])) < TOL
+    assert rel_err(hidden, T(g["hidden"])) < TOL
+    prompt = torch.full((3, 1), eos, dtype=torch.long)
+    assert np.array_equal(O.generate(sd0, spec, images, prompt, 16, top_k=1).numpy(), g["greedy"])
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd0.items()}
+    sd["decoder.lm_head.weight"] = sd["decoder.transformer.wte.weight"]
+    tids, msk = O.wrapper_inputs(labels, eos_token_id=eos, bos_token_id=eos)
+    _, lg, _ = O.ved_forward(sd, spec, images, tids, attn_msk=msk)
+    loss = O.lm_loss(lg, labels, None)
+    assert abs(float(loss.detach()) - float(g["train_loss"])) < 1e-5 * abs(float(g["train_loss"]))
+    loss.backward()
+    n = 0
+    for key, val in g.items():
+        if key.startswith("gnorm::"):
+            k = key.split("::")[1]
+            assert abs(float(sd[k].grad.norm()) - float(val)) <= 1e-4 * max(float(val), 1e-8), k
+            n += 1
+        elif key.startswith("grad::"):
+            assert rel_err(sd[key.split("::")[1]].grad, T(val)) < 1e-4, key
+        elif key.startswith("grad_head::"):
+            k = key.split("::")[1]
+            gr = sd[k].grad
+            want = T(val)
+            got = gr[:want.shape[0]] if want.dim() == 2 and gr.dim() == 2 else gr[:32, :32]
+            assert rel_err(got, want) < 1e-4, key
+    assert n >= 9
