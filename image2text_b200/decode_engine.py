@@ -54,7 +54,10 @@ class DecodeEngine:
             mode = "kernels"
         # bf16, more sequences than the megakernel's 8: split-K tensor-core GEMMs over the batch beat the per-stage FMA
         # kernels from 9 sequences on (16 sequences: 24.4k vs 11.4k tok/s); fp32 keeps the exact-FMA kernels up to 16
-        if (batch >= int(os.environ.get("I2T_DECODE_GEMM_MIN", "9")) and self.cd == torch.bfloat16) or batch > 16:
+        if (batch >= int(os.environ.get("I2T_DECODE_GEMM_MIN", "9")) and self.cd == torch.bfloat16) or batch > 16 \
+                or max(C, self.F) > 3072:
+            # (wider than 3072, e.g. gpu/nano.yaml's 1280 x 5120 MLP: the weight-streaming linear stages the whole input row
+            # block in shared memory, which 16 rows x 5120 fp32 exceed -- the GEMM path has no such limit)
             mode = "gemm"           # projections as tensor-core GEMMs over the batch
         if mode in ("mega2", "mega3") and (self.cd != torch.bfloat16 or C > 768 or C % 64 or self.F % 64 or self.F > 3072
                                            or max(self.Tmax, spec["n_cls"]) > 256 or batch * spec["n_head"] > 132
