@@ -65,6 +65,7 @@ SIGNATURES = {
     "i2t_embed_bwd": (c_int, [P, P, P, L, L, L, L, L, P]),
     "i2t_gradnorm_scale": (c_int, [P, P, P, L, I, P]),
     "i2t_lm_loss": (c_int, [P, P, P, P, P, P, P, L, L, L, L, L, F, F, I, I, F, L, L, L, L, F, I, P]),
+    "i2t_contrastive_loss": (c_int, [P, P, P, P, P, P, L, L, L, F, I, I, F, L, L, F, P]),
     "i2t_scale_inplace": (c_int, [P, P, L, I, P]),
     "i2t_l2norm_fwd": (c_int, [P, P, L, L, F, P]),
     "i2t_l2norm_bwd": (c_int, [P, P, P, L, L, F, P]),

@@ -401,3 +401,32 @@ class PeerLookupFn(torch.autograd.Function):
         call("i2t_peer_lookup_bwd", ptr(dout), ptr(key), ptr(emb_in), ptr(emb_out), ptr(idx), ptr(score), ptr(dot), ptr(lpos),
              ptr(rpos), ptr(dql), ptr(dqr), ptr(dkey), ptr(demb_in), ptr(demb_out), M, H, U, K, D, O, stream())
         return dql, dqr, dkey, demb_in, demb_out, None
+
+
+class ContrastiveLossFn(torch.autograd.Function):
+    """training/wrapper.py:98-118 after the similarity GEMM: masked, weighted cross entropy of pred (R, R) against the diagonal."""
+
+    @staticmethod
+    def forward(ctx, pred, labels, L, temperature, weight_fn, eos_weight, eos_id, ignore_index):
+        pred = pred.contiguous().float()
+        R = pred.shape[0]
+        B = R // L
+        labels = labels.contiguous()
+        dev = pred.device
+        weights = torch.empty(R, device=dev, dtype=torch.float32)
+        rows = torch.empty(R, device=dev, dtype=torch.float32)
+        loss = torch.empty((), device=dev, dtype=torch.float32)
+        dpred = torch.empty_like(pred) if ctx.needs_input_grad[0] else None
+        call("i2t_contrastive_loss", ptr(pred), ptr(labels), ptr(weights), ptr(rows), ptr(loss), ptr(dpred), B, L, labels.shape[1],
+             float(temperature), int(weight_fn == "inverse_sqrt_position"), int(eos_weight is not None),
+             float(eos_weight if eos_weight is not None else 0.0), int(eos_id), int(ignore_index), 1.0, stream())
+        if dpred is not None:
+            ctx.save_for_backward(dpred)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gloss):
+        (dpred,) = ctx.saved_tensors
+        scale = gloss.reshape(1).to(torch.float32).contiguous()
+        call("i2t_scale_inplace", ptr(dpred), ptr(scale), dpred.numel(), dt(dpred), stream())
+        return dpred, None, None, None, None, None, None, None

@@ -314,6 +314,82 @@ extern "C" int i2t_lm_loss(const void* logits, const void* teacher_logits, const
   return I2T_OK;
 }
 
+// ---- contrastive auxiliary loss: training/wrapper.py:98-118 after its (B*L, C) x (C, B*L) similarity GEMM -------------
+// One CTA per row r of pred (R x R fp32, R = B * L): cross entropy of pred[r, :] / tau against target r over the VALID columns
+// (labels != ignore_index; the reference writes -inf into the others), times the loss weight of row r; an infinite loss (the
+// target column itself is masked) counts as 0, like the reference's isinf filter.  dpred (optional) = d loss / d pred.
+namespace i2t {
+__global__ void __launch_bounds__(256) contrastive_ce_kernel(const float* __restrict__ pred, const int64_t* __restrict__ labels,
+                                                             const float* __restrict__ weights, float* __restrict__ loss_rows,
+                                                             float* __restrict__ dpred, int R, int L, int64_t ld_labels,
+                                                             float inv_tau, int64_t ignore_index, float grad_scale) {
+  __shared__ float red[8];
+  __shared__ float s_bcast;
+  const int r = blockIdx.x, t = threadIdx.x;
+  const float* row = pred + (int64_t)r * R;
+  auto valid = [&](int c) { return labels[(int64_t)(c / L) * ld_labels + (c % L)] != ignore_index; };
+  float mx = -INFINITY;
+  for (int c = t; c < R; c += 256)
+    if (valid(c)) mx = fmaxf(mx, row[c] * inv_tau);
+  mx = warp_max(mx);
+  if ((t & 31) == 0) red[t >> 5] = mx;
+  __syncthreads();
+  if (t == 0) {
+    float m = red[0];
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+    s_bcast = m;
+  }
+  __syncthreads();
+  mx = s_bcast;
+  __syncthreads();
+  float sum = 0.f;
+  for (int c = t; c < R; c += 256)
+    if (valid(c)) sum += expf(row[c] * inv_tau - mx);
+  sum = warp_sum(sum);
+  if ((t & 31) == 0) red[t >> 5] = sum;
+  __syncthreads();
+  if (t == 0) {
+    float s2 = 0.f;
+    for (int i = 0; i < 8; ++i) s2 += red[i];
+    s_bcast = s2;
+  }
+  __syncthreads();
+  sum = s_bcast;
+  const bool finite = valid(r) && sum > 0.f;          // target column masked (or nothing valid): the loss is inf -> dropped
+  const float w = weights[r];
+  const float lse = mx + logf(sum);
+  if (t == 0) loss_rows[r] = finite ? w * (lse - row[r] * inv_tau) : 0.f;
+  if (dpred != nullptr) {
+    float* drow = dpred + (int64_t)r * R;
+    const float k = finite ? w * inv_tau * grad_scale : 0.f;
+    for (int c = t; c < R; c += 256) {
+      float g = 0.f;
+      if (finite && valid(c)) g = k * (expf(row[c] * inv_tau - lse) - (c == r ? 1.f : 0.f));
+      drow[c] = g;
+    }
+  }
+}
+}  // namespace i2t
+
+// pred (R, R) fp32 with R = B * L; labels (B, ld_labels) int64; weights (R) / loss_rows (R) fp32 scratch; loss_out: device scalar
+extern "C" int i2t_contrastive_loss(const float* pred, const int64_t* labels, float* weights, float* loss_rows, float* loss_out,
+                                    float* dpred, int64_t B, int64_t L, int64_t ld_labels, float temperature,
+                                    int inv_sqrt_position, int use_eos_weight, float eos_weight, int64_t eos_id,
+                                    int64_t ignore_index, float grad_scale, void* stream) {
+  I2T_REQUIRE(pred && labels && weights && loss_rows && loss_out, "contrastive_loss: null pointer");
+  I2T_REQUIRE(B > 0 && L > 0 && L <= ld_labels && temperature > 0.f && B * L < (1ll << 30), "contrastive_loss: bad sizes");
+  cudaStream_t st = (cudaStream_t)stream;
+  loss_weights_kernel<<<(unsigned)B, 256, 0, st>>>(labels, weights, (int)L, ld_labels, inv_sqrt_position, eos_weight, use_eos_weight,
+                                                  eos_id, ignore_index, (int)B);
+  I2T_LAUNCHED();
+  contrastive_ce_kernel<<<(unsigned)(B * L), 256, 0, st>>>(pred, labels, weights, loss_rows, dpred, (int)(B * L), (int)L, ld_labels,
+                                                          1.0f / temperature, ignore_index, grad_scale);
+  I2T_LAUNCHED();
+  sum_rows_kernel<<<1, 256, 0, st>>>(loss_rows, loss_out, (int)(B * L));
+  I2T_LAUNCHED();
+  return I2T_OK;
+}
+
 extern "C" int i2t_scale_inplace(void* x, const float* scale_ptr, int64_t n, int dtype, void* stream) {
   I2T_REQUIRE(x && scale_ptr && n >= 0 && valid_dtype(dtype), "scale_inplace: bad arguments");
   if (n == 0) return I2T_OK;

@@ -26,8 +26,6 @@ class ModelTrainerWrapper(nn.Module):
     def __init__(self, model_config: VisionEncoderDecoderConfig, tokenizer, trainer_config: TrainerWrapperConfig,
                  ignore_index: int = -100, device="cuda", compute_dtype: torch.dtype = torch.float32, **model_kw):
         super().__init__()
-        if trainer_config.add_contrastive_loss:
-            raise NotImplementedError("contrastive auxiliary loss (reference training/wrapper.py:98-118) is not built")
         self.model = VisionEncoderDecoder(config=model_config, device=device, compute_dtype=compute_dtype, **model_kw)
         self.is_momentum = trainer_config.moco_momentum is not None and trainer_config.moco_alpha is not None
         self.model_m = VisionEncoderDecoder(config=model_config, device=device, compute_dtype=compute_dtype, **model_kw) \
@@ -41,6 +39,8 @@ class ModelTrainerWrapper(nn.Module):
         self.mask_fraction = trainer_config.mask_fraction
         self.random_mask_fraction = trainer_config.random_mask_fraction
         self.eos_token_weight = trainer_config.eos_token_weight
+        self.add_contrastive_loss = trainer_config.add_contrastive_loss
+        self.contrastive_temperature = trainer_config.training_contrastive_temperature
         self.momentum = trainer_config.moco_momentum
         self.alpha = trainer_config.moco_alpha
         self._ema = EmaUpdater()
@@ -126,6 +126,26 @@ class ModelTrainerWrapper(nn.Module):
             reducer.exchange_after_replay()
         return st["loss"]
 
+    def target_emb(self, input_ids):
+        return self.model.decoder.get_inputs_embeds(input_ids)          # training/wrapper.py:62-63
+
+    def compute_contrastive_loss(self, hidden_state, labels):
+        """training/wrapper.py:98-118: every hidden row against the input embedding of every label of the batch (a (B*L, C) x
+        (C, B*L) similarity GEMM), cross entropy against the diagonal over the non-ignored columns, weighted like the LM loss."""
+        from .autograd_ops import ContrastiveLossFn, linear
+        L = min(hidden_state.shape[-2], labels.shape[-1])
+        labels = labels[..., :L].contiguous()
+        hidden = hidden_state[..., :L, :].contiguous()
+        keep = labels != self.ignore_index
+        target = self.target_emb(torch.where(keep, labels, torch.zeros_like(labels)))           # (B, L, C) rows of wte
+        C = hidden.shape[-1]
+        cd = self.model.compute_dtype
+        h2, t2 = hidden.reshape(-1, C), target.reshape(-1, C)
+        pred = linear(h2 if cd == torch.float32 else h2.to(cd), t2, t2 if cd == torch.float32 else t2.to(cd), None, None, 0,
+                      torch.float32)
+        return ContrastiveLossFn.apply(pred, labels, L, self.contrastive_temperature, self.weight_fn, self.eos_token_weight,
+                                       self.tokenizer.eos_token_id, self.ignore_index)
+
     def compute_lm_loss(self, lm_logits, labels, lm_logits_moco=None):
         return LmLossFn.apply(lm_logits, lm_logits_moco, labels, self.temperature, self.alpha, self.weight_fn,
                               self.eos_token_weight, self.tokenizer.eos_token_id, self.ignore_index,
@@ -149,12 +169,16 @@ class ModelTrainerWrapper(nn.Module):
         corrupted = torch.cat((bos, corrupted), dim=1)[:, :sl].contiguous()
         attn_msk = torch.cat((torch.ones((bs, 1), device=keep.device, dtype=torch.bool), keep), dim=1)[:, :sl]
         step = "train" if is_train else "val"
-        lm_logits, _ = self(images, corrupted, attn_msk)
+        lm_logits, hidden_state = self(images, corrupted, attn_msk)
         lm_logits_moco = None
         if self.is_momentum and is_train:
             lm_logits_moco, _ = self.forward_m(images, corrupted, attn_msk)
         loss = self.compute_lm_loss(lm_logits, labels, lm_logits_moco)
         metrics = {f"{step}_loss_lm": loss.detach()}
+        if self.add_contrastive_loss:                                   # training/wrapper.py:206-209
+            loss_contrastive = self.compute_contrastive_loss(hidden_state, labels)
+            metrics[f"{step}_loss_contrastive"] = loss_contrastive.detach()
+            loss = loss + loss_contrastive
         if is_train:
             self._momentum_update()
         return loss, metrics

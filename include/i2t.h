@@ -314,6 +314,13 @@ int i2t_lm_loss(const void* logits, const void* teacher_logits, const int64_t* l
                 float temperature, float alpha, int inv_sqrt_position, int use_eos_weight, float eos_weight,
                 int64_t eos_id, int64_t ignore_index, int64_t ld_logits, int64_t ld_teacher, float grad_scale, int dtype,
                 void* stream);
+/* Contrastive auxiliary loss, training/wrapper.py:98-118, after the similarity GEMM pred = H Ht^T (R x R fp32, R = B*L, H = the
+ * decoder's hidden rows, Ht = wte[labels]): sum_r w_r * CE(pred[r, valid columns] / temperature, target r), w = the LM-loss
+ * weights of get_weights (:80-96), columns whose label is ignore_index masked, infinite row losses dropped.  weights / loss_rows:
+ * fp32 scratch (R); loss_out: device scalar; dpred (R x R, optional) = grad_scale * d loss / d pred. */
+int i2t_contrastive_loss(const float* pred, const int64_t* labels, float* weights, float* loss_rows, float* loss_out, float* dpred,
+                         int64_t B, int64_t L, int64_t ld_labels, float temperature, int inv_sqrt_position, int use_eos_weight,
+                         float eos_weight, int64_t eos_id, int64_t ignore_index, float grad_scale, void* stream);
 /* y = x / max(||x||_2, eps) per row and its backward: F.normalize(p=2, dim=-1) at models/encoder.py:118-119 */
 int i2t_l2norm_fwd(const float* x, float* y, int64_t rows, int64_t cols, float eps, void* stream);
 int i2t_l2norm_bwd(const float* x, const float* dy, float* dx, int64_t rows, int64_t cols, float eps, void* stream);

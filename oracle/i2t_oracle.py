@@ -548,6 +548,24 @@ def lm_loss(logits: Tensor, labels: Tensor, logits_moco: Optional[Tensor] = None
     return -(picked * w).sum()
 
 
+def contrastive_loss(sd, hidden_state: Tensor, labels: Tensor, temperature: float = 1.0, ignore_index: int = -100,
+                     wte_key: str = "decoder.transformer.wte.weight", **wkw) -> Tensor:
+    """training/wrapper.py:98-118: hidden rows vs. the input embeddings of every label of the batch, CE against the diagonal over
+    the non-ignored columns, weighted like the LM loss; rows whose own column is masked (infinite CE) count as 0."""
+    labels = labels[..., :hidden_state.size(-2)].contiguous()
+    if hidden_state.size(-2) > labels.size(-1):
+        hidden_state = hidden_state[..., :labels.size(-1), :]
+    weights = loss_weights(labels, ignore_index=ignore_index, **wkw)
+    keep = labels != ignore_index
+    target = sd[wte_key][torch.where(keep, labels, torch.zeros_like(labels))]
+    pred = hidden_state.reshape(-1, hidden_state.size(-1)) @ target.reshape(-1, target.size(-1)).T
+    pred = torch.where(keep.view(1, -1), pred, torch.full_like(pred, float("-inf")))
+    tgt = torch.arange(pred.size(0), device=pred.device)
+    losses = F.cross_entropy(pred / temperature, tgt, reduction="none")
+    losses = torch.where(losses.isinf(), torch.zeros_like(losses), losses)
+    return (losses.view(-1) * weights.view(-1)).sum()
+
+
 def wrapper_inputs(labels: Tensor, eos_token_id=50256, bos_token_id=50256, ignore_index=-100):
     """training/wrapper.py:154-159,184-196 (no MLM corruption: mask_fraction = 0).
     Returns (decoder input ids with BOS prepended and last dropped, (B,s) row-valid mask)."""

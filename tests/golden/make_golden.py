@@ -262,6 +262,34 @@ def case_beam(ref, out):
     restore_vit_patch(ref)
 
 
+def case_contrastive(ref, out):
+    """training/wrapper.py:98-118,206-209: the contrastive auxiliary loss (add_contrastive_loss), tiny model."""
+    small_vit_patch(ref, layers=2, image=32)
+    over = dict(vit_layers=2, vit_image=32)
+    tc, mdl, spec, sd, model = build(ref, "tiny", over)
+    eos = spec["vocab_size"] - 1
+    images = synth_images(3, 32, seed=11)
+    labels = synth_labels(3, 20, spec["vocab_size"], seed=12, min_len=3, max_len=14, eos=eos)
+    tok = ref_harness.fake_tokenizer(vocab_size=spec["vocab_size"], eos=eos, bos=eos)
+    cfg = ref.CM.VisionEncoderDecoderConfig.model_validate(mdl)
+    tcfg = dict(add_contrastive_loss=True, training_contrastive_temperature=0.7, weight_fn="inverse_sqrt_position", eos_token_weight=2.0)
+    wrapper = ref.TW.ModelTrainerWrapper(cfg, tok, ref.CT.TrainerWrapperConfig(**tcfg), -100)
+    wrapper.model.load_state_dict(sd, strict=True)
+    wrapper.train()
+    loss, metrics = wrapper.train_step(images, labels)
+    loss.backward()
+    res = dict(labels=labels.numpy(), loss=f32(loss), loss_lm=f32(metrics["train_loss_lm"]),
+               loss_contrastive=f32(metrics["train_loss_contrastive"]))
+    named = dict(wrapper.model.named_parameters())
+    for k, p in named.items():
+        if p.grad is not None:
+            res[f"gnorm::{k}"] = f32(p.grad.norm())
+    for k in ("decoder.transformer.wte.weight", "decoder.transformer.h.3.mlp.c_proj.weight", "decoder.transformer.ln_f.weight"):
+        res[f"grad::{k}"] = f32(named[k].grad)
+    out["tiny_contrastive"] = res
+    restore_vit_patch(ref)
+
+
 def case_peer(ref, out):
     """SURVEY.md 8f-2 (the gpu/nano.yaml variant): PretrainedViT + PEER tail + bridging Linear + cross-attention-only decoder,
     small dims (configs/tiny_peer.yaml): forward, greedy ids and one training step (loss + gradients of the PEER parameters)."""

@@ -234,3 +234,32 @@ def test_bf16_training_sees_the_updated_weights(graphed):
     fresh.load_state_dict(w.model.state_dict())
     fresh.eval()
     assert torch.equal(a, fresh.generate(images, prompt, max_new_tokens=8, top_k=1))
+
+
+def test_contrastive_auxiliary_loss_matches_reference(golden):
+    """training/wrapper.py:98-118,206-209 (add_contrastive_loss): LM + contrastive loss and every gradient norm against the
+    reference-made fixture tests/golden/tiny_contrastive.npz (similarity GEMM + the masked, weighted CE kernel)."""
+    g = golden("tiny_contrastive")
+    kw = dict(add_contrastive_loss=True, training_contrastive_temperature=0.7, weight_fn="inverse_sqrt_position", eos_token_weight=2.0)
+    w, spec, sd = make_wrapper("tiny", kw, eos=612)
+    w.train()
+    images = synth_images(3, 32, seed=11).cuda()
+    labels = T(g["labels"]).cuda()
+    loss, metrics = w.train_step(images, labels)
+    assert abs(float(metrics["train_loss_lm"]) - float(g["loss_lm"])) < 1e-4 * abs(float(g["loss_lm"]))
+    assert abs(float(metrics["train_loss_contrastive"]) - float(g["loss_contrastive"])) < 1e-4 * abs(float(g["loss_contrastive"]))
+    assert abs(float(loss.detach()) - float(g["loss"])) < 1e-4 * abs(float(g["loss"]))
+    loss.backward()
+    named = dict(w.model.named_parameters())
+    n = 0
+    for key, val in g.items():
+        if key.startswith("gnorm::"):
+            k = key.split("::")[1]
+            if k not in named:
+                continue
+            gn = float(named[k].grad.norm())
+            assert abs(gn - float(val)) <= 3e-4 * max(float(val), 1e-7), (k, gn, float(val))
+            n += 1
+        elif key.startswith("grad::"):
+            assert rel_err(named[key.split("::")[1]].grad.cpu(), T(val)) < 3e-4, key
+    assert n > 50

@@ -226,3 +226,33 @@ def test_peer_tail_variant_forward_greedy_and_grads(golden):
             got = gr[:want.shape[0]] if want.dim() == 2 and gr.dim() == 2 else gr[:32, :32]
             assert rel_err(got, want) < 1e-4, key
     assert n >= 9
+
+
+def test_contrastive_auxiliary_loss(golden):
+    """training/wrapper.py:98-118,206-209 (add_contrastive_loss) against the reference-made fixture: both losses and gradients."""
+    g = golden("tiny_contrastive")
+    _, spec, sd0 = spec_and_weights("tiny")
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd0.items()}
+    sd["decoder.lm_head.weight"] = sd["decoder.transformer.wte.weight"]
+    images = synth_images(3, 32, seed=11)
+    eos = spec["vocab_size"] - 1
+    labels = T(g["labels"])
+    ids, msk = O.wrapper_inputs(labels, eos_token_id=eos, bos_token_id=eos)
+    _, logits, hidden = O.ved_forward(sd, spec, images, ids, attn_msk=msk)
+    wkw = dict(weight_fn="inverse_sqrt_position", eos_token_weight=2.0, eos_token_id=eos)
+    lm = O.lm_loss(logits, labels, None, **wkw)
+    con = O.contrastive_loss(sd, hidden, labels, temperature=0.7, **wkw)
+    assert abs(float(lm.detach()) - float(g["loss_lm"])) < 1e-5 * abs(float(g["loss_lm"]))
+    assert abs(float(con.detach()) - float(g["loss_contrastive"])) < 1e-5 * abs(float(g["loss_contrastive"]))
+    (lm + con).backward()
+    n = 0
+    for key, val in g.items():
+        if key.startswith("gnorm::"):
+            k = key.split("::")[1]
+            if k == "decoder.lm_head.weight":
+                k = "decoder.transformer.wte.weight"
+            assert abs(float(sd[k].grad.norm()) - float(val)) <= 1e-4 * max(float(val), 1e-8), k
+            n += 1
+        elif key.startswith("grad::"):
+            assert rel_err(sd[key.split("::")[1]].grad, T(val)) < 1e-4, key
+    assert n > 50
