@@ -421,7 +421,10 @@ class DecodeEngine:
                 xi += 1
             lin(self.x, lp + "ln_2", lp + "mlp.c_fc.weight", lp + "mlp.c_fc.bias", self.h, F, F, C, act=ops.ACT_GELU_TANH)
             lin(self.h, None, lp + "mlp.c_proj.weight", lp + "mlp.c_proj.bias", self.x, C, C, F, residual=self.x)
-        if sample:
+        if sample == "logits":           # beam search: the caller picks the tokens, reorders the cache and advances
+            V = spec["vocab_size"]
+            lin(self.x, dp + "ln_f", "decoder.lm_head.weight", None, self.logits, V, V, C)
+        elif sample:
             V = spec["vocab_size"]
             lin(self.x, dp + "ln_f", "decoder.lm_head.weight", None, self.logits, V, V, C)
             call("i2t_sample", ptr(self.logits), V, B, V, ptr(self.ids), self.ids.shape[1], pos, 1, 0, temperature,
@@ -490,7 +493,9 @@ class DecodeEngine:
             hact = self.h if cd == torch.float32 else self.h16
             call("i2t_dec_act", ptr(self.h), ptr(hact), self.h.numel(), ops.ACT_GELU_TANH, ydt, st)
             proj(hact, lp + "mlp.c_proj.weight", lp + "mlp.c_proj.bias", self.x, residual=self.x)
-        if sample:
+        if sample == "logits":
+            ops.gemm(ln(dp + "ln_f"), W.c("decoder.lm_head.weight"), out=self.logits)
+        elif sample:
             ops.gemm(ln(dp + "ln_f"), W.c("decoder.lm_head.weight"), out=self.logits)
             call("i2t_sample", ptr(self.logits), self.ldl, B, V, ptr(self.ids), self.ids.shape[1], pos, 1, 0, temperature,
                  int(top_k) if top_k is not None else 0, float(self.nucleus_p or 0.0), ptr(self.ngrams), self.n_ngrams, 0,
@@ -505,6 +510,50 @@ class DecodeEngine:
             self._mega_step(sample, temperature, top_k)
         else:
             self._kernel_step(sample, temperature, top_k)
+
+    # ------------------------------------------------------------------ beam search (generation_utils.py) ------------
+    def beam_begin(self, enc_rows: torch.Tensor, prompt_rows: torch.Tensor):
+        """Start a KV-cached beam search over B = beam_width x batch hypothesis rows: cross K/V of every row, the prompt tokens
+        but the last pushed through the cache.  Step-wise modes only ('kernels' / 'gemm')."""
+        assert self.mode in ("kernels", "gemm")
+        self.model.sync_compute_weights()
+        P = prompt_rows.shape[1]
+        self._prefill_cross(enc_rows)
+        self.ids.zero_()
+        self.ids[:, :P].copy_(prompt_rows)
+        self.pos.zero_()
+        self.ticket.zero_()
+        self.nucleus_p = None
+        for _ in range(P - 1):
+            self._step(False, 1.0, None)
+
+    def beam_logits(self) -> torch.Tensor:
+        """Logits (B, V) of the token after the current position (one decode step over the cache; nothing is sampled, the
+        position does not move).  The step is captured into a CUDA graph on its second use."""
+        ent = self.graphs.get("beam_logits")
+        if ent is None:
+            ent = self.graphs["beam_logits"] = dict(calls=0, graph=None)
+        if ent["graph"] is None and ent["calls"] < 1:
+            self._step("logits", 1.0, None)
+            ent["calls"] += 1
+        else:
+            if ent["graph"] is None:
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._step("logits", 1.0, None)
+                ent["graph"] = g
+            ent["graph"].replay()
+        return self.logits
+
+    def beam_advance(self, src_rows: torch.Tensor, tokens: torch.Tensor, cur: int):
+        """Consolidation: hypothesis row r continues row src_rows[r] with token tokens[r].  The cached K / V rows [0, cur) and the
+        token history are gathered ON THE DEVICE (index_select along the hypothesis axis), then the position advances."""
+        self.kcache[:, :, :cur] = self.kcache[:, :, :cur].index_select(1, src_rows)
+        self.vcache[:, :, :cur] = self.vcache[:, :, :cur].index_select(1, src_rows)
+        self.ids[:, :cur] = self.ids[:, :cur].index_select(0, src_rows)
+        self.ids[:, cur] = tokens
+        call("i2t_dec_advance", ptr(self.pos), stream())
 
     def _prefill_cross(self, enc: torch.Tensor):
         """K/V projections of the (fixed) encoder output, once per generate call: the k,v rows of

@@ -271,9 +271,16 @@ def test_beam_search_matches_reference_golden(golden):
                                     eos_token_id=611, consolidation_temperature=0.0, length_boost=1.0)),
                      ("topk_eos", dict(beam_width=4, temperature=0.0, top_k=12, max_new_tokens=12, beam_expansion_factor=3,
                                        eos_token_id=7, consolidation_temperature=0.0, length_boost=1.3))):
-        ids, scores = BeamSearchTokenGenerator(m, **kw)(images, prompt)
+        gen = BeamSearchTokenGenerator(m, **kw)
+        ids, scores = gen(images, prompt)                           # KV-cached: decode steps + cache reorder by the surviving beams
+        assert ("beam", kw["beam_width"] * 2, m.compute_dtype) in m._decode_engines
         assert np.array_equal(ids.cpu().numpy(), g[name + "_ids"]), name
         assert float(np.abs(scores.cpu().numpy() - g[name + "_scores"]).max()) < 2e-3, name
+        ids2, scores2 = gen(images, prompt)                         # second call: the logits step is a CUDA-graph replay
+        assert torch.equal(ids, ids2)
+        gen.cacheless = True                                        # the reference's own algorithm (full forward per step)
+        ids3, scores3 = gen(images, prompt)
+        assert torch.equal(ids, ids3) and float((scores - scores3).abs().max()) < 1e-3
     # sampled expansions / consolidation: shapes, prompt kept, scores finite and sorted consistently with the API
     ids, scores = BeamSearchTokenGenerator(m, beam_width=3, temperature=0.9, top_k=20, max_new_tokens=8, eos_token_id=611,
                                            consolidation_temperature=0.7)(images, prompt)
