@@ -34,6 +34,7 @@ SIGNATURES = {
     "i2t_patch_im2col": (c_int, [P, P, L, L, L, L, I, P]),
     "i2t_vit_assemble": (c_int, [P, P, P, P, L, L, L, I, P]),
     "i2t_lsh_tail": (c_int, [P, P, P, P, P, P, P, L, L, L, L, L, L, P]),
+    "i2t_lsh_tail_bwd": (c_int, [P, P, P, L, L, L, L, L, P]),
     "i2t_peer_lookup_fwd": (c_int, [P, P, P, P, P, P, P, P, P, P, P, L, L, L, L, L, L, P]),
     "i2t_peer_lookup_bwd": (c_int, [P, P, P, P, P, P, P, P, P, P, P, P, P, P, L, L, L, L, L, L, P]),
     "i2t_embed_fwd": (c_int, [P, P, P, P, P, L, L, L, L, L, P]),

@@ -23,6 +23,11 @@ class LayerNormFn(torch.autograd.Function):
             y, mean, rstd = ops.layernorm(x, gamma, beta, eps, out_dtype, want_stats=True)
             ctx.save_for_backward(x, gamma, mean, rstd)
             ctx.has_beta = beta is not None
+            # ops.grad_sinks(): the kernel accumulates (+=) d gamma / d beta, so it can write the .grad buffers themselves
+            ctx.sinks = None
+            if ctx.needs_input_grad[1] and ops.sink_use(gamma, False) and (beta is None or ops.sink_use(beta, False)):
+                ctx.sinks = (gamma, beta)
+                ops.sink_use(gamma), ops.sink_use(beta)
         else:
             y = ops.layernorm(x, gamma, beta, eps, out_dtype)
         return y
@@ -32,6 +37,13 @@ class LayerNormFn(torch.autograd.Function):
         x, gamma, mean, rstd = ctx.saved_tensors
         dy = dy.contiguous()
         want_g = ctx.needs_input_grad[1]
+        if ctx.sinks is not None:
+            pg, pb = ctx.sinks
+            dx = ops.layernorm_bwd(dy, x, gamma, mean, rstd, pg.grad, pb.grad if pb is not None else None, dx_dtype=x.dtype)
+            ops.sink_done(pg)
+            if pb is not None:
+                ops.sink_done(pb)
+            return dx, None, None, None, None
         dgamma = torch.zeros_like(gamma, dtype=torch.float32) if want_g else None
         dbeta = torch.zeros_like(gamma, dtype=torch.float32) if (want_g and ctx.has_beta) else None
         dx = ops.layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, dx_dtype=x.dtype)
@@ -46,7 +58,7 @@ class LinearFn(torch.autograd.Function):
     models/layers.py:454-461 applied to the packed c_attn output."""
 
     @staticmethod
-    def forward(ctx, x2d, w, w_c, bias, residual, act, out_dtype, pad_rows=False, drop=None, tok_drop=None):
+    def forward(ctx, x2d, w, w_c, bias, residual, act, out_dtype, pad_rows=False, drop=None, tok_drop=None, sink=None):
         need = any(ctx.needs_input_grad)      # grad mode is always off inside Function.forward
         out = None
         if pad_rows and w_c.shape[0] % 8 != 0:
@@ -76,6 +88,7 @@ class LinearFn(torch.autograd.Function):
             ctx.has_res = residual is not None
             ctx.res_dtype = residual.dtype if residual is not None else None
             ctx.drop, ctx.tok_drop = drop, tok_drop
+            ctx.sink_w, ctx.sink_b = _sinks_of(ctx, w, bias, sink)
         return y
 
     @staticmethod
@@ -97,13 +110,39 @@ class LinearFn(torch.autograd.Function):
             # dW[N,K] = dY^T[N,M] X[M,K]  (fp32 master gradient)
             M, N = g.shape
             K = x2d.shape[1]
-            dw = torch.empty((N, K), device=g.device, dtype=torch.float32)
-            ops.gemm(g, x2d, out=dw, a_kmajor=False, b_kmajor=False, M=N, N=K, K=M, lda=g.stride(0), ldb=x2d.stride(0),
-                     ldc=K)
+            if ctx.sink_w is not None:             # ops.grad_sinks(): W.grad[rows] += dY^T X, nothing for autograd to add
+                pw, rows = ctx.sink_w
+                ops.gemm(g, x2d, out=pw.grad if rows is None else pw.grad[rows], accumulate=True, a_kmajor=False, b_kmajor=False,
+                         M=N, N=K, K=M, lda=g.stride(0), ldb=x2d.stride(0), ldc=K)
+                ops.sink_done(pw)
+            else:
+                dw = torch.empty((N, K), device=g.device, dtype=torch.float32)
+                ops.gemm(g, x2d, out=dw, a_kmajor=False, b_kmajor=False, M=N, N=K, K=M, lda=g.stride(0), ldb=x2d.stride(0),
+                         ldc=K)
         if ctx.has_bias and ctx.needs_input_grad[3]:
-            db = torch.zeros(g.shape[1], device=g.device, dtype=torch.float32)
-            ops.colsum_(g, db)
-        return dx, dw, None, db, dres, None, None, None, None, None
+            db = _bias_grad(ctx, g)
+        return dx, dw, None, db, dres, None, None, None, None, None, None
+
+
+def _sinks_of(ctx, w, bias, sink):
+    """(parameter, rows) targets of the weight / bias gradient under ops.grad_sinks(), else (None, None).  `sink` =
+    (weight parameter, row slice, bias parameter) when w / bias are row views of packed parameters."""
+    pw, rows, pb = sink if sink is not None else (w, None, bias)
+    sw = (pw, rows) if (ctx.needs_input_grad[1] and ops.sink_use(pw)) else None
+    sb = (pb, rows) if (bias is not None and ctx.needs_input_grad[3] and ops.sink_use(pb)) else None
+    return sw, sb
+
+
+def _bias_grad(ctx, g):
+    """d bias = column sums of the output gradient (i2t_colsum accumulates: into .grad under ops.grad_sinks())."""
+    if ctx.sink_b is not None:
+        pb, rows = ctx.sink_b
+        ops.colsum_(g, pb.grad if rows is None else pb.grad[rows])
+        ops.sink_done(pb)
+        return None
+    db = torch.zeros(g.shape[1], device=g.device, dtype=torch.float32)
+    ops.colsum_(g, db)
+    return db
 
 
 def _grad_in(dy, cd, drop, tok_drop):
@@ -120,8 +159,8 @@ def _grad_in(dy, cd, drop, tok_drop):
 
 
 def linear(x2d, w, w_c, bias=None, residual=None, act=ops.ACT_NONE, out_dtype=torch.float32, pad_rows=False, drop=None,
-           tok_drop=None):
-    return LinearFn.apply(x2d, w, w_c, bias, residual, act, out_dtype, pad_rows, drop, tok_drop)
+           tok_drop=None, sink=None):
+    return LinearFn.apply(x2d, w, w_c, bias, residual, act, out_dtype, pad_rows, drop, tok_drop, sink)
 
 
 class AttnFn(torch.autograd.Function):
@@ -195,6 +234,7 @@ class EmbedFn(torch.autograd.Function):
             x = ops.dropout_add(x, None, drop)
         ctx.save_for_backward(ids)
         ctx.meta = (B, T, n_prompt, S, wte.shape, prompt is not None, wpe.shape[0], drop)
+        ctx.sink_wpe = wpe if (ctx.needs_input_grad[3] and ops.sink_use(wpe)) else None
         return x
 
     @staticmethod
@@ -211,7 +251,10 @@ class EmbedFn(torch.autograd.Function):
         if ctx.needs_input_grad[2]:
             dwte = torch.zeros(wte_shape, device=dx.device, dtype=torch.float32)
             call("i2t_embed_bwd", ptr(ids), ptr(dx), ptr(dwte), B, T, n_prompt, S, C, stream())
-        if ctx.needs_input_grad[3]:
+        if ctx.sink_wpe is not None:               # ops.grad_sinks(): wpe.grad[:T] += column sums
+            ops.colsum_(dx.view(B, T * C), ctx.sink_wpe.grad.view(-1)[:T * C])
+            ops.sink_done(ctx.sink_wpe)
+        elif ctx.needs_input_grad[3]:
             dwpe = torch.zeros((wpe_rows, C), device=dx.device, dtype=torch.float32)   # rows >= T stay zero
             ops.colsum_(dx.view(B, T * C), dwpe.view(-1)[:T * C])
         return None, dprompt, dwte, dwpe, None, None, None
@@ -335,6 +378,7 @@ class Conv1DFn(torch.autograd.Function):
             ctx.has_res = residual is not None
             ctx.res_dtype = residual.dtype if residual is not None else None
             ctx.drop = drop
+            ctx.sink_w, ctx.sink_b = _sinks_of(ctx, w, bias, None)
         return y
 
     @staticmethod
@@ -353,11 +397,16 @@ class Conv1DFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             M, N = g.shape
             K = x2d.shape[1]
-            dw = torch.empty((K, N), device=g.device, dtype=torch.float32)                    # dW (K,N) = X^T dY
-            ops.gemm(x2d, g, out=dw, a_kmajor=False, b_kmajor=False, M=K, N=N, K=M, lda=x2d.stride(0), ldb=g.stride(0), ldc=N)
+            if ctx.sink_w is not None:                                                        # dW (K,N) = X^T dY
+                pw = ctx.sink_w[0]
+                ops.gemm(x2d, g, out=pw.grad, accumulate=True, a_kmajor=False, b_kmajor=False, M=K, N=N, K=M, lda=x2d.stride(0),
+                         ldb=g.stride(0), ldc=N)
+                ops.sink_done(pw)
+            else:
+                dw = torch.empty((K, N), device=g.device, dtype=torch.float32)
+                ops.gemm(x2d, g, out=dw, a_kmajor=False, b_kmajor=False, M=K, N=N, K=M, lda=x2d.stride(0), ldb=g.stride(0), ldc=N)
         if ctx.has_bias and ctx.needs_input_grad[3]:
-            db = torch.zeros(g.shape[1], device=g.device, dtype=torch.float32)
-            ops.colsum_(g, db)
+            db = _bias_grad(ctx, g)
         return dx, dw, None, db, dres, None, None, None
 
 

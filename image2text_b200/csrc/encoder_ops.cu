@@ -185,6 +185,44 @@ extern "C" int i2t_lsh_tail(const float* feat, const void* const* proj, const vo
   return I2T_OK;
 }
 
+// EmbeddingBag(mean) backward of the LSH tail: d emb[i][row, :] += d out[b, s, :] / n_proj for the n_proj rows image b picked in
+// table i = s * n_res + r.  grid = (n_cls * n_res, B).  The table pointers travel by value in the launch parameters (the gradient
+// buffers belong to the caller and differ from call to call: no device-side pointer table to keep in step).
+#define I2T_LSH_MAX_TABLES 64
+struct LshGradTables { float* t[I2T_LSH_MAX_TABLES]; };
+
+__global__ void __launch_bounds__(256)
+lsh_tail_bwd_kernel(const float* __restrict__ dout, const int32_t* __restrict__ bucket, LshGradTables tabs, int n_cls, int n_res,
+                    int n_proj, int E) {
+  const int i = blockIdx.x, s = i / n_res;
+  const int64_t b = blockIdx.y;
+  float* T = tabs.t[i];
+  const int32_t* rows = bucket + (b * n_cls * n_res + i) * n_proj;
+  const float* g = dout + (b * n_cls + s) * E;
+  const float invp = 1.0f / (float)n_proj;
+  for (int e = threadIdx.x; e < E; e += 256) {
+    const float v = g[e] * invp;
+    for (int p = 0; p < n_proj; ++p) atomicAdd(T + (int64_t)rows[p] * E + e, v);
+  }
+}
+
+extern "C" int i2t_lsh_tail_bwd(const float* dout, const int32_t* bucket, void* const* demb_host, int64_t B, int64_t n_cls,
+                                int64_t n_res, int64_t n_proj, int64_t E, void* stream) {
+  I2T_REQUIRE(dout && bucket && demb_host, "lsh_tail_bwd: null pointer");
+  I2T_REQUIRE(B > 0 && B <= 65535 && n_cls > 0 && n_res > 0 && n_proj > 0 && E > 0, "lsh_tail_bwd: bad sizes");
+  I2T_REQUIRE(n_cls * n_res <= I2T_LSH_MAX_TABLES, "lsh_tail_bwd: %lld tables (max %d)", (long long)(n_cls * n_res),
+              I2T_LSH_MAX_TABLES);
+  LshGradTables tabs;
+  for (int64_t i = 0; i < n_cls * n_res; ++i) {
+    I2T_REQUIRE(demb_host[i], "lsh_tail_bwd: null table gradient");
+    tabs.t[i] = (float*)demb_host[i];
+  }
+  dim3 g((unsigned)(n_cls * n_res), (unsigned)B);
+  lsh_tail_bwd_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(dout, bucket, tabs, (int)n_cls, (int)n_res, (int)n_proj, (int)E);
+  I2T_LAUNCHED();
+  return I2T_OK;
+}
+
 extern "C" int i2t_embed_fwd(const int64_t* ids, const float* prompt, const float* wte, const float* wpe, float* x,
                              int64_t B, int64_t T, int64_t n_prompt, int64_t S, int64_t C, void* stream) {
   I2T_REQUIRE(wte && wpe && x && B > 0 && T > 0 && C % 4 == 0, "embed_fwd: bad arguments");

@@ -26,10 +26,12 @@ def _lin(W, key_w, key_b, x2d, residual=None, act=ops.ACT_NONE, out_dtype=torch.
     w = W[key_w]
     wc = W.c(key_w)
     b = W.get(key_b) if key_b else None
+    sink = None
     if rows is not None:
+        sink = (w, rows, b)          # ops.grad_sinks(): the gradients of the row views go straight into the packed .grad
         w, wc = w[rows], wc[rows]
         b = b[rows] if b is not None else None
-    return linear(x2d, w, wc, b, residual, act, out_dtype, drop=drop, tok_drop=tok_drop)
+    return linear(x2d, w, wc, b, residual, act, out_dtype, drop=drop, tok_drop=tok_drop, sink=sink)
 
 
 def _site(drop, p):
@@ -108,22 +110,33 @@ class _LshTailFn(torch.autograd.Function):
         if need:
             ctx.save_for_backward(idx)
             ctx.meta = (n_cls, n_res, n_proj, E, [w.shape for w in emb_weights])
+            # ops.grad_sinks(): all tables or none accumulate into their .grad (one kernel either way)
+            ctx.sinks = None
+            if all(ops.sink_use(w, count=False) for w in emb_weights):
+                ctx.sinks = [w for w in emb_weights if ops.sink_use(w)]
         return out
 
     @staticmethod
     def backward(ctx, dout):
+        import ctypes
         (idx,) = ctx.saved_tensors
         n_cls, n_res, n_proj, E, shapes = ctx.meta
         dout = dout.contiguous().float()
-        grads = []
-        # tiny tables (<= 672 rows): index_add_ is an accumulation into the gradient buffer, not model arithmetic
-        for s in range(n_cls):
-            for r in range(n_res):
-                g = torch.zeros(shapes[s * n_res + r], device=dout.device, dtype=torch.float32)
-                rows = idx[:, s, r, :].reshape(-1).long()
-                src = (dout[:, s, :] / n_proj).repeat_interleave(n_proj, dim=0)
-                g.index_add_(0, rows, src)
-                grads.append(g)
+        B = dout.shape[0]
+        if ctx.sinks is not None:
+            targets, grads = [w.grad for w in ctx.sinks], [None] * len(shapes)
+        else:                      # one zeroed buffer, one view per table
+            flat = torch.zeros(sum(s[0] * s[1] for s in shapes), device=dout.device, dtype=torch.float32)
+            targets, off = [], 0
+            for s in shapes:
+                targets.append(flat[off:off + s[0] * s[1]].view(s))
+                off += s[0] * s[1]
+            grads = targets
+        host = (ctypes.c_void_p * len(targets))(*[t.data_ptr() for t in targets])
+        call("i2t_lsh_tail_bwd", ptr(dout), ptr(idx), ctypes.addressof(host), B, n_cls, n_res, n_proj, E, stream())
+        if ctx.sinks is not None:
+            for w in ctx.sinks:
+                ops.sink_done(w)
         return (None, None, None, None, None, None, *grads)
 
 

@@ -2,6 +2,7 @@
 and streams only; every arithmetic operation below is a libi2t kernel."""
 from __future__ import annotations
 
+import contextlib
 from typing import NamedTuple, Optional
 
 import torch
@@ -36,6 +37,53 @@ class DropCtx:
         i = self.base + self.n
         self.n += 1
         return DropSite(float(p), self.state, i) if p > 0.0 else None
+
+
+class _GradSinks:
+    """State of `grad_sinks()`; `uses` counts the backward nodes that still owe a contribution to a parameter."""
+    on = False
+    notify = None
+    uses: dict = {}
+
+
+@contextlib.contextmanager
+def grad_sinks(notify=None):
+    """Inside this context the backward kernels of the parameter-consuming ops (linear / Conv1D weight and bias gradients,
+    LayerNorm gamma / beta, position embeddings, the LSH EmbeddingBags) ADD their result straight into the parameter's
+    existing fp32 ``.grad`` buffer and hand autograd no gradient for it: no temporary, no zero fill, no AccumulateGrad ``add_``
+    and no ``slice_backward`` for row views of a packed weight (nn.MultiheadAttention.in_proj_weight).  The arithmetic is the one
+    autograd would do (grad += contribution).  AccumulateGrad hooks do not fire for such parameters; `notify(param)` is called
+    instead, once per parameter, when its last contribution has been added (the data-parallel reducer's hook).  Used while a
+    micro-step is captured into a CUDA graph (wrapper.train_step_graphed), where ``.grad`` buffers already exist and are static."""
+    st = _GradSinks
+    prev = (st.on, st.notify, st.uses)
+    st.on, st.notify, st.uses = True, notify, {}
+    try:
+        yield
+    finally:
+        st.on, st.notify, st.uses = prev
+
+
+def sink_use(p, count: bool = True) -> bool:
+    """Forward-time: will the gradient contribution of this use of parameter `p` be added into ``p.grad`` in place?"""
+    st = _GradSinks
+    if not st.on or p is None or not isinstance(p, torch.nn.Parameter) or not p.requires_grad:
+        return False
+    g = p.grad
+    if g is None or g.dtype != torch.float32 or not g.is_contiguous() or g.shape != p.shape:
+        return False
+    if count:
+        st.uses[id(p)] = st.uses.get(id(p), 0) + 1
+    return True
+
+
+def sink_done(p):
+    """Backward-time: one contribution to ``p.grad`` has been queued; after the last one the reducer is told."""
+    st = _GradSinks
+    left = st.uses.get(id(p), 1) - 1
+    st.uses[id(p)] = left
+    if left == 0 and st.notify is not None:
+        st.notify(p)
 
 
 def dt(t: torch.Tensor) -> int:

@@ -7,7 +7,8 @@ surface, same loss definitions:
     fused pass over the vocabulary (``i2t_lm_loss``), never materialising the (B,T,V+1) one-hot of :136-141;
   * the EMA teacher update is one in-place multi-tensor launch (``i2t_ema_multi``) instead of a per-parameter
     allocate-and-rebind loop (:53-60).  It runs every micro-step before backward, like the reference.
-The contrastive auxiliary loss (:98-118, off in every reference YAML) is not built.
+The contrastive auxiliary loss (:98-118, off in every reference YAML) is `compute_contrastive_loss` (one similarity GEMM + a
+masked cross-entropy kernel).
 """
 from __future__ import annotations
 
@@ -104,7 +105,10 @@ class ModelTrainerWrapper(nn.Module):
             try:
                 self._grad_prescale = float(loss_scale)       # folded into dlogits by the loss kernel (no rescale pass)
                 import contextlib
-                with (reducer.capturing() if reducer is not None else contextlib.nullcontext()):
+                from . import ops
+                # ops.grad_sinks: the captured backward adds weight gradients straight into the (static) .grad buffers
+                with (reducer.capturing() if reducer is not None else contextlib.nullcontext()), \
+                        ops.grad_sinks(notify=reducer._hook if reducer is not None else None):
                     with torch.cuda.graph(g):
                         loss, _ = self._step(st["images"], st["labels"], True)
                         (loss * loss_scale).backward()

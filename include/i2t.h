@@ -113,6 +113,12 @@ int i2t_lsh_tail(const float* feat, const void* const* proj, const void* const* 
                  const int32_t* num_bins, float* out, int32_t* bucket_out, int64_t B, int64_t D, int64_t n_cls,
                  int64_t n_res, int64_t n_proj, int64_t E, void* stream);
 
+/* Backward of the tail's EmbeddingBag(mode="mean") lookups (models/layers.py:139-144): demb_host is a HOST array of
+ * n_cls*n_res device pointers (slot-major) to fp32 gradient tables of the emb[i] shapes; the kernel ADDS
+ * dout[b,s,:] / n_proj into the rows `bucket` (as written by i2t_lsh_tail) names.  The hashing has no gradient. */
+int i2t_lsh_tail_bwd(const float* dout, const int32_t* bucket, void* const* demb_host, int64_t B, int64_t n_cls,
+                     int64_t n_res, int64_t n_proj, int64_t E, void* stream);
+
 /* ---- PEER tail core: models/layers.py:73-109 minus its dense projections (i2t_gemm) ---------------------------- */
 /* ql / qr (M,H,U) fp32: scores of the left / right query units (query . W_left/right); key (M,H,D): key projection;
  * emb_in (E,D), emb_out (E,O).  Per (row, head): top-K of ql and qr, top-K of their K x K sums, softmax, expert id =

@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--moco", action="store_true")
     ap.add_argument("--no-dropout", action="store_true", help="switch every dropout off (the parity configuration)")
     ap.add_argument("--profile", action="store_true")
+    ap.add_argument("--profile-glue", action="store_true", help="list the torch (aten) ops of one eager micro-step by call site")
     ap.add_argument("--config", default="nano", choices=["nano", "gpt2"])
     ap.add_argument("--batch", type=int, default=0, help="per-GPU micro-batch (0 = the YAML value)")
     ap.add_argument("--graph", type=int, default=1, help="1: forward+backward of a micro-step replayed as a CUDA graph")
@@ -121,6 +122,32 @@ def main():
             one_step()
             torch.cuda.synchronize()
         print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=70))
+    if args.profile_glue and rank == 0:
+        # every aten op of one eager micro-step (forward + backward) with the Python line that issued it; pure view ops are skipped
+        import traceback
+        from torch.utils._python_dispatch import TorchDispatchMode
+        views = {"view", "_unsafe_view", "slice", "select", "detach", "alias", "as_strided", "t", "transpose", "permute", "expand",
+                 "unsqueeze", "squeeze", "reshape", "empty", "empty_like", "empty_strided", "new_empty", "_local_scalar_dense",
+                 "unbind", "split", "split_with_sizes", "narrow", "view_as", "is_same_size", "stride", "size", "numel"}
+        sites = {}
+
+        class Log(TorchDispatchMode):
+            def __torch_dispatch__(self, func, types, a=(), kw=None):
+                name = func.__name__.split(".")[0]
+                if name not in views:
+                    fr = [f for f in traceback.extract_stack() if "image2text_b200" in f.filename]
+                    site = f"{os.path.basename(fr[-1].filename)}:{fr[-1].lineno} {fr[-1].name}" if fr else "autograd engine"
+                    sites[(name, site)] = sites.get((name, site), 0) + 1
+                return func(*a, **(kw or {}))
+
+        from image2text_b200 import ops
+        with Log(), ops.grad_sinks():                 # what a captured micro-step issues (wrapper.train_step_graphed)
+            loss, _ = w.train_step(images, labels)
+            (loss / accum).backward()
+            torch.cuda.synchronize()
+        for (name, site), n in sorted(sites.items(), key=lambda kv: -kv[1]):
+            print(f"{n:5d} x {name:28s} {site}")
+        return
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):

@@ -323,6 +323,30 @@ def test_lsh_tail_matches_oracle_indices_and_values():
     assert relerr(out, ref) < 2e-6
 
 
+def test_lsh_tail_backward_is_the_embedding_bag_mean_scatter():
+    """d emb[idx[b,s,r,p]] += d out[b,s] / n_proj (F.embedding_bag(mode='mean') backward, models/layers.py:139-144), against the
+    CPU autograd of the same lookups; second call: the kernel ADDS to what the buffers hold (gradient accumulation)."""
+    import ctypes
+    B, n_cls, n_res, n_proj, E, bins = 5, 3, 2, 8, 96, (4, 9)
+    g = torch.Generator().manual_seed(31)
+    dout = rnd(B, n_cls, E, seed=32)
+    rows = [(bins[r] + 1) * n_proj for r in range(n_res)]
+    idx = torch.stack([torch.stack([torch.stack([torch.randint(0, bins[r] + 1, (n_proj,), generator=g) +
+                                                 (bins[r] + 1) * torch.arange(n_proj) for r in range(n_res)])
+                                    for _ in range(n_cls)]) for _ in range(B)])                     # (B, n_cls, n_res, n_proj)
+    tabs = [torch.zeros(rows[r], E, requires_grad=True) for _ in range(n_cls) for r in range(n_res)]
+    out = torch.stack([sum(torch.nn.functional.embedding_bag(idx[:, s, r], tabs[s * n_res + r], mode="mean")
+                           for r in range(n_res)) for s in range(n_cls)], dim=1)
+    (out * dout).sum().backward()
+    dev = [torch.zeros(rows[r], E, device=DEV) for _ in range(n_cls) for r in range(n_res)]
+    host = (ctypes.c_void_p * len(dev))(*[t.data_ptr() for t in dev])
+    doutd, idxd = dout.to(DEV), idx.to(DEV).int().contiguous()
+    for rep in (1, 2):
+        call("i2t_lsh_tail_bwd", ptr(doutd), ptr(idxd), ctypes.addressof(host), B, n_cls, n_res, n_proj, E, stream())
+        for t, ref in zip(dev, tabs):
+            assert relerr(t, rep * ref.grad) < 2e-6
+
+
 def test_embed_prompt_concat():
     B, S, n, C, V, blk = 3, 20, 4, 128, 97, 22
     ids = torch.randint(0, V, (B, S), generator=torch.Generator().manual_seed(25))

@@ -182,6 +182,41 @@ def test_graphed_micro_step_accumulates_the_same_gradients():
     assert checked > 20
 
 
+def test_grad_sinks_add_the_same_gradients_in_place():
+    """ops.grad_sinks(): the backward kernels add weight / bias / LayerNorm / wpe / LSH-table gradients straight into existing
+    .grad buffers (no AccumulateGrad add, no slice_backward of the packed in_proj weight).  Same accumulated result as plain
+    autograd over two micro-steps, and every parameter is announced exactly once per backward."""
+    from image2text_b200 import ops
+    plain, spec, sd = make_wrapper("tiny", {}, eos=612)
+    sunk, _, _ = make_wrapper("tiny", {}, eos=612)
+    plain.train()
+    sunk.train()
+    batches = [(synth_images(3, 32, seed=50 + i).cuda(),
+                synth_labels(3, 20, spec["vocab_size"], seed=60 + i, min_len=3, max_len=14, eos=612).cuda()) for i in range(3)]
+    for i, (im, lb) in enumerate(batches):
+        lp, _ = plain.train_step(im, lb)
+        lp.backward()
+        if i == 0:                                   # the first backward creates the .grad buffers
+            ls, _ = sunk.train_step(im, lb)
+            ls.backward()
+            continue
+        told = []
+        with ops.grad_sinks(notify=told.append):
+            ls, _ = sunk.train_step(im, lb)
+            ls.backward()
+        assert float(ls) == float(lp)
+        assert len(told) == len({id(p) for p in told}) and len(told) > 20
+    pp, ps = dict(plain.model.named_parameters()), dict(sunk.model.named_parameters())
+    sunk_ids = {id(p) for p in told}
+    n = 0
+    for k, p in pp.items():
+        if p.grad is None:
+            continue
+        assert rel_err(ps[k].grad.cpu(), p.grad.cpu()) < 2e-5, k
+        n += id(ps[k]) in sunk_ids
+    assert n > 20
+
+
 @pytest.mark.parametrize("graphed", [False, True])
 def test_bf16_training_sees_the_updated_weights(graphed):
     """The fused optimiser / EMA kernels write fp32 masters through raw pointers; the bf16 copies every bf16 GEMM and the decode
