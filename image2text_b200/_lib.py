@@ -25,6 +25,7 @@ SIGNATURES = {
     "i2t_set_sampler_greedy_fast_path": (None, [I]),
     "i2t_layernorm_fwd": (c_int, [P, P, P, P, P, P, L, L, L, F, I, I, P]),
     "i2t_layernorm_bwd": (c_int, [P, P, P, P, P, P, P, P, L, L, I, I, I, P]),
+    "i2t_layernorm_bwd_add": (c_int, [P, P, P, P, P, P, P, P, P, L, L, I, I, I, P]),
     "i2t_gemm": (c_int, [P, P, P, P, P, L, L, L, L, L, L, I, I, I, I, I, I, I, P]),
     "i2t_gemm_ex": (c_int, [P, P, P, P, P, L, L, L, L, L, L, I, I, I, I, I, I, I, I, P]),
     "i2t_colsum": (c_int, [P, P, L, L, L, I, P]),
@@ -34,6 +35,7 @@ SIGNATURES = {
     "i2t_patch_im2col": (c_int, [P, P, L, L, L, L, I, P]),
     "i2t_vit_assemble": (c_int, [P, P, P, P, L, L, L, I, P]),
     "i2t_lsh_tail": (c_int, [P, P, P, P, P, P, P, L, L, L, L, L, L, P]),
+    "i2t_attn_bwd_trace": (c_int, [P]),
     "i2t_lsh_tail_bwd": (c_int, [P, P, P, L, L, L, L, L, P]),
     "i2t_peer_lookup_fwd": (c_int, [P, P, P, P, P, P, P, P, P, P, P, L, L, L, L, L, L, P]),
     "i2t_peer_lookup_bwd": (c_int, [P, P, P, P, P, P, P, P, P, P, P, P, P, P, L, L, L, L, L, L, P]),

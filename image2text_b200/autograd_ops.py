@@ -12,42 +12,73 @@ from ._lib import call
 from .ops import dt, ptr, stream
 
 
+def _ln_forward(ctx, x, gamma, beta, eps, out_dtype):
+    x = x.contiguous()
+    need = any(ctx.needs_input_grad)
+    if need:
+        y, mean, rstd = ops.layernorm(x, gamma, beta, eps, out_dtype, want_stats=True)
+        ctx.save_for_backward(x, gamma, mean, rstd)
+        ctx.has_beta = beta is not None
+        # ops.grad_sinks(): the kernel accumulates (+=) d gamma / d beta, so it can write the .grad buffers themselves
+        ctx.sinks = None
+        if ctx.needs_input_grad[1] and ops.sink_use(gamma, False) and (beta is None or ops.sink_use(beta, False)):
+            ctx.sinks = (gamma, beta)
+            ops.sink_use(gamma), ops.sink_use(beta)
+    else:
+        y = ops.layernorm(x, gamma, beta, eps, out_dtype)
+    return x, y
+
+
+def _ln_backward(ctx, dy, dskip=None):
+    x, gamma, mean, rstd = ctx.saved_tensors
+    dy = dy.contiguous()
+    if dskip is not None:
+        dskip = dskip.contiguous()
+        if dskip.dtype != x.dtype:
+            dskip = dskip.to(x.dtype)
+    want_g = ctx.needs_input_grad[1]
+    if ctx.sinks is not None:
+        pg, pb = ctx.sinks
+        dx = ops.layernorm_bwd(dy, x, gamma, mean, rstd, pg.grad, pb.grad if pb is not None else None, dx_dtype=x.dtype,
+                               dx_add=dskip)
+        ops.sink_done(pg)
+        if pb is not None:
+            ops.sink_done(pb)
+        return dx, None, None, None, None
+    dgamma = torch.zeros_like(gamma, dtype=torch.float32) if want_g else None
+    dbeta = torch.zeros_like(gamma, dtype=torch.float32) if (want_g and ctx.has_beta) else None
+    dx = ops.layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, dx_dtype=x.dtype, dx_add=dskip)
+    return dx, dgamma, dbeta, None, None
+
+
 class LayerNormFn(torch.autograd.Function):
     """F.layer_norm over the last dim: reference models/layers.py:357-358 (eps 1e-5), torchvision eps 1e-6."""
 
     @staticmethod
     def forward(ctx, x, gamma, beta, eps, out_dtype):
-        x = x.contiguous()
-        need = any(ctx.needs_input_grad)
-        if need:
-            y, mean, rstd = ops.layernorm(x, gamma, beta, eps, out_dtype, want_stats=True)
-            ctx.save_for_backward(x, gamma, mean, rstd)
-            ctx.has_beta = beta is not None
-            # ops.grad_sinks(): the kernel accumulates (+=) d gamma / d beta, so it can write the .grad buffers themselves
-            ctx.sinks = None
-            if ctx.needs_input_grad[1] and ops.sink_use(gamma, False) and (beta is None or ops.sink_use(beta, False)):
-                ctx.sinks = (gamma, beta)
-                ops.sink_use(gamma), ops.sink_use(beta)
-        else:
-            y = ops.layernorm(x, gamma, beta, eps, out_dtype)
-        return y
+        return _ln_forward(ctx, x, gamma, beta, eps, out_dtype)[1]
 
     @staticmethod
     def backward(ctx, dy):
-        x, gamma, mean, rstd = ctx.saved_tensors
-        dy = dy.contiguous()
-        want_g = ctx.needs_input_grad[1]
-        if ctx.sinks is not None:
-            pg, pb = ctx.sinks
-            dx = ops.layernorm_bwd(dy, x, gamma, mean, rstd, pg.grad, pb.grad if pb is not None else None, dx_dtype=x.dtype)
-            ops.sink_done(pg)
-            if pb is not None:
-                ops.sink_done(pb)
-            return dx, None, None, None, None
-        dgamma = torch.zeros_like(gamma, dtype=torch.float32) if want_g else None
-        dbeta = torch.zeros_like(gamma, dtype=torch.float32) if (want_g and ctx.has_beta) else None
-        dx = ops.layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, dx_dtype=x.dtype)
-        return dx, dgamma, dbeta, None, None
+        return _ln_backward(ctx, dy)
+
+
+class LayerNormSkipFn(torch.autograd.Function):
+    """The LayerNorm of a pre-LN block together with the skip connection that leaves the same tensor (x feeds ln_k AND the
+    residual add, models/layers.py:597-606): returns (LayerNorm(x), x).  The gradient of x is the sum over both paths; taking
+    both through one node lets the backward kernel add the skip gradient in its single pass over the rows instead of autograd
+    running one more elementwise add per residual join."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps, out_dtype):
+        x, y = _ln_forward(ctx, x, gamma, beta, eps, out_dtype)
+        return y, x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, dy, dskip):
+        if dy is None:                     # the normalised branch went unused
+            return dskip, None, None, None, None
+        return _ln_backward(ctx, dy, dskip)
 
 
 class LinearFn(torch.autograd.Function):

@@ -451,6 +451,12 @@ int attn_bwd_tc(const void* q, const void* k, const void* v, const void* dout, c
 int attn_fwd_tc5(const void* q, const void* k, const void* v, void* out, float* lse, int64_t B, int64_t H, int64_t Tq, int64_t Tk,
                  int64_t head_dim, int64_t q_bs, int64_t q_rs, int64_t kv_bs, int64_t kv_rs, int mode, int64_t n_prompt,
                  DropArgs drop, cudaStream_t st);
+int attn_bwd_tc5(const void* q, const void* k, const void* v, const void* out, const void* dout, const float* lse, float* dq_acc,
+                 void* dk, void* dv, int64_t B, int64_t H, int64_t Tq, int64_t Tk, int64_t head_dim, int64_t q_bs, int64_t q_rs,
+                 int64_t kv_bs, int64_t kv_rs, int mode, int64_t n_prompt, DropArgs drop, cudaStream_t st);
+int attn_bwd_tc5r(const void* q, const void* k, const void* v, const void* out, const void* dout, const float* lse, void* dq, void* dk,
+                  void* dv, int64_t B, int64_t H, int64_t Tq, int64_t Tk, int64_t head_dim, int64_t q_bs, int64_t q_rs, int64_t kv_bs,
+                  int64_t kv_rs, int mode, int64_t n_prompt, DropArgs drop, cudaStream_t st);
 // 0: fp32-math kernels; 1 (default): tensor cores -- tcgen05 forward where eligible, mma.sync otherwise; 2: mma.sync only
 static std::atomic<int> g_attn_tc{1};
 
@@ -525,7 +531,24 @@ static int launch_attn_bwd(const void* q, const void* k, const void* v, const vo
   // workspace: delta (B*H*Tq) then dq accumulator (B*H*Tq*HS), fp32
   float* delta = ws;
   float* dq_acc = ws + (B * H * Tq + 3) / 4 * 4;      // keep the accumulator 16-byte aligned (float4 reads in the scatter)
+  if (sizeof(T) == 2 && g_attn_tc.load() == 1) {      // <= 256 rows: one tcgen05 kernel, no workspace
+    const int r = attn_bwd_tc5r(q, k, v, out, dout, lse, dq, dk, dv, B, H, Tq, Tk, HS, q_bs, q_rs, kv_bs, kv_rs, mode, n_prompt, drop, st);
+    if (r < 0) return r;
+    if (r == 1) return I2T_OK;
+  }
   I2T_CUDA(cudaMemsetAsync(dq_acc, 0, (size_t)(B * H * Tq * HS) * sizeof(float), st));
+  if (sizeof(T) == 2 && g_attn_tc.load() == 1) {      // tcgen05 backward: computes delta itself
+    const int r = attn_bwd_tc5(q, k, v, out, dout, lse, dq_acc, dk, dv, B, H, Tq, Tk, HS, q_bs, q_rs, kv_bs, kv_rs, mode, n_prompt,
+                               drop, st);
+    if (r < 0) return r;
+    if (r == 1) {
+      const int64_t total_tc = B * H * Tq * (HS / 4);
+      I2T_CUDA(launch_pdl(attn_dq_scatter_kernel<T, HS>, dim3((unsigned)ceil_div(total_tc, 256)), dim3(256), 0, st, (const float*)dq_acc,
+                          (T*)dq, (int)H, (int)Tq, q_bs, q_rs, total_tc));
+      I2T_LAUNCHED();
+      return I2T_OK;
+    }
+  }
   const int64_t rows = B * Tq * H;
   I2T_CUDA(launch_pdl(attn_delta_kernel<T, HS>, dim3((unsigned)ceil_div(rows, 4)), dim3(128), 0, st, (const T*)out, (const T*)dout, delta,
                       (int)H, (int)Tq, rows));

@@ -72,9 +72,9 @@ __global__ void __launch_bounds__(128) ln_fwd_kernel(const TX* __restrict__ x, c
 template <typename TDY, typename TX, typename TDX, int MAXV>
 __global__ void __launch_bounds__(128, MAXV <= 6 ? 4 : 1) ln_bwd_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x,
                                                      const float* __restrict__ gamma, const float* __restrict__ mean,
-                                                     const float* __restrict__ rstd, TDX* __restrict__ dx,
-                                                     float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                     int64_t rows, int cols) {
+                                                     const float* __restrict__ rstd, const TDX* __restrict__ dx_add,
+                                                     TDX* __restrict__ dx, float* __restrict__ dgamma,
+                                                     float* __restrict__ dbeta, int64_t rows, int cols) {
   extern __shared__ float red[];  // [4 warps][cols] reused for dgamma then dbeta
   pdl_launch_dependents();     // programmatic dependent launch: this grid may have started before its predecessor finished
   pdl_wait();
@@ -105,6 +105,7 @@ __global__ void __launch_bounds__(128, MAXV <= 6 ? 4 : 1) ln_bwd_kernel(const TD
     s1 = warp_sum(s1) / (float)cols;
     s2 = warp_sum(s2) / (float)cols;
     TDX* dxr = dx + row * (int64_t)cols;
+    const TDX* addr = dx_add ? dx_add + row * (int64_t)cols : nullptr;   // gradient arriving over the residual connection
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
       const int c = lane + i * 32;
@@ -114,6 +115,10 @@ __global__ void __launch_bounds__(128, MAXV <= 6 ? 4 : 1) ln_bwd_kernel(const TD
         o.y = rs * (g_[i].y - s1 - xh[i].y * s2);
         o.z = rs * (g_[i].z - s1 - xh[i].z * s2);
         o.w = rs * (g_[i].w - s1 - xh[i].w * s2);
+        if (addr) {
+          const float4 a = load4(addr + c * 4);
+          o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+        }
         store4(dxr + c * 4, o);
       }
     }
@@ -156,21 +161,21 @@ static int launch_fwd(const void* x, const float* gamma, const float* beta, void
 }
 
 template <typename TDY, typename TX, typename TDX>
-static int launch_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, void* dx,
-                      float* dgamma, float* dbeta, int64_t rows, int64_t cols, cudaStream_t st) {
+static int launch_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, const void* dx_add,
+                      void* dx, float* dgamma, float* dbeta, int64_t rows, int64_t cols, cudaStream_t st) {
   int64_t ctas = ceil_div(rows, 4);
   const int64_t cap = (int64_t)num_sms() * 4;
   if (ctas > cap) ctas = cap;
   const size_t smem = (size_t)4 * cols * sizeof(float);
   if (cols <= 768) {      // the model width: exactly 6 vectors per lane -> 128 registers, 4 CTAs per SM
     I2T_CUDA(launch_pdl(ln_bwd_kernel<TDY, TX, TDX, 6>, dim3((unsigned)ctas), dim3(128), smem, st, (const TDY*)dy, (const TX*)x, gamma,
-                        mean, rstd, (TDX*)dx, dgamma, dbeta, rows, (int)cols));
+                        mean, rstd, (const TDX*)dx_add, (TDX*)dx, dgamma, dbeta, rows, (int)cols));
   } else if (cols <= 1024) {
     I2T_CUDA(launch_pdl(ln_bwd_kernel<TDY, TX, TDX, 8>, dim3((unsigned)ctas), dim3(128), smem, st, (const TDY*)dy, (const TX*)x, gamma,
-                        mean, rstd, (TDX*)dx, dgamma, dbeta, rows, (int)cols));
+                        mean, rstd, (const TDX*)dx_add, (TDX*)dx, dgamma, dbeta, rows, (int)cols));
   } else {
     I2T_CUDA(launch_pdl(ln_bwd_kernel<TDY, TX, TDX, 16>, dim3((unsigned)ctas), dim3(128), smem, st, (const TDY*)dy, (const TX*)x, gamma,
-                        mean, rstd, (TDX*)dx, dgamma, dbeta, rows, (int)cols));
+                        mean, rstd, (const TDX*)dx_add, (TDX*)dx, dgamma, dbeta, rows, (int)cols));
   }
   I2T_LAUNCHED();
   return I2T_OK;
@@ -198,9 +203,9 @@ extern "C" int i2t_layernorm_fwd(const void* x, const float* gamma, const float*
   return launch_fwd<__nv_bfloat16, __nv_bfloat16>(x, gamma, beta, y, mean, rstd, rows, cols, x_row_stride, eps, st);
 }
 
-extern "C" int i2t_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
-                                 void* dx, float* dgamma, float* dbeta, int64_t rows, int64_t cols, int dy_dtype,
-                                 int x_dtype, int dx_dtype, void* stream) {
+static int layernorm_bwd_any(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                             const void* dx_add, void* dx, float* dgamma, float* dbeta, int64_t rows, int64_t cols, int dy_dtype,
+                             int x_dtype, int dx_dtype, void* stream) {
   I2T_REQUIRE(dy && x && gamma && mean && rstd && dx, "layernorm_bwd: null pointer");
   I2T_REQUIRE(rows >= 0 && cols > 0 && cols % 4 == 0 && cols <= 2048, "layernorm_bwd: cols=%lld unsupported", (long long)cols);
   I2T_REQUIRE(valid_dtype(dy_dtype) && valid_dtype(x_dtype) && valid_dtype(dx_dtype), "layernorm_bwd: bad dtype");
@@ -208,10 +213,23 @@ extern "C" int i2t_layernorm_bwd(const void* dy, const void* x, const float* gam
   cudaStream_t st = (cudaStream_t)stream;
   const int key = dy_dtype * 4 + x_dtype * 2 + dx_dtype;
   switch (key) {
-    case 0: return launch_bwd<float, float, float>(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, rows, cols, st);
-    case 1: return launch_bwd<float, float, __nv_bfloat16>(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, rows, cols, st);
-    case 5: return launch_bwd<__nv_bfloat16, float, __nv_bfloat16>(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, rows, cols, st);
-    case 4: return launch_bwd<__nv_bfloat16, float, float>(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, rows, cols, st);
+    case 0: return launch_bwd<float, float, float>(dy, x, gamma, mean, rstd, dx_add, dx, dgamma, dbeta, rows, cols, st);
+    case 1: return launch_bwd<float, float, __nv_bfloat16>(dy, x, gamma, mean, rstd, dx_add, dx, dgamma, dbeta, rows, cols, st);
+    case 5: return launch_bwd<__nv_bfloat16, float, __nv_bfloat16>(dy, x, gamma, mean, rstd, dx_add, dx, dgamma, dbeta, rows, cols, st);
+    case 4: return launch_bwd<__nv_bfloat16, float, float>(dy, x, gamma, mean, rstd, dx_add, dx, dgamma, dbeta, rows, cols, st);
     default: return fail(I2T_ERR_INVALID, "layernorm_bwd: dtype combination (%d,%d,%d) not built", dy_dtype, x_dtype, dx_dtype);
   }
+}
+
+extern "C" int i2t_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                                 void* dx, float* dgamma, float* dbeta, int64_t rows, int64_t cols, int dy_dtype,
+                                 int x_dtype, int dx_dtype, void* stream) {
+  return layernorm_bwd_any(dy, x, gamma, mean, rstd, nullptr, dx, dgamma, dbeta, rows, cols, dy_dtype, x_dtype, dx_dtype, stream);
+}
+
+extern "C" int i2t_layernorm_bwd_add(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                                     const void* dx_add, void* dx, float* dgamma, float* dbeta, int64_t rows, int64_t cols,
+                                     int dy_dtype, int x_dtype, int dx_dtype, void* stream) {
+  I2T_REQUIRE(dx_add, "layernorm_bwd_add: null dx_add");
+  return layernorm_bwd_any(dy, x, gamma, mean, rstd, dx_add, dx, dgamma, dbeta, rows, cols, dy_dtype, x_dtype, dx_dtype, stream);
 }

@@ -63,6 +63,16 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t saddr) {
   d |= (uint64_t)2 << 61;            // SWIZZLE_128B
   return d;
 }
+// the same with the distance between the 64-element MN panels given by the caller (a [128 K rows][128 B] panel is 16384 B)
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn_lbo(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"

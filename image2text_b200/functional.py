@@ -12,13 +12,20 @@ import torch
 
 from . import ops
 from ._lib import call
-from .autograd_ops import AttnFn, EmbedFn, LayerNormFn, NormalizeGradientsFn, XAttnFn, linear
+from .autograd_ops import AttnFn, EmbedFn, LayerNormFn, LayerNormSkipFn, NormalizeGradientsFn, XAttnFn, linear
 from .model_spec import layer_has_cross_attn
 from .ops import ptr, stream
 
 
 def _ln(W, key_w, key_b, x, eps, out_dtype):
     return LayerNormFn.apply(x, W[key_w], W.get(key_b), eps, out_dtype)
+
+
+def _ln_skip(W, key_w, key_b, x, eps, out_dtype):
+    """(LayerNorm(x), x): use the returned x for the block's skip connection (one backward pass for both, LayerNormSkipFn)."""
+    if torch.is_grad_enabled() and x.requires_grad:
+        return LayerNormSkipFn.apply(x, W[key_w], W.get(key_b), eps, out_dtype)
+    return LayerNormFn.apply(x, W[key_w], W.get(key_b), eps, out_dtype), x
 
 
 def _lin(W, key_w, key_b, x2d, residual=None, act=ops.ACT_NONE, out_dtype=torch.float32, rows: Optional[slice] = None,
@@ -54,13 +61,13 @@ def vit_trunk(W, spec, images: torch.Tensor, cd: torch.dtype, pre: str) -> torch
     T = x.shape[1]
     for i in range(spec["vit_layers"]):
         lp = f"{pre}encoder.layers.encoder_layer_{i}."
-        y = _ln(W, lp + "ln_1.weight", lp + "ln_1.bias", x, 1e-6, cd)
+        y, x = _ln_skip(W, lp + "ln_1.weight", lp + "ln_1.bias", x, 1e-6, cd)
         qkv = _lin(W, lp + "self_attention.in_proj_weight", lp + "self_attention.in_proj_bias", y.view(B * T, d),
                    out_dtype=cd)
         a = AttnFn.apply(qkv, B, T, H, ops.MASK_NONE, 0)
         x = _lin(W, lp + "self_attention.out_proj.weight", lp + "self_attention.out_proj.bias", a,
                  residual=x.view(B * T, d)).view(B, T, d)
-        y = _ln(W, lp + "ln_2.weight", lp + "ln_2.bias", x, 1e-6, cd)
+        y, x = _ln_skip(W, lp + "ln_2.weight", lp + "ln_2.bias", x, 1e-6, cd)
         h = _lin(W, lp + "mlp.0.weight", lp + "mlp.0.bias", y.view(B * T, d), act=ops.ACT_GELU_ERF, out_dtype=cd)
         x = _lin(W, lp + "mlp.3.weight", lp + "mlp.3.bias", h, residual=x.view(B * T, d)).view(B, T, d)
     # final LayerNorm only on token 0 (the reference normalises all tokens and then keeps x[:, 0])
@@ -255,17 +262,17 @@ def hf_gpt2_forward(W, spec, ids: torch.Tensor, encoder_output: torch.Tensor, cd
 
     for i in range(spec["n_layer"]):
         lp = f"{dp}h.{i}."
-        y = _ln(W, lp + "ln_1.weight", lp + "ln_1.bias", x, 1e-5, cd)
+        y, x = _ln_skip(W, lp + "ln_1.weight", lp + "ln_1.bias", x, 1e-5, cd)
         qkv = c1d(lp + "attn.c_attn", y.view(B * T, C), out_dtype=cd)
         a = AttnFn.apply(qkv, B, T, H, ops.MASK_CAUSAL, 0, _site(drop, pd))
         x = c1d(lp + "attn.c_proj", a, residual=x.view(B * T, C), dsite=_site(drop, pd)).view(B, T, C)
         if cross:
-            y = _ln(W, lp + "ln_cross_attn.weight", lp + "ln_cross_attn.bias", x, 1e-5, cd)
+            y, x = _ln_skip(W, lp + "ln_cross_attn.weight", lp + "ln_cross_attn.bias", x, 1e-5, cd)
             q = c1d(lp + "crossattention.q_attn", y.view(B * T, C), out_dtype=cd)
             kv = c1d(lp + "crossattention.c_attn", enc_c, out_dtype=cd)
             a = XAttnFn.apply(q, kv, B, T, S_enc, H, _site(drop, pd))
             x = c1d(lp + "crossattention.c_proj", a, residual=x.view(B * T, C), dsite=_site(drop, pd)).view(B, T, C)
-        y = _ln(W, lp + "ln_2.weight", lp + "ln_2.bias", x, 1e-5, cd)
+        y, x = _ln_skip(W, lp + "ln_2.weight", lp + "ln_2.bias", x, 1e-5, cd)
         h = c1d(lp + "mlp.c_fc", y.view(B * T, C), act=ops.ACT_GELU_TANH, out_dtype=cd)
         x = c1d(lp + "mlp.c_proj", h, residual=x.view(B * T, C), dsite=_site(drop, pd)).view(B, T, C)
     hidden = _ln(W, dp + "ln_f.weight", dp + "ln_f.bias", x, 1e-5, torch.float32)
@@ -309,7 +316,7 @@ def decoder_forward(W, spec, ids: torch.Tensor, encoder_output: torch.Tensor, cd
     grads = torch.is_grad_enabled()
     for depth in range(spec["n_layer"]):
         lp = f"{dp}h.{depth}."
-        y = _ln(W, lp + "ln_1.weight", lp + "ln_1.bias", x, 1e-5, cd)
+        y, x = _ln_skip(W, lp + "ln_1.weight", lp + "ln_1.bias", x, 1e-5, cd)
         ts = _site(drop, pa)
         qkv = _lin(W, lp + "attn.c_attn.weight", lp + "attn.c_attn.bias", y.view(B * T, C), out_dtype=cd,
                    tok_drop=(ts, C, 3) if ts is not None else None)
@@ -320,14 +327,14 @@ def decoder_forward(W, spec, ids: torch.Tensor, encoder_output: torch.Tensor, cd
         if use_cross:
             if not layer_has_cross_attn(spec, depth):
                 raise ValueError("Model not configured for cross attn inputs!!!")
-            y = _ln(W, lp + "ln_3.weight", lp + "ln_3.bias", x, 1e-5, cd)
+            y, x = _ln_skip(W, lp + "ln_3.weight", lp + "ln_3.bias", x, 1e-5, cd)
             kw, kb = lp + "cross_attn.in_proj_weight", lp + "cross_attn.in_proj_bias"
             q = _lin(W, kw, kb, y.view(B * T, C), out_dtype=cd, rows=slice(0, C))
             kv = _lin(W, kw, kb, enc_c, out_dtype=cd, rows=slice(C, 3 * C))            # raw encoder output, no LN
             a = XAttnFn.apply(q, kv, B, T, S_enc, H, _site(drop, pd))
             x = _lin(W, lp + "cross_attn.out_proj.weight", lp + "cross_attn.out_proj.bias", a,
                      residual=x.view(B * T, C)).view(B, T, C)
-        y = _ln(W, lp + "ln_2.weight", lp + "ln_2.bias", x, 1e-5, cd)
+        y, x = _ln_skip(W, lp + "ln_2.weight", lp + "ln_2.bias", x, 1e-5, cd)
         h = _lin(W, lp + "mlp.c_fc.weight", lp + "mlp.c_fc.bias", y.view(B * T, C), act=ops.ACT_GELU_TANH, out_dtype=cd)
         x = _lin(W, lp + "mlp.c_proj.weight", lp + "mlp.c_proj.bias", h, residual=x.view(B * T, C),
                  drop=_site(drop, pd)).view(B, T, C)

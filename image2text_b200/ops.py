@@ -134,12 +134,18 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: Optional[torch.Tensor]
     return (y, mean, rstd) if want_stats else y
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, dx_dtype=torch.float32):
+def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, dx_dtype=torch.float32, dx_add=None):
+    """dx (+ dx_add: the gradient that reaches x over the skip connection, same dtype / shape as dx)."""
     C = x.shape[-1]
     rows = x.numel() // C
     dx = torch.empty(x.shape, device=x.device, dtype=dx_dtype)
-    call("i2t_layernorm_bwd", ptr(dy), ptr(x), ptr(gamma), ptr(mean), ptr(rstd), ptr(dx), ptr(dgamma), ptr(dbeta), rows, C,
-         dt(dy), dt(x), dt(dx), stream())
+    if dx_add is None:
+        call("i2t_layernorm_bwd", ptr(dy), ptr(x), ptr(gamma), ptr(mean), ptr(rstd), ptr(dx), ptr(dgamma), ptr(dbeta), rows, C,
+             dt(dy), dt(x), dt(dx), stream())
+    else:
+        assert dx_add.dtype == dx_dtype and dx_add.is_contiguous() and dx_add.numel() == dx.numel()
+        call("i2t_layernorm_bwd_add", ptr(dy), ptr(x), ptr(gamma), ptr(mean), ptr(rstd), ptr(dx_add), ptr(dx), ptr(dgamma),
+             ptr(dbeta), rows, C, dt(dy), dt(x), dt(dx), stream())
     return dx
 
 

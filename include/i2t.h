@@ -59,6 +59,11 @@ int i2t_layernorm_fwd(const void* x, const float* gamma, const float* beta, void
 int i2t_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
                       void* dx, float* dgamma, float* dbeta, int64_t rows, int64_t cols, int dy_dtype, int x_dtype,
                       int dx_dtype, void* stream);
+/* The same with dx = (LayerNorm backward) + dx_add: the pre-LN block's residual join (x feeds both the LayerNorm branch and the
+ * skip connection, models/layers.py:597-606), one pass instead of a separate add.  dx_add has dx's dtype and shape. */
+int i2t_layernorm_bwd_add(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                          const void* dx_add, void* dx, float* dgamma, float* dbeta, int64_t rows, int64_t cols, int dy_dtype,
+                          int x_dtype, int dx_dtype, void* stream);
 
 /* ---- dense contraction: every nn.Linear / Conv1D / conv_proj on the path
  *      (models/layers.py:452,469,482,484; models/decoder.py:256; nn.MultiheadAttention in/out proj
@@ -92,6 +97,9 @@ int i2t_attn_fwd(const void* q, const void* k, const void* v, void* out, float* 
 /* Backward of the above (autograd of reference models/layers.py:465).  dq,dk,dv are written with the same strides
  * as q,k,v; out/dout are (B,Tq,H*head_dim).  workspace: i2t_attn_bwd_workspace_bytes(...) bytes of device memory. */
 int64_t i2t_attn_bwd_workspace_bytes(int64_t B, int64_t H, int64_t Tq, int64_t head_dim);
+/* Debugging aid for the tcgen05 backward (sequences <= 256 rows): with I2T_ATTN_BWD_DEBUG=-1 in the environment CTA (0,0) of every
+ * launch stamps its timeline in SM clock ticks; copies the 32 stamps of the latest launch to host_out (synchronises the device). */
+int i2t_attn_bwd_trace(long long* host_out);
 int i2t_attn_bwd(const void* q, const void* k, const void* v, const void* out, const void* dout, const float* lse,
                  void* dq, void* dk, void* dv, void* workspace, int64_t B, int64_t H, int64_t Tq, int64_t Tk,
                  int64_t head_dim, int64_t q_batch_stride, int64_t q_row_stride, int64_t kv_batch_stride,

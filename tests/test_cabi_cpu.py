@@ -53,6 +53,20 @@ def test_sm100a_tensor_core_and_tma_instructions_present(built_lib):
     sass = subprocess.run(["cuobjdump", "-sass", built_lib], capture_output=True, text=True).stdout
     assert "UTCHMMA" in sass and "UTMALDG" in sass and "LDTM" in sass
     assert "sm_100a" in sass
+    # per kernel: the GEMM, the attention forward AND both attention backward kernels issue tcgen05 MMAs fed by TMA, and read their
+    # accumulators back from tensor memory
+    per_kernel = {}
+    name = None
+    for line in sass.splitlines():
+        if "Function :" in line:
+            name = line.split("Function :")[1].strip()
+        elif name is not None:
+            for op in ("UTCHMMA", "UTMALDG", "LDTM"):
+                if op in line:
+                    per_kernel.setdefault(name, set()).add(op)
+    for kernel in ("gemm_tc_kernel", "attn_fwd_tc5_kernel", "attn_bwd_tc5_kernel", "attn_bwd_tc5r_kernel"):
+        hits = [ops for n, ops in per_kernel.items() if kernel in n]
+        assert hits and all(ops == {"UTCHMMA", "UTMALDG", "LDTM"} for ops in hits), (kernel, hits)
 
 
 def test_product_package_does_not_import_the_oracle():
