@@ -150,6 +150,33 @@ __device__ __forceinline__ void b5_softmax_half(uint32_t taddr_s, uint32_t taddr
   }
 }
 
+// Coalesced drains.  A thread owns one accumulator ROW, so storing it straight to global memory touches 32 different cache lines
+// per warp instruction (the LSU serialises them: measured 1.6 us per 128 x 64 tile pair, and the store storm also held up the MMA
+// thread's next issue).  Instead the bf16 tile is staged in shared memory (128-byte rows, chunks XOR-swizzled by the row) and the
+// 256 softmax threads write it out 8 lanes per row: 4 rows = 4 lines per warp instruction.
+__device__ __forceinline__ void b5_stage32(const uint32_t (&v)[32], uint8_t* tile, int r, int wg) {
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    uint4 pk;
+    pk.x = b5_pack(__uint_as_float(v[8 * t]), __uint_as_float(v[8 * t + 1]));
+    pk.y = b5_pack(__uint_as_float(v[8 * t + 2]), __uint_as_float(v[8 * t + 3]));
+    pk.z = b5_pack(__uint_as_float(v[8 * t + 4]), __uint_as_float(v[8 * t + 5]));
+    pk.w = b5_pack(__uint_as_float(v[8 * t + 6]), __uint_as_float(v[8 * t + 7]));
+    *reinterpret_cast<uint4*>(tile + r * 128 + (((wg * 4 + t) ^ (r & 7)) << 4)) = pk;
+  }
+}
+// tile row i -> gbase + i * row_stride (elements), rows [0, rows_valid); tid = 0..255
+__device__ __forceinline__ void b5_store_tile(const uint8_t* tile, __nv_bfloat16* gbase, int64_t row_stride, int rows_valid, int tid) {
+#pragma unroll
+  for (int pass = 0; pass < 4; ++pass) {
+    const int row = pass * 32 + (tid >> 3), c = tid & 7;
+    if (row < rows_valid)
+      *reinterpret_cast<uint4*>(gbase + (int64_t)row * row_stride + c * 8) =
+          *reinterpret_cast<const uint4*>(tile + row * 128 + ((c ^ (row & 7)) << 4));
+  }
+}
+__device__ __forceinline__ void b5_sync_softmax_warps() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
 // 32 fp32 accumulator columns of one TMEM row -> 32 bf16 (64 bytes) at dst
 __device__ __forceinline__ void b5_store32(const uint32_t (&v)[32], __nv_bfloat16* dst) {
 #pragma unroll
@@ -434,7 +461,9 @@ attn_bwd_tc5r_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_slot;
+  if (trace_on && threadIdx.x == 32) g_r5_trace[13] = clock64();     // barriers + TMEM ready
   pdl_wait();
+  if (trace_on && threadIdx.x == 32) g_r5_trace[14] = clock64();     // predecessor grid complete
 
   if (warp == 0) {
     if (lane == 0) {
@@ -458,6 +487,7 @@ attn_bwd_tc5r_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         tma_load_2d(sK + B5_TILE, &tmK, col, b * Tk + B5_BK, &bar_kv[1]);
         tma_load_2d(sV + B5_TILE, &tmV, col, b * Tk + B5_BK, &bar_kv[1]);
       }
+      if (trace_on) g_r5_trace[15] = clock64();                        // all loads issued
     }
   } else if (warp == 1) {
     if (lane == 0) {
@@ -572,13 +602,30 @@ attn_bwd_tc5r_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           uint32_t v0[32], v1[32];
           tmem_ld32(trow + B5_COL_DV + (uint32_t)(wg * 32), v0);
           tmem_ld32(trow + B5_COL_DK + (uint32_t)(wg * 32), v1);
+          if (trace_c) g_r5_trace[29 + (j + 1 < nk ? 0 : 1)] = clock64();   // dK / dV read from TMEM
           if (j + 1 < nk) {
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             b5_arrive(&bar_kvfree);
           }
-          if (kj < Tk) {
-            b5_store32(v0, dv + (int64_t)b * kv_bs + (int64_t)kj * kv_rs + (int64_t)h * B5_HS + wg * 32);
-            b5_store32(v1, dk + (int64_t)b * kv_bs + (int64_t)kj * kv_rs + (int64_t)h * B5_HS + wg * 32);
+          // the pair's MMAs are complete: the P / dS panels are free until the next softmax
+          b5_stage32(v0, sP, r, wg);
+          b5_stage32(v1, sP + B5_TILE, r, wg);
+          if (j + 1 == nk) {                                             // last key block: dQ_0 / dQ_1 are complete as well
+            for (int i2 = 0; i2 < nq; ++i2) {
+              tmem_ld32(trow + B5_COL_DQ + (uint32_t)(64 * i2 + wg * 32), v0);
+              b5_stage32(v0, sdS + i2 * B5_TILE, r, wg);
+            }
+          }
+          b5_sync_softmax_warps();
+          const int tid = threadIdx.x - 128;
+          b5_store_tile(sP, dv + (int64_t)b * kv_bs + (int64_t)(j * B5_BK) * kv_rs + (int64_t)h * B5_HS, kv_rs, Tk - j * B5_BK, tid);
+          b5_store_tile(sP + B5_TILE, dk + (int64_t)b * kv_bs + (int64_t)(j * B5_BK) * kv_rs + (int64_t)h * B5_HS, kv_rs, Tk - j * B5_BK, tid);
+          if (j + 1 == nk) {
+            for (int i2 = 0; i2 < nq; ++i2)
+              b5_store_tile(sdS + i2 * B5_TILE, dq + (int64_t)b * q_bs + (int64_t)(i2 * B5_BQ) * q_rs + (int64_t)h * B5_HS, q_rs,
+                            Tq - i2 * B5_BQ, tid);
+          } else {
+            b5_sync_softmax_warps();                                     // the panels are rewritten by the next softmax
           }
           if (trace_c) g_r5_trace[20 + 4 * t] = clock64();   // dK / dV stored
         }
@@ -590,13 +637,6 @@ attn_bwd_tc5r_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         b5_store32(z, dv + (int64_t)b * kv_bs + (int64_t)kj * kv_rs + (int64_t)h * B5_HS + wg * 32);
         b5_store32(z, dk + (int64_t)b * kv_bs + (int64_t)kj * kv_rs + (int64_t)h * B5_HS + wg * 32);
       }
-    }
-    // every pair has been committed and awaited (the last pair of the last key block is a drain point): dQ_0, dQ_1
-    for (int i = 0; i < nq; ++i) {
-      uint32_t v[32];
-      tmem_ld32(trow + B5_COL_DQ + (uint32_t)(64 * i + wg * 32), v);
-      const int qi = i * B5_BQ + r;
-      if (qi < Tq) b5_store32(v, dq + (int64_t)b * q_bs + (int64_t)qi * q_rs + (int64_t)h * B5_HS + wg * 32);
     }
     if (trace_c) g_r5_trace[31] = clock64();          // dQ stored
   }

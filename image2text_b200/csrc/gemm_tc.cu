@@ -194,6 +194,20 @@ __device__ __forceinline__ void tc_stage_chunk(uint8_t* box, int r_in_tile, cons
     }
   }
 }
+// 32 bf16 of row r_in_tile into a 64-byte-pitch box, 16-byte pieces XOR-swizzled by ((row >> 1) & 3) (CU_TENSOR_MAP_SWIZZLE_64B)
+__device__ __forceinline__ void tc_stage_chunk64(uint8_t* box, int r_in_tile, const float (&v)[32]) {
+  uint8_t* rowp = box + r_in_tile * 64;
+  const int sw = (r_in_tile >> 1) & 3;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    uint4 pk;
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * t], v[8 * t + 1]), h1 = __floats2bfloat162_rn(v[8 * t + 2], v[8 * t + 3]);
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * t + 4], v[8 * t + 5]), h3 = __floats2bfloat162_rn(v[8 * t + 6], v[8 * t + 7]);
+    pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+    pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+    *reinterpret_cast<uint4*>(rowp + ((t ^ sw) << 4)) = pk;
+  }
+}
 constexpr int TC_STORE_BOX_BYTES = 128 * 128;        // one staging box: 128 rows x 128 bytes
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 epilogue warps
 // The tile's bias slice goes to shared memory BEFORE the epilogue waits for the accumulator, so its L2 latency hides behind
@@ -212,7 +226,7 @@ __device__ __forceinline__ void tc_stage_bias(const TcEpilogue& epi, float* sbia
 // running CTAs share the weight tile in L2).  The TMA producer and the MMA issuer run ahead across tile boundaries
 // through the 6-stage ring; the accumulator is double buffered in TMEM (2 x 128 columns), so the four epilogue warps
 // drain tile i while the tensor core already works on tile i+1.
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, int BN>      // BN = 128, or 96 (N = 768 at M = 2048: 128 tiles instead of 96 on the 148 SMs)
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, int num_k_blocks, int m_tiles, int n_tiles, int splits, int b_is_weight,
@@ -226,6 +240,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float sbias[TC_BN];
+  constexpr int B_TX = B_MN ? TC_B_BYTES : BN * TC_BK * 2;          // bytes one stage of B brings (MN-major: two 64-wide boxes)
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
   uint8_t* smemA = smem;
@@ -276,10 +291,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       };
       auto load_b = [&](int s, int kb, int n_blk) {
         if (!B_MN) {
-          tma_load_2d(smemB + s * TC_B_BYTES, &tmB, kb * TC_BK, n_blk * TC_BN, &full_bar[s]);
+          tma_load_2d(smemB + s * TC_B_BYTES, &tmB, kb * TC_BK, n_blk * BN, &full_bar[s]);       // box {64 k, BN rows}
         } else {
-          tma_load_2d(smemB + s * TC_B_BYTES, &tmB, n_blk * TC_BN, kb * TC_BK, &full_bar[s]);
-          tma_load_2d(smemB + s * TC_B_BYTES + TC_B_BYTES / 2, &tmB, n_blk * TC_BN + 64, kb * TC_BK, &full_bar[s]);
+          tma_load_2d(smemB + s * TC_B_BYTES, &tmB, n_blk * BN, kb * TC_BK, &full_bar[s]);
+          tma_load_2d(smemB + s * TC_B_BYTES + TC_B_BYTES / 2, &tmB, n_blk * BN + 64, kb * TC_BK, &full_bar[s]);
         }
       };
       int it = 0;                                            // running k-block counter across tiles
@@ -294,7 +309,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           first = false;
           const int npre = b_is_weight ? min(TC_STAGES, kb1 - kb0) : 0;
           for (int i = 0; i < npre; ++i) {
-            mbar_expect_tx(&full_bar[i], TC_A_BYTES + TC_B_BYTES);           // all slots are free at kernel start
+            mbar_expect_tx(&full_bar[i], TC_A_BYTES + B_TX);           // all slots are free at kernel start
             load_b(i, kb0 + i, n_blk);
           }
           pdl_wait();
@@ -306,7 +321,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int s = it % TC_STAGES;
           const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
           mbar_wait(&empty_bar[s], ph ^ 1u);
-          mbar_expect_tx(&full_bar[s], TC_A_BYTES + TC_B_BYTES);
+          mbar_expect_tx(&full_bar[s], TC_A_BYTES + B_TX);
           load_a(s, kb, m_blk);
           load_b(s, kb, n_blk);
         }
@@ -316,7 +331,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N=128, M=128 (cute::UMMA::InstrDescriptor)
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(A_MN ? 1u : 0u) << 15) |
-                             ((uint32_t)(B_MN ? 1u : 0u) << 16) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+                             ((uint32_t)(B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       int it = 0, i = 0;
       for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++i) {
         const int kb0 = (w / num_tiles) * kpb, kb1 = min(kb0 + kpb, num_k_blocks);
@@ -351,29 +366,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     pdl_wait();               // C / residual belong to the previous kernels (the bias does not, but it is staged per tile)
     int i = 0;
     uint32_t box_count = 0;
-    const int chunks_per_box = epi.c_dtype == I2T_F32 ? 1 : 2;
+    // bf16 output: two 32-column chunks fill one 128-byte-wide box; the 96-column tile stores 64-byte-wide boxes instead
+    // (one per chunk, SWIZZLE_64B tensor map: see gemm_tc_try)
+    const bool narrow = BN == 96 && epi.c_dtype != I2T_F32;
+    const int chunks_per_box = (epi.c_dtype == I2T_F32 || narrow) ? 1 : 2;
     for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++i) {
       const int t = w % num_tiles, split = w / num_tiles;
       const int m_blk = t % m_tiles, n_blk = t / m_tiles;
       const int b = i & 1;
       const bool use_bias = epi.bias != nullptr && split == 0;
-      if (use_bias) tc_stage_bias<TC_BN>(epi, sbias, (int64_t)n_blk * TC_BN, r_in_tile);
+      if (use_bias) tc_stage_bias<BN>(epi, sbias, (int64_t)n_blk * BN, r_in_tile);
       mbar_wait(&tmem_full_bar[b], ((uint32_t)i >> 1) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int64_t row0 = (int64_t)m_blk * TC_BM;
       const int64_t row = row0 + r_in_tile;
       const bool row_ok = row < epi.M;
 #pragma unroll 1
-      for (int c = 0; c < TC_BN / 32; ++c) {
+      for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(b * TC_BN + c * 32), r);
-        if (c == TC_BN / 32 - 1) {
+        if (c == BN / 32 - 1) {
           // the accumulator is in registers: hand the TMEM buffer back before the (slow) global stores
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
           if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[b])) : "memory");
         }
-        const int64_t n0 = (int64_t)n_blk * TC_BN + c * 32;
+        const int64_t n0 = (int64_t)n_blk * BN + c * 32;
         if (!epi.tma_store) {
           if (!row_ok || n0 >= epi.N) continue;
           if (splits > 1) tc_epilogue_chunk_splitk(epi, r, row, n0, use_bias ? sbias + c * 32 : nullptr);
@@ -383,13 +401,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float v[32];
         tc_chunk_math(epi, r, v, row, n0, row_ok, use_bias ? sbias + c * 32 : nullptr);
         uint8_t* box = smemC + (box_count & 1u) * TC_STORE_BOX_BYTES;
-        tc_stage_chunk(box, r_in_tile, v, epi.c_dtype, c % chunks_per_box);
+        if (narrow) tc_stage_chunk64(box, r_in_tile, v);
+        else tc_stage_chunk(box, r_in_tile, v, epi.c_dtype, c % chunks_per_box);
         if ((c + 1) % chunks_per_box == 0) {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           epi_bar_sync();
           if (issuer) {
-            const int col0 = (int)((int64_t)n_blk * TC_BN + (c + 1 - chunks_per_box) * 32);
+            const int col0 = (int)((int64_t)n_blk * BN + (c + 1 - chunks_per_box) * 32);
             if (col0 < epi.N && row0 < epi.M) {
               tma_store_2d(&tmC, box, col0, (int)row0);
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -678,15 +697,17 @@ struct MapKeyHash {
 
 // 2-D bf16 [rows][cols] (cols contiguous, pitch ld elements), box {64 cols, box_rows}, 128-byte swizzle, zero fill out
 // of bounds.  K-major operand: cols = K, box_rows = 128.  MN-major operand: cols = MN, rows = K, box_rows = 64.
-static int make_map_dt(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, bool f32, CUtensorMap* out);
+static int make_map_dt(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, bool f32, CUtensorMap* out,
+                       bool narrow = false);
 int tc_make_map(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, CUtensorMap* out) {
   return make_map_dt(ptr, rows, cols, ld, box_rows, false, out);
 }
 // same for either element type: the box is always 128 bytes wide (64 bf16 / 32 fp32) and 128-byte swizzled
-static int make_map_dt(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, bool f32, CUtensorMap* out) {
+// (narrow: bf16 box of 32 columns = 64 bytes, 64-byte swizzle -- the store boxes of the 96-column tile)
+static int make_map_dt(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, bool f32, CUtensorMap* out, bool narrow) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-  MapKey key{ptr, rows, cols, ld, box_rows | (f32 ? 0x10000 : 0)};
+  MapKey key{ptr, rows, cols, ld, box_rows | (f32 ? 0x10000 : 0) | (narrow ? 0x20000 : 0)};
   {
     std::lock_guard<std::mutex> g(mu);
     auto it = cache.find(key);
@@ -699,10 +720,10 @@ static int make_map_dt(const void* ptr, int64_t rows, int64_t cols, int64_t ld, 
   if (fn == nullptr) return fail(I2T_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * (f32 ? 4 : 2)};
-  cuuint32_t box[2] = {f32 ? 32u : 64u, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(f32 || narrow) ? 32u : 64u, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(out, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, narrow ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(I2T_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   {
@@ -713,19 +734,19 @@ static int make_map_dt(const void* ptr, int64_t rows, int64_t cols, int64_t ld, 
   return I2T_OK;
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, int BN>
 static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, int kblocks, const TcEpilogue& epi, dim3 grid,
                      int splits, int b_is_weight, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
     if (e != cudaSuccess) return fail(I2T_ERR_CUDA, "cudaFuncSetAttribute(gemm_tc_kernel): %s", cudaGetErrorString(e));
     attr_set = true;
   }
   const int m_tiles = (int)grid.y, n_tiles = (int)grid.x;
   const int ctas = (int)std::min<int64_t>((int64_t)m_tiles * n_tiles * splits, (int64_t)num_sms());
   // programmatic stream serialization: the kernel calls griddepcontrol.wait before it touches A, C or the residual
-  cudaError_t e = launch_pdl(gemm_tc_kernel<A_MN, B_MN>, dim3(ctas), dim3(TC_THREADS), TC_SMEM, st, ma, mb, mc, kblocks, m_tiles,
+  cudaError_t e = launch_pdl(gemm_tc_kernel<A_MN, B_MN, BN>, dim3(ctas), dim3(TC_THREADS), TC_SMEM, st, ma, mb, mc, kblocks, m_tiles,
                              n_tiles, splits, b_is_weight, epi);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   if (e != cudaSuccess) {
@@ -756,6 +777,7 @@ static int pick_splits(int64_t tiles, int kb, int sms) {
   return best_cost <= 0.85 * cost(1) ? best : 1;
 }
 
+static std::atomic<int> g_tile96{getenv("I2T_GEMM_TILE96") ? atoi(getenv("I2T_GEMM_TILE96")) : 1};   // A/B switch for the 96-column tile
 static std::atomic<int> g_tma_store{1};    // 1: CTA-pair epilogue through shared memory + TMA stores; 0: per-thread row stores
 static std::atomic<int> g_pair_mode{1};   // 1: CTA-pair kernel where the problem has enough 256-row tiles; 0: never
 
@@ -828,7 +850,8 @@ int gemm_tc_try(const void* A, const void* B, const float* bias, const void* res
   if (rc != I2T_OK) return rc;
   // CTA-pair tiles (256 x 256, else 256 x 128) when they fill at least ~3/4 of the 74 SM pairs; otherwise 128 x 128 tiles
   if (g_pair_mode.load() == 1) {
-    const int64_t want = (int64_t)(num_sms() / 2) * 3 / 4;
+    static const int64_t want_env = getenv("I2T_GEMM_PAIR_MIN") ? atoi(getenv("I2T_GEMM_PAIR_MIN")) : 0;    // tuning experiments
+    const int64_t want = want_env > 0 ? want_env : (int64_t)(num_sms() / 2) * 3 / 4;
     const int64_t mt = ceil_div(M, 256);
     int bn = 0;
     if (mt * ceil_div(N, 256) >= want) bn = 256;
@@ -850,17 +873,8 @@ int gemm_tc_try(const void* A, const void* B, const float* bias, const void* res
                        : launch_pair_layout<128>(ma, mb, mc, kb, epi, (int)mt, nt, a_kmajor, b_kmajor, st);
     }
   }
-  rc = b_kmajor ? tc_make_map(B, N, K, ldb, TC_BN, &mb) : tc_make_map(B, K, N, ldb, 64, &mb);
-  if (rc != I2T_OK) return rc;
   {
     const int esz = c_dtype == I2T_F32 ? 4 : 2;
-    CUtensorMap mc = ma;
-    epi.tma_store = 0;
-    if (!accumulate && aligned16(C) && (ldc * esz) % 16 == 0 && epi.debug == 0 && g_tma_store.load() == 1) {
-      rc = make_map_dt(C, M, N, ldc, 128, c_dtype == I2T_F32, &mc);
-      if (rc != I2T_OK) return rc;
-      epi.tma_store = 1;
-    }
     dim3 grid((unsigned)ceil_div(N, TC_BN), (unsigned)ceil_div(M, TC_BM));
     // split-K: few output tiles and a long K (decode projections over a batch, weight gradients) leave most SMs idle and
     // each busy SM bound by its own TMA rate; K slices on the idle SMs add their partial tiles with fp32 atomics.
@@ -869,6 +883,22 @@ int gemm_tc_try(const void* A, const void* B, const float* bias, const void* res
     if (g_split_k.load() == 1 && c_dtype == I2T_F32 && act == I2T_ACT_NONE && (residual == nullptr || residual == C) &&
         epi.debug == 0)
       splits = pick_splits((int64_t)grid.x * grid.y, kb, num_sms());
+    // 96-column tiles: when the 128 x 128 tiling leaves SMs idle and 128 x 96 tiles still fit one wave (N = 768 at M = 2048:
+    // 96 -> 128 tiles on 148 SMs), every CTA's serial work shrinks by a quarter.  Not with split-K (its own way to fill the SMs).
+    int bn = TC_BN;
+    if (g_tile96.load() == 1 && splits == 1 && epi.debug == 0) {
+      const int64_t t128 = (int64_t)grid.x * grid.y, t96 = (int64_t)ceil_div(N, 96) * grid.y;
+      if (t128 < num_sms() && t96 <= num_sms() && t96 > t128 && N >= 96) bn = 96;
+    }
+    rc = b_kmajor ? tc_make_map(B, N, K, ldb, bn, &mb) : tc_make_map(B, K, N, ldb, 64, &mb);
+    if (rc != I2T_OK) return rc;
+    CUtensorMap mc = ma;
+    epi.tma_store = 0;
+    if (!accumulate && aligned16(C) && (ldc * esz) % 16 == 0 && epi.debug == 0 && g_tma_store.load() == 1) {
+      rc = make_map_dt(C, M, N, ldc, 128, c_dtype == I2T_F32, &mc, bn == 96 && c_dtype != I2T_F32);
+      if (rc != I2T_OK) return rc;
+      epi.tma_store = 1;
+    }
     if (splits > 1) {
       epi.tma_store = 0;
       if (!accumulate && residual == nullptr)
@@ -878,10 +908,17 @@ int gemm_tc_try(const void* A, const void* B, const float* bias, const void* res
     // the stream writes it: the decode step's weights.  (Training cannot promise that: a bf16 weight shadow may have been
     // refreshed by the kernel right before this one.)
     const int b_is_weight = (flags & I2T_GEMM_B_STABLE) ? 1 : 0;
-    if (a_kmajor && b_kmajor) return launch_tc<false, false>(ma, mb, mc, kb, epi, grid, splits, b_is_weight, st);
-    if (a_kmajor && !b_kmajor) return launch_tc<false, true>(ma, mb, mc, kb, epi, grid, splits, b_is_weight, st);
-    if (!a_kmajor && b_kmajor) return launch_tc<true, false>(ma, mb, mc, kb, epi, grid, splits, b_is_weight, st);
-    return launch_tc<true, true>(ma, mb, mc, kb, epi, grid, splits, b_is_weight, st);
+    if (bn == 96) {
+      grid.x = (unsigned)ceil_div(N, 96);
+      if (a_kmajor && b_kmajor) return launch_tc<false, false, 96>(ma, mb, mc, kb, epi, grid, splits, b_is_weight, st);
+      if (a_kmajor && !b_kmajor) return launch_tc<false, true, 96>(ma, mb, mc, kb, epi, grid, splits, b_is_weight, st);
+      if (!a_kmajor && b_kmajor) return launch_tc<true, false, 96>(ma, mb, mc, kb, epi, grid, splits, b_is_weight, st);
+      return launch_tc<true, true, 96>(ma, mb, mc, kb, epi, grid, splits, b_is_weight, st);
+    }
+    if (a_kmajor && b_kmajor) return launch_tc<false, false, 128>(ma, mb, mc, kb, epi, grid, splits, b_is_weight, st);
+    if (a_kmajor && !b_kmajor) return launch_tc<false, true, 128>(ma, mb, mc, kb, epi, grid, splits, b_is_weight, st);
+    if (!a_kmajor && b_kmajor) return launch_tc<true, false, 128>(ma, mb, mc, kb, epi, grid, splits, b_is_weight, st);
+    return launch_tc<true, true, 128>(ma, mb, mc, kb, epi, grid, splits, b_is_weight, st);
   }
 }
 

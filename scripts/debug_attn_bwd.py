@@ -35,6 +35,7 @@ if os.environ.get("I2T_ATTN_BWD_DEBUG") == "-1":
         names.update({1 + 4 * t: f"mma  pair{t} operands ready", 2 + 4 * t: f"mma  pair{t} S/dP issued", 3 + 4 * t: f"mma  pair{t} P/dS arrived",
                       4 + 4 * t: f"mma  pair{t} dV/dK/dQ issued", 17 + 4 * t: f"soft pair{t} S/dP complete", 18 + 4 * t: f"soft pair{t} P/dS written",
                       19 + 4 * t: f"soft pair{t} mma2 complete", 20 + 4 * t: f"soft pair{t} dK/dV stored"})
-    names.update({16: "soft row scalars read", 31: "soft dQ stored"})
+    names.update({16: "soft row scalars read", 31: "soft dQ stored", 13: "barriers + TMEM ready", 14: "predecessor complete",
+                  15: "tma  all loads issued", 29: "soft dK/dV of key block 0 in registers", 30: "soft dK/dV of key block 1 in registers"})
     for i, v in sorted(((i, buf[i]) for i in range(32) if buf[i]), key=lambda kv: kv[1]):
         print(f"{(v - t0) / 1.9e3:8.2f} us  {names.get(i, i)}")

@@ -126,6 +126,48 @@ def test_gemm_bf16_tcgen05_mn_major_layouts(M, N, K, layout):
     acc = torch.ones(M, N, device=DEV)
     ops.gemm(A, Bm, out=acc, a_kmajor=layout[0] == "n", b_kmajor=layout[1] == "t", accumulate=True)
     assert relerr(acc, ref + 1.0) < 1e-5
+    # bf16 output (the dgrad that feeds the next backward kernel): N = 768 at M ~ 2048 takes the 128 x 96 tile whose bf16 boxes
+    # are 64 bytes wide
+    o16 = ops.gemm(A, Bm, a_kmajor=layout[0] == "n", b_kmajor=layout[1] == "t", out_dtype=torch.bfloat16)
+    assert relerr(o16.float(), ref) < 8e-3
+
+
+def test_gemm_bf16_96_column_tile_matches_the_128_column_tile():
+    """The tile-shape switch (I2T_GEMM_TILE96) must not change results beyond fp32 summation order: same shapes through both tilings,
+    every epilogue (bias, GELU, fp32 residual, bf16 / fp32 output, odd N tail)."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, torch
+sys.path.insert(0, ".")
+from image2text_b200 import ops
+g = torch.Generator(device="cuda").manual_seed(5)
+outs = []
+for (M, N, K) in [(2048, 768, 768), (1576, 768, 3072), (256, 200, 136), (300, 97, 64)]:
+    a = (torch.randn(M, K, device="cuda", generator=g)).bfloat16()
+    b = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    res = torch.randn(M, N, device="cuda", generator=g)
+    outs.append(ops.gemm(a, b, bias=bias, residual=res, act=ops.ACT_GELU_TANH, out_dtype=torch.float32))
+    Np = (N + 7) // 8 * 8
+    o = torch.zeros(M, Np, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, b, bias=bias, out=o[:, :N], ldc=Np)
+    outs.append(o.float())
+    bt = b.t().contiguous()
+    outs.append(ops.gemm(a, bt, b_kmajor=False, out_dtype=torch.bfloat16).float() if N % 8 == 0 else o.float())
+torch.save([o.cpu() for o in outs], sys.argv[1])
+'''
+    import os
+    import tempfile
+    res = {}
+    with tempfile.TemporaryDirectory() as td:
+        for flag in ("1", "0"):
+            path = os.path.join(td, f"o{flag}.pt")
+            subprocess.run([sys.executable, "-c", code, path], check=True, env=dict(os.environ, I2T_GEMM_TILE96=flag),
+                           cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+            res[flag] = torch.load(path)
+    for x, y in zip(res["1"], res["0"]):
+        assert relerr(x, y) < 2e-3 and float((x - y).abs().max()) < 0.1
 
 
 @pytest.mark.parametrize("M,N,K", [(4096, 2304, 768), (2000, 4000, 200), (768, 3072, 2048), (16384, 776, 136)])
