@@ -126,7 +126,7 @@ class VisionEncoderDecoder(nn.Module):
         else:
             schema = type(schema)((k, v) for k, v in schema.items() if not k.startswith("encoder"))
             if spec["n_embd_out_vit"] != spec["n_embd"]:            # the reference bridges with a Linear (:33-37)
-                encoder = nn.Sequential(encoder, nn.Linear(spec["n_embd_out_vit"], spec["n_embd"]))
+                encoder = nn.Sequential(encoder, nn.Linear(spec["n_embd_out_vit"], spec["n_embd"], bias=False))
             self.encoder = encoder.to(torch.device(device))
         self.decoder = _Side("decoder", spec)
         self.decoder._bind(self)
