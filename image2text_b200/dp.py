@@ -105,6 +105,7 @@ class GradientAllReducer:
         """Wrap the capture of a micro-step (forward + backward) so that the hooks record the per-bucket events."""
         self._capturing = True
         self._events = [None] * len(self.buckets)
+        self._superseded = []
         self._reset()
         try:
             yield
@@ -182,9 +183,15 @@ class GradientAllReducer:
         if self._capturing:
             bi = self.bucket_of[id(p)]
             self.pending[bi] -= 1
-            if self.pending[bi] == 0:
+            # `<= 0`: a parameter may be announced twice in one backward -- once by a kernel that added its contribution straight
+            # into .grad (ops.grad_sinks) and once by AccumulateGrad for a contribution that came through autograd (the tied
+            # wte / lm_head weight: LM-head wgrad + embedding gradient).  Every arrival after the count ran out re-records the
+            # bucket's event, so the exchange waits for the LAST contribution.
+            if self.pending[bi] <= 0:
                 ev = torch.cuda.Event(external=True)
                 ev.record()                      # an event-record node of the graph being captured
+                if self._events[bi] is not None:
+                    self._superseded.append(self._events[bi])     # its record node stays in the graph: the event must outlive it
                 self._events[bi] = ev
             return
         if not self.sync_enabled:
