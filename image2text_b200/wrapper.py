@@ -87,8 +87,10 @@ class ModelTrainerWrapper(nn.Module):
         addresses; parameters that received no gradient in the two eager calls are unused and stay untouched).  Returns the detached
         loss (a static tensor that the next replay overwrites).
         Data parallel: pass the `GradientAllReducer` as `reducer` (always) and `sync=True` on the last micro-step of an
-        optimiser step: the captured graph carries one external event per gradient bucket, and the bucketed all-reduce of a
-        synchronising replay is queued behind those events -- it overlaps the rest of the backward (dp.py)."""
+        optimiser step; `reducer.finish()` then exchanges the buckets after the replay (NVLink moves them in a few ms).  With
+        `GradientAllReducer(graph_events=True)` the captured graph instead carries one external event per gradient bucket and the
+        all-reduce of a synchronising replay is queued behind those events, overlapping the rest of the backward -- measured
+        slower on B200, because every event node interrupts the replay's launch chain (dp.py)."""
         key = (tuple(images.shape), images.dtype, tuple(labels.shape), float(loss_scale))
         st = getattr(self, "_graph_state", None)
         if st is None or st["key"] != key:
@@ -107,8 +109,9 @@ class ModelTrainerWrapper(nn.Module):
                 import contextlib
                 from . import ops
                 # ops.grad_sinks: the captured backward adds weight gradients straight into the (static) .grad buffers
-                with (reducer.capturing() if reducer is not None else contextlib.nullcontext()), \
-                        ops.grad_sinks(notify=reducer._hook if reducer is not None else None):
+                events = reducer is not None and reducer.graph_events
+                with (reducer.capturing() if events else contextlib.nullcontext()), \
+                        ops.grad_sinks(notify=reducer._hook if events else None):
                     with torch.cuda.graph(g):
                         loss, _ = self._step(st["images"], st["labels"], True)
                         (loss * loss_scale).backward()
@@ -126,7 +129,7 @@ class ModelTrainerWrapper(nn.Module):
         if self.model_m is not None:
             self.model_m.sync_compute_weights()
         st["graph"].replay()
-        if reducer is not None and sync:
+        if reducer is not None and sync and reducer.graph_events:
             reducer.exchange_after_replay()
         return st["loss"]
 

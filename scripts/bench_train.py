@@ -87,14 +87,21 @@ def main():
         if id(p) not in chosen:
             p.requires_grad_(False)
     opt = AdamW(groups)
-    red = GradientAllReducer([p for g in groups for p in g["params"]])
+    # I2T_DP_OVERLAP=1: in-graph bucket events (exchange overlapped with the backward; measured slower, see dp.py)
+    red = GradientAllReducer([p for g in groups for p in g["params"]], graph_events=os.environ.get("I2T_DP_OVERLAP", "0") == "1")
     red.attach_optimizer(opt)
     red.broadcast_parameters(w.model)
     w.copy_momentum_params()
     images = synth_images(bs, 224, seed=1234 + rank).cuda()
     labels = synth_labels(bs, 256, seed=1234 + rank).cuda()
 
+    sections = os.environ.get("I2T_BENCH_SECTIONS") == "1"          # per-section device times of every step (rank 0 prints)
+    sec_ev = []
+
     def one_step():
+        if sections:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev[0].record()
         for micro in range(accum):
             last = micro == accum - 1
             # graphed micro-steps never fire the all-reduce hooks (a replay runs no Python): with --graph every micro-step is
@@ -108,14 +115,23 @@ def main():
                 else:
                     loss, _ = w.train_step(images, labels)
                     (loss / accum).backward()
+        if sections:
+            ev[1].record()
         red.finish()
+        if sections:
+            ev[2].record()
         opt.step()
         opt.zero_grad(set_to_none=False)
+        if sections:
+            ev[3].record()
+            sec_ev.append(ev)
         return loss
 
     for _ in range(args.warmup):
         one_step()
     torch.cuda.synchronize()
+    if args.profile and world > 1:
+        raise SystemExit("--profile runs one extra step on rank 0 only: single process only")
     if args.profile and rank == 0:
         from torch.profiler import ProfilerActivity, profile
         with profile(activities=[ProfilerActivity.CUDA]) as prof:
@@ -159,6 +175,10 @@ def main():
         t = torch.tensor([ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t)
+    if sections and rank == 0:
+        e = sec_ev[-1]
+        print(f"sections of the last step (ms, device time on the main stream): micro-steps {e[0].elapsed_time(e[1]):.2f}, "
+              f"reducer.finish {e[1].elapsed_time(e[2]):.2f}, optimizer {e[2].elapsed_time(e[3]):.2f}")
     imgs = bs * accum * args.steps * world
     gflop_img = (243.4 + (104.5 if args.moco else 0.0)) if args.config == "nano" else (340.0 + (113.4 if args.moco else 0.0))
     if rank == 0:

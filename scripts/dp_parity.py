@@ -59,13 +59,13 @@ if rank == 0:
     print(f"DP parity world={world}: buckets={nb} tensors={len(want)} worst rel err={worst:.2e} -> {'OK' if flag.item() == 1 else 'FAIL'}")
 
 
-def grads_graphed(shard_rank, micro=5):
+def grads_graphed(shard_rank, micro=5, graph_events=True):
     """CUDA-graphed micro-steps (calls 1-2 eager, 3 captures, 3-5 replay): the exchange of the last replay is queued behind
     the per-bucket events recorded inside the graph (GradientAllReducer.exchange_after_replay)."""
     w = ModelTrainerWrapper(tc.model, tok, TrainerWrapperConfig(), -100, device=f"cuda:{local}", spec_overrides=over)
     w.model.load_state_dict(synth_state_dict(w.model.spec, seed=0))
     w.train()
-    red = GradientAllReducer(w.model.parameters(), bucket_mb=0.25)
+    red = GradientAllReducer(w.model.parameters(), bucket_mb=0.25, graph_events=graph_events)
     images = synth_images(3, 32, seed=100 + shard_rank).cuda()
     labels = synth_labels(3, 20, 613, seed=200 + shard_rank, min_len=3, max_len=14, eos=612).cuda()
     for i in range(micro):
@@ -88,5 +88,19 @@ dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
     print(f"DP parity (graphed micro-steps, exchange behind in-graph events) world={world}: bucket events={n_ev} "
           f"worst rel err={worst_g:.2e} -> {'OK' if flag.item() == 1 else 'FAIL'}")
+all_ok = flag.item() == 1
+# default reducer: no in-graph events, every bucket exchanged by finish() after the last replay
+got_e, n_ev_e = grads_graphed(rank, graph_events=False)
+worst_e = 0.0
+for k in want:
+    ref = 5.0 * want[k] / world
+    worst_e = max(worst_e, float((got_e[k] - ref).abs().max() / ref.abs().max().clamp_min(1e-20)))
+ok_e = worst_e < 1e-5 and set(got_e) == set(want) and n_ev_e == 0
+flag = torch.tensor([1.0 if ok_e else 0.0], device="cuda")
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print(f"DP parity (graphed micro-steps, exchange after the last replay) world={world}: worst rel err={worst_e:.2e} "
+          f"-> {'OK' if flag.item() == 1 else 'FAIL'}")
+all_ok = all_ok and flag.item() == 1
 dist.destroy_process_group()
-sys.exit(0 if flag.item() == 1 else 1)
+sys.exit(0 if all_ok else 1)
