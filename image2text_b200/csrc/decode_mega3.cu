@@ -28,7 +28,7 @@
 //   18 rot (tile u belongs to CTA (u + rot) % grid) | 19 where the embedding is published (generation 0) | 20 input row
 //   pitch in elements (0 = K: lets a K-split op read a column range of a wider buffer) | 21 group size Gs (0 = grid): only
 //   the first Gs CTAs of the rotation take part, tile u belongs to CTA ((u % Gs) + rot) % grid -- fewer CTAs fan the
-//   activations out of L2 when an op has few tiles per CTA anyway | 22 1 = tcgen05 stage (weights packed as UMMA atoms) | 23 unused
+//   activations out of L2 when an op has few tiles per CTA anyway | 22 1 = tcgen05 stage (weights packed as UMMA atoms) | 23 folded residual: 1 + combine-table row
 // cmb[c][8] (combine: out = bias + residual + sum of n partial buffers, the second half of a K-split projection) =
 //   0 n partials | 1 first partial f32 (generation 0) | 2 bytes between partials | 3 bias f32* | 4 residual (generation 0)
 //   5 output (generation 0) | 6 N (row length) | 7 rot
@@ -114,6 +114,7 @@ struct __align__(16) M3Fixed {
   int hist[M3_B][M3_MAX_KEYS + 8];               // token history of every sequence (n-gram ban)
   int tok[M3_B];                                  // the tokens this step embeds
   unsigned long long best[M3_CWARPS][2];
+  uint4 fold[M3_CWARPS * 8][3];                   // folded combine: residual / partial rows of an epilogue thread, fetched by cp.async
 };
 
 // Dynamic shared memory: [ring | M3Fixed | work | lin | att | cmb | sched | (sampler scratch, sampling mode only)].
@@ -595,9 +596,23 @@ __device__ __forceinline__ void m3_linear(const M3Args& a, int op, const M3Sm& S
       float4 e_bias = make_float4(0.f, 0.f, 0.f, 0.f);
       uint4 e_res = make_uint4(0u, 0u, 0u, 0u);
       const float* resp = nullptr;
-      if (e_on) {                                      // epilogue operands do not depend on the MMAs: request them now
+      bool folded = false;                             // folded combine: the residual is residual' + bias' + partial row(s) of
+      if (e_on) {                                      // another op, fetched into f->fold by cp.async (no registers held meanwhile)
+        // epilogue operands do not depend on the MMAs: request them now
         if (bias != nullptr) e_bias = __ldg(reinterpret_cast<const float4*>(bias + nq));
-        if (mode == 0 && d[6] != 0) {
+        if (mode == 0 && d[23] != 0) {
+          const int64_t* c = m3_cmb(S, (int)d[23] - 1);
+          folded = true;
+          resp = m3_gen<const float>(c[4], a.gen_stride, gen) + (int64_t)eb * ldo + nq;
+          const float* pap = m3_gen<const float>(c[1], a.gen_stride, gen) + (int64_t)eb * ldo + nq;
+          uint4* slot = f->fold[warp * 8 + lane];
+          m3_cp_async16(slot, resp);
+          m3_cp_async16(slot + 1, pap);
+          if (c[0] > 1) m3_cp_async16(slot + 2, reinterpret_cast<const uint8_t*>(pap) + c[2]);
+          m3_cp_commit();
+          const float4 b2 = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(c[3]) + nq));
+          e_bias.x += b2.x; e_bias.y += b2.y; e_bias.z += b2.z; e_bias.w += b2.w;     // (no activation on a residual op)
+        } else if (mode == 0 && d[6] != 0) {
           resp = m3_gen<const float>(d[6], a.gen_stride, gen) + (int64_t)eb * ldo + nq;
           e_res = m3_ld16(resp);
         }
@@ -679,12 +694,32 @@ __device__ __forceinline__ void m3_linear(const M3Args& a, int op, const M3Sm& S
         v.z = m3_act(v.z + e_bias.z, act); v.w = m3_act(v.w + e_bias.w, act);
         if (resp != nullptr) {
           uint32_t spins = 0;
+          if (folded) {
+            m3_cp_wait0();
+            e_res = f->fold[warp * 8 + lane][0];
+          }
           while (!m3_ok32(e_res)) {
             if (m3_giveup(spins, a.error_flag)) break;
             e_res = m3_ld16(resp);
           }
           v.x += __uint_as_float(e_res.x); v.y += __uint_as_float(e_res.y);
           v.z += __uint_as_float(e_res.z); v.w += __uint_as_float(e_res.w);
+          if (folded) {
+            const int64_t* c = m3_cmb(S, (int)d[23] - 1);
+            const float* pap = m3_gen<const float>(c[1], a.gen_stride, gen) + (int64_t)eb * ldo + nq;
+            const int np = (int)c[0];                  // 1 or 2 partial rows
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              if (j >= np) break;
+              const float* pp = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(pap) + j * c[2]);
+              uint4 e = f->fold[warp * 8 + lane][1 + j];
+              while (!m3_ok32(e)) {
+                if (m3_giveup(spins, a.error_flag)) break;
+                e = m3_ld16(pp);
+              }
+              v.x += __uint_as_float(e.x); v.y += __uint_as_float(e.y); v.z += __uint_as_float(e.z); v.w += __uint_as_float(e.w);
+            }
+          }
         }
         if (lm_head) {
           const float vv[4] = {v.x, v.y, v.z, v.w};

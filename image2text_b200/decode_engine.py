@@ -209,6 +209,10 @@ class DecodeEngine:
         # (same parity tests pass), but an M128 SS-MMA fetches 128 A rows from shared memory for a tile of 16: 373 vs 281 us per
         # step (gpurun r2m / r2n) -- experimental, off by default
         tc = 1 if os.environ.get("I2T_M3_TC", "0") == "1" else 0
+        # folded combine (default): the down projection is split into two K = 1536 halves; the first writes an fp32 partial row,
+        # the epilogue of the SECOND adds that partial, the bias and the residual and publishes the block's output itself -- no
+        # separate combine stage, one hop less per layer.  I2T_M3_FOLD=0: the four-way split with its combine stage.
+        fold = os.environ.get("I2T_M3_FOLD", "1") != "0" and not tc
         loads = [0] * G                      # bytes of packed weights per CTA so far (tile -> CTA balancing)
         cursor = [0]                         # exchange-buffer bump allocator (bytes within one generation)
 
@@ -238,7 +242,7 @@ class DecodeEngine:
             """byte offset inside one generation of the exchange buffers (resolved to an address below)"""
 
         def add_lin(wkey, bkey, ln, inp, out, residual, N, K, act=0, mode=0, kc=None, vc=None, in_mode=0, rows=None, ldo=None,
-                    wpe=None, flags=0, pub=0, cols=None, in_ld=0):
+                    wpe=None, flags=0, pub=0, cols=None, in_ld=0, fold_res=0):
             w = W.c(wkey)
             b = W.get(bkey) if bkey else None
             if rows is not None:
@@ -260,7 +264,7 @@ class DecodeEngine:
                 gs = (total + 1) // 2
             rot = balance(total, tb, gs)
             lin.append([0, P(b), P(g), P(be), inp, out, residual, N, K, act, mode, P(kc), P(vc), in_mode, P(wpe),
-                        ldo if ldo is not None else N, self.Tmax * C, flags, rot, pub, in_ld, gs if gs != G else 0, tc_op, 0])
+                        ldo if ldo is not None else N, self.Tmax * C, flags, rot, pub, in_ld, gs if gs != G else 0, tc_op, fold_res])
             wsrc.append((w, N, K, tb, rot, gs, tc_op))
             sched.append([0, len(lin) - 1, 0, 0])
 
@@ -300,7 +304,15 @@ class DecodeEngine:
             h_d, x3 = xnew(B8 * F * 2), xnew(x32)
             add_lin(lp + "mlp.c_fc.weight", lp + "mlp.c_fc.bias", lp + "ln_2", x1, h_d, 0, F, C, act=ops.ACT_GELU_TANH,
                     flags=FL_OUT16)
-            if F > 768 and F % 768 == 0 and F // 768 <= 8:
+            if fold and F % 1536 == 0 and F // 1536 == 2 and C <= 768:
+                # two K = 1536 halves (96 two-chunk tiles: the same two chunks per busy CTA as the four-way split); the second
+                # half's epilogue folds the first half's partial row in
+                part = xnew(x32)
+                add_lin(lp + "mlp.c_proj.weight", None, None, h_d, part, 0, C, 1536, flags=FL_IN16, cols=slice(0, 1536), in_ld=F)
+                cmb.append([1, part, 0, P(W[lp + "mlp.c_proj.bias"]), x1, 0, C, 0])
+                add_lin(lp + "mlp.c_proj.weight", None, None, X(int(h_d) + 1536 * 2), x3, 0, C, 1536, flags=FL_IN16,
+                        cols=slice(1536, 3072), in_ld=F, fold_res=len(cmb))
+            elif F > 768 and F % 768 == 0 and F // 768 <= 8:
                 # K-split down projection: F / 768 independent single-chunk ops (192 units instead of 48 four-chunk tiles: every
                 # SM takes part, a unit stages 12 KB of the hidden row instead of 48 KB) writing fp32 partial rows, then a
                 # light combine stage adds them (fixed order), the bias and the residual

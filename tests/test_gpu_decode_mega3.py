@@ -94,6 +94,19 @@ def test_mega3_nano_topk16_teacher_forced():
     check_picks_vs_oracle("nano", m, images, got, 1, top_k=16)
 
 
+def test_mega3_four_way_split_with_combine_stage(monkeypatch):
+    """I2T_M3_FOLD=0: the down projection as four K = 768 partial ops + a combine stage (the default folds the first K half into
+    the epilogue of the second).  Same oracle bar; both variants are deterministic."""
+    monkeypatch.setenv("I2T_M3_FOLD", "0")
+    m = build("nano", torch.bfloat16)
+    images = synth_images(8, 224, seed=1234).cuda()
+    prompt = torch.full((8, 1), 50256, dtype=torch.long, device="cuda")
+    eng = DecodeEngine(m, 8, mode="mega3")
+    got = eng.generate(images, prompt, 20, 1.0, 1, seed=0)
+    assert torch.equal(got, eng.generate(images, prompt, 20, 1.0, 1, seed=0))
+    check_picks_vs_oracle("nano", m, images, got, 1, top_k=1)
+
+
 def test_mega3_repacks_after_a_weight_update():
     """The packed weight streams follow the fp32 masters: an in-place change of a decoder weight changes the ids."""
     m = build("tiny", torch.bfloat16)
