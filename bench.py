@@ -349,7 +349,7 @@ def run_ours(args):
         roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel for this workload (one launch = 64 steps) from the
                     # committed ncu --set full capture
-                    "traffic": 16837838424 if (cd == torch.bfloat16 and NEW_TOKENS == 64 and CAPTIONS == 8) else None,
+                    "traffic": 16800550608 if (cd == torch.bfloat16 and NEW_TOKENS == 64 and CAPTIONS == 8) else None,
                     "traffic_source": "ncu --set full, profiles/r02_ncu_full_decode_mega3_bf16_raw.csv (per launch of 64 steps)",
                     "peak_source": peak_src, "kernel": kernel_desc,
                     "algorithmic_bytes_per_launch": int(step_bytes * NEW_TOKENS), "us_per_launch": round(step_ms * 1e3 * NEW_TOKENS, 1),
