@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(256) vit_assemble_kernel(const TP* __restrict_
   store4(x + r * C + cv * 4, v);
 }
 
-// grid = (n_cls, B); block = 256.  Every (image, slot) hashes the same normalised feature against its own
+// grid = (n_cls, B, ceil(E / 256)); block = 256.  Every (image, slot) hashes the same normalised feature against its own
 // projections, bucketises, and averages the selected EmbeddingBag rows.
 __global__ void __launch_bounds__(256)
 lsh_tail_kernel(const float* __restrict__ feat, const float* const* __restrict__ proj, const float* const* __restrict__ grid_,
@@ -88,8 +88,10 @@ lsh_tail_kernel(const float* __restrict__ feat, const float* const* __restrict__
     const int groups = 256 / n_proj;
     const int g = t / n_proj, p = t % n_proj;
     float acc = 0.f;
-    if (g < groups)
-      for (int k = g; k < D; k += groups) acc = fmaf(f[k], P[(int64_t)k * n_proj + p], acc);
+    if (g < groups) {
+#pragma unroll 8
+      for (int k = g; k < D; k += groups) acc = fmaf(f[k], P[(int64_t)k * n_proj + p], acc);     // (loads in flight, FMAs in order)
+    }
     if (g < groups) part[g * n_proj + p] = acc;
     __syncthreads();
     if (t < n_proj) {
@@ -99,17 +101,22 @@ lsh_tail_kernel(const float* __restrict__ feat, const float* const* __restrict__
       for (int i = 0; i < nb; ++i) bucket += (G[i] < z) ? 1 : 0;
       const int idx = bucket + (nb + 1) * t;
       rowidx[r * n_proj + t] = idx;
-      if (bucket_out) bucket_out[((b * n_cls + s) * n_res + r) * n_proj + t] = idx;
+      if (bucket_out && blockIdx.z == 0) bucket_out[((b * n_cls + s) * n_res + r) * n_proj + t] = idx;
     }
     __syncthreads();
   }
+  // gather: grid.z slices of 256 output columns (one per thread), so the 64 (slot, image) pairs spread over 192 CTAs and a thread's
+  // n_res * n_proj row reads are independent loads in flight (was: 3 columns per thread in one CTA per pair, 124 us of latency)
   const float invp = 1.0f / (float)n_proj;
-  for (int e = t; e < E; e += 256) {
+  const int e = blockIdx.z * 256 + t;
+  if (e < E) {
     float tot = 0.f;
     for (int r = 0; r < n_res; ++r) {
       const float* T = emb[s * n_res + r];
-      float a = 0.f;
-      for (int p = 0; p < n_proj; ++p) a += T[(int64_t)rowidx[r * n_proj + p] * E + e];
+      const int* ri = rowidx + r * n_proj;
+      float a = 0.f;                       // (one accumulator, rows in order: the summation order of the reference's EmbeddingBag)
+#pragma unroll 8
+      for (int p = 0; p < n_proj; ++p) a += T[(int64_t)ri[p] * E + e];
       tot += a * invp;
     }
     out[(b * n_cls + s) * E + e] = tot;
@@ -177,7 +184,7 @@ extern "C" int i2t_lsh_tail(const float* feat, const void* const* proj, const vo
   I2T_REQUIRE(n_proj > 0 && n_proj <= 256 && 256 % n_proj == 0, "lsh_tail: n_proj=%lld must divide 256", (long long)n_proj);
   const size_t smem = (size_t)(D + 256) * sizeof(float) + (size_t)(n_res * n_proj) * sizeof(int);
   I2T_REQUIRE(smem <= 48 * 1024, "lsh_tail: feature too wide for shared memory");
-  dim3 g((unsigned)n_cls, (unsigned)B);
+  dim3 g((unsigned)n_cls, (unsigned)B, (unsigned)ceil_div(E, 256));
   lsh_tail_kernel<<<g, 256, smem, (cudaStream_t)stream>>>(feat, (const float* const*)proj, (const float* const*)grid,
                                                           (const float* const*)emb, num_bins, out, bucket_out, (int)D,
                                                           (int)n_cls, (int)n_res, (int)n_proj, (int)E);
