@@ -260,7 +260,11 @@ def _ref_attention(qkv, B, T, H, mode, n_prompt):
 
 @pytest.mark.parametrize("B,T,H,hs,mode,n_prompt", [(2, 197, 12, 64, 0, 0), (2, 256, 12, 64, 2, 8), (3, 70, 4, 32, 1, 0),
                                                     (1, 64, 2, 64, 2, 4), (2, 48, 4, 32, 2, 4), (2, 272, 12, 64, 1, 0),
-                                                    (1, 300, 4, 64, 0, 0), (3, 130, 3, 64, 2, 16)])
+                                                    (1, 300, 4, 64, 0, 0), (3, 130, 3, 64, 2, 16),
+                                                    # block-boundary cases of the tcgen05 kernels: one row, one row into the second /
+                                                    # third 128-row block, one row short of a full block, the 384-key maximum of the forward
+                                                    (1, 1, 1, 64, 1, 0), (2, 129, 2, 64, 1, 0), (1, 255, 1, 64, 2, 3),
+                                                    (1, 257, 2, 64, 1, 0), (1, 384, 2, 64, 0, 0)])
 def test_attention_fwd_bwd(B, T, H, hs, mode, n_prompt):
     C = H * hs
     qkv = rnd(B * T, 3 * C, seed=14)
