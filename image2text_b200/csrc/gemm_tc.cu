@@ -435,7 +435,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // (0.016 vs 0.031 B/MAC), which is what large GEMMs need to leave the L2-bandwidth bound.
 //   full[s]   : leader's barrier; BOTH CTAs' TMA loads complete_tx on it (the peer addresses it through mapa)
 //   empty[s], tmem_full[b] : per CTA; tcgen05.commit ... multicast::cluster arrives on both
-//   tmem_empty[b] : leader's; 8 arrivals (4 epilogue warps x 2 CTAs)
+//   tmem_empty[b] : leader's; 16 arrivals (8 epilogue warps x 2 CTAs)
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_rank() {
   uint32_t r;
@@ -482,8 +482,9 @@ struct PairCfg {
   static constexpr int TMEM_COLS = 2 * BN;                     // double-buffered accumulator
 };
 
+constexpr int TC_PAIR_THREADS = 384;          // warps 0-3: TMA / MMA / TMEM allocator / idle; warps 4-11: two epilogue warpgroups
 template <bool A_MN, bool B_MN, int BN>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_PAIR_THREADS, 1)
 gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, int num_k_blocks, int m_tiles, int n_tiles, TcEpilogue epi) {
   using Cfg = PairCfg<BN>;
@@ -517,7 +518,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full_bar[b], 1);
-      mbar_init(&tmem_empty_bar[b], 8);      // 4 epilogue warps of each CTA
+      mbar_init(&tmem_empty_bar[b], 16);     // 8 epilogue warps of each CTA
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -595,28 +596,47 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else if (warp >= 4) {
-    const int wq = warp & 3;
+    // TWO epilogue warpgroups (warps 4-7 and 8-11; a warp may touch the TMEM lanes 32 (warp % 4) ..).  Group g drains the store
+    // boxes g, g + 2, ... of a tile through its OWN staging box and issues its own TMA stores, so a 256-column accumulator leaves in
+    // half the time: at K = 768 the pair kernel was paced by its epilogue (tmem load -> math -> staging -> store per 32 columns:
+    // 71 % tensor pipe with one group).
+    const int wq = warp & 3, eg = (warp - 4) >> 2;
     const int r_in_tile = wq * 32 + lane;
-    const bool issuer = warp == 4 && lane == 0;
+    const bool issuer = wq == 0 && lane == 0;
+    auto group_sync = [&]() {
+      if (eg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+      else asm volatile("bar.sync 2, 128;" ::: "memory");
+    };
     if (issuer && epi.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
     int i = 0;
-    uint32_t box_count = 0;                                   // staging boxes written so far (alternating buffers)
     const int chunks_per_box = epi.c_dtype == I2T_F32 ? 1 : 2;
+    const int n_chunks = BN / 32;
+    int last_c = 0;                                            // this group's last chunk of a tile
+    for (int c = 0; c < n_chunks; ++c)
+      if (((c / chunks_per_box) & 1) == eg) last_c = c;
+    uint8_t* box = smemC + eg * TC_STORE_BOX_BYTES;
+    const int etid = (warp - 4) * 32 + lane;                   // 0..255 over both groups
     for (int t = pair; t < num_tiles; t += num_pairs, ++i) {
       const int m_blk = t % m_tiles, n_blk = t / m_tiles;
       const int b = i & 1;
       const bool use_bias = epi.bias != nullptr;
-      if (use_bias) tc_stage_bias<BN>(epi, sbias, (int64_t)n_blk * BN, r_in_tile);
+      if (use_bias) {                                          // the tile's bias slice, staged by all 256 epilogue threads
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+#pragma unroll
+        for (int j = etid; j < BN; j += 256) sbias[j] = ((int64_t)n_blk * BN + j < epi.N) ? epi.bias[(int64_t)n_blk * BN + j] : 0.f;
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+      }
       mbar_wait(&tmem_full_bar[b], ((uint32_t)i >> 1) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int64_t row0 = (int64_t)m_blk * 256 + (int64_t)rank * 128;
       const int64_t row = row0 + r_in_tile;
       const bool row_ok = row < epi.M;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = 0; c < n_chunks; ++c) {
+        if (((c / chunks_per_box) & 1) != eg) continue;        // the other group's box
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(b * BN + c * 32), r);
-        if (c == BN / 32 - 1) {
+        if (c == last_c) {
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
           if (lane == 0) {
@@ -631,16 +651,18 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tc_epilogue_chunk(epi, r, row, n0, use_bias ? sbias + c * 32 : nullptr);
           continue;
         }
-        // staged path (uniform control flow for all 128 epilogue threads: out-of-range rows / columns are clipped by TMA)
+        // staged path (uniform control flow for the 128 threads of the group: out-of-range rows / columns are clipped by TMA)
         float v[32];
         tc_chunk_math(epi, r, v, row, n0, row_ok, use_bias ? sbias + c * 32 : nullptr);
-        uint8_t* box = smemC + (box_count & 1u) * TC_STORE_BOX_BYTES;
+        if (c % chunks_per_box == 0) {
+          // first chunk of a box: the group's previous store must have finished READING the staging box
+          if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          group_sync();
+        }
         tc_stage_chunk(box, r_in_tile, v, epi.c_dtype, c % chunks_per_box);
         if ((c + 1) % chunks_per_box == 0) {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          // the previous store (other buffer) must have finished READING before anyone refills that buffer next round
-          if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          epi_bar_sync();
+          group_sync();
           if (issuer) {
             const int col0 = (int)((int64_t)n_blk * BN + (c + 1 - chunks_per_box) * 32);
             if (col0 < epi.N && row0 < epi.M) {
@@ -648,7 +670,6 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
           }
-          ++box_count;
         }
       }
     }
@@ -795,7 +816,7 @@ static int launch_pair(const CUtensorMap& ma, const CUtensorMap& mb, const CUten
   const int pairs = (int)std::min<int64_t>((int64_t)m_tiles * n_tiles, (int64_t)(num_sms() / 2));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * pairs);
-  cfg.blockDim = dim3(TC_THREADS);
+  cfg.blockDim = dim3(TC_PAIR_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
