@@ -226,8 +226,9 @@ __device__ __forceinline__ void tc_stage_bias(const TcEpilogue& epi, float* sbia
 // running CTAs share the weight tile in L2).  The TMA producer and the MMA issuer run ahead across tile boundaries
 // through the 6-stage ring; the accumulator is double buffered in TMEM (2 x 128 columns), so the four epilogue warps
 // drain tile i while the tensor core already works on tile i+1.
+constexpr int TC_EPI2_THREADS = 384;          // warps 0-3: TMA / MMA / TMEM allocator / idle; warps 4-11: two epilogue warpgroups
 template <bool A_MN, bool B_MN, int BN>      // BN = 128, or 96 (N = 768 at M = 2048: 128 tiles instead of 96 on the 148 SMs)
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_EPI2_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, int num_k_blocks, int m_tiles, int n_tiles, int splits, int b_is_weight,
                TcEpilogue epi) {
@@ -262,7 +263,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full_bar[b], 1);
-      mbar_init(&tmem_empty_bar[b], 4);      // one arrival per epilogue warp
+      mbar_init(&tmem_empty_bar[b], 8);      // one arrival per epilogue warp (two warpgroups)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -359,33 +360,53 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp >= 4) {
-    const int wq = warp & 3;  // TMEM lane quarter this warp may touch
+    // TWO epilogue warpgroups (warps 4-7 and 8-11; a warp may touch the TMEM lanes 32 (warp % 4) ..): group g drains the store
+    // boxes g, g + 2, ... of a tile through its own staging box with its own TMA-store issuer (see the pair kernel)
+    const int wq = warp & 3, eg = (warp - 4) >> 2;
     const int r_in_tile = wq * 32 + lane;
-    const bool issuer = warp == 4 && lane == 0;
+    const bool issuer = wq == 0 && lane == 0;
+    auto group_sync = [&]() {
+      if (eg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+      else asm volatile("bar.sync 2, 128;" ::: "memory");
+    };
     if (issuer && epi.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
     pdl_wait();               // C / residual belong to the previous kernels (the bias does not, but it is staged per tile)
     int i = 0;
-    uint32_t box_count = 0;
     // bf16 output: two 32-column chunks fill one 128-byte-wide box; the 96-column tile stores 64-byte-wide boxes instead
     // (one per chunk, SWIZZLE_64B tensor map: see gemm_tc_try)
     const bool narrow = BN == 96 && epi.c_dtype != I2T_F32;
     const int chunks_per_box = (epi.c_dtype == I2T_F32 || narrow) ? 1 : 2;
+    constexpr int n_chunks = BN / 32;
+    int last_c = -1;                                           // this group's last chunk of a tile (-1: none, BN = 32 ...)
+    for (int c = 0; c < n_chunks; ++c)
+      if (((c / chunks_per_box) & 1) == eg) last_c = c;
+    uint8_t* box = smemC + eg * TC_STORE_BOX_BYTES;
+    const int etid = (warp - 4) * 32 + lane;                   // 0..255 over both groups
     for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++i) {
       const int t = w % num_tiles, split = w / num_tiles;
       const int m_blk = t % m_tiles, n_blk = t / m_tiles;
       const int b = i & 1;
       const bool use_bias = epi.bias != nullptr && split == 0;
-      if (use_bias) tc_stage_bias<BN>(epi, sbias, (int64_t)n_blk * BN, r_in_tile);
+      if (use_bias) {                                          // the tile's bias slice, staged by all 256 epilogue threads
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+        for (int j = etid; j < BN; j += 256) sbias[j] = ((int64_t)n_blk * BN + j < epi.N) ? epi.bias[(int64_t)n_blk * BN + j] : 0.f;
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+      }
       mbar_wait(&tmem_full_bar[b], ((uint32_t)i >> 1) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int64_t row0 = (int64_t)m_blk * TC_BM;
       const int64_t row = row0 + r_in_tile;
       const bool row_ok = row < epi.M;
+      if (last_c < 0) {                                        // nothing to read: hand the accumulator straight back
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[b])) : "memory");
+      }
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = 0; c < n_chunks; ++c) {
+        if (((c / chunks_per_box) & 1) != eg) continue;        // the other group's box
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(b * TC_BN + c * 32), r);
-        if (c == BN / 32 - 1) {
+        if (c == last_c) {
           // the accumulator is in registers: hand the TMEM buffer back before the (slow) global stores
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
@@ -400,13 +421,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         float v[32];
         tc_chunk_math(epi, r, v, row, n0, row_ok, use_bias ? sbias + c * 32 : nullptr);
-        uint8_t* box = smemC + (box_count & 1u) * TC_STORE_BOX_BYTES;
+        if (c % chunks_per_box == 0) {
+          // first chunk of a box: the group's previous store must have finished READING the staging box
+          if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          group_sync();
+        }
         if (narrow) tc_stage_chunk64(box, r_in_tile, v);
         else tc_stage_chunk(box, r_in_tile, v, epi.c_dtype, c % chunks_per_box);
         if ((c + 1) % chunks_per_box == 0) {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          epi_bar_sync();
+          group_sync();
           if (issuer) {
             const int col0 = (int)((int64_t)n_blk * BN + (c + 1 - chunks_per_box) * 32);
             if (col0 < epi.N && row0 < epi.M) {
@@ -414,7 +438,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
           }
-          ++box_count;
         }
       }
     }
@@ -767,7 +790,7 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const CUtenso
   const int m_tiles = (int)grid.y, n_tiles = (int)grid.x;
   const int ctas = (int)std::min<int64_t>((int64_t)m_tiles * n_tiles * splits, (int64_t)num_sms());
   // programmatic stream serialization: the kernel calls griddepcontrol.wait before it touches A, C or the residual
-  cudaError_t e = launch_pdl(gemm_tc_kernel<A_MN, B_MN, BN>, dim3(ctas), dim3(TC_THREADS), TC_SMEM, st, ma, mb, mc, kblocks, m_tiles,
+  cudaError_t e = launch_pdl(gemm_tc_kernel<A_MN, B_MN, BN>, dim3(ctas), dim3(TC_EPI2_THREADS), TC_SMEM, st, ma, mb, mc, kblocks, m_tiles,
                              n_tiles, splits, b_is_weight, epi);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   if (e != cudaSuccess) {
