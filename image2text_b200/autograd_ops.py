@@ -97,18 +97,22 @@ class LinearFn(torch.autograd.Function):
             # the gradient that comes back with the same pitch satisfies TMA's 16-byte row-pitch rule for dgrad / wgrad
             N = w_c.shape[0]
             out = torch.empty((x2d.shape[0], (N + 7) // 8 * 8), device=x2d.device, dtype=out_dtype)[:, :N]
+        # B operand = a parameter (or its bf16 shadow): nothing between two optimiser steps writes it, and the kernels that do
+        # (optimiser, EMA, shadow refresh) never trigger their dependents early -- the GEMM may fetch its first weight tiles
+        # before the previous kernel has finished (I2T_GEMM_B_STABLE)
+        bs = isinstance(w, torch.nn.Parameter)
         if drop is not None:
             assert act == ops.ACT_NONE and out is None and out_dtype == torch.float32
             z = None
-            y = ops.dropout_add(ops.gemm(x2d, w_c, bias=bias, out_dtype=x2d.dtype), residual, drop)
+            y = ops.dropout_add(ops.gemm(x2d, w_c, bias=bias, out_dtype=x2d.dtype, b_stable=bs), residual, drop)
         elif need and act != ops.ACT_NONE:
-            z = ops.gemm(x2d, w_c, bias=bias, out_dtype=x2d.dtype)
+            z = ops.gemm(x2d, w_c, bias=bias, out_dtype=x2d.dtype, b_stable=bs)
             y = torch.empty(z.shape, device=z.device, dtype=out_dtype)
             call("i2t_act_fwd", ptr(z), ptr(y), z.numel(), act, dt(z), dt(y), stream())
             assert residual is None
         else:
             z = None
-            y = ops.gemm(x2d, w_c, bias=bias, residual=residual, act=act, out_dtype=out_dtype, out=out)
+            y = ops.gemm(x2d, w_c, bias=bias, residual=residual, act=act, out_dtype=out_dtype, out=out, b_stable=bs)
         if tok_drop is not None:
             site, seg, nseg = tok_drop
             ops.token_dropout_(y, seg, nseg, site)
@@ -119,6 +123,7 @@ class LinearFn(torch.autograd.Function):
             ctx.has_res = residual is not None
             ctx.res_dtype = residual.dtype if residual is not None else None
             ctx.drop, ctx.tok_drop = drop, tok_drop
+            ctx.b_stable = bs
             ctx.sink_w, ctx.sink_b = _sinks_of(ctx, w, bias, sink)
         return y
 
@@ -136,7 +141,7 @@ class LinearFn(torch.autograd.Function):
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             # dX[M,K] = dY[M,N] W[N,K]
-            dx = ops.gemm(g, w_c, out_dtype=x2d.dtype, a_kmajor=True, b_kmajor=False)
+            dx = ops.gemm(g, w_c, out_dtype=x2d.dtype, a_kmajor=True, b_kmajor=False, b_stable=ctx.b_stable)
         if ctx.needs_input_grad[1]:
             # dW[N,K] = dY^T[N,M] X[M,K]  (fp32 master gradient)
             M, N = g.shape
@@ -390,18 +395,19 @@ class Conv1DFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x2d, w, w_c, bias, residual, act, out_dtype, drop=None):
         need = any(ctx.needs_input_grad)
+        bs = isinstance(w, torch.nn.Parameter)                # (see LinearFn: weights are stable between optimiser steps)
         if drop is not None:                                  # HF resid_pdrop before the residual add
             assert act == ops.ACT_NONE and out_dtype == torch.float32
             z = None
-            y = ops.dropout_add(ops.gemm(x2d, w_c, bias=bias, out_dtype=x2d.dtype, b_kmajor=False), residual, drop)
+            y = ops.dropout_add(ops.gemm(x2d, w_c, bias=bias, out_dtype=x2d.dtype, b_kmajor=False, b_stable=bs), residual, drop)
         elif need and act != ops.ACT_NONE:
-            z = ops.gemm(x2d, w_c, bias=bias, out_dtype=x2d.dtype, b_kmajor=False)
+            z = ops.gemm(x2d, w_c, bias=bias, out_dtype=x2d.dtype, b_kmajor=False, b_stable=bs)
             y = torch.empty(z.shape, device=z.device, dtype=out_dtype)
             call("i2t_act_fwd", ptr(z), ptr(y), z.numel(), act, dt(z), dt(y), stream())
             assert residual is None
         else:
             z = None
-            y = ops.gemm(x2d, w_c, bias=bias, residual=residual, act=act, out_dtype=out_dtype, b_kmajor=False)
+            y = ops.gemm(x2d, w_c, bias=bias, residual=residual, act=act, out_dtype=out_dtype, b_kmajor=False, b_stable=bs)
         if need:
             ctx.save_for_backward(x2d, w_c, z)
             ctx.act = act
@@ -409,6 +415,7 @@ class Conv1DFn(torch.autograd.Function):
             ctx.has_res = residual is not None
             ctx.res_dtype = residual.dtype if residual is not None else None
             ctx.drop = drop
+            ctx.b_stable = bs
             ctx.sink_w, ctx.sink_b = _sinks_of(ctx, w, bias, None)
         return y
 
@@ -424,7 +431,7 @@ class Conv1DFn(torch.autograd.Function):
             g = dz
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = ops.gemm(g, w_c, out_dtype=x2d.dtype, a_kmajor=True, b_kmajor=True)          # dX = dY W^T, W (K,N) is [n'][k']
+            dx = ops.gemm(g, w_c, out_dtype=x2d.dtype, a_kmajor=True, b_kmajor=True, b_stable=ctx.b_stable)   # dX = dY W^T, W (K,N) is [n'][k']
         if ctx.needs_input_grad[1]:
             M, N = g.shape
             K = x2d.shape[1]
