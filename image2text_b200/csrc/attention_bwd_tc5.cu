@@ -81,24 +81,17 @@ __device__ __forceinline__ void b5_visible(int mode, int n_prompt, int Tq, int T
 // 64-key panels prow / drow (128-byte rows, 16-byte chunks XOR-swizzled by the row like the TMA tiles).
 __device__ __forceinline__ void b5_softmax_half(uint32_t taddr_s, uint32_t taddr_dp, int kbase, int lo, int hi, float l2, float delta,
                                                 float scale, const DropArgs& drop, const DropKey& dkey, uint32_t rng_row, uint8_t* prow,
-                                                uint8_t* drow, int r, int dbg = 0) {
+                                                uint8_t* drow, int r) {
   const float scale_log2 = scale * 1.4426950408889634f;
-  if (dbg >= 3) return;
 #pragma unroll 1
   for (int c = 0; c < 2; ++c) {
     const int c0 = kbase + c * 32;                                  // first key of this 32-key chunk
     uint32_t sv[32], dpv[32];
-    if (dbg < 2) {
-      tmem_ld32(taddr_s + (uint32_t)(c * 32), sv);
-      tmem_ld32(taddr_dp + (uint32_t)(c * 32), dpv);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) sv[i] = dpv[i] = 0u;
-    }
+    tmem_ld32(taddr_s + (uint32_t)(c * 32), sv);
+    tmem_ld32(taddr_dp + (uint32_t)(c * 32), dpv);
     float* p = reinterpret_cast<float*>(sv);                        // P and dS are formed in place (register budget: 168 / thread)
     float* ds = reinterpret_cast<float*>(dpv);
-    if (dbg >= 1) {
-    } else if (c0 >= lo && c0 + 32 <= hi) {
+    if (c0 >= lo && c0 + 32 <= hi) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) p[i] = b5_ex2(fmaf(p[i], scale_log2, -l2));
     } else if (c0 + 32 > lo && c0 < hi) {
@@ -108,8 +101,7 @@ __device__ __forceinline__ void b5_softmax_half(uint32_t taddr_s, uint32_t taddr
 #pragma unroll
       for (int i = 0; i < 32; ++i) p[i] = 0.f;
     }
-    if (dbg >= 1) {
-    } else if (drop.thr != 0u) {     // the forward's masks: 8 Philox calls per 32 keys (rng.cuh: drop_attn4)
+    if (drop.thr != 0u) {     // the forward's masks: 8 Philox calls per 32 keys (rng.cuh: drop_attn4)
 #pragma unroll
       for (int bl = 0; bl < 2; ++bl) {
 #pragma unroll
@@ -590,7 +582,7 @@ attn_bwd_tc5r_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         b5_softmax_half(trow + B5_COL_S + (uint32_t)(wg * 64), trow + B5_COL_DP + (uint32_t)(wg * 64), j * B5_BK + wg * 64, lo, hi, l2i,
                         di, scale, drop, dkey, (uint32_t)(((int64_t)b * H + h) * Tq + qi), sP + wg * B5_TILE + r * 128,
-                        sdS + wg * B5_TILE + r * 128, r, dbg);
+                        sdS + wg * B5_TILE + r * 128, r);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         b5_arrive(&bar_p);
@@ -689,7 +681,7 @@ int attn_bwd_tc5r(const void* q, const void* k, const void* v, const void* out, 
     if (e != cudaSuccess) return fail(I2T_ERR_CUDA, "cudaFuncSetAttribute(attn_bwd_tc5r_kernel): %s", cudaGetErrorString(e));
     attr = true;
   }
-  static const int dbg = getenv("I2T_ATTN_BWD_DEBUG") ? atoi(getenv("I2T_ATTN_BWD_DEBUG")) : 0;   // timing experiments only
+  static const int dbg = (getenv("I2T_ATTN_BWD_DEBUG") && atoi(getenv("I2T_ATTN_BWD_DEBUG")) < 0) ? -1 : 0;   // -1: CTA (0,0) stamps its timeline
   dim3 grid((unsigned)H, (unsigned)B);
   (void)launch_pdl(attn_bwd_tc5r_kernel, grid, dim3(B5_THREADS), (size_t)R5_SMEM, st, mq, mk, mv, mdo, mo, lse, (__nv_bfloat16*)dq, (__nv_bfloat16*)dk, (__nv_bfloat16*)dv, (int)H, (int)Tq, (int)Tk, q_bs,
                    q_rs, kv_bs, kv_rs, mode, (int)n_prompt, 1.0f / sqrtf((float)head_dim), drop, dbg);
