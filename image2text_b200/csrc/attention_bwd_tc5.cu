@@ -101,7 +101,8 @@ __device__ __forceinline__ void b5_softmax_half(uint32_t taddr_s, uint32_t taddr
 #pragma unroll
       for (int i = 0; i < 32; ++i) p[i] = 0.f;
     }
-    if (drop.thr != 0u) {     // the forward's masks: 8 Philox calls per 32 keys (rng.cuh: drop_attn4)
+    if (drop.thr != 0u && c0 + 32 > lo && c0 < hi) {     // the forward's masks: 8 Philox calls per 32 keys (rng.cuh: drop_attn4);
+                                                         // a chunk without a visible key has P = 0 already
 #pragma unroll
       for (int bl = 0; bl < 2; ++bl) {
 #pragma unroll

@@ -208,7 +208,8 @@ attn_fwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
           for (int i = 0; i < 32; ++i) p[i] = 0.f;
         }
-        if (drop.thr != 0u) {   // dropout on the probabilities (l keeps every key): 8 Philox calls per 32 keys
+        if (drop.thr != 0u && c0 + 32 > lo && c0 < hi) {   // dropout on the probabilities (l keeps every key): 8 Philox calls per
+                                                           // 32 keys; chunks without a visible key are zero already
           const DropKey dkey = drop_key(drop);
           const uint32_t row = (uint32_t)(((int64_t)b * H + h) * Tq + qi);
 #pragma unroll
