@@ -101,24 +101,28 @@ __device__ __forceinline__ void b5_softmax_half(uint32_t taddr_s, uint32_t taddr
 #pragma unroll
       for (int i = 0; i < 32; ++i) p[i] = 0.f;
     }
-    if (drop.thr != 0u && c0 + 32 > lo && c0 < hi) {     // the forward's masks: 8 Philox calls per 32 keys (rng.cuh: drop_attn4);
+    if (drop.thr != 0u && c0 + 32 > lo && c0 < hi) {     // the forward's masks: 4 Philox calls per 32 keys (rng.cuh: drop_attn8);
                                                          // a chunk without a visible key has P = 0 already
 #pragma unroll
       for (int bl = 0; bl < 2; ++bl) {
 #pragma unroll
-        for (int pr = 0; pr < 4; ++pr) {
-          const Philox4 rr = drop_attn4(drop, dkey, rng_row, (uint32_t)(c0 >> 4) + bl, (uint32_t)pr);
-          const int e0 = bl * 16 + 2 * pr;
-          const float m0 = rr.x < drop.thr ? 0.f : drop.inv_keep, m1 = rr.y < drop.thr ? 0.f : drop.inv_keep;
-          const float m2 = rr.z < drop.thr ? 0.f : drop.inv_keep, m3 = rr.w < drop.thr ? 0.f : drop.inv_keep;
-          ds[e0] = p[e0] * (ds[e0] * m0 - delta) * scale;
-          ds[e0 + 1] = p[e0 + 1] * (ds[e0 + 1] * m1 - delta) * scale;
-          ds[e0 + 8] = p[e0 + 8] * (ds[e0 + 8] * m2 - delta) * scale;
-          ds[e0 + 9] = p[e0 + 9] * (ds[e0 + 9] * m3 - delta) * scale;
-          p[e0] *= m0;
-          p[e0 + 1] *= m1;
-          p[e0 + 8] *= m2;
-          p[e0 + 9] *= m3;
+        for (int hh = 0; hh < 2; ++hh) {                     // one call = 8 keys: pairs 2 hh and 2 hh + 1 of the 16-key block
+          const Philox4 rr = drop_attn8(drop, dkey, rng_row, (uint32_t)(c0 >> 4) + bl, (uint32_t)hh);
+#pragma unroll
+          for (int sp = 0; sp < 2; ++sp) {
+            const int e0 = bl * 16 + 2 * (2 * hh + sp);
+            const uint32_t w0 = sp == 0 ? rr.x : rr.z, w1 = sp == 0 ? rr.y : rr.w;
+            const float m0 = (w0 & 0xFFFFu) < drop.thr16 ? 0.f : drop.inv_keep, m1 = (w0 >> 16) < drop.thr16 ? 0.f : drop.inv_keep;
+            const float m2 = (w1 & 0xFFFFu) < drop.thr16 ? 0.f : drop.inv_keep, m3 = (w1 >> 16) < drop.thr16 ? 0.f : drop.inv_keep;
+            ds[e0] = p[e0] * (ds[e0] * m0 - delta) * scale;
+            ds[e0 + 1] = p[e0 + 1] * (ds[e0 + 1] * m1 - delta) * scale;
+            ds[e0 + 8] = p[e0 + 8] * (ds[e0 + 8] * m2 - delta) * scale;
+            ds[e0 + 9] = p[e0 + 9] * (ds[e0 + 9] * m3 - delta) * scale;
+            p[e0] *= m0;
+            p[e0 + 1] *= m1;
+            p[e0 + 8] *= m2;
+            p[e0 + 9] *= m3;
+          }
         }
       }
     } else {

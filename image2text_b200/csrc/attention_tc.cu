@@ -170,11 +170,12 @@ attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __r
         const uint32_t row = (uint32_t)(((int64_t)b * H + h) * Tq + qi);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
-          const Philox4 r = drop_attn4(drop, dkey, row, (uint32_t)(k0 >> 4) + kk, (uint32_t)tq);
-          if (r.x < drop.thr) s[2 * kk][half * 2] = 0.f;
-          if (r.y < drop.thr) s[2 * kk][half * 2 + 1] = 0.f;
-          if (r.z < drop.thr) s[2 * kk + 1][half * 2] = 0.f;
-          if (r.w < drop.thr) s[2 * kk + 1][half * 2 + 1] = 0.f;
+          const Philox4 r = drop_attn8(drop, dkey, row, (uint32_t)(k0 >> 4) + kk, (uint32_t)tq >> 1);
+          const int hb = (tq & 1) * 4;                     // this thread's four half-words of the call
+          if (philox_half(r, hb) < drop.thr16) s[2 * kk][half * 2] = 0.f;
+          if (philox_half(r, hb + 1) < drop.thr16) s[2 * kk][half * 2 + 1] = 0.f;
+          if (philox_half(r, hb + 2) < drop.thr16) s[2 * kk + 1][half * 2] = 0.f;
+          if (philox_half(r, hb + 3) < drop.thr16) s[2 * kk + 1][half * 2 + 1] = 0.f;
         }
       }
     }
@@ -341,15 +342,16 @@ attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __r
     for (int nt = 0; nt < 8; ++nt) {
       float mk[4] = {1.f, 1.f, 1.f, 1.f};
       if (drop.thr != 0u) {
-        // the forward's mask: for query qi the words of block (keys k0 + w*16 ..+15), pair (g >> 1) cover keys g and g + 8
-        // of this thread at lanes (g & 1) and 2 + (g & 1)
+        // the forward's mask: for query qi the half-words of block (keys k0 + w*16 ..+15), pair (g >> 1) cover keys g and g + 8
+        // of this thread at half-words 4 (pair & 1) + (g & 1) and + 2 (rng.cuh: drop_attn8)
 #pragma unroll
         for (int e1 = 0; e1 < 2; ++e1) {
           const int qi = q0 + nt * 8 + tq * 2 + e1;
-          const Philox4 r = drop_attn4(drop, dkey, (uint32_t)(((int64_t)b * H + h) * Tq + qi), (uint32_t)((k0 + w * 16) >> 4),
-                                       (uint32_t)(g >> 1) & 3u);
-          mk[e1] = philox_word(r, g & 1) >= drop.thr ? drop.inv_keep : 0.f;
-          mk[2 + e1] = philox_word(r, 2 + (g & 1)) >= drop.thr ? drop.inv_keep : 0.f;
+          const uint32_t pr = (uint32_t)(g >> 1) & 3u;
+          const Philox4 r = drop_attn8(drop, dkey, (uint32_t)(((int64_t)b * H + h) * Tq + qi), (uint32_t)((k0 + w * 16) >> 4), pr >> 1);
+          const int hb = (int)(pr & 1u) * 4;
+          mk[e1] = philox_half(r, hb + (g & 1)) >= drop.thr16 ? drop.inv_keep : 0.f;
+          mk[2 + e1] = philox_half(r, hb + 2 + (g & 1)) >= drop.thr16 ? drop.inv_keep : 0.f;
         }
       }
 #pragma unroll

@@ -208,19 +208,24 @@ attn_fwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
           for (int i = 0; i < 32; ++i) p[i] = 0.f;
         }
-        if (drop.thr != 0u && c0 + 32 > lo && c0 < hi) {   // dropout on the probabilities (l keeps every key): 8 Philox calls per
-                                                           // 32 keys; chunks without a visible key are zero already
+        if (drop.thr != 0u && c0 + 32 > lo && c0 < hi) {   // dropout on the probabilities (l keeps every key): 4 Philox calls per
+                                                           // 32 keys (16 bits per key); chunks without a visible key are zero already
           const DropKey dkey = drop_key(drop);
           const uint32_t row = (uint32_t)(((int64_t)b * H + h) * Tq + qi);
 #pragma unroll
           for (int bl = 0; bl < 2; ++bl) {
 #pragma unroll
-            for (int pr = 0; pr < 4; ++pr) {
-              const Philox4 rr = drop_attn4(drop, dkey, row, (uint32_t)((j * A5_BK + c * 32) >> 4) + bl, (uint32_t)pr);
-              if (rr.x < drop.thr) p[bl * 16 + 2 * pr] = 0.f;
-              if (rr.y < drop.thr) p[bl * 16 + 2 * pr + 1] = 0.f;
-              if (rr.z < drop.thr) p[bl * 16 + 8 + 2 * pr] = 0.f;
-              if (rr.w < drop.thr) p[bl * 16 + 9 + 2 * pr] = 0.f;
+            for (int hh = 0; hh < 2; ++hh) {                 // one call = 8 keys: pairs 2 hh and 2 hh + 1 of the 16-key block
+              const Philox4 rr = drop_attn8(drop, dkey, row, (uint32_t)((j * A5_BK + c * 32) >> 4) + bl, (uint32_t)hh);
+#pragma unroll
+              for (int sp = 0; sp < 2; ++sp) {
+                const int e0 = bl * 16 + 2 * (2 * hh + sp);
+                const uint32_t w0 = sp == 0 ? rr.x : rr.z, w1 = sp == 0 ? rr.y : rr.w;
+                if ((w0 & 0xFFFFu) < drop.thr16) p[e0] = 0.f;
+                if ((w0 >> 16) < drop.thr16) p[e0 + 1] = 0.f;
+                if ((w1 & 0xFFFFu) < drop.thr16) p[e0 + 8] = 0.f;
+                if ((w1 >> 16) < drop.thr16) p[e0 + 9] = 0.f;
+              }
             }
           }
         }

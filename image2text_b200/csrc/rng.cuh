@@ -15,6 +15,7 @@ struct DropArgs {
   const unsigned long long* state;   // device: [0] = seed, [1] = step offset
   uint32_t site;                     // which dropout call of the forward pass this is
   uint32_t thr;                      // keep iff random u32 >= thr; thr = round(p * 2^32)
+  uint32_t thr16;                    // attention-probability sites spend 16 random bits per key: keep iff u16 >= thr16 = round(p * 2^16)
   float inv_keep;                    // 1 / (1 - p)
 };
 
@@ -23,10 +24,13 @@ inline DropArgs make_drop(float p, const void* state, int64_t site) {
   d.state = (const unsigned long long*)state;
   d.site = (uint32_t)site;
   d.thr = 0u;
+  d.thr16 = 0u;
   d.inv_keep = 1.0f;
   if (p > 0.f && state != nullptr) {
     double t = (double)p * 4294967296.0 + 0.5;
     d.thr = t >= 4294967295.0 ? 4294967295u : (uint32_t)t;
+    const double t16 = (double)p * 65536.0 + 0.5;
+    d.thr16 = t16 >= 65535.0 ? 65535u : (uint32_t)t16;
     d.inv_keep = 1.0f / (1.0f - p);
   }
   return d;
@@ -62,19 +66,26 @@ __device__ __forceinline__ DropKey drop_key(const DropArgs& d) {
 __device__ __forceinline__ Philox4 drop_elem4(const DropArgs& d, const DropKey& k, uint64_t e4) {
   return philox4x32_10((uint32_t)e4, (uint32_t)(e4 >> 32), d.site, k.off, k.k0, k.k1);
 }
-// attention-probability sites: row = (b*H + h)*Tq + qi; the four words belong to keys
-//   kj = 16*blk + {2*pair, 2*pair + 1, 8 + 2*pair, 9 + 2*pair}        (blk = kj >> 4, pair = (kj >> 1) & 3)
-// i.e. exactly the four key columns one thread of an m16n8k16 accumulator pair owns in a query row.
-__device__ __forceinline__ Philox4 drop_attn4(const DropArgs& d, const DropKey& k, uint32_t row, uint32_t blk, uint32_t pair) {
-  return philox4x32_10(row, blk * 4u + pair, d.site | 0x80000000u, k.off, k.k0, k.k1);
+// attention-probability sites: row = (b*H + h)*Tq + qi.  One Philox call yields EIGHT 16-bit values (the Philox rounds, not the
+// softmax, dominated the dropout attention kernels: 16 bits per key halve the calls; p is resolved to 2^-16).  Call (blk, h) covers,
+// in the 16-key block blk = kj >> 4, the pairs t = 2h and 2h + 1 (t = (kj >> 1) & 3), i.e. keys 16 blk + {4h .. 4h+3, 4h+8 .. 4h+11};
+// half-word j = 4 (t & 1) + 2 ((kj >> 3) & 1) + (kj & 1) of the call belongs to key kj: half-words 4 (t & 1) + {0, 1, 2, 3} are the
+// four key columns {2t, 2t+1, 8+2t, 9+2t} one thread of an m16n8k16 accumulator pair owns in a query row.
+__device__ __forceinline__ Philox4 drop_attn8(const DropArgs& d, const DropKey& k, uint32_t row, uint32_t blk, uint32_t h) {
+  return philox4x32_10(row, blk * 2u + h, d.site | 0x80000000u, k.off, k.k0, k.k1);
 }
 __device__ __forceinline__ uint32_t philox_word(const Philox4& r, int lane) {
   return lane == 0 ? r.x : lane == 1 ? r.y : lane == 2 ? r.z : r.w;
 }
+__device__ __forceinline__ uint32_t philox_half(const Philox4& r, int j) {           // half-word j = 0..7
+  const uint32_t w = philox_word(r, j >> 1);
+  return (j & 1) ? (w >> 16) : (w & 0xFFFFu);
+}
 // single element (slow path: the fp32 parity kernels)
 __device__ __forceinline__ bool drop_attn_keep(const DropArgs& d, const DropKey& k, uint32_t row, int kj) {
-  const Philox4 r = drop_attn4(d, k, row, (uint32_t)kj >> 4, ((uint32_t)kj >> 1) & 3u);
-  return philox_word(r, (((uint32_t)kj >> 3) & 1u) * 2 + ((uint32_t)kj & 1u)) >= d.thr;
+  const uint32_t t = ((uint32_t)kj >> 1) & 3u;
+  const Philox4 r = drop_attn8(d, k, row, (uint32_t)kj >> 4, t >> 1);
+  return philox_half(r, (int)((t & 1u) * 4u + (((uint32_t)kj >> 3) & 1u) * 2u + ((uint32_t)kj & 1u))) >= d.thr16;
 }
 
 }  // namespace i2t

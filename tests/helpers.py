@@ -125,14 +125,21 @@ class DropMasks:
         return self._mult(np.stack(w[:3], axis=1), p)
 
     def attn(self, p, B, H, Tq, Tk):
+        """csrc/rng.cuh drop_attn8: 16 random bits per key; call (kj >> 4, t >> 1) with t = (kj >> 1) & 3, half-word
+        4 (t & 1) + 2 ((kj >> 3) & 1) + (kj & 1); keep iff the half-word >= round(p * 2^16)."""
         site = self._next()
         if p <= 0:
             return None
         row = np.arange(B * H * Tq, dtype=np.uint64)[:, None]
         kj = np.arange(Tk, dtype=np.uint64)[None, :]
-        c1 = (kj >> np.uint64(4)) * np.uint64(4) + ((kj >> np.uint64(1)) & np.uint64(3))
-        lane = (((kj >> np.uint64(3)) & np.uint64(1)) * np.uint64(2) + (kj & np.uint64(1))).astype(np.int64)
+        t = (kj >> np.uint64(1)) & np.uint64(3)
+        c1 = (kj >> np.uint64(4)) * np.uint64(2) + (t >> np.uint64(1))
+        half = ((t & np.uint64(1)) * np.uint64(4) + ((kj >> np.uint64(3)) & np.uint64(1)) * np.uint64(2) + (kj & np.uint64(1))).astype(np.int64)
         w = philox4x32_10(row, c1, site | 0x80000000, self.off, self.k0, self.k1)
         stacked = np.stack(w, axis=-1)                                   # (rows, Tk, 4)
-        words = np.take_along_axis(stacked, np.broadcast_to(lane[..., None], stacked.shape[:2] + (1,)), axis=-1)[..., 0]
-        return self._mult(words, p).reshape(B, H, Tq, Tk)
+        words = np.take_along_axis(stacked, np.broadcast_to((half >> 1)[..., None], stacked.shape[:2] + (1,)), axis=-1)[..., 0]
+        vals = (words.astype(np.uint64) >> (np.uint64(16) * (half & 1).astype(np.uint64))) & np.uint64(0xFFFF)
+        thr16 = min(int(p * 65536.0 + 0.5), 65535)
+        keep = vals >= np.uint64(thr16)
+        mult = torch.from_numpy(np.where(keep, np.float32(1.0 / (1.0 - p)), np.float32(0.0)).astype(np.float32))
+        return mult.reshape(B, H, Tq, Tk)
