@@ -92,6 +92,12 @@ class LinearFn(torch.autograd.Function):
     def forward(ctx, x2d, w, w_c, bias, residual, act, out_dtype, pad_rows=False, drop=None, tok_drop=None, sink=None):
         need = any(ctx.needs_input_grad)      # grad mode is always off inside Function.forward
         out = None
+        # an fp32 input of a bf16 linear (the final hidden state in front of the LM head) is cast HERE, not by an autograd node of
+        # its own: the data gradient then leaves the dgrad GEMM in fp32 directly (split-K eligible: K = 50257 at M = B*T rows),
+        # with no bf16 round trip and no cast kernel in the backward
+        x_dtype = x2d.dtype
+        if x2d.dtype != w_c.dtype:
+            x2d = x2d.to(w_c.dtype)
         if pad_rows and w_c.shape[0] % 8 != 0:
             # rows padded to a multiple of 8 elements (e.g. V = 50257 -> pitch 50264): the output is a strided view, and
             # the gradient that comes back with the same pitch satisfies TMA's 16-byte row-pitch rule for dgrad / wgrad
@@ -124,6 +130,7 @@ class LinearFn(torch.autograd.Function):
             ctx.res_dtype = residual.dtype if residual is not None else None
             ctx.drop, ctx.tok_drop = drop, tok_drop
             ctx.b_stable = bs
+            ctx.x_dtype = x_dtype
             ctx.sink_w, ctx.sink_b = _sinks_of(ctx, w, bias, sink)
         return y
 
@@ -141,7 +148,7 @@ class LinearFn(torch.autograd.Function):
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             # dX[M,K] = dY[M,N] W[N,K]
-            dx = ops.gemm(g, w_c, out_dtype=x2d.dtype, a_kmajor=True, b_kmajor=False, b_stable=ctx.b_stable)
+            dx = ops.gemm(g, w_c, out_dtype=ctx.x_dtype, a_kmajor=True, b_kmajor=False, b_stable=ctx.b_stable)
         if ctx.needs_input_grad[1]:
             # dW[N,K] = dY^T[N,M] X[M,K]  (fp32 master gradient)
             M, N = g.shape

@@ -277,7 +277,6 @@ def hf_gpt2_forward(W, spec, ids: torch.Tensor, encoder_output: torch.Tensor, cd
         x = c1d(lp + "mlp.c_proj", h, residual=x.view(B * T, C), dsite=_site(drop, pd)).view(B, T, C)
     hidden = _ln(W, dp + "ln_f.weight", dp + "ln_f.bias", x, 1e-5, torch.float32)
     text = hidden[:, n_prompt:, :].reshape(B * (T - n_prompt), C)
-    text = text if cd == torch.float32 else text.to(cd)
     logits = linear(text, W["decoder.backbone.lm_head.weight"], W.c("decoder.backbone.lm_head.weight"), None, None,
                     ops.ACT_NONE, cd, pad_rows=True).view(B, T - n_prompt, -1)
     return logits, hidden
@@ -343,7 +342,6 @@ def decoder_forward(W, spec, ids: torch.Tensor, encoder_output: torch.Tensor, cd
     hidden = _ln(W, dp + "ln_f.weight", dp + "ln_f.bias", x, 1e-5, torch.float32)
     # logits only for the text rows (the reference computes all rows, then slices [offset:], :132)
     text = hidden[:, n_prompt:, :].reshape(B * (T - n_prompt), C)
-    text = text if cd == torch.float32 else text.to(cd)
     # logits come out in the compute dtype (bf16 under the reference's autocast) with rows padded to a
     # multiple of 8 elements; the (B, T, V) result is a strided view of that buffer
     logits = linear(text, W["decoder.lm_head.weight"], W.c("decoder.lm_head.weight"), None, None, ops.ACT_NONE,
