@@ -74,6 +74,7 @@ SIGNATURES = {
     "i2t_l2norm_bwd": (c_int, [P, P, P, L, L, F, P]),
     "i2t_attn_fwd_dropout": (c_int, [P, P, P, P, P, L, L, L, L, L, L, L, L, L, I, L, I, I, F, P, L, P]),
     "i2t_attn_bwd_dropout": (c_int, [P, P, P, P, P, P, P, P, P, P, L, L, L, L, L, L, L, L, L, I, L, I, F, P, L, P]),
+    "i2t_attn_bwd_dropout_tok": (c_int, [P, P, P, P, P, P, P, P, P, P, L, L, L, L, L, L, I, L, I, F, P, L, F, L, P]),
     "i2t_dropout_add_fwd": (c_int, [P, P, P, L, F, P, L, I, P]),
     "i2t_dropout_bwd": (c_int, [P, P, L, F, P, L, I, I, P]),
     "i2t_token_dropout": (c_int, [P, L, L, L, L, F, P, L, I, P]),

@@ -120,7 +120,7 @@ class LinearFn(torch.autograd.Function):
             z = None
             y = ops.gemm(x2d, w_c, bias=bias, residual=residual, act=act, out_dtype=out_dtype, out=out, b_stable=bs)
         if tok_drop is not None:
-            site, seg, nseg = tok_drop
+            site, seg, nseg = tok_drop[:3]
             ops.token_dropout_(y, seg, nseg, site)
         if need:
             ctx.save_for_backward(x2d, w_c, z)
@@ -195,9 +195,9 @@ def _grad_in(dy, cd, drop, tok_drop):
         g = ops.dropout_bwd(dy.contiguous(), cd, drop)
     else:
         g = dy if dy.dtype == cd else dy.to(cd)      # autocast: the linear's grad flows in the activation dtype
-    if tok_drop is not None:
-        site, seg, nseg = tok_drop      # dy is the attention backward's freshly written dqkv: scaled in place
-        ops.token_dropout_(g, seg, nseg, site)
+    if tok_drop is not None and not (len(tok_drop) > 3 and tok_drop[3]):
+        site, seg, nseg = tok_drop[:3]  # dy is the attention backward's freshly written dqkv: scaled in place
+        ops.token_dropout_(g, seg, nseg, site)       # (4th element set: the attention backward has applied the masks already)
     return g
 
 
@@ -209,15 +209,18 @@ def linear(x2d, w, w_c, bias=None, residual=None, act=ops.ACT_NONE, out_dtype=to
 class AttnFn(torch.autograd.Function):
     """Self attention on a packed (B*T, 3C) qkv buffer: reference models/layers.py:465 (+ the mask algebra of
     vision_encoder_decoder.py:75-111 / layers.py:581-595 folded into `mask_mode`), torchvision :113.
-    `drop`: dropout_p of the SDPA call (training mode), regenerated -- not stored -- by the backward kernel."""
+    `drop`: dropout_p of the SDPA call (training mode), regenerated -- not stored -- by the backward kernel.
+    `tok`: the token-level q / k / v dropout site already applied to `qkv` by the producing linear; the backward then returns the
+    gradient of the packed buffer multiplied by those masks (the linear skips its own masking pass)."""
 
     @staticmethod
-    def forward(ctx, qkv, B, T, H, mask_mode, n_prompt, drop=None):
+    def forward(ctx, qkv, B, T, H, mask_mode, n_prompt, drop=None, tok=None):
         qkv = qkv.contiguous()
         if any(ctx.needs_input_grad):
             out, lse = ops.attention_packed(qkv, B, T, H, mask_mode, n_prompt, want_lse=True, drop=drop)
             ctx.save_for_backward(qkv, out, lse)
             ctx.meta = (B, T, H, mask_mode, n_prompt, drop)
+            ctx.tok = tok
         else:
             out = ops.attention_packed(qkv, B, T, H, mask_mode, n_prompt, drop=drop)
         return out
@@ -226,8 +229,9 @@ class AttnFn(torch.autograd.Function):
     def backward(ctx, dout):
         qkv, out, lse = ctx.saved_tensors
         B, T, H, mask_mode, n_prompt, drop = ctx.meta
-        dqkv = ops.attention_packed_bwd(qkv, out, dout.contiguous().to(qkv.dtype), lse, B, T, H, mask_mode, n_prompt, drop=drop)
-        return dqkv, None, None, None, None, None, None
+        dqkv = ops.attention_packed_bwd(qkv, out, dout.contiguous().to(qkv.dtype), lse, B, T, H, mask_mode, n_prompt, drop=drop,
+                                        tok=ctx.tok)
+        return dqkv, None, None, None, None, None, None, None
 
 
 class XAttnFn(torch.autograd.Function):

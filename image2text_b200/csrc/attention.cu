@@ -456,7 +456,7 @@ int attn_bwd_tc5(const void* q, const void* k, const void* v, const void* out, c
                  int64_t kv_bs, int64_t kv_rs, int mode, int64_t n_prompt, DropArgs drop, cudaStream_t st);
 int attn_bwd_tc5r(const void* q, const void* k, const void* v, const void* out, const void* dout, const float* lse, void* dq, void* dk,
                   void* dv, int64_t B, int64_t H, int64_t Tq, int64_t Tk, int64_t head_dim, int64_t q_bs, int64_t q_rs, int64_t kv_bs,
-                  int64_t kv_rs, int mode, int64_t n_prompt, DropArgs drop, cudaStream_t st);
+                  int64_t kv_rs, int mode, int64_t n_prompt, DropArgs drop, DropArgs tok, cudaStream_t st);
 // 0: fp32-math kernels; 1 (default): tensor cores -- tcgen05 forward where eligible, mma.sync otherwise; 2: mma.sync only
 static std::atomic<int> g_attn_tc{1};
 
@@ -527,14 +527,19 @@ template <typename T, int HS>
 static int launch_attn_bwd(const void* q, const void* k, const void* v, const void* out, const void* dout,
                            const float* lse, void* dq, void* dk, void* dv, float* ws, int64_t B, int64_t H, int64_t Tq,
                            int64_t Tk, int64_t q_bs, int64_t q_rs, int64_t kv_bs, int64_t kv_rs, int mode,
-                           int64_t n_prompt, DropArgs drop, cudaStream_t st) {
+                           int64_t n_prompt, DropArgs drop, cudaStream_t st, DropArgs tok = make_drop(0.f, nullptr, 0),
+                           bool* tok_done = nullptr) {
   // workspace: delta (B*H*Tq) then dq accumulator (B*H*Tq*HS), fp32
   float* delta = ws;
   float* dq_acc = ws + (B * H * Tq + 3) / 4 * 4;      // keep the accumulator 16-byte aligned (float4 reads in the scatter)
   if (sizeof(T) == 2 && g_attn_tc.load() == 1) {      // <= 256 rows: one tcgen05 kernel, no workspace
-    const int r = attn_bwd_tc5r(q, k, v, out, dout, lse, dq, dk, dv, B, H, Tq, Tk, HS, q_bs, q_rs, kv_bs, kv_rs, mode, n_prompt, drop, st);
+    const int r = attn_bwd_tc5r(q, k, v, out, dout, lse, dq, dk, dv, B, H, Tq, Tk, HS, q_bs, q_rs, kv_bs, kv_rs, mode, n_prompt, drop,
+                                tok, st);
     if (r < 0) return r;
-    if (r == 1) return I2T_OK;
+    if (r == 1) {
+      if (tok_done != nullptr) *tok_done = true;       // the kernel scaled dq / dk / dv by the token masks on its way out
+      return I2T_OK;
+    }
   }
   I2T_CUDA(cudaMemsetAsync(dq_acc, 0, (size_t)(B * H * Tq * HS) * sizeof(float), st));
   if (sizeof(T) == 2 && g_attn_tc.load() == 1) {      // tcgen05 backward: computes delta itself
@@ -589,7 +594,7 @@ static int attn_bwd_impl(const void* q, const void* k, const void* v, const void
                          const float* lse, void* dq, void* dk, void* dv, void* workspace, int64_t B, int64_t H,
                          int64_t Tq, int64_t Tk, int64_t head_dim, int64_t q_batch_stride, int64_t q_row_stride,
                          int64_t kv_batch_stride, int64_t kv_row_stride, int mask_mode, int64_t n_prompt, int dtype,
-                         DropArgs drop, void* stream) {
+                         DropArgs drop, void* stream, DropArgs tok = make_drop(0.f, nullptr, 0), bool* tok_done = nullptr) {
   I2T_REQUIRE(q && k && v && out && dout && lse && dq && dk && dv && workspace, "attn_bwd: null pointer");
   I2T_REQUIRE(B > 0 && H > 0 && Tq > 0 && Tk > 0 && B <= 65535 && H <= 65535, "attn_bwd: bad sizes");
   I2T_REQUIRE(head_dim == 64 || head_dim == 32, "attn_bwd: head_dim %lld not built (32, 64)", (long long)head_dim);
@@ -599,7 +604,7 @@ static int attn_bwd_impl(const void* q, const void* k, const void* v, const void
   cudaStream_t st = (cudaStream_t)stream;
   float* ws = (float*)workspace;
 #define I2T_ATTB(T, HSV) \
-  return launch_attn_bwd<T, HSV>(q, k, v, out, dout, lse, dq, dk, dv, ws, B, H, Tq, Tk, q_batch_stride, q_row_stride, kv_batch_stride, kv_row_stride, mask_mode, n_prompt, drop, st)
+  return launch_attn_bwd<T, HSV>(q, k, v, out, dout, lse, dq, dk, dv, ws, B, H, Tq, Tk, q_batch_stride, q_row_stride, kv_batch_stride, kv_row_stride, mask_mode, n_prompt, drop, st, tok, tok_done)
   if (dtype == I2T_F32) {
     if (head_dim == 64) I2T_ATTB(float, 64);
     I2T_ATTB(float, 32);
@@ -618,6 +623,33 @@ extern "C" int i2t_attn_bwd(const void* q, const void* k, const void* v, const v
                             void* stream) {
   return attn_bwd_impl(q, k, v, out, dout, lse, dq, dk, dv, workspace, B, H, Tq, Tk, head_dim, q_batch_stride, q_row_stride,
                        kv_batch_stride, kv_row_stride, mask_mode, n_prompt, dtype, make_drop(0.f, nullptr, 0), stream);
+}
+
+extern "C" int i2t_token_dropout(void* x, int64_t rows, int64_t ld, int64_t seg, int64_t nseg, float p, const void* rng_state,
+                                 int64_t site, int dtype, void* stream);
+
+// i2t_attn_bwd_dropout for the packed self-attention buffer of reference models/layers.py:447-469, plus the BACKWARD of the token-level
+// q / k / v dropout (:454-461) that was applied to that buffer in the forward: dq / dk / dv (the three C-wide segments of one
+// (B*T, 3C) gradient buffer) come out multiplied by the (row, segment) masks of `tok_site`.  The tcgen05 kernel does it while it
+// stores its accumulators; any other kernel is followed by the stand-alone token-dropout pass -- same result either way.
+extern "C" int i2t_attn_bwd_dropout_tok(const void* q, const void* k, const void* v, const void* out, const void* dout,
+                                        const float* lse, void* dq, void* dk, void* dv, void* workspace, int64_t B, int64_t H,
+                                        int64_t T, int64_t head_dim, int64_t batch_stride, int64_t row_stride, int mask_mode,
+                                        int64_t n_prompt, int dtype, float p_drop, const void* rng_state, int64_t site, float p_tok,
+                                        int64_t tok_site, void* stream) {
+  I2T_REQUIRE(p_drop >= 0.f && p_drop < 1.f && p_tok > 0.f && p_tok < 1.f, "attn_bwd_dropout_tok: p must be in [0,1) / (0,1)");
+  I2T_REQUIRE(rng_state != nullptr, "attn_bwd_dropout_tok: rng_state is null");
+  const int64_t C = H * head_dim;
+  const size_t es = dtype == I2T_F32 ? 4 : 2;
+  I2T_REQUIRE(dq && (const char*)dk == (const char*)dq + C * es && (const char*)dv == (const char*)dq + 2 * C * es && row_stride >= 3 * C,
+              "attn_bwd_dropout_tok: dq / dk / dv must be the three segments of one packed gradient buffer");
+  bool done = false;
+  const int rc = attn_bwd_impl(q, k, v, out, dout, lse, dq, dk, dv, workspace, B, H, T, T, head_dim, batch_stride, row_stride,
+                               batch_stride, row_stride, mask_mode, n_prompt, dtype, make_drop(p_drop, rng_state, site), stream,
+                               make_drop(p_tok, rng_state, tok_site), &done);
+  if (rc != I2T_OK || done) return rc;
+  I2T_REQUIRE(batch_stride == T * row_stride, "attn_bwd_dropout_tok: batches must be row-contiguous");
+  return i2t_token_dropout(dq, B * T, row_stride, C, 3, p_tok, rng_state, tok_site, dtype, stream);
 }
 
 extern "C" int i2t_attn_bwd_dropout(const void* q, const void* k, const void* v, const void* out, const void* dout,

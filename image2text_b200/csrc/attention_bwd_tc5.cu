@@ -151,14 +151,14 @@ __device__ __forceinline__ void b5_softmax_half(uint32_t taddr_s, uint32_t taddr
 // per warp instruction (the LSU serialises them: measured 1.6 us per 128 x 64 tile pair, and the store storm also held up the MMA
 // thread's next issue).  Instead the bf16 tile is staged in shared memory (128-byte rows, chunks XOR-swizzled by the row) and the
 // 256 softmax threads write it out 8 lanes per row: 4 rows = 4 lines per warp instruction.
-__device__ __forceinline__ void b5_stage32(const uint32_t (&v)[32], uint8_t* tile, int r, int wg) {
+__device__ __forceinline__ void b5_stage32(const uint32_t (&v)[32], uint8_t* tile, int r, int wg, float sc = 1.f) {
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
     uint4 pk;
-    pk.x = b5_pack(__uint_as_float(v[8 * t]), __uint_as_float(v[8 * t + 1]));
-    pk.y = b5_pack(__uint_as_float(v[8 * t + 2]), __uint_as_float(v[8 * t + 3]));
-    pk.z = b5_pack(__uint_as_float(v[8 * t + 4]), __uint_as_float(v[8 * t + 5]));
-    pk.w = b5_pack(__uint_as_float(v[8 * t + 6]), __uint_as_float(v[8 * t + 7]));
+    pk.x = b5_pack(__uint_as_float(v[8 * t]) * sc, __uint_as_float(v[8 * t + 1]) * sc);
+    pk.y = b5_pack(__uint_as_float(v[8 * t + 2]) * sc, __uint_as_float(v[8 * t + 3]) * sc);
+    pk.z = b5_pack(__uint_as_float(v[8 * t + 4]) * sc, __uint_as_float(v[8 * t + 5]) * sc);
+    pk.w = b5_pack(__uint_as_float(v[8 * t + 6]) * sc, __uint_as_float(v[8 * t + 7]) * sc);
     *reinterpret_cast<uint4*>(tile + r * 128 + (((wg * 4 + t) ^ (r & 7)) << 4)) = pk;
   }
 }
@@ -402,7 +402,7 @@ attn_bwd_tc5r_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                      const __grid_constant__ CUtensorMap tmO, const float* __restrict__ lse,
                      __nv_bfloat16* __restrict__ dq, __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv, int H, int Tq, int Tk,
                      int64_t q_bs, int64_t q_rs, int64_t kv_bs, int64_t kv_rs, int mode, int n_prompt, float scale, DropArgs drop,
-                     int dbg) {
+                     DropArgs tok, int dbg) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t pad = ((raw + 1023u) & ~1023u) - raw;
@@ -541,8 +541,9 @@ attn_bwd_tc5r_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const int r = wq * 32 + lane;
     const uint32_t trow = tmem_base + ((uint32_t)(wq * 32) << 16);
     const bool trace_c = trace_on && threadIdx.x == 128;
-    DropKey dkey{0u, 0u, 0u};
+    DropKey dkey{0u, 0u, 0u}, tkey{0u, 0u, 0u};
     if (drop.thr != 0u) dkey = drop_key(drop);
+    if (tok.thr != 0u) tkey = drop_key(tok);
     // ---- per-row scalars.  delta[i][r] = dO_i[r,:] . O_i[r,:]: warpgroup i takes query block i, both rows come from the swizzled
     // shared-memory tiles (O_i is parked in P panel i, whose row r only this thread writes later), exchanged through s_delta ----
     float l2[2], delta[2];
@@ -605,12 +606,25 @@ attn_bwd_tc5r_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             b5_arrive(&bar_kvfree);
           }
           // the pair's MMAs are complete: the P / dS panels are free until the next softmax
-          b5_stage32(v0, sP, r, wg);
-          b5_stage32(v1, sP + B5_TILE, r, wg);
+          // token-level q / k / v dropout of the reference's attention (models/layers.py:454-461), backward half: the gradient of
+          // the packed qkv buffer is scaled per (row, segment) on its way out instead of by a separate pass over the buffer
+          float kd = 1.f, vd = 1.f;
+          if (tok.thr != 0u) {
+            const Philox4 tr = drop_elem4(tok, tkey, (uint64_t)((int64_t)b * Tk + kj));
+            kd = tr.y >= tok.thr ? tok.inv_keep : 0.f;
+            vd = tr.z >= tok.thr ? tok.inv_keep : 0.f;
+          }
+          b5_stage32(v0, sP, r, wg, vd);
+          b5_stage32(v1, sP + B5_TILE, r, wg, kd);
           if (j + 1 == nk) {                                             // last key block: dQ_0 / dQ_1 are complete as well
             for (int i2 = 0; i2 < nq; ++i2) {
               tmem_ld32(trow + B5_COL_DQ + (uint32_t)(64 * i2 + wg * 32), v0);
-              b5_stage32(v0, sdS + i2 * B5_TILE, r, wg);
+              float qd = 1.f;
+              if (tok.thr != 0u) {
+                const Philox4 tr = drop_elem4(tok, tkey, (uint64_t)((int64_t)b * Tq + i2 * B5_BQ + r));
+                qd = tr.x >= tok.thr ? tok.inv_keep : 0.f;
+              }
+              b5_stage32(v0, sdS + i2 * B5_TILE, r, wg, qd);
             }
           }
           b5_sync_softmax_warps();
@@ -659,7 +673,7 @@ namespace i2t {
 // returns 1 when it handled the call (dq, dk, dv written; no workspace used), 0 when the shape is not eligible
 int attn_bwd_tc5r(const void* q, const void* k, const void* v, const void* out, const void* dout, const float* lse, void* dq, void* dk,
                   void* dv, int64_t B, int64_t H, int64_t Tq, int64_t Tk, int64_t head_dim, int64_t q_bs, int64_t q_rs, int64_t kv_bs,
-                  int64_t kv_rs, int mode, int64_t n_prompt, DropArgs drop, cudaStream_t st) {
+                  int64_t kv_rs, int mode, int64_t n_prompt, DropArgs drop, DropArgs tok, cudaStream_t st) {
   if (head_dim != B5_HS || Tq > 2 * B5_BQ || Tk > 2 * B5_BK) return 0;
   if (mode != I2T_MASK_NONE && Tk > Tq && (Tk + B5_BK - 1) / B5_BK > (Tq + B5_BQ - 1) / B5_BQ) return 0;
   if (q_bs != Tq * q_rs || kv_bs != Tk * kv_rs) return 0;
@@ -689,7 +703,7 @@ int attn_bwd_tc5r(const void* q, const void* k, const void* v, const void* out, 
   static const int dbg = (getenv("I2T_ATTN_BWD_DEBUG") && atoi(getenv("I2T_ATTN_BWD_DEBUG")) < 0) ? -1 : 0;   // -1: CTA (0,0) stamps its timeline
   dim3 grid((unsigned)H, (unsigned)B);
   (void)launch_pdl(attn_bwd_tc5r_kernel, grid, dim3(B5_THREADS), (size_t)R5_SMEM, st, mq, mk, mv, mdo, mo, lse, (__nv_bfloat16*)dq, (__nv_bfloat16*)dk, (__nv_bfloat16*)dv, (int)H, (int)Tq, (int)Tk, q_bs,
-                   q_rs, kv_bs, kv_rs, mode, (int)n_prompt, 1.0f / sqrtf((float)head_dim), drop, dbg);
+                   q_rs, kv_bs, kv_rs, mode, (int)n_prompt, 1.0f / sqrtf((float)head_dim), drop, tok, dbg);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(I2T_ERR_CUDA, "attn_bwd_tc5r launch failed: %s", cudaGetErrorString(e));

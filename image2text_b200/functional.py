@@ -317,9 +317,10 @@ def decoder_forward(W, spec, ids: torch.Tensor, encoder_output: torch.Tensor, cd
         lp = f"{dp}h.{depth}."
         y, x = _ln_skip(W, lp + "ln_1.weight", lp + "ln_1.bias", x, 1e-5, cd)
         ts = _site(drop, pa)
+        # the backward of the token-level q / k / v masks rides on the attention backward (AttnFn `tok`), not on a pass of its own
         qkv = _lin(W, lp + "attn.c_attn.weight", lp + "attn.c_attn.bias", y.view(B * T, C), out_dtype=cd,
-                   tok_drop=(ts, C, 3) if ts is not None else None)
-        a = AttnFn.apply(qkv, B, T, H, mask_mode, n_prompt, _site(drop, pd))
+                   tok_drop=(ts, C, 3, True) if ts is not None else None)
+        a = AttnFn.apply(qkv, B, T, H, mask_mode, n_prompt, _site(drop, pd), ts)
         x = _lin(W, lp + "attn.c_proj.weight", lp + "attn.c_proj.bias", a, residual=x.view(B * T, C),
                  drop=_site(drop, pd)).view(B, T, C)
         use_cross = cross is not None and (depth % 2 == 0 if spec["skip_alternate_cross_attn"] else True)

@@ -208,7 +208,10 @@ def attention_packed(qkv: torch.Tensor, B: int, T: int, H: int, mask_mode: int, 
     return (out, lse) if want_lse else out
 
 
-def attention_packed_bwd(qkv, out, dout, lse, B, T, H, mask_mode, n_prompt, drop: Optional[DropSite] = None):
+def attention_packed_bwd(qkv, out, dout, lse, B, T, H, mask_mode, n_prompt, drop: Optional[DropSite] = None,
+                         tok: Optional[DropSite] = None):
+    """`tok`: the token-level q / k / v dropout site the forward applied to `qkv` (token_dropout_): the returned gradient of the packed
+    buffer is already multiplied by those masks (by the tcgen05 kernel on its way out, or by a trailing pass)."""
     C = qkv.shape[1] // 3
     hs = C // H
     dqkv = torch.empty_like(qkv)
@@ -217,6 +220,12 @@ def attention_packed_bwd(qkv, out, dout, lse, B, T, H, mask_mode, n_prompt, drop
     ws = torch.empty(ws_bytes, device=qkv.device, dtype=torch.uint8)
     es = qkv.element_size()
     b0, d0 = qkv.data_ptr(), dqkv.data_ptr()
+    if tok is not None:
+        assert drop is None or drop.state is tok.state
+        call("i2t_attn_bwd_dropout_tok", b0, b0 + C * es, b0 + 2 * C * es, ptr(out), ptr(dout), ptr(lse), d0, d0 + C * es, d0 + 2 * C * es,
+             ptr(ws), B, H, T, hs, T * 3 * C, 3 * C, mask_mode, n_prompt, dt(qkv), drop.p if drop is not None else 0.0, ptr(tok.state),
+             drop.site if drop is not None else 0, tok.p, tok.site, stream())
+        return dqkv
     _attn_bwd(drop, b0, b0 + C * es, b0 + 2 * C * es, ptr(out), ptr(dout), ptr(lse), d0, d0 + C * es, d0 + 2 * C * es,
               ptr(ws), B, H, T, T, hs, T * 3 * C, 3 * C, T * 3 * C, 3 * C, mask_mode, n_prompt, dt(qkv))
     return dqkv

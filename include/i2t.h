@@ -357,6 +357,13 @@ int i2t_attn_bwd_dropout(const void* q, const void* k, const void* v, const void
                          int64_t head_dim, int64_t q_batch_stride, int64_t q_row_stride, int64_t kv_batch_stride,
                          int64_t kv_row_stride, int mask_mode, int64_t n_prompt, int dtype, float p_drop,
                          const void* rng_state, int64_t site, void* stream);
+/* The same for the packed self-attention buffer (q, k, v = the three C-wide segments of one (B*T, 3C) buffer, likewise dq / dk / dv),
+ * plus the backward of the token-level q / k / v dropout of models/layers.py:454-461 that the forward applied to that buffer
+ * (i2t_token_dropout with probability p_tok at site tok_site): the gradients come out multiplied by the (row, segment) masks. */
+int i2t_attn_bwd_dropout_tok(const void* q, const void* k, const void* v, const void* out, const void* dout, const float* lse,
+                             void* dq, void* dk, void* dv, void* workspace, int64_t B, int64_t H, int64_t T, int64_t head_dim,
+                             int64_t batch_stride, int64_t row_stride, int mask_mode, int64_t n_prompt, int dtype, float p_drop,
+                             const void* rng_state, int64_t site, float p_tok, int64_t tok_site, void* stream);
 /* out[i] = residual[i] + keep(i) * y[i] / (1-p)   (residual optional; out fp32; n % 4 == 0): resid_dropout
  * models/layers.py:469 + the residual add :596, _MLP.dropout :485 + :606, transformer.drop models/decoder.py:236-243 */
 int i2t_dropout_add_fwd(const void* y, const float* residual, float* out, int64_t n, float p, const void* rng_state,

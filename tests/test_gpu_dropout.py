@@ -272,3 +272,24 @@ def test_hf_gpt2_layout_dropout_matches_oracle():
     named = dict(m.named_parameters())
     for k in keys:
         assert rel_err(named[k].grad.cpu(), sdo[k].grad) < 1e-3, k
+
+
+@pytest.mark.parametrize("B,T,H,dtype", [(2, 256, 3, torch.bfloat16), (2, 197, 2, torch.bfloat16), (1, 272, 2, torch.bfloat16),
+                                         (2, 70, 2, torch.float32)])
+def test_token_dropout_backward_rides_on_the_attention_backward(B, T, H, dtype):
+    """attention_packed_bwd(tok=site) == attention_packed_bwd followed by token_dropout_ on the packed gradient: the tcgen05 kernel
+    scales dq / dk / dv by the (row, segment) masks while it stores them (<= 256 rows), every other kernel is followed by the
+    stand-alone pass inside the same C call."""
+    C = H * 64
+    qkv = rnd(B * T, 3 * C, seed=21).to(DEV).to(dtype)
+    dout = rnd(B * T, C, seed=22).to(DEV).to(dtype)
+    st = state()
+    drop, tok = ops.DropSite(0.1, st, 5), ops.DropSite(0.2, st, 6)
+    out, lse = ops.attention_packed(qkv, B, T, H, ops.MASK_CAUSAL, 0, want_lse=True, drop=drop)
+    want = ops.attention_packed_bwd(qkv, out, dout, lse, B, T, H, ops.MASK_CAUSAL, 0, drop=drop)
+    ops.token_dropout_(want, C, 3, tok)
+    got = ops.attention_packed_bwd(qkv, out, dout, lse, B, T, H, ops.MASK_CAUSAL, 0, drop=drop, tok=tok)
+    zeros = (want == 0).all(dim=0).sum()                    # whole columns are never zero; whole (row, segment) blocks are
+    assert float((want.float().abs().sum(dim=1) == 0).float().mean()) < 0.05 and int(zeros) == 0
+    assert rel_err(got.float().cpu(), want.float().cpu()) < (1e-2 if dtype == torch.bfloat16 else 1e-6)
+    assert torch.equal(got == 0, want == 0)                 # exactly the same (row, segment) blocks are dropped
