@@ -69,8 +69,10 @@ __global__ void __launch_bounds__(128) ln_fwd_kernel(const TX* __restrict__ x, c
 // Backward.  Each CTA (4 warps) walks rows with a grid stride; every lane keeps the dgamma/dbeta partial
 // sums of the columns it owns in registers, reduced across the CTA's warps in shared memory and
 // flushed with one atomicAdd per column per CTA.
-template <typename TDY, typename TX, typename TDX, int MAXV>
-__global__ void __launch_bounds__(128, MAXV <= 6 ? 4 : 1) ln_bwd_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x,
+// WG: dgamma / dbeta wanted; without them (frozen LayerNorms, most of nano.yaml) the column accumulators go: 48 registers less,
+// 6 CTAs per SM instead of 4.
+template <typename TDY, typename TX, typename TDX, int MAXV, bool WG>
+__global__ void __launch_bounds__(128, MAXV <= 6 ? (WG ? 4 : 6) : 1) ln_bwd_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x,
                                                      const float* __restrict__ gamma, const float* __restrict__ mean,
                                                      const float* __restrict__ rstd, const TDX* __restrict__ dx_add,
                                                      TDX* __restrict__ dx, float* __restrict__ dgamma,
@@ -80,9 +82,9 @@ __global__ void __launch_bounds__(128, MAXV <= 6 ? 4 : 1) ln_bwd_kernel(const TD
   pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = cols >> 2;
-  float4 ag[MAXV], ab[MAXV];
+  float4 ag[WG ? MAXV : 1], ab[WG ? MAXV : 1];
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < (WG ? MAXV : 1); ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int64_t row = (int64_t)blockIdx.x * 4 + warp; row < rows; row += (int64_t)gridDim.x * 4) {
     const TDY* dyr = dy + row * (int64_t)cols;
     const TX* xr = x + row * (int64_t)cols;
@@ -95,8 +97,10 @@ __global__ void __launch_bounds__(128, MAXV <= 6 ? 4 : 1) ln_bwd_kernel(const TD
       if (c < nvec) {
         const float4 d = load4(dyr + c * 4), xv = load4(xr + c * 4), g = load4(gamma + c * 4);
         xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-        ag[i].x += d.x * xh[i].x; ag[i].y += d.y * xh[i].y; ag[i].z += d.z * xh[i].z; ag[i].w += d.w * xh[i].w;
-        ab[i].x += d.x; ab[i].y += d.y; ab[i].z += d.z; ab[i].w += d.w;
+        if (WG) {
+          ag[i].x += d.x * xh[i].x; ag[i].y += d.y * xh[i].y; ag[i].z += d.z * xh[i].z; ag[i].w += d.w * xh[i].w;
+          ab[i].x += d.x; ab[i].y += d.y; ab[i].z += d.z; ab[i].w += d.w;
+        }
         g_[i] = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
         s1 += (g_[i].x + g_[i].y) + (g_[i].z + g_[i].w);
         s2 += (g_[i].x * xh[i].x + g_[i].y * xh[i].y) + (g_[i].z * xh[i].z + g_[i].w * xh[i].w);
@@ -123,7 +127,7 @@ __global__ void __launch_bounds__(128, MAXV <= 6 ? 4 : 1) ln_bwd_kernel(const TD
       }
     }
   }
-  if (dgamma == nullptr && dbeta == nullptr) return;
+  if (!WG || (dgamma == nullptr && dbeta == nullptr)) return;
   for (int pass = 0; pass < 2; ++pass) {
     float* dst = pass == 0 ? dgamma : dbeta;
     __syncthreads();
@@ -131,7 +135,7 @@ __global__ void __launch_bounds__(128, MAXV <= 6 ? 4 : 1) ln_bwd_kernel(const TD
 #pragma unroll
       for (int i = 0; i < MAXV; ++i) {
         const int c = lane + i * 32;
-        if (c < nvec) store4(red + warp * cols + c * 4, pass == 0 ? ag[i] : ab[i]);
+        if (c < nvec) store4(red + warp * cols + c * 4, pass == 0 ? ag[WG ? i : 0] : ab[WG ? i : 0]);
       }
     }
     __syncthreads();
@@ -164,19 +168,21 @@ template <typename TDY, typename TX, typename TDX>
 static int launch_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, const void* dx_add,
                       void* dx, float* dgamma, float* dbeta, int64_t rows, int64_t cols, cudaStream_t st) {
   int64_t ctas = ceil_div(rows, 4);
-  const int64_t cap = (int64_t)num_sms() * 4;
+  const int64_t cap = (int64_t)num_sms() * ((dgamma != nullptr || dbeta != nullptr) ? 4 : 6);
   if (ctas > cap) ctas = cap;
-  const size_t smem = (size_t)4 * cols * sizeof(float);
-  if (cols <= 768) {      // the model width: exactly 6 vectors per lane -> 128 registers, 4 CTAs per SM
-    I2T_CUDA(launch_pdl(ln_bwd_kernel<TDY, TX, TDX, 6>, dim3((unsigned)ctas), dim3(128), smem, st, (const TDY*)dy, (const TX*)x, gamma,
-                        mean, rstd, (const TDX*)dx_add, (TDX*)dx, dgamma, dbeta, rows, (int)cols));
+  const bool wg = dgamma != nullptr || dbeta != nullptr;
+  const size_t smem = wg ? (size_t)4 * cols * sizeof(float) : 0;
+#define I2T_LNB(MV, WGV)                                                                                                              \
+  I2T_CUDA(launch_pdl(ln_bwd_kernel<TDY, TX, TDX, MV, WGV>, dim3((unsigned)ctas), dim3(128), smem, st, (const TDY*)dy, (const TX*)x, gamma, \
+                      mean, rstd, (const TDX*)dx_add, (TDX*)dx, dgamma, dbeta, rows, (int)cols))
+  if (cols <= 768) {      // the model width: exactly 6 vectors per lane
+    if (wg) I2T_LNB(6, true); else I2T_LNB(6, false);
   } else if (cols <= 1024) {
-    I2T_CUDA(launch_pdl(ln_bwd_kernel<TDY, TX, TDX, 8>, dim3((unsigned)ctas), dim3(128), smem, st, (const TDY*)dy, (const TX*)x, gamma,
-                        mean, rstd, (const TDX*)dx_add, (TDX*)dx, dgamma, dbeta, rows, (int)cols));
+    if (wg) I2T_LNB(8, true); else I2T_LNB(8, false);
   } else {
-    I2T_CUDA(launch_pdl(ln_bwd_kernel<TDY, TX, TDX, 16>, dim3((unsigned)ctas), dim3(128), smem, st, (const TDY*)dy, (const TX*)x, gamma,
-                        mean, rstd, (const TDX*)dx_add, (TDX*)dx, dgamma, dbeta, rows, (int)cols));
+    if (wg) I2T_LNB(16, true); else I2T_LNB(16, false);
   }
+#undef I2T_LNB
   I2T_LAUNCHED();
   return I2T_OK;
 }
